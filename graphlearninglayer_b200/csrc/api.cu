@@ -1,0 +1,233 @@
+// C ABI of libgll_b200.so (see include/gll_b200.h) and the fused forward / backward drivers.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace gll {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+const DeviceInfo& device_info() {
+  static thread_local DeviceInfo cache[64];
+  static thread_local bool have[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!have[dev]) {
+    DeviceInfo di;
+    di.device = dev;
+    di.sms = 148;
+    di.max_smem_optin = 227 * 1024;
+    cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&di.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (di.sms <= 0) di.sms = 148;
+    cache[dev] = di;
+    have[dev] = true;
+  }
+  return cache[dev];
+}
+
+namespace {
+
+__global__ void pack_grad_kernel(const void* __restrict__ g, int is_f64, int m, int l, int lp, float* __restrict__ rhs) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)m * lp) return;
+  int r = (int)(t / lp), c = (int)(t % lp);
+  float v = 0.f;
+  if (c < l) v = is_f64 ? (float)((const double*)g)[(size_t)r * l + c] : ((const float*)g)[(size_t)r * l + c];
+  rhs[t] = v;
+}
+
+__global__ void unpack_pred_kernel(const float* __restrict__ u, int m, int l, int lp, void* __restrict__ pred, int is_f64) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)m * l) return;
+  int r = (int)(t / l), c = (int)(t % l);
+  float v = u[(size_t)r * lp + c];
+  if (is_f64)
+    ((double*)pred)[t] = (double)v;
+  else
+    ((float*)pred)[t] = v;
+}
+
+}  // namespace
+
+int pack_grad(const void* g, int is_f64, int m, int l, int lp, float* rhs, cudaStream_t st) {
+  pack_grad_kernel<<<ceil_div((long long)m * lp, 256), 256, 0, st>>>(g, is_f64, m, l, lp, rhs);
+  GLL_LAUNCH_CHECK();
+  return GLL_OK;
+}
+
+int unpack_pred(const float* ut_u, int m, int l, int lp, void* pred, int is_f64, cudaStream_t st) {
+  unpack_pred_kernel<<<ceil_div((long long)m * l, 256), 256, 0, st>>>(ut_u, m, l, lp, pred, is_f64);
+  GLL_LAUNCH_CHECK();
+  return GLL_OK;
+}
+
+static int make_layout(int n, int k, int l, int k_lab, gll_layout* L) {
+  if (!L || n < 1 || k < 2 || l < 1 || k_lab < 0 || k_lab >= n) return GLL_ERR_ARG;
+  const size_t emax = gll_max_edges(n, k), lp = (size_t)padded_classes(l), m = (size_t)(n - k_lab);
+  size_t off = 0;
+  auto put = [&](size_t bytes) {
+    size_t o = align_up(off, 256);
+    off = o + bytes;
+    return o;
+  };
+  L->knn_idx = put(4 * (size_t)n * k);
+  L->knn_dist = put(4 * (size_t)n * k);
+  L->row_ptr = put(4 * ((size_t)n + 1));
+  L->col = put(4 * emax);
+  L->dist = put(4 * emax);
+  L->w = put(4 * emax);
+  L->gv = put(4 * emax);
+  L->eps = put(4 * (size_t)n);
+  L->kappa = put(4 * (size_t)n);
+  L->deg = put(4 * (size_t)n);
+  L->bvec = put(4 * (size_t)n);
+  L->uu_ptr = put(4 * (m + 1));
+  L->uu_col = put(4 * emax);
+  L->uu_val = put(4 * emax);
+  L->diag = put(4 * m);
+  L->rhs = put(4 * m * lp);
+  L->ut = put(4 * (size_t)n * lp);
+  L->wt = put(4 * (size_t)n * lp);
+  L->info = put(4 * GLL_INFO_WORDS);
+  L->total = align_up(off, 256);
+  return GLL_OK;
+}
+
+}  // namespace gll
+
+using namespace gll;
+
+extern "C" {
+
+const char* gll_last_error(void) { return g_err; }
+int gll_version(void) { return 100; }
+int gll_device_sm_count(void) { return device_info().sms; }
+int gll_padded_classes(int l) { return padded_classes(l); }
+size_t gll_max_edges(int n, int k) { return (size_t)2 * (size_t)n * (size_t)(k - 1); }
+
+int gll_state_layout(int n, int k, int l, int k_lab, gll_layout* out) {
+  int rc = make_layout(n, k, l, k_lab, out);
+  if (rc) set_error("gll_state_layout: bad sizes n=%d k=%d l=%d k_lab=%d", n, k, l, k_lab);
+  return rc;
+}
+
+size_t gll_knn_workspace_bytes(int n, int d, int k) { return knn_ws_bytes(n, d, k); }
+size_t gll_graph_workspace_bytes(int n, int k) { return graph_ws_bytes(n, k); }
+size_t gll_weights_workspace_bytes(int n, int k) { return weights_ws_bytes(n, k); }
+size_t gll_cg_workspace_bytes(int m, int l) { return cg_ws_bytes(m, l); }
+
+size_t gll_workspace_bytes(int n, int d, int k, int l, int k_lab) {
+  size_t b = knn_ws_bytes(n, d, k);
+  size_t t = graph_ws_bytes(n, k);
+  if (t > b) b = t;
+  t = weights_ws_bytes(n, k);
+  if (t > b) b = t;
+  t = cg_ws_bytes(n - k_lab > 0 ? n - k_lab : 1, l);
+  if (t > b) b = t;
+  return b;
+}
+
+int gll_knn(const float* X, int n, int d, int k, int* knn_idx, float* knn_dist, int* info, void* workspace,
+            size_t workspace_bytes, void* stream) {
+  return knn_run(X, n, d, k, knn_idx, knn_dist, info, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gll_graph_build(const int* knn_idx, const float* knn_dist, int n, int k, int* row_ptr, int* col, float* dist, int* info,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  return graph_run(knn_idx, knn_dist, n, k, row_ptr, col, dist, info, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gll_edge_weights(const int* knn_idx, const float* knn_dist, const int* row_ptr, const int* col, const float* dist,
+                     const float* Y, int n, int k, int l, int k_lab, int eps_auto, float eps_fixed, float tau, float* eps,
+                     int* kappa, float* w, float* deg, int* uu_ptr, int* uu_col, float* uu_val, float* diag, float* rhs,
+                     float* ut, int* info, void* workspace, size_t workspace_bytes, void* stream) {
+  return weights_run(knn_idx, knn_dist, row_ptr, col, dist, Y, n, k, l, k_lab, eps_auto, eps_fixed, tau, eps, kappa, w, deg,
+                     uu_ptr, uu_col, uu_val, diag, rhs, ut, info, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gll_cg_solve(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, const float* rhs, int m, int l,
+                 float tol, int max_iter, float* x, int* iters_out, float* resid_out, int* status_out, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  return cg_run(uu_ptr, uu_col, uu_val, diag, rhs, m, l, tol, max_iter, x, iters_out, resid_out, status_out, workspace,
+                workspace_bytes, (cudaStream_t)stream);
+}
+
+int gll_backward_edges(const float* X, int n, int d, int l, int k_lab, int eps_auto, const int* row_ptr, const int* col,
+                       const float* dist, const float* w, const float* eps, const int* kappa, const float* ut,
+                       const float* wt, float* gv, float* bvec, float* dX, void* stream) {
+  return backward_edges_run(X, n, d, l, k_lab, eps_auto, row_ptr, col, dist, w, eps, kappa, ut, wt, gv, bvec, dX,
+                            (cudaStream_t)stream);
+}
+
+int gll_forward(const float* X, const float* Y, int n, int d, int k, int l, int k_lab, int eps_auto, float eps_fixed,
+                float tau, float cg_tol, int cg_max_iter, void* state, void* pred_out, int pred_is_f64, void* workspace,
+                size_t workspace_bytes, void* stream) {
+  GLL_REQUIRE(X && state && pred_out && workspace, "null pointer");
+  gll_layout L;
+  if (gll_state_layout(n, k, l, k_lab, &L)) return GLL_ERR_ARG;
+  if (workspace_bytes < gll_workspace_bytes(n, d, k, l, k_lab)) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, gll_workspace_bytes(n, d, k, l, k_lab));
+    return GLL_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  char* S = (char*)state;
+  int* info = (int*)(S + L.info);
+  const int m = n - k_lab, lp = padded_classes(l);
+  GLL_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int) * GLL_INFO_WORDS, st));
+  int rc = knn_run(X, n, d, k, (int*)(S + L.knn_idx), (float*)(S + L.knn_dist), info, workspace, workspace_bytes, st);
+  if (rc) return rc;
+  rc = graph_run((int*)(S + L.knn_idx), (float*)(S + L.knn_dist), n, k, (int*)(S + L.row_ptr), (int*)(S + L.col),
+                 (float*)(S + L.dist), info, workspace, workspace_bytes, st);
+  if (rc) return rc;
+  rc = weights_run((int*)(S + L.knn_idx), (float*)(S + L.knn_dist), (int*)(S + L.row_ptr), (int*)(S + L.col),
+                   (float*)(S + L.dist), Y, n, k, l, k_lab, eps_auto, eps_fixed, tau, (float*)(S + L.eps),
+                   (int*)(S + L.kappa), (float*)(S + L.w), (float*)(S + L.deg), (int*)(S + L.uu_ptr), (int*)(S + L.uu_col),
+                   (float*)(S + L.uu_val), (float*)(S + L.diag), (float*)(S + L.rhs), (float*)(S + L.ut), info, workspace,
+                   workspace_bytes, st);
+  if (rc) return rc;
+  float* u_out = (float*)(S + L.ut) + (size_t)k_lab * lp;
+  rc = cg_run((int*)(S + L.uu_ptr), (int*)(S + L.uu_col), (float*)(S + L.uu_val), (float*)(S + L.diag),
+              (float*)(S + L.rhs), m, l, cg_tol, cg_max_iter, u_out, info + GLL_INFO_CG_ITERS_FWD,
+              (float*)(info + GLL_INFO_CG_RESID_FWD), info + GLL_INFO_STATUS, workspace, workspace_bytes, st);
+  if (rc) return rc;
+  return unpack_pred(u_out, m, l, lp, pred_out, pred_is_f64, st);
+}
+
+int gll_backward(const float* X, const void* grad_out, int grad_is_f64, int n, int d, int k, int l, int k_lab, int eps_auto,
+                 float cg_tol, int cg_max_iter, void* state, float* dX, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+  GLL_REQUIRE(X && grad_out && state && dX && workspace, "null pointer");
+  gll_layout L;
+  if (gll_state_layout(n, k, l, k_lab, &L)) return GLL_ERR_ARG;
+  if (workspace_bytes < gll_workspace_bytes(n, d, k, l, k_lab)) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, gll_workspace_bytes(n, d, k, l, k_lab));
+    return GLL_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  char* S = (char*)state;
+  int* info = (int*)(S + L.info);
+  const int m = n - k_lab, lp = padded_classes(l);
+  float* wt = (float*)(S + L.wt);
+  if (k_lab > 0) GLL_CUDA_CHECK(cudaMemsetAsync(wt, 0, sizeof(float) * (size_t)k_lab * lp, st));  // GLL.py:104
+  int rc = pack_grad(grad_out, grad_is_f64, m, l, lp, (float*)(S + L.rhs), st);
+  if (rc) return rc;
+  rc = cg_run((int*)(S + L.uu_ptr), (int*)(S + L.uu_col), (float*)(S + L.uu_val), (float*)(S + L.diag),
+              (float*)(S + L.rhs), m, l, cg_tol, cg_max_iter, wt + (size_t)k_lab * lp, info + GLL_INFO_CG_ITERS_BWD,
+              (float*)(info + GLL_INFO_CG_RESID_BWD), info + GLL_INFO_STATUS, workspace, workspace_bytes, st);
+  if (rc) return rc;
+  return backward_edges_run(X, n, d, l, k_lab, eps_auto, (int*)(S + L.row_ptr), (int*)(S + L.col), (float*)(S + L.dist),
+                            (float*)(S + L.w), (float*)(S + L.eps), (int*)(S + L.kappa), (float*)(S + L.ut), wt,
+                            (float*)(S + L.gv), (float*)(S + L.bvec), dX, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+// K5 + K6 -- backward edge pass (GLL.py:104-159).
+//   K5  G_ij = -<wt_i - wt_j, ut_i - ut_j>   (GLL.py:111-120, the per-class graph.gradient loop collapsed per edge)
+//       gv_ij = G_ij V_ij,  V_ij = -8 W_ij/(eps_i eps_j)                                   (GLL.py:146, 217)
+//       b_i = sum_j G_ij modV_ij,  modV_ij = d^2 V_ij / (2 eps_i^2)   (auto only)          (GLL.py:126, 218)
+//   K6  dX_i = sum_j t_ij (x_i - x_j),  t_ij = gv_ij - [j == kappa(i)] b_i - [kappa(j) == i] b_j
+//       == laplacian(G.*V) X - laplacian(C.*b, symmetrized) X                              (GLL.py:128-159)
+// K6 is a row-local gather (t is symmetric), so nothing is scattered and no floating-point atomics are used.
+#include "common.cuh"
+
+namespace gll {
+namespace {
+
+__global__ void __launch_bounds__(256)
+edge_grad_kernel(int n, int lp, int k_lab, int eps_auto, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                 const float* __restrict__ dist, const float* __restrict__ w, const float* __restrict__ eps,
+                 const float* __restrict__ ut, const float* __restrict__ wt, float* __restrict__ gv,
+                 float* __restrict__ bvec) {
+  const int i = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const int e0 = row_ptr[i], e1 = row_ptr[i + 1];
+  const double ei = (double)eps[i];
+  const float4* ui = reinterpret_cast<const float4*>(ut + (size_t)i * lp);
+  const float4* wi = reinterpret_cast<const float4*>(wt + (size_t)i * lp);
+  const int Q = lp >> 2;
+  double bsum = 0.0;
+  for (int e = e0 + lane; e < e1; e += 32) {
+    const int j = col[e];
+    double G = 0.0;
+    if (i >= k_lab || j >= k_lab) {  // both labeled: wt_i = wt_j = 0, G = 0
+      const float4* uj = reinterpret_cast<const float4*>(ut + (size_t)j * lp);
+      const float4* wj = reinterpret_cast<const float4*>(wt + (size_t)j * lp);
+      for (int c = 0; c < Q; ++c) {
+        const float4 a = __ldg(wi + c), b = __ldg(wj + c), u = __ldg(ui + c), v = __ldg(uj + c);
+        G -= ((double)a.x - (double)b.x) * ((double)u.x - (double)v.x);
+        G -= ((double)a.y - (double)b.y) * ((double)u.y - (double)v.y);
+        G -= ((double)a.z - (double)b.z) * ((double)u.z - (double)v.z);
+        G -= ((double)a.w - (double)b.w) * ((double)u.w - (double)v.w);
+      }
+    }
+    const double ej = (double)eps[j];
+    const double V = -8.0 * (double)w[e] / ei / ej;
+    gv[e] = (float)(G * V);
+    if (eps_auto) {
+      const double dd = (double)dist[e];
+      bsum += G * (dd * dd * V / (ei * ei) / 2.0);
+    }
+  }
+  if (eps_auto) {
+    bsum = warp_sum(bsum);
+    if (lane == 0) bvec[i] = (float)bsum;
+  }
+}
+
+constexpr int ROW_CHUNK = 128;
+
+template <int W>
+__device__ __forceinline__ void load_chunk(const float* __restrict__ base, int c, float (&v)[W]) {
+  if constexpr (W == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(base) + c);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    v[0] = __ldg(base + c);
+  }
+}
+
+// block per row; a thread owns up to 4 feature chunks (W floats each) per pass and keeps them in registers
+template <int W>
+__global__ void __launch_bounds__(256)
+row_gather_kernel(const float* __restrict__ X, int n, int d, int eps_auto, const int* __restrict__ row_ptr,
+                  const int* __restrict__ col, const int* __restrict__ kappa, const float* __restrict__ gv,
+                  const float* __restrict__ bvec, float* __restrict__ dX) {
+  __shared__ int sj[ROW_CHUNK];
+  __shared__ float stc[ROW_CHUNK];
+  const int i = blockIdx.x;
+  const int e0 = row_ptr[i], e1 = row_ptr[i + 1];
+  const int ki = eps_auto ? kappa[i] : -1;
+  const float bi = eps_auto ? bvec[i] : 0.f;
+  const int cols = d / W;
+  const float* xrow = X + (size_t)i * d;
+  for (int cbase = 0; cbase < cols; cbase += 4 * blockDim.x) {
+    double acc[4][W];
+    float xi[4][W];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = cbase + u * blockDim.x + threadIdx.x;
+#pragma unroll
+      for (int t = 0; t < W; ++t) acc[u][t] = 0.0, xi[u][t] = 0.f;
+      if (c < cols) load_chunk<W>(xrow, c, xi[u]);
+    }
+    for (int eb = e0; eb < e1; eb += ROW_CHUNK) {
+      const int cnt = min(ROW_CHUNK, e1 - eb);
+      __syncthreads();
+      for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+        const int j = col[eb + t];
+        float tc = gv[eb + t];
+        if (eps_auto) {
+          if (j == ki) tc -= bi;
+          if (kappa[j] == i) tc -= bvec[j];
+        }
+        sj[t] = j;
+        stc[t] = tc;
+      }
+      __syncthreads();
+      for (int t = 0; t < cnt; ++t) {
+        const float tc = stc[t];
+        if (tc == 0.f) continue;
+        const float* xj = X + (size_t)sj[t] * d;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = cbase + u * blockDim.x + threadIdx.x;
+          if (c < cols) {
+            float v[W];
+            load_chunk<W>(xj, c, v);
+#pragma unroll
+            for (int q = 0; q < W; ++q) acc[u][q] += (double)tc * ((double)xi[u][q] - (double)v[q]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = cbase + u * blockDim.x + threadIdx.x;
+      if (c < cols) {
+        if constexpr (W == 4) {
+          reinterpret_cast<float4*>(dX + (size_t)i * d)[c] =
+              make_float4((float)acc[u][0], (float)acc[u][1], (float)acc[u][2], (float)acc[u][3]);
+        } else {
+          dX[(size_t)i * d + c] = (float)acc[u][0];
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int backward_edges_run(const float* X, int n, int d, int l, int k_lab, int eps_auto, const int* row_ptr, const int* col,
+                       const float* dist, const float* w, const float* eps, const int* kappa, const float* ut,
+                       const float* wt, float* gv, float* bvec, float* dX, cudaStream_t st) {
+  GLL_REQUIRE(X && row_ptr && col && dist && w && eps && ut && wt && gv && bvec && dX, "null pointer");
+  GLL_REQUIRE(!eps_auto || kappa, "kappa missing");
+  const int lp = padded_classes(l);
+  edge_grad_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(n, lp, k_lab, eps_auto, row_ptr, col, dist, w, eps,
+                                                                     ut, wt, gv, bvec);
+  GLL_LAUNCH_CHECK();
+  const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dX) & 15) == 0);
+  const int cols = vec4 ? d / 4 : d;
+  int threads = min(256, max(32, ceil_div(cols, 32) * 32));
+  if (vec4)
+    row_gather_kernel<4><<<n, threads, 0, st>>>(X, n, d, eps_auto, row_ptr, col, kappa, gv, bvec, dX);
+  else
+    row_gather_kernel<1><<<n, threads, 0, st>>>(X, n, d, eps_auto, row_ptr, col, kappa, gv, bvec, dX);
+  GLL_LAUNCH_CHECK();
+  return GLL_OK;
+}
+
+}  // namespace gll

@@ -1,0 +1,350 @@
+// K4 -- persistent multi-right-hand-side Jacobi-CG (replaces spsolve at GLL.py:53 and GLL.py:93; semantics of
+// stable_conjgrad GLL.py:247-276: all class columns advance together, per-column freeze once r_c^T r_c <= tol^2,
+// stop when max_c ||r_c||_2 <= tol or max_iter; the p = r alias of GLL.py:254 is NOT reproduced).
+//
+// ONE cooperative launch runs the whole solve.  A = diag - offdiag(val) on the unlabeled block, x0 = 0.
+// Per iteration (three grid-wide barriers, the first two carry the dot-product reductions):
+//   phase 1  Ap_i = diag_i p_i - sum_j W_ij p_j      warp per row; lane = (neighbour slot s, class quad q): 128-bit
+//            gathers of p_j, shuffle reduction over s; fused partial <p, Ap>
+//   phase 2  x += a p ; r -= a Ap ; z = r/diag       lanes tile S rows x Q quads = one contiguous 128-bit span per
+//            warp; fused partial <r,z>, <r,r>
+//   phase 3  p = z + b p
+// Reductions are deterministic: per-warp shuffle tree -> per-block fixed-order sum -> per-grid partials
+// [column][block] summed by one warp per column in a fixed order (no floating-point atomics anywhere).
+// Vectors written by other CTAs are read with ld.global.cg (L2), never through a possibly stale L1 line.
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace gll {
+namespace {
+
+constexpr int CG_THREADS = 1024;
+constexpr int CG_WARPS = CG_THREADS / 32;
+constexpr int CG_MAX_LP = 128;
+
+struct CgParams {
+  const int* ptr;
+  const int* col;
+  const float* val;
+  const float* diag;
+  const float* rhs;
+  float* x;
+  float* r;
+  float* p;
+  float* ap;
+  double* partial;    // [2 buffers][2*lp columns][grid]
+  unsigned* barrier;  // zeroed before launch
+  int m, lp, rows_per_block, max_iter;
+  float tol;
+  int* iters_out;
+  float* resid_out;
+  int* status_out;
+};
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += 1;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned target = epoch * gridDim.x;
+    while (ld_acquire(counter) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// sum over the neighbour-slot index s of lane = s*Q + q; result valid on lanes < Q
+__device__ __forceinline__ float4 reduce_over_s(float4 a, int s, int S, int Q) {
+  int top = 1;
+  while (top < S) top <<= 1;
+  int span = S;
+  for (int st = top >> 1; st >= 1; st >>= 1) {
+    float4 o;
+    o.x = __shfl_down_sync(FULL, a.x, st * Q);
+    o.y = __shfl_down_sync(FULL, a.y, st * Q);
+    o.z = __shfl_down_sync(FULL, a.z, st * Q);
+    o.w = __shfl_down_sync(FULL, a.w, st * Q);
+    if (s < st && s + st < span) {
+      a.x += o.x;
+      a.y += o.y;
+      a.z += o.z;
+      a.w += o.w;
+    }
+    span = min(span, st);
+  }
+  return a;
+}
+
+// Deterministic grid-wide sum of NV float4 accumulators per lane (lane owns class quad q), with a grid barrier.
+// out[v*lp + c] (shared, double) holds the result on return.
+template <int NV>
+__device__ __forceinline__ void grid_reduce(float4 (&acc)[NV], const CgParams& P, int s, int q, int S, int Q, bool active,
+                                            double* wpart, double* out, int& buf, unsigned& epoch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lp = P.lp;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    float4 a = active ? acc[v] : make_float4(0.f, 0.f, 0.f, 0.f);
+    a = reduce_over_s(a, s, S, Q);
+    if (lane < Q) {
+      double* d = wpart + ((size_t)v * CG_WARPS + warp) * lp + 4 * lane;
+      d[0] = (double)a.x;
+      d[1] = (double)a.y;
+      d[2] = (double)a.z;
+      d[3] = (double)a.w;
+    }
+  }
+  __syncthreads();
+  const int G = gridDim.x;
+  double* mine = P.partial + (size_t)buf * (2 * CG_MAX_LP) * G;
+  for (int c = threadIdx.x; c < NV * lp; c += CG_THREADS) {
+    const int v = c / lp, cc = c - v * lp;
+    double t = 0.0;
+    for (int w = 0; w < CG_WARPS; ++w) t += wpart[((size_t)v * CG_WARPS + w) * lp + cc];
+    mine[(size_t)c * G + blockIdx.x] = t;
+  }
+  grid_barrier(P.barrier, epoch);
+  for (int c = warp; c < NV * lp; c += CG_WARPS) {
+    double t = 0.0;
+    for (int b = lane; b < G; b += 32) t += __ldcg(mine + (size_t)c * G + b);
+    t = warp_sum(t);
+    if (lane == 0) out[c] = t;
+  }
+  buf ^= 1;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(CG_THREADS, 1) cg_persistent_kernel(CgParams P) {
+  extern __shared__ __align__(16) double sm[];
+  const int lp = P.lp, Q = lp >> 2, S = 32 / Q;
+  double* wpart = sm;                            // [2][CG_WARPS][lp]
+  double* red = wpart + 2 * CG_WARPS * lp;       // [2*lp]
+  double* rz = red + 2 * lp;                     // [lp]
+  double* rr = rz + lp;                          // [lp]
+  float* alpha = reinterpret_cast<float*>(rr + lp);  // [lp]
+  float* beta = alpha + lp;                          // [lp]
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = lane / Q, q = lane - s * Q;
+  const bool active = lane < S * Q;
+  const int row_begin = blockIdx.x * P.rows_per_block;
+  const int row_end = min(P.m, row_begin + P.rows_per_block);
+  const double tol2 = (double)P.tol * (double)P.tol;
+  unsigned epoch = 0;
+  int buf = 0;
+
+  // ---- init: x = 0, r = b, p = z = r/diag ----
+  {
+    float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+    for (int i0 = row_begin + warp * S; i0 < row_end; i0 += CG_WARPS * S) {
+      const int i = i0 + s;
+      if (active && i < row_end) {
+        const size_t o = (size_t)i * lp + 4 * q;
+        const float4 b = ldcg4(P.rhs + o);
+        const float dinv = 1.f / __ldg(P.diag + i);
+        const float4 z = make_float4(b.x * dinv, b.y * dinv, b.z * dinv, b.w * dinv);
+        st4(P.x + o, make_float4(0.f, 0.f, 0.f, 0.f));
+        st4(P.r + o, b);
+        st4(P.p + o, z);
+        acc[0].x += b.x * z.x; acc[0].y += b.y * z.y; acc[0].z += b.z * z.z; acc[0].w += b.w * z.w;
+        acc[1].x += b.x * b.x; acc[1].y += b.y * b.y; acc[1].z += b.z * b.z; acc[1].w += b.w * b.w;
+      }
+    }
+    grid_reduce<2>(acc, P, s, q, S, Q, active, wpart, red, buf, epoch);
+    for (int c = threadIdx.x; c < lp; c += CG_THREADS) {
+      rz[c] = red[c];
+      rr[c] = red[lp + c];
+    }
+    __syncthreads();
+  }
+
+  int it = 0;
+  bool nonfinite = false;
+  double maxrr = 0.0;
+  while (true) {
+    maxrr = 0.0;
+    for (int c = 0; c < lp; ++c) {
+      const double v = rr[c];
+      if (!(v == v) || isinf(v)) nonfinite = true;
+      maxrr = fmax(maxrr, v);
+    }
+    if (nonfinite || sqrt(maxrr) <= (double)P.tol || it >= P.max_iter) break;
+    ++it;
+
+    // ---- phase 1: Ap = A p, partial <p, Ap> ----
+    float4 dot[1] = {make_float4(0.f, 0.f, 0.f, 0.f)};
+    for (int i = row_begin + warp; i < row_end; i += CG_WARPS) {
+      const int e0 = __ldg(P.ptr + i), e1 = __ldg(P.ptr + i + 1);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (active) {
+        for (int e = e0 + s; e < e1; e += S) {
+          const int j = __ldg(P.col + e);
+          const float wv = __ldg(P.val + e);
+          const float4 pj = ldcg4(P.p + (size_t)j * lp + 4 * q);
+          a.x = fmaf(wv, pj.x, a.x);
+          a.y = fmaf(wv, pj.y, a.y);
+          a.z = fmaf(wv, pj.z, a.z);
+          a.w = fmaf(wv, pj.w, a.w);
+        }
+      }
+      a = reduce_over_s(a, s, S, Q);
+      if (lane < Q) {
+        const size_t o = (size_t)i * lp + 4 * lane;
+        const float4 pi = ldcg4(P.p + o);
+        const float dg = __ldg(P.diag + i);
+        const float4 ap = make_float4(fmaf(dg, pi.x, -a.x), fmaf(dg, pi.y, -a.y), fmaf(dg, pi.z, -a.z), fmaf(dg, pi.w, -a.w));
+        st4(P.ap + o, ap);
+        dot[0].x = fmaf(pi.x, ap.x, dot[0].x);
+        dot[0].y = fmaf(pi.y, ap.y, dot[0].y);
+        dot[0].z = fmaf(pi.z, ap.z, dot[0].z);
+        dot[0].w = fmaf(pi.w, ap.w, dot[0].w);
+      }
+    }
+    // dot lives on lanes < Q only (s == 0): zero the rest so that the s-reduction is a no-op for them
+    if (lane >= Q) dot[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    grid_reduce<1>(dot, P, s, q, S, Q, active, wpart, red, buf, epoch);
+    for (int c = threadIdx.x; c < lp; c += CG_THREADS) {
+      const bool live = rr[c] > tol2;
+      alpha[c] = live ? (float)(rz[c] / red[c]) : 0.f;
+    }
+    __syncthreads();
+
+    // ---- phase 2: x += alpha p, r -= alpha Ap, partial <r,z>, <r,r> ----
+    float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+    const float4 al = active ? *reinterpret_cast<const float4*>(alpha + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i0 = row_begin + warp * S; i0 < row_end; i0 += CG_WARPS * S) {
+      const int i = i0 + s;
+      if (active && i < row_end) {
+        const size_t o = (size_t)i * lp + 4 * q;
+        float4 x = ldcg4(P.x + o), r = ldcg4(P.r + o);
+        const float4 p = ldcg4(P.p + o), ap = ldcg4(P.ap + o);
+        const float dinv = 1.f / __ldg(P.diag + i);
+        x.x = fmaf(al.x, p.x, x.x); x.y = fmaf(al.y, p.y, x.y); x.z = fmaf(al.z, p.z, x.z); x.w = fmaf(al.w, p.w, x.w);
+        r.x = fmaf(-al.x, ap.x, r.x); r.y = fmaf(-al.y, ap.y, r.y); r.z = fmaf(-al.z, ap.z, r.z); r.w = fmaf(-al.w, ap.w, r.w);
+        st4(P.x + o, x);
+        st4(P.r + o, r);
+        acc[0].x += r.x * r.x * dinv; acc[0].y += r.y * r.y * dinv; acc[0].z += r.z * r.z * dinv; acc[0].w += r.w * r.w * dinv;
+        acc[1].x += r.x * r.x; acc[1].y += r.y * r.y; acc[1].z += r.z * r.z; acc[1].w += r.w * r.w;
+      }
+    }
+    grid_reduce<2>(acc, P, s, q, S, Q, active, wpart, red, buf, epoch);
+    for (int c = threadIdx.x; c < lp; c += CG_THREADS) {
+      const double rz_new = red[c], rr_new = red[lp + c];
+      beta[c] = (rr_new > tol2 && rz[c] != 0.0) ? (float)(rz_new / rz[c]) : 0.f;
+      rz[c] = rz_new;
+      rr[c] = rr_new;
+    }
+    __syncthreads();
+
+    // ---- phase 3: p = z + beta p ----
+    const float4 be = active ? *reinterpret_cast<const float4*>(beta + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i0 = row_begin + warp * S; i0 < row_end; i0 += CG_WARPS * S) {
+      const int i = i0 + s;
+      if (active && i < row_end) {
+        const size_t o = (size_t)i * lp + 4 * q;
+        const float4 r = ldcg4(P.r + o);
+        float4 p = ldcg4(P.p + o);
+        const float dinv = 1.f / __ldg(P.diag + i);
+        p.x = fmaf(be.x, p.x, r.x * dinv);
+        p.y = fmaf(be.y, p.y, r.y * dinv);
+        p.z = fmaf(be.z, p.z, r.z * dinv);
+        p.w = fmaf(be.w, p.w, r.w * dinv);
+        st4(P.p + o, p);
+      }
+    }
+    grid_barrier(P.barrier, epoch);
+  }
+
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const float resid = (float)sqrt(maxrr);
+    if (P.iters_out) *P.iters_out = it;
+    if (P.resid_out) *P.resid_out = resid;
+    if (P.status_out) {
+      int st = 0;
+      if (nonfinite) st |= GLL_STATUS_NONFINITE;
+      if (!nonfinite && !(resid <= P.tol)) st |= GLL_STATUS_CG_NOT_CONVERGED;
+      if (st) atomicOr(P.status_out, st);
+    }
+  }
+}
+
+size_t cg_smem_bytes(int lp) {
+  return sizeof(double) * ((size_t)2 * CG_WARPS * lp + 2 * lp + 2 * lp) + sizeof(float) * 2 * lp;
+}
+
+int cg_grid(int m) {
+  int g = ceil_div(m, CG_WARPS);
+  return max(1, min(g, device_info().sms));
+}
+
+}  // namespace
+
+size_t cg_ws_bytes(int m, int l) {
+  const int lp = padded_classes(l);
+  size_t v = align_up(sizeof(float) * (size_t)m * lp, 256);
+  return 3 * v + align_up(sizeof(double) * 2 * (2 * CG_MAX_LP) * (size_t)device_info().sms, 256) + 256 + 1024;
+}
+
+int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, const float* rhs, int m, int l,
+           float tol, int max_iter, float* x, int* iters_out, float* resid_out, int* status_out, void* ws, size_t ws_bytes,
+           cudaStream_t st) {
+  GLL_REQUIRE(uu_ptr && uu_col && uu_val && diag && rhs && x && ws, "null pointer");
+  GLL_REQUIRE(m >= 1 && l >= 1, "bad sizes");
+  const int lp = padded_classes(l);
+  GLL_REQUIRE(lp <= CG_MAX_LP, "at most 128 classes per solve");
+  if (ws_bytes < cg_ws_bytes(m, l)) {
+    set_error("CG workspace too small: %zu < %zu", ws_bytes, cg_ws_bytes(m, l));
+    return GLL_ERR_WORKSPACE;
+  }
+  Carver cv(ws, ws_bytes);
+  CgParams P;
+  P.ptr = uu_ptr;
+  P.col = uu_col;
+  P.val = uu_val;
+  P.diag = diag;
+  P.rhs = rhs;
+  P.x = x;
+  P.r = cv.take<float>((size_t)m * lp);
+  P.p = cv.take<float>((size_t)m * lp);
+  P.ap = cv.take<float>((size_t)m * lp);
+  P.partial = cv.take<double>((size_t)2 * (2 * CG_MAX_LP) * device_info().sms);
+  P.barrier = cv.take<unsigned>(64);
+  P.m = m;
+  P.lp = lp;
+  P.max_iter = max_iter;
+  P.tol = tol;
+  P.iters_out = iters_out;
+  P.resid_out = resid_out;
+  P.status_out = status_out;
+  const int grid = cg_grid(m);
+  const int S = 32 / (lp / 4);
+  int rpb = ceil_div(m, grid);
+  rpb = ceil_div(rpb, S) * S;  // keep phase-2/3 spans aligned to whole lane groups
+  P.rows_per_block = rpb;
+  const size_t smem = cg_smem_bytes(lp);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GLL_CUDA_CHECK(cudaFuncSetAttribute(cg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)cg_smem_bytes(CG_MAX_LP)));
+    attr_set = true;
+  }
+  GLL_CUDA_CHECK(cudaMemsetAsync(P.barrier, 0, 256, st));
+  void* args[] = {&P};
+  GLL_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)cg_persistent_kernel, dim3(grid), dim3(CG_THREADS), args, smem, st));
+  return GLL_OK;
+}
+
+}  // namespace gll

@@ -1,0 +1,125 @@
+// Shared helpers for the gll_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gll_b200.h"
+
+namespace gll {
+
+void set_error(const char* fmt, ...);
+
+#define GLL_CUDA_CHECK(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      gll::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return GLL_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define GLL_LAUNCH_CHECK()                                                                \
+  do {                                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess) {                                                              \
+      gll::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return GLL_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define GLL_REQUIRE(cond, msg)                \
+  do {                                        \
+    if (!(cond)) {                            \
+      gll::set_error("%s (%s)", msg, #cond);  \
+      return GLL_ERR_ARG;                     \
+    }                                         \
+  } while (0)
+
+constexpr int WARP = 32;
+constexpr unsigned FULL = 0xffffffffu;
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// bump allocator over a caller-provided workspace
+struct Carver {
+  char* base;
+  size_t off, cap;
+  Carver(void* p, size_t bytes) : base((char*)p), off(0), cap(bytes) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t o = align_up(off, 256);
+    off = o + count * sizeof(T);
+    return (T*)(base + o);
+  }
+  bool ok() const { return off <= cap; }
+};
+
+struct DeviceInfo {
+  int device;
+  int sms;
+  int max_smem_optin;
+};
+const DeviceInfo& device_info();
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// order-preserving map float -> uint32 (handles negatives), and back
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// ---- internal launchers (one per stage), implemented in the .cu files ----
+int knn_run(const float* X, int n, int d, int k, int* knn_idx, float* knn_dist, int* info, void* ws,
+            size_t ws_bytes, cudaStream_t st);
+size_t knn_ws_bytes(int n, int d, int k);
+
+int graph_run(const int* knn_idx, const float* knn_dist, int n, int k, int* row_ptr, int* col, float* dist,
+              int* info, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t graph_ws_bytes(int n, int k);
+
+int weights_run(const int* knn_idx, const float* knn_dist, const int* row_ptr, const int* col, const float* dist,
+                const float* Y, int n, int k, int l, int k_lab, int eps_auto, float eps_fixed, float tau,
+                float* eps, int* kappa, float* w, float* deg, int* uu_ptr, int* uu_col, float* uu_val,
+                float* diag, float* rhs, float* ut, int* info, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t weights_ws_bytes(int n, int k);
+
+int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, const float* rhs, int m,
+           int l, float tol, int max_iter, float* x, int* iters_out, float* resid_out, int* status_out, void* ws,
+           size_t ws_bytes, cudaStream_t st);
+size_t cg_ws_bytes(int m, int l);
+
+int backward_edges_run(const float* X, int n, int d, int l, int k_lab, int eps_auto, const int* row_ptr,
+                       const int* col, const float* dist, const float* w, const float* eps, const int* kappa,
+                       const float* ut, const float* wt, float* gv, float* bvec, float* dX, cudaStream_t st);
+
+// exclusive prefix sum of int32 counts[0..n) into out[0..n] (out[n] = total). scratch: scan_ws_bytes(n).
+size_t scan_ws_bytes(int n);
+int exclusive_scan(const int* counts, int n, int* out, void* scratch, cudaStream_t st);
+
+// small utility kernels (api.cu)
+int pack_grad(const void* g, int is_f64, int m, int l, int lp, float* rhs, cudaStream_t st);
+int unpack_pred(const float* ut_u, int m, int l, int lp, void* pred, int is_f64, cudaStream_t st);
+
+inline int padded_classes(int l) { return (l + 3) / 4 * 4; }
+
+}  // namespace gll

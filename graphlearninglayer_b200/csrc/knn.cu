@@ -1,0 +1,476 @@
+// K1 -- exact k-nearest-neighbour search (replaces gl.weightmatrix.knnsearch(..., 'annoy'), GLL.py:181-189).
+//
+// Pipeline (all on one stream, no host sync):
+//   sqnorm      : ||x_i||^2 (fp64 accumulate -> fp32) and the global max
+//   gemm_topk   : tiled Gram GEMM  d~^2_ij = |x_i|^2 + |x_j|^2 - 2 x_i.x_j  with a FUSED per-row top-KC epilogue:
+//                 a tile's distances are filtered against the row's running threshold and only the survivors
+//                 touch shared memory; the n x n matrix never reaches HBM.  Column range split across CTAs.
+//   rerank      : merge the per-split candidate lists, recompute the KC survivors as sum (x_i-x_j)^2 in fp64
+//                 (bit-symmetric in i,j), order by (distance, index), emit k entries with self in slot 0, and
+//                 PROVE completeness: every non-candidate has approximate distance >= L_i, so its true distance
+//                 is >= L_i - err; rows where that does not exceed the k-th exact distance are queued for
+//   fallback    : brute-force fp64 search for the queued rows only.
+//
+// This file holds the fp32 SIMT Gram path (any d, any alignment).  The tcgen05/TMA Gram path for d % 64 == 0
+// lives in knn_tc.cu and reuses the rerank / fallback kernels through knn_finish().
+#include <math.h>
+
+#include "common.cuh"
+#include "knn_common.cuh"
+
+namespace gll {
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, PAD = 4;
+constexpr int GEMM_THREADS = 256;
+constexpr int LDS_A = BM + PAD, LDS_B = BN + PAD;
+
+constexpr size_t gemm_smem_bytes() {
+  return sizeof(float) * (2 * BK * LDS_A + 2 * BK * LDS_B) + sizeof(u64) * (BM * KC + BM * BN) +
+         sizeof(float) * BM + sizeof(int) * BM;
+}
+
+__global__ void sqnorm_kernel(const float* __restrict__ X, int n, int d, float* __restrict__ sq,
+                              unsigned* __restrict__ sqmax_bits) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const float* x = X + (size_t)warp * d;
+  double s = 0.0;
+  for (int t = lane; t < d; t += 32) {
+    double v = (double)x[t];
+    s += v * v;
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    float f = (float)s;
+    sq[warp] = f;
+    if (f == f) atomicMax(sqmax_bits, __float_as_uint(f));  // non-negative floats order like their bits
+  }
+}
+
+template <bool VEC4>
+__device__ __forceinline__ void load_tile_regs(const float* __restrict__ X, int n, int d, int rbase, int k0, int tid,
+                                               float4 (&reg)[2]) {
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    int f = tid + t * GEMM_THREADS;
+    int r = f >> 2, kq = f & 3;
+    int gi = rbase + r, gk = k0 + kq * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gi < n) {
+      const float* p = X + (size_t)gi * d + gk;
+      if (VEC4) {
+        if (gk < d) v = __ldg(reinterpret_cast<const float4*>(p));
+      } else {
+        if (gk + 0 < d) v.x = __ldg(p + 0);
+        if (gk + 1 < d) v.y = __ldg(p + 1);
+        if (gk + 2 < d) v.z = __ldg(p + 2);
+        if (gk + 3 < d) v.w = __ldg(p + 3);
+      }
+    }
+    reg[t] = v;
+  }
+}
+
+__device__ __forceinline__ void store_tile_smem(float* __restrict__ S, int lds, int tid, const float4 (&reg)[2]) {
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    int f = tid + t * GEMM_THREADS;
+    int r = f >> 2, kq = f & 3;
+    S[(kq * 4 + 0) * lds + r] = reg[t].x;
+    S[(kq * 4 + 1) * lds + r] = reg[t].y;
+    S[(kq * 4 + 2) * lds + r] = reg[t].z;
+    S[(kq * 4 + 3) * lds + r] = reg[t].w;
+  }
+}
+
+// grid: (row tiles, column splits).  cand: [n][splits][KC] sorted keys.
+template <bool VEC4>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+knn_gemm_topk_kernel(const float* __restrict__ X, const float* __restrict__ sq, int n, int d, int cols_per_split,
+                     int splits, u64* __restrict__ cand) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* As = reinterpret_cast<float*>(smem_raw);
+  float* Bs = As + 2 * BK * LDS_A;
+  u64* topk = reinterpret_cast<u64*>(Bs + 2 * BK * LDS_B);
+  u64* pend = topk + BM * KC;
+  float* thr = reinterpret_cast<float*>(pend + BM * BN);
+  int* pcnt = reinterpret_cast<int*>(thr + BM);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int row0 = blockIdx.x * BM;
+  const int split = blockIdx.y;
+  const int c_begin = split * cols_per_split;
+  const int c_end = min(n, c_begin + cols_per_split);
+
+  for (int t = tid; t < BM * KC; t += GEMM_THREADS) topk[t] = KEY_INF;
+  for (int t = tid; t < BM; t += GEMM_THREADS) {
+    thr[t] = INFINITY;
+    pcnt[t] = 0;
+  }
+  __syncthreads();
+
+  const int ktiles = (d + BK - 1) / BK;
+  for (int c0 = c_begin; c0 < c_end; c0 += BN) {
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    float4 ra[2], rb[2];
+    load_tile_regs<VEC4>(X, n, d, row0, 0, tid, ra);
+    load_tile_regs<VEC4>(X, n, d, c0, 0, tid, rb);
+    store_tile_smem(As, LDS_A, tid, ra);
+    store_tile_smem(Bs, LDS_B, tid, rb);
+    __syncthreads();
+    for (int kt = 0; kt < ktiles; ++kt) {
+      const int cur = kt & 1;
+      if (kt + 1 < ktiles) {
+        load_tile_regs<VEC4>(X, n, d, row0, (kt + 1) * BK, tid, ra);
+        load_tile_regs<VEC4>(X, n, d, c0, (kt + 1) * BK, tid, rb);
+      }
+      const float* A = As + cur * BK * LDS_A;
+      const float* B = Bs + cur * BK * LDS_B;
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        float4 a0 = *reinterpret_cast<const float4*>(A + kk * LDS_A + ty * 4);
+        float4 a1 = *reinterpret_cast<const float4*>(A + kk * LDS_A + 64 + ty * 4);
+        float4 b0 = *reinterpret_cast<const float4*>(B + kk * LDS_B + tx * 4);
+        float4 b1 = *reinterpret_cast<const float4*>(B + kk * LDS_B + 64 + tx * 4);
+        float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      if (kt + 1 < ktiles) {
+        store_tile_smem(As + (cur ^ 1) * BK * LDS_A, LDS_A, tid, ra);
+        store_tile_smem(Bs + (cur ^ 1) * BK * LDS_B, LDS_B, tid, rb);
+      }
+      __syncthreads();
+    }
+
+    // ---- fused epilogue: threshold filter, survivors appended to the row's pending list ----
+    float sqj[8];
+    int gjv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int cc = (j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4);
+      gjv[j] = c0 + cc;
+      sqj[j] = (gjv[j] < c_end) ? __ldg(sq + gjv[j]) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int rr = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+      int gi = row0 + rr;
+      if (gi >= n) continue;
+      float t = thr[rr];
+      float sqi = __ldg(sq + gi);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (gjv[j] < c_end && gjv[j] != gi) {
+          float dist = fmaf(-2.f, acc[i][j], sqi + sqj[j]);
+          if (dist < t) {
+            int p = atomicAdd(&pcnt[rr], 1);
+            pend[rr * BN + p] = make_key(dist, gjv[j]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- drain: each warp folds the pending entries of its 16 rows into the sorted top-KC lists ----
+    for (int rr = warp * (BM / 8); rr < (warp + 1) * (BM / 8); ++rr) {
+      int c = pcnt[rr];
+      if (c > 0) {
+        u64 mine = topk[rr * KC + lane];
+        for (int t = 0; t < c; ++t) list_insert(mine, pend[rr * BN + t], lane);
+        topk[rr * KC + lane] = mine;
+        if (lane == KC - 1) thr[rr] = (mine == KEY_INF) ? INFINITY : key_dist(mine);
+        if (lane == 0) pcnt[rr] = 0;
+      }
+    }
+    __syncthreads();
+  }
+
+  for (int rr = warp * (BM / 8); rr < (warp + 1) * (BM / 8); ++rr) {
+    int gi = row0 + rr;
+    if (gi < n) cand[((size_t)gi * splits + split) * KC + lane] = topk[rr * KC + lane];
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// rerank + completeness proof + fallback (shared with the tensor-core path)
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int RERANK_WARPS = 4;
+
+template <bool VEC4>
+__device__ __forceinline__ double exact_d2(const float* __restrict__ xi_s, const float* __restrict__ xj, int d,
+                                           int lane) {
+  double part = 0.0;
+  if (VEC4) {
+    const float4* a = reinterpret_cast<const float4*>(xi_s);
+    const float4* b = reinterpret_cast<const float4*>(xj);
+    int q = d >> 2;
+#pragma unroll 4
+    for (int t = lane; t < q; t += 32) {
+      float4 u = a[t], v = __ldg(b + t);
+      double d0 = (double)u.x - (double)v.x, d1 = (double)u.y - (double)v.y;
+      double d2 = (double)u.z - (double)v.z, d3 = (double)u.w - (double)v.w;
+      part += d0 * d0;
+      part += d1 * d1;
+      part += d2 * d2;
+      part += d3 * d3;
+    }
+  } else {
+#pragma unroll 4
+    for (int t = lane; t < d; t += 32) {
+      double df = (double)xi_s[t] - (double)__ldg(xj + t);
+      part += df * df;
+    }
+  }
+  return warp_sum(part);  // xor butterfly: identical on all lanes, and exact_d2(i,j) == exact_d2(j,i) bitwise
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(RERANK_WARPS * 32)
+knn_rerank_kernel(const float* __restrict__ X, const float* __restrict__ sq, const unsigned* __restrict__ sqmax_bits,
+                  int n, int d, int k, int splits, const u64* __restrict__ cand, float err_coef,
+                  int* __restrict__ knn_idx, float* __restrict__ knn_dist, int* __restrict__ flag_count,
+                  int* __restrict__ flag_rows) {
+  extern __shared__ __align__(16) float xs[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * RERANK_WARPS + warp;
+  if (i >= n) return;
+  float* xi = xs + (size_t)warp * d;
+  for (int t = lane; t < d; t += 32) xi[t] = X[(size_t)i * d + t];
+
+  u64 mine = KEY_INF;
+  if (splits == 1) {
+    mine = cand[(size_t)i * KC + lane];
+  } else {
+    for (int s = 0; s < splits; ++s) {
+      u64 c = cand[((size_t)i * splits + s) * KC + lane];
+      for (int t = 0; t < KC; ++t) {
+        u64 x = __shfl_sync(FULL, c, t);
+        if (x == KEY_INF) break;
+        list_insert(mine, x, lane);
+      }
+    }
+  }
+  u64 last = __shfl_sync(FULL, mine, KC - 1);
+  const float lower = (last == KEY_INF) ? INFINITY : key_dist(last);  // every non-candidate has d~^2 >= lower
+  __syncwarp();
+
+  double myd2 = INFINITY;
+  int myj = -1;
+  for (int c = 0; c < KC; ++c) {
+    u64 kc = __shfl_sync(FULL, mine, c);
+    if (kc == KEY_INF) break;
+    int j = key_idx(kc);
+    double v = exact_d2<VEC4>(xi, X + (size_t)j * d, d, lane);
+    if (lane == c) {
+      myd2 = v;
+      myj = j;
+    }
+  }
+  int rank = 0;
+  for (int c = 0; c < KC; ++c) {
+    double od = __shfl_sync(FULL, myd2, c);
+    int oj = __shfl_sync(FULL, myj, c);
+    if (oj >= 0 && (od < myd2 || (od == myd2 && oj < myj))) ++rank;
+  }
+  if (myj >= 0 && rank < k - 1) {
+    knn_idx[(size_t)i * k + 1 + rank] = myj;
+    knn_dist[(size_t)i * k + 1 + rank] = (float)sqrt(myd2);
+  }
+  if (lane == 0) {
+    knn_idx[(size_t)i * k] = i;
+    knn_dist[(size_t)i * k] = 0.f;
+  }
+  // completeness proof
+  unsigned who = __ballot_sync(FULL, myj >= 0 && rank == k - 2);
+  bool ok = false;
+  if (who) {
+    double dk = __shfl_sync(FULL, myd2, __ffs(who) - 1);
+    float sqm = __uint_as_float(*sqmax_bits);
+    double errb = (double)err_coef * ((double)sq[i] + (double)sqm);
+    ok = ((double)lower - errb > dk) || (lower == INFINITY);
+  }
+  if (!ok && lane == 0) {
+    int p = atomicAdd(flag_count, 1);
+    flag_rows[p] = i;
+  }
+}
+
+constexpr int FB_WARPS = 8;
+
+__device__ __forceinline__ void list_insert_d(double& md, int& mj, double xd, int xj, int lane) {
+  bool lt = (md < xd) || (md == xd && mj < xj);
+  int pos = __popc(__ballot_sync(FULL, lt));
+  double pd = __shfl_up_sync(FULL, md, 1);
+  int pj = __shfl_up_sync(FULL, mj, 1);
+  if (lane > pos) {
+    md = pd;
+    mj = pj;
+  } else if (lane == pos) {
+    md = xd;
+    mj = xj;
+  }
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(FB_WARPS * 32)
+knn_fallback_kernel(const float* __restrict__ X, int n, int d, int k, const int* __restrict__ flag_count,
+                    const int* __restrict__ flag_rows, int* __restrict__ knn_idx, float* __restrict__ knn_dist,
+                    int* __restrict__ info) {
+  extern __shared__ __align__(16) float xs[];
+  __shared__ double sd[FB_WARPS][32];
+  __shared__ int sj[FB_WARPS][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nflag = *flag_count;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && info != nullptr) {
+    info[GLL_INFO_KNN_FALLBACK_ROWS] = nflag;
+    if (nflag > 0) atomicOr(&info[GLL_INFO_STATUS], GLL_STATUS_KNN_FALLBACK);
+  }
+  for (int f = blockIdx.x; f < nflag; f += gridDim.x) {
+    const int i = flag_rows[f];
+    for (int t = threadIdx.x; t < d; t += blockDim.x) xs[t] = X[(size_t)i * d + t];
+    __syncthreads();
+    double md = INFINITY;
+    int mj = 0x7fffffff;
+    for (int j = warp; j < n; j += FB_WARPS) {
+      if (j == i) continue;
+      double v = exact_d2<VEC4>(xs, X + (size_t)j * d, d, lane);
+      list_insert_d(md, mj, v, j, lane);
+    }
+    sd[warp][lane] = md;
+    sj[warp][lane] = mj;
+    __syncthreads();
+    if (warp == 0) {
+      for (int w = 1; w < FB_WARPS; ++w)
+        for (int t = 0; t < 32; ++t) {
+          int xj = sj[w][t];
+          if (xj == 0x7fffffff) break;
+          list_insert_d(md, mj, sd[w][t], xj, lane);
+        }
+      if (lane < k - 1 && mj != 0x7fffffff) {
+        knn_idx[(size_t)i * k + 1 + lane] = mj;
+        knn_dist[(size_t)i * k + 1 + lane] = (float)sqrt(md);
+      }
+      if (lane == 0) {
+        knn_idx[(size_t)i * k] = i;
+        knn_dist[(size_t)i * k] = 0.f;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+int knn_finish(const float* X, const float* sq, const unsigned* sqmax_bits, int n, int d, int k, int splits,
+               const u64* cand, float err_coef, int* knn_idx, float* knn_dist, int* flag_count, int* flag_rows,
+               int* info, cudaStream_t st) {
+  const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  size_t smem = sizeof(float) * (size_t)RERANK_WARPS * d;
+  int blocks = ceil_div(n, RERANK_WARPS);
+  if (vec4) {
+    if (smem > 48 * 1024)
+      GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_rerank_kernel<true><<<blocks, RERANK_WARPS * 32, smem, st>>>(X, sq, sqmax_bits, n, d, k, splits, cand,
+                                                                      err_coef, knn_idx, knn_dist, flag_count, flag_rows);
+  } else {
+    if (smem > 48 * 1024)
+      GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_rerank_kernel<false><<<blocks, RERANK_WARPS * 32, smem, st>>>(X, sq, sqmax_bits, n, d, k, splits, cand,
+                                                                       err_coef, knn_idx, knn_dist, flag_count, flag_rows);
+  }
+  GLL_LAUNCH_CHECK();
+  size_t fsmem = sizeof(float) * (size_t)d;
+  int fblocks = device_info().sms * 2;
+  if (vec4)
+    knn_fallback_kernel<true><<<fblocks, FB_WARPS * 32, fsmem, st>>>(X, n, d, k, flag_count, flag_rows, knn_idx, knn_dist, info);
+  else
+    knn_fallback_kernel<false><<<fblocks, FB_WARPS * 32, fsmem, st>>>(X, n, d, k, flag_count, flag_rows, knn_idx, knn_dist, info);
+  GLL_LAUNCH_CHECK();
+  return GLL_OK;
+}
+
+static int simt_splits(int n, int* cols_per_split) {
+  int row_tiles = ceil_div(n, BM), col_tiles = ceil_div(n, BN);
+  int want = ceil_div(2 * device_info().sms, row_tiles);
+  want = max(1, min(want, min(col_tiles, KNN_MAX_SPLITS)));
+  int tiles_per = ceil_div(col_tiles, want);
+  *cols_per_split = tiles_per * BN;
+  return ceil_div(col_tiles, tiles_per);
+}
+
+size_t knn_ws_bytes(int n, int d, int k) {
+  (void)d;
+  (void)k;
+  size_t b = 0;
+  b += align_up(sizeof(float) * (size_t)n, 256);                        // sq
+  b += 256;                                                             // sqmax + flag_count
+  b += align_up(sizeof(u64) * (size_t)n * KNN_MAX_SPLITS * KC, 256);    // cand
+  b += align_up(sizeof(int) * (size_t)n, 256);                          // flag_rows
+  return b + 1024;
+}
+
+int knn_run(const float* X, int n, int d, int k, int* knn_idx, float* knn_dist, int* info, void* ws,
+            size_t ws_bytes, cudaStream_t st) {
+  GLL_REQUIRE(X && knn_idx && knn_dist && ws, "null pointer");
+  GLL_REQUIRE(n >= k && k >= 2 && k <= KC + 1, "need n >= k and 2 <= k <= 33");
+  GLL_REQUIRE(d >= 1, "d must be positive");
+  if (ws_bytes < knn_ws_bytes(n, d, k)) {
+    set_error("kNN workspace too small: %zu < %zu", ws_bytes, knn_ws_bytes(n, d, k));
+    return GLL_ERR_WORKSPACE;
+  }
+  Carver cv(ws, ws_bytes);
+  float* sq = cv.take<float>(n);
+  unsigned* small = cv.take<unsigned>(64);
+  unsigned* sqmax_bits = small;
+  int* flag_count = reinterpret_cast<int*>(small + 1);
+  u64* cand = cv.take<u64>((size_t)n * KNN_MAX_SPLITS * KC);
+  int* flag_rows = cv.take<int>(n);
+
+  GLL_CUDA_CHECK(cudaMemsetAsync(small, 0, 256, st));
+  sqnorm_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(X, n, d, sq, sqmax_bits);
+  GLL_LAUNCH_CHECK();
+
+  int rc = knn_tc_candidates(X, sq, n, d, cand, st);  // tensor-core path when the shape allows it
+  int splits;
+  float err_coef;
+  if (rc > 0) {
+    splits = rc;
+    err_coef = knn_tc_err_coef(d);
+  } else if (rc < 0) {
+    return rc;
+  } else {
+    int cps;
+    splits = simt_splits(n, &cps);
+    const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+    dim3 grid(ceil_div(n, BM), splits);
+    size_t smem = gemm_smem_bytes();
+    if (vec4) {
+      GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      knn_gemm_topk_kernel<true><<<grid, GEMM_THREADS, smem, st>>>(X, sq, n, d, cps, splits, cand);
+    } else {
+      GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      knn_gemm_topk_kernel<false><<<grid, GEMM_THREADS, smem, st>>>(X, sq, n, d, cps, splits, cand);
+    }
+    GLL_LAUNCH_CHECK();
+    // |fl(d~^2) - d^2| <= (gamma_d + 4u)(|x_i|^2 + |x_j|^2), gamma_d = d u/(1 - d u), u = 2^-24 (sequential fp32 FMA chain)
+    const double u = 5.9604644775390625e-8;
+    err_coef = (float)(((double)d * u / (1.0 - (double)d * u) + 4.0 * u) * 1.0001);
+  }
+  return knn_finish(X, sq, sqmax_bits, n, d, k, splits, cand, err_coef, knn_idx, knn_dist, flag_count, flag_rows, info, st);
+}
+
+}  // namespace gll

@@ -1,0 +1,38 @@
+// Pieces shared by the SIMT (knn.cu) and tensor-core (knn_tc.cu) kNN candidate kernels.
+#pragma once
+#include "common.cuh"
+
+namespace gll {
+
+typedef unsigned long long u64;
+constexpr int KC = 32;               // candidates kept per row (one per lane)
+constexpr int KNN_MAX_SPLITS = 16;   // column-range splits per row tile
+constexpr u64 KEY_INF = ~0ull;
+
+// key = (order-preserving bits of the approximate squared distance, column index): u64 compare == (dist, idx) compare
+__device__ __forceinline__ u64 make_key(float dist, int j) {
+  return ((u64)float_to_ordered(dist) << 32) | (uint32_t)j;
+}
+__device__ __forceinline__ float key_dist(u64 k) { return ordered_to_float((uint32_t)(k >> 32)); }
+__device__ __forceinline__ int key_idx(u64 k) { return (int)(uint32_t)k; }
+
+// Insert x into an ascending list of 32 keys held one per lane (keys are unique). No-op if x is larger than all.
+__device__ __forceinline__ void list_insert(u64& mine, u64 x, int lane) {
+  int pos = __popc(__ballot_sync(FULL, mine < x));
+  u64 prev = __shfl_up_sync(FULL, mine, 1);
+  if (lane > pos)
+    mine = prev;
+  else if (lane == pos)
+    mine = x;
+}
+
+// Tensor-core candidate generation. Returns the number of column splits written to cand ([n][splits][KC]),
+// 0 if the shape is not handled by that path (caller uses the SIMT path), or a negative error code.
+int knn_tc_candidates(const float* X, const float* sq, int n, int d, u64* cand, cudaStream_t st);
+float knn_tc_err_coef(int d);
+
+int knn_finish(const float* X, const float* sq, const unsigned* sqmax_bits, int n, int d, int k, int splits,
+               const u64* cand, float err_coef, int* knn_idx, float* knn_dist, int* flag_count, int* flag_rows,
+               int* info, cudaStream_t st);
+
+}  // namespace gll

@@ -1,0 +1,152 @@
+/* gll_b200.h -- C ABI of libgll_b200.so: the B200 (sm_100a) implementation of the GraphLearningLayer
+ * hot path (forward + backward of LaplaceLearningSparseHard).
+ *
+ * The reference (pure Python, /root/reference/GLL.py) has no FFI; every entry point below cites the
+ * reference code it replaces.  Conventions for ALL entry points:
+ *   - plain pointers and sizes only; every array pointer is a DEVICE pointer unless it says "host";
+ *   - dense matrices row-major, fp32 values, int32 indices;
+ *   - the library never allocates or frees device memory: the caller passes a workspace
+ *     (size from the matching *_workspace_bytes query) and owns every buffer;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     enqueued on it and nothing synchronises with the host unless stated;
+ *   - return value 0 = success, negative = error (gll_last_error() gives a thread-local message).
+ *   - labeled ("base") nodes are the FIRST k_lab rows (GLL.py:11,32-38).
+ */
+#ifndef GLL_B200_H
+#define GLL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLL_OK 0
+#define GLL_ERR_ARG (-1)      /* bad argument (null pointer, unsupported size) */
+#define GLL_ERR_WORKSPACE (-2) /* workspace too small */
+#define GLL_ERR_CUDA (-3)     /* a CUDA runtime call failed */
+
+/* bits of info[GLL_INFO_STATUS] */
+#define GLL_STATUS_CG_NOT_CONVERGED 1 /* GLL.py:273-274 prints 'max iter reached' */
+#define GLL_STATUS_EPS_TINY 2         /* GLL.py:240-241 warns "Epsilon in KNN is very close to zero." */
+#define GLL_STATUS_NONFINITE 4
+#define GLL_STATUS_KNN_FALLBACK 8     /* some rows needed the exact brute-force kNN fallback (informational) */
+
+/* slots of the int32 info[16] block that lives in the state buffer */
+#define GLL_INFO_STATUS 0
+#define GLL_INFO_NNZ 1        /* E: directed edges of the symmetrised graph */
+#define GLL_INFO_NNZ_UU 2     /* off-diagonal nnz of L_uu */
+#define GLL_INFO_CG_ITERS_FWD 3
+#define GLL_INFO_CG_ITERS_BWD 4
+#define GLL_INFO_KNN_FALLBACK_ROWS 5
+#define GLL_INFO_CG_RESID_FWD 6 /* float bits: max_c ||r_c||_2 at exit */
+#define GLL_INFO_CG_RESID_BWD 7
+#define GLL_INFO_WORDS 16
+
+const char* gll_last_error(void);
+int gll_version(void);
+/* number of SMs / device ordinal the library sees for the current device (host query). */
+int gll_device_sm_count(void);
+
+/* Class columns are padded to a multiple of 4 so that every class row is float4-addressable. */
+int gll_padded_classes(int l);
+/* Upper bound of directed edges: 2*n*(k-1). */
+size_t gll_max_edges(int n, int k);
+
+/* ---------------------------------------------------------------------------------------------
+ * Byte offsets (256-B aligned) of the arrays kept between forward and backward.  Replaces the Python
+ * attributes the reference stores on ctx (GLL.py:69-70: W, V, Luu, label_matrix, mod_V, C, knn_ind, X, Pred).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct gll_layout {
+  size_t knn_idx;  /* int32 [n*k]      kNN lists, self in slot 0              (GLL.py:183) */
+  size_t knn_dist; /* float [n*k]      distances, fp32                        (GLL.py:183) */
+  size_t row_ptr;  /* int32 [n+1]      CSR of the symmetrised graph           (GLL.py:196-198) */
+  size_t col;      /* int32 [Emax]     sorted within each row */
+  size_t dist;     /* float [Emax]     one distance per undirected edge */
+  size_t w;        /* float [Emax]     W_ij = exp(-4 d^2/(eps_i eps_j))        (GLL.py:216,233) */
+  size_t gv;       /* float [Emax]     backward scratch: G_ij * V_ij           (GLL.py:146) */
+  size_t eps;      /* float [n]        bandwidths                             (GLL.py:205,226) */
+  size_t kappa;    /* int32 [n]        kappa(i) = last kNN entry (replaces the dense C, GLL.py:209-213) */
+  size_t deg;      /* float [n]        degree = row sum of W                   (GLL.py:29) */
+  size_t bvec;     /* float [n]        backward: b_i = sum_j G_ij modV_ij      (GLL.py:126) */
+  size_t uu_ptr;   /* int32 [m+1]      compact CSR of the off-diagonal of L_uu (GLL.py:37) */
+  size_t uu_col;   /* int32 [Emax]     column index rebased to the unlabeled block */
+  size_t uu_val;   /* float [Emax]     W_ij (the solver applies diag*p - sum W p) */
+  size_t diag;     /* float [m]        deg_i + tau                             (GLL.py:48) */
+  size_t rhs;      /* float [m*lp]     B = -L_ul Y, later the adjoint rhs      (GLL.py:53,93) */
+  size_t ut;       /* float [n*lp]     [Y; Pred]                               (GLL.py:109) */
+  size_t wt;       /* float [n*lp]     [0; w]                                  (GLL.py:104) */
+  size_t info;     /* int32 [GLL_INFO_WORDS] */
+  size_t total;    /* bytes to allocate */
+} gll_layout;
+
+int gll_state_layout(int n, int k, int l, int k_lab, gll_layout* out);
+size_t gll_workspace_bytes(int n, int d, int k, int l, int k_lab);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage entry points (each is also what the parity tests call)
+ * ------------------------------------------------------------------------------------------- */
+
+/* K1. Exact k nearest neighbours of every row of X (n x d), Euclidean, self in slot 0 with distance 0,
+ * remaining slots ordered by (distance, index).  Replaces gl.weightmatrix.knnsearch(...,'annoy') at
+ * GLL.py:181-189.  Candidate selection runs as a tiled Gram GEMM with a fused per-row top-k epilogue (the
+ * n x n matrix never reaches HBM); kept distances are recomputed as sqrt(sum (x_i-x_j)^2) in fp64 and
+ * rounded to fp32; rows whose candidate set cannot be proven complete are redone by brute force.
+ * info may be NULL; otherwise info[GLL_INFO_KNN_FALLBACK_ROWS] / GLL_STATUS_KNN_FALLBACK are updated. */
+size_t gll_knn_workspace_bytes(int n, int d, int k);
+int gll_knn(const float* X, int n, int d, int k, int* knn_idx, float* knn_dist, int* info,
+            void* workspace, size_t workspace_bytes, void* stream);
+
+/* K2. Symmetrise (elementwise max == union graph) and build the CSR; zero distances and self loops are
+ * not edges.  Replaces the scipy sequence at GLL.py:192-198. col/dist need gll_max_edges(n,k) entries. */
+size_t gll_graph_workspace_bytes(int n, int k);
+int gll_graph_build(const int* knn_idx, const float* knn_dist, int n, int k, int* row_ptr, int* col,
+                    float* dist, int* info, void* workspace, size_t workspace_bytes, void* stream);
+
+/* K3. Bandwidths, weights, degree, and the linear system of the unlabeled block.
+ * eps_auto != 0: eps_i = knn_dist[i][k-1], kappa_i = knn_idx[i][k-1] (GLL.py:205-211); else eps_i = eps_fixed
+ * (GLL.py:226).  W (GLL.py:216/233), deg (GLL.py:29), diag = deg + tau, compact off-diagonal CSR of
+ * L_uu (GLL.py:37,48), rhs = W_ul Y = -L_ul Y (GLL.py:53), and ut[:k_lab] = Y.  Y is k_lab x l fp32. */
+size_t gll_weights_workspace_bytes(int n, int k);
+int gll_edge_weights(const int* knn_idx, const float* knn_dist, const int* row_ptr, const int* col,
+                     const float* dist, const float* Y, int n, int k, int l, int k_lab, int eps_auto,
+                     float eps_fixed, float tau, float* eps, int* kappa, float* w, float* deg, int* uu_ptr,
+                     int* uu_col, float* uu_val, float* diag, float* rhs, float* ut, int* info,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* K4. Multi-right-hand-side Jacobi-preconditioned CG on A = diag - offdiag(uu_val), x0 = 0, all class
+ * columns at once, per-column freeze and absolute 2-norm stop like stable_conjgrad (GLL.py:247-276; the
+ * p = r alias of GLL.py:254 is not reproduced).  Replaces spsolve at GLL.py:53 and GLL.py:93.
+ * One persistent cooperative launch runs all iterations.  rhs and x are m x lp (lp = padded classes);
+ * x may alias nothing else.  iters_out / resid_out are device pointers (may be NULL). */
+size_t gll_cg_workspace_bytes(int m, int l);
+int gll_cg_solve(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag,
+                 const float* rhs, int m, int l, float tol, int max_iter, float* x, int* iters_out,
+                 float* resid_out, int* status_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* K5+K6. Backward edge pass (GLL.py:104-159): G_ij = -<wt_i-wt_j, ut_i-ut_j>, gv = G*V, b_i = sum_j G_ij modV_ij
+ * (auto only), dX_i = sum_j t_ij (x_i - x_j) with t_ij = gv_ij - [j==kappa(i)] b_i - [kappa(j)==i] b_j. */
+int gll_backward_edges(const float* X, int n, int d, int l, int k_lab, int eps_auto, const int* row_ptr,
+                       const int* col, const float* dist, const float* w, const float* eps, const int* kappa,
+                       const float* ut, const float* wt, float* gv, float* bvec, float* dX, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused drivers: what LaplaceLearningSparseHard.forward / .backward call (GLL.py:13-73, 75-177).
+ * `state` is a buffer of gll_state_layout(...).total bytes that must stay alive (and untouched) between the
+ * two calls; `workspace` may be reused by anybody in between.
+ * pred_out: m x l, float64 when pred_is_f64 != 0 (the reference returns float64, GLL.py:66) else fp32.
+ * grad_out: m x l, float64 when grad_is_f64 != 0 else fp32.  dX: n x d fp32 (GLL.py:154,159).
+ * ------------------------------------------------------------------------------------------- */
+int gll_forward(const float* X, const float* Y, int n, int d, int k, int l, int k_lab, int eps_auto,
+                float eps_fixed, float tau, float cg_tol, int cg_max_iter, void* state, void* pred_out,
+                int pred_is_f64, void* workspace, size_t workspace_bytes, void* stream);
+
+int gll_backward(const float* X, const void* grad_out, int grad_is_f64, int n, int d, int k, int l, int k_lab,
+                 int eps_auto, float cg_tol, int cg_max_iter, void* state, float* dX, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLL_B200_H */
