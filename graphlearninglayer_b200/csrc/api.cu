@@ -2,6 +2,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace gll {
@@ -35,6 +39,42 @@ const DeviceInfo& device_info() {
   return cache[dev];
 }
 
+// ------------------------------------------------------------------------------------------------ profiling
+namespace {
+struct ProfRec {
+  int id;
+  cudaEvent_t e0, e1;
+};
+std::mutex g_prof_mu;
+std::vector<ProfRec*> g_prof_recs;
+std::atomic<int> g_prof_on{0};
+std::atomic<long long> g_launches[KID_COUNT];
+const char* const g_kernel_names[KID_COUNT] = {
+    "sqnorm", "knn_gram_topk_simt", "knn_gram_topk_tcgen05", "knn_rerank", "knn_fallback", "graph_count", "scan",
+    "graph_fill", "graph_sort_rows", "edge_weights", "uu_fill", "cg_persistent", "pack_unpack", "edge_grad",
+    "row_gather", "convert"};
+}  // namespace
+
+ProfScope::ProfScope(int id_, cudaStream_t st_) : id(id_), st(st_), slot(nullptr) {
+  g_launches[id].fetch_add(1, std::memory_order_relaxed);
+  if (g_prof_on.load(std::memory_order_relaxed)) {
+    ProfRec* r = new ProfRec;
+    r->id = id;
+    cudaEventCreate(&r->e0);
+    cudaEventCreate(&r->e1);
+    cudaEventRecord(r->e0, st);
+    slot = r;
+  }
+}
+ProfScope::~ProfScope() {
+  if (slot) {
+    ProfRec* r = (ProfRec*)slot;
+    cudaEventRecord(r->e1, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_recs.push_back(r);
+  }
+}
+
 namespace {
 
 __global__ void pack_grad_kernel(const void* __restrict__ g, int is_f64, int m, int l, int lp, float* __restrict__ rhs) {
@@ -60,12 +100,14 @@ __global__ void unpack_pred_kernel(const float* __restrict__ u, int m, int l, in
 }  // namespace
 
 int pack_grad(const void* g, int is_f64, int m, int l, int lp, float* rhs, cudaStream_t st) {
+  GLL_PROF(KID_PACK, st);
   pack_grad_kernel<<<ceil_div((long long)m * lp, 256), 256, 0, st>>>(g, is_f64, m, l, lp, rhs);
   GLL_LAUNCH_CHECK();
   return GLL_OK;
 }
 
 int unpack_pred(const float* ut_u, int m, int l, int lp, void* pred, int is_f64, cudaStream_t st) {
+  GLL_PROF(KID_PACK, st);
   unpack_pred_kernel<<<ceil_div((long long)m * l, 256), 256, 0, st>>>(ut_u, m, l, lp, pred, is_f64);
   GLL_LAUNCH_CHECK();
   return GLL_OK;
@@ -114,6 +156,42 @@ int gll_version(void) { return 100; }
 int gll_device_sm_count(void) { return device_info().sms; }
 int gll_padded_classes(int l) { return padded_classes(l); }
 size_t gll_max_edges(int n, int k) { return (size_t)2 * (size_t)n * (size_t)(k - 1); }
+
+int gll_kernel_count(void) { return KID_COUNT; }
+const char* gll_kernel_name(int id) { return (id >= 0 && id < KID_COUNT) ? g_kernel_names[id] : ""; }
+long long gll_launch_count(int id) {
+  if (id >= 0 && id < KID_COUNT) return g_launches[id].load();
+  long long t = 0;
+  for (int i = 0; i < KID_COUNT; ++i) t += g_launches[i].load();
+  return t;
+}
+void gll_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
+int gll_profile_collect(double* ms_sum, long long* count) {
+  std::vector<ProfRec*> recs;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    recs.swap(g_prof_recs);
+  }
+  for (int i = 0; i < KID_COUNT; ++i) {
+    if (ms_sum) ms_sum[i] = 0.0;
+    if (count) count[i] = 0;
+  }
+  int rc = GLL_OK;
+  for (ProfRec* r : recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r->e1) != cudaSuccess || cudaEventElapsedTime(&ms, r->e0, r->e1) != cudaSuccess) {
+      set_error("gll_profile_collect: event query failed");
+      rc = GLL_ERR_CUDA;
+    } else {
+      if (ms_sum) ms_sum[r->id] += (double)ms;
+      if (count) count[r->id] += 1;
+    }
+    cudaEventDestroy(r->e0);
+    cudaEventDestroy(r->e1);
+    delete r;
+  }
+  return rc;
+}
 
 int gll_state_layout(int n, int k, int l, int k_lab, gll_layout* out) {
   int rc = make_layout(n, k, l, k_lab, out);

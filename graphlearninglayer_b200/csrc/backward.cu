@@ -140,16 +140,22 @@ int backward_edges_run(const float* X, int n, int d, int l, int k_lab, int eps_a
   GLL_REQUIRE(X && row_ptr && col && dist && w && eps && ut && wt && gv && bvec && dX, "null pointer");
   GLL_REQUIRE(!eps_auto || kappa, "kappa missing");
   const int lp = padded_classes(l);
-  edge_grad_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(n, lp, k_lab, eps_auto, row_ptr, col, dist, w, eps,
+  {
+    GLL_PROF(KID_EDGE_GRAD, st);
+    edge_grad_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(n, lp, k_lab, eps_auto, row_ptr, col, dist, w, eps,
                                                                      ut, wt, gv, bvec);
+  }
   GLL_LAUNCH_CHECK();
   const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dX) & 15) == 0);
   const int cols = vec4 ? d / 4 : d;
   int threads = min(256, max(32, ceil_div(cols, 32) * 32));
-  if (vec4)
-    row_gather_kernel<4><<<n, threads, 0, st>>>(X, n, d, eps_auto, row_ptr, col, kappa, gv, bvec, dX);
-  else
-    row_gather_kernel<1><<<n, threads, 0, st>>>(X, n, d, eps_auto, row_ptr, col, kappa, gv, bvec, dX);
+  {
+    GLL_PROF(KID_ROW_GATHER, st);
+    if (vec4)
+      row_gather_kernel<4><<<n, threads, 0, st>>>(X, n, d, eps_auto, row_ptr, col, kappa, gv, bvec, dX);
+    else
+      row_gather_kernel<1><<<n, threads, 0, st>>>(X, n, d, eps_auto, row_ptr, col, kappa, gv, bvec, dX);
+  }
   GLL_LAUNCH_CHECK();
   return GLL_OK;
 }

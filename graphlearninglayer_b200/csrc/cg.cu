@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) cg_persistent_kernel(CgParams P
   const bool active = lane < S * Q;
   const int row_begin = blockIdx.x * P.rows_per_block;
   const int row_end = min(P.m, row_begin + P.rows_per_block);
-  const double tol2 = (double)P.tol * (double)P.tol;
+  double tol = (double)P.tol, tol2 = tol * tol;  // P.tol < 0: relative, resolved after the initial reduction
   unsigned epoch = 0;
   int buf = 0;
 
@@ -169,6 +169,12 @@ __global__ void __launch_bounds__(CG_THREADS, 1) cg_persistent_kernel(CgParams P
       rr[c] = red[lp + c];
     }
     __syncthreads();
+    if (P.tol < 0.f) {  // relative to the largest right-hand-side column norm (every thread computes the same value)
+      double mx = 0.0;
+      for (int c = 0; c < lp; ++c) mx = fmax(mx, rr[c]);
+      tol = -(double)P.tol * sqrt(mx);
+      tol2 = tol * tol;
+    }
   }
 
   int it = 0;
@@ -181,7 +187,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) cg_persistent_kernel(CgParams P
       if (!(v == v) || isinf(v)) nonfinite = true;
       maxrr = fmax(maxrr, v);
     }
-    if (nonfinite || sqrt(maxrr) <= (double)P.tol || it >= P.max_iter) break;
+    if (nonfinite || sqrt(maxrr) <= tol || it >= P.max_iter) break;
     ++it;
 
     // ---- phase 1: Ap = A p, partial <p, Ap> ----
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) cg_persistent_kernel(CgParams P
     if (P.status_out) {
       int st = 0;
       if (nonfinite) st |= GLL_STATUS_NONFINITE;
-      if (!nonfinite && !(resid <= P.tol)) st |= GLL_STATUS_CG_NOT_CONVERGED;
+      if (!nonfinite && !(sqrt(maxrr) <= tol)) st |= GLL_STATUS_CG_NOT_CONVERGED;
       if (st) atomicOr(P.status_out, st);
     }
   }
@@ -343,6 +349,7 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
   }
   GLL_CUDA_CHECK(cudaMemsetAsync(P.barrier, 0, 256, st));
   void* args[] = {&P};
+  GLL_PROF(KID_CG, st);
   GLL_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)cg_persistent_kernel, dim3(grid), dim3(CG_THREADS), args, smem, st));
   return GLL_OK;
 }

@@ -88,6 +88,22 @@ __device__ __forceinline__ float ordered_to_float(uint32_t u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
+// ---- per-kernel launch counter and optional CUDA-event timing (gll_profile_* in the C ABI) ----
+enum KernelId {
+  KID_SQNORM = 0, KID_GRAM_TOPK, KID_GRAM_TOPK_TC, KID_RERANK, KID_KNN_FALLBACK, KID_GRAPH_COUNT, KID_SCAN,
+  KID_GRAPH_FILL, KID_GRAPH_SORT, KID_WEIGHTS, KID_UU_FILL, KID_CG, KID_PACK, KID_EDGE_GRAD, KID_ROW_GATHER,
+  KID_CONVERT, KID_COUNT
+};
+// RAII: counts the launch; when profiling is on, brackets it with two events on the launch stream.
+struct ProfScope {
+  int id;
+  cudaStream_t st;
+  void* slot;
+  ProfScope(int id, cudaStream_t st);
+  ~ProfScope();
+};
+#define GLL_PROF(id, st) gll::ProfScope _prof_scope_##id(gll::id, st)
+
 // ---- internal launchers (one per stage), implemented in the .cu files ----
 int knn_run(const float* X, int n, int d, int k, int* knn_idx, float* knn_dist, int* info, void* ws,
             size_t ws_bytes, cudaStream_t st);

@@ -101,18 +101,30 @@ size_t scan_ws_bytes(int n) { return align_up(sizeof(int) * (size_t)(2 * (ceil_d
 
 int exclusive_scan(const int* counts, int n, int* out, void* scratch, cudaStream_t st) {
   if (n <= 32768) {
-    scan_single_kernel<<<1, 1024, 0, st>>>(counts, n, out);
+    {
+      GLL_PROF(KID_SCAN, st);
+      scan_single_kernel<<<1, 1024, 0, st>>>(counts, n, out);
+    }
     GLL_LAUNCH_CHECK();
     return GLL_OK;
   }
   int tiles = ceil_div(n, SCAN_TILE);
   int* sums = (int*)scratch;
   int* offs = sums + tiles + 1;
-  scan_tile_kernel<<<tiles, SCAN_THREADS, 0, st>>>(counts, n, out, sums);
+  {
+    GLL_PROF(KID_SCAN, st);
+    scan_tile_kernel<<<tiles, SCAN_THREADS, 0, st>>>(counts, n, out, sums);
+  }
   GLL_LAUNCH_CHECK();
-  scan_single_kernel<<<1, 1024, 0, st>>>(sums, tiles, offs);
+  {
+    GLL_PROF(KID_SCAN, st);
+    scan_single_kernel<<<1, 1024, 0, st>>>(sums, tiles, offs);
+  }
   GLL_LAUNCH_CHECK();
-  scan_add_kernel<<<tiles, SCAN_THREADS, 0, st>>>(out, n, offs);
+  {
+    GLL_PROF(KID_SCAN, st);
+    scan_add_kernel<<<tiles, SCAN_THREADS, 0, st>>>(out, n, offs);
+  }
   GLL_LAUNCH_CHECK();
   return GLL_OK;
 }
@@ -219,13 +231,22 @@ int graph_run(const int* knn_idx, const float* knn_dist, int n, int k, int* row_
   GLL_CUDA_CHECK(cudaMemsetAsync(len, 0, (size_t)((char*)cursor - (char*)len) + sizeof(int) * (size_t)(n + 1), st));
   long long total = (long long)n * k;
   int blocks = ceil_div(total, 256);
-  graph_count_kernel<<<blocks, 256, 0, st>>>(knn_idx, knn_dist, n, k, len);
+  {
+    GLL_PROF(KID_GRAPH_COUNT, st);
+    graph_count_kernel<<<blocks, 256, 0, st>>>(knn_idx, knn_dist, n, k, len);
+  }
   GLL_LAUNCH_CHECK();
   int rc = exclusive_scan(len, n, row_ptr, scan_ws, st);
   if (rc) return rc;
-  graph_fill_kernel<<<blocks, 256, 0, st>>>(knn_idx, knn_dist, n, k, row_ptr, cursor, col_tmp, dist_tmp);
+  {
+    GLL_PROF(KID_GRAPH_FILL, st);
+    graph_fill_kernel<<<blocks, 256, 0, st>>>(knn_idx, knn_dist, n, k, row_ptr, cursor, col_tmp, dist_tmp);
+  }
   GLL_LAUNCH_CHECK();
-  graph_sort_rows_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(row_ptr, n, col_tmp, dist_tmp, col, dist, info);
+  {
+    GLL_PROF(KID_GRAPH_SORT, st);
+    graph_sort_rows_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(row_ptr, n, col_tmp, dist_tmp, col, dist, info);
+  }
   GLL_LAUNCH_CHECK();
   return GLL_OK;
 }

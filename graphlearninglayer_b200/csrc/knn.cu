@@ -384,21 +384,30 @@ int knn_finish(const float* X, const float* sq, const unsigned* sqmax_bits, int 
   if (vec4) {
     if (smem > 48 * 1024)
       GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knn_rerank_kernel<true><<<blocks, RERANK_WARPS * 32, smem, st>>>(X, sq, sqmax_bits, n, d, k, splits, cand,
+    {
+      GLL_PROF(KID_RERANK, st);
+      knn_rerank_kernel<true><<<blocks, RERANK_WARPS * 32, smem, st>>>(X, sq, sqmax_bits, n, d, k, splits, cand,
                                                                       err_coef, knn_idx, knn_dist, flag_count, flag_rows);
+    }
   } else {
     if (smem > 48 * 1024)
       GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knn_rerank_kernel<false><<<blocks, RERANK_WARPS * 32, smem, st>>>(X, sq, sqmax_bits, n, d, k, splits, cand,
+    {
+      GLL_PROF(KID_RERANK, st);
+      knn_rerank_kernel<false><<<blocks, RERANK_WARPS * 32, smem, st>>>(X, sq, sqmax_bits, n, d, k, splits, cand,
                                                                        err_coef, knn_idx, knn_dist, flag_count, flag_rows);
+    }
   }
   GLL_LAUNCH_CHECK();
   size_t fsmem = sizeof(float) * (size_t)d;
   int fblocks = device_info().sms * 2;
-  if (vec4)
-    knn_fallback_kernel<true><<<fblocks, FB_WARPS * 32, fsmem, st>>>(X, n, d, k, flag_count, flag_rows, knn_idx, knn_dist, info);
-  else
-    knn_fallback_kernel<false><<<fblocks, FB_WARPS * 32, fsmem, st>>>(X, n, d, k, flag_count, flag_rows, knn_idx, knn_dist, info);
+  {
+    GLL_PROF(KID_KNN_FALLBACK, st);
+    if (vec4)
+      knn_fallback_kernel<true><<<fblocks, FB_WARPS * 32, fsmem, st>>>(X, n, d, k, flag_count, flag_rows, knn_idx, knn_dist, info);
+    else
+      knn_fallback_kernel<false><<<fblocks, FB_WARPS * 32, fsmem, st>>>(X, n, d, k, flag_count, flag_rows, knn_idx, knn_dist, info);
+  }
   GLL_LAUNCH_CHECK();
   return GLL_OK;
 }
@@ -441,7 +450,10 @@ int knn_run(const float* X, int n, int d, int k, int* knn_idx, float* knn_dist, 
   int* flag_rows = cv.take<int>(n);
 
   GLL_CUDA_CHECK(cudaMemsetAsync(small, 0, 256, st));
-  sqnorm_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(X, n, d, sq, sqmax_bits);
+  {
+    GLL_PROF(KID_SQNORM, st);
+    sqnorm_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(X, n, d, sq, sqmax_bits);
+  }
   GLL_LAUNCH_CHECK();
 
   int rc = knn_tc_candidates(X, sq, n, d, cand, st);  // tensor-core path when the shape allows it
@@ -460,10 +472,16 @@ int knn_run(const float* X, int n, int d, int k, int* knn_idx, float* knn_dist, 
     size_t smem = gemm_smem_bytes();
     if (vec4) {
       GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      knn_gemm_topk_kernel<true><<<grid, GEMM_THREADS, smem, st>>>(X, sq, n, d, cps, splits, cand);
+      {
+        GLL_PROF(KID_GRAM_TOPK, st);
+        knn_gemm_topk_kernel<true><<<grid, GEMM_THREADS, smem, st>>>(X, sq, n, d, cps, splits, cand);
+      }
     } else {
       GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      knn_gemm_topk_kernel<false><<<grid, GEMM_THREADS, smem, st>>>(X, sq, n, d, cps, splits, cand);
+      {
+        GLL_PROF(KID_GRAM_TOPK, st);
+        knn_gemm_topk_kernel<false><<<grid, GEMM_THREADS, smem, st>>>(X, sq, n, d, cps, splits, cand);
+      }
     }
     GLL_LAUNCH_CHECK();
     // |fl(d~^2) - d^2| <= (gamma_d + 4u)(|x_i|^2 + |x_j|^2), gamma_d = d u/(1 - d u), u = 2^-24 (sequential fp32 FMA chain)

@@ -101,13 +101,19 @@ int weights_run(const int* knn_idx, const float* knn_dist, const int* row_ptr, c
   Carver cv(ws, ws_bytes);
   int* uu_cnt = cv.take<int>(n + 1);
   void* scan_ws = cv.take<char>(scan_ws_bytes(n + 1));
-  weights_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(knn_idx, knn_dist, row_ptr, col, dist, Y, n, k, l, lp,
+  {
+    GLL_PROF(KID_WEIGHTS, st);
+    weights_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(knn_idx, knn_dist, row_ptr, col, dist, Y, n, k, l, lp,
                                                                    k_lab, eps_auto, eps_fixed, tau, eps, kappa, w, deg,
                                                                    uu_cnt, diag, rhs, ut, info);
+  }
   GLL_LAUNCH_CHECK();
   int rc = exclusive_scan(uu_cnt, m, uu_ptr, scan_ws, st);
   if (rc) return rc;
-  uu_fill_kernel<<<ceil_div((long long)m * 32, 256), 256, 0, st>>>(row_ptr, col, w, m, k_lab, uu_ptr, uu_col, uu_val, info);
+  {
+    GLL_PROF(KID_UU_FILL, st);
+    uu_fill_kernel<<<ceil_div((long long)m * 32, 256), 256, 0, st>>>(row_ptr, col, w, m, k_lab, uu_ptr, uu_col, uu_val, info);
+  }
   GLL_LAUNCH_CHECK();
   return GLL_OK;
 }

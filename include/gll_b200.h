@@ -49,6 +49,17 @@ int gll_version(void);
 /* number of SMs / device ordinal the library sees for the current device (host query). */
 int gll_device_sm_count(void);
 
+/* Launch accounting and optional per-kernel timing (used by bench.py; off by default).  Every kernel launch of
+ * the library increments a counter; gll_launch_count(id) reads one kernel's counter, id < 0 the total.  With
+ * gll_profile_enable(1) each launch is bracketed by two CUDA events on its own stream; gll_profile_collect()
+ * synchronises on them, writes per-kernel summed milliseconds and launch counts (arrays of gll_kernel_count()
+ * entries, either may be NULL) and clears the records. */
+int gll_kernel_count(void);
+const char* gll_kernel_name(int id);
+long long gll_launch_count(int id);
+void gll_profile_enable(int on);
+int gll_profile_collect(double* ms_sum, long long* count);
+
 /* Class columns are padded to a multiple of 4 so that every class row is float4-addressable. */
 int gll_padded_classes(int l);
 /* Upper bound of directed edges: 2*n*(k-1). */
@@ -118,6 +129,7 @@ int gll_edge_weights(const int* knn_idx, const float* knn_dist, const int* row_p
 /* K4. Multi-right-hand-side Jacobi-preconditioned CG on A = diag - offdiag(uu_val), x0 = 0, all class
  * columns at once, per-column freeze and absolute 2-norm stop like stable_conjgrad (GLL.py:247-276; the
  * p = r alias of GLL.py:254 is not reproduced).  Replaces spsolve at GLL.py:53 and GLL.py:93.
+ * tol > 0: absolute (the reference's meaning); tol < 0: |tol| times the largest column 2-norm of rhs.
  * One persistent cooperative launch runs all iterations.  rhs and x are m x lp (lp = padded classes);
  * x may alias nothing else.  iters_out / resid_out are device pointers (may be NULL). */
 size_t gll_cg_workspace_bytes(int m, int l);

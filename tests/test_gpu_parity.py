@@ -1,0 +1,421 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Every check goes through the C ABI of
+libgll_b200.so -- stage entry points directly, or gll_forward/gll_backward via the autograd Function -- and compares
+with the fp64 oracle (oracle/gll_oracle.py) and with the fixtures produced by the unmodified reference GLL.py.
+
+Tolerances (BASELINE.json north_star): kNN index sets bit-exact modulo documented distance ties; pred and dX within
+1e-5 relative (max|delta| / max|ref|) in fp32.
+"""
+import ctypes as C
+import os
+import warnings
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import golden_names, load_golden
+from oracle import gll_oracle as O
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # north_star: pred and dL/dfeatures within 1e-5 relative in fp32
+
+
+@pytest.fixture(scope="module")
+def gll():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import graphlearninglayer_b200 as pkg
+    from graphlearninglayer_b200 import _lib
+
+    return pkg, _lib
+
+
+def dev_t(a, dtype):
+    return torch.as_tensor(np.ascontiguousarray(a)).to("cuda", dtype).contiguous()
+
+
+def run_knn(_lib, X, k=25):
+    n, d = X.shape
+    Xc = dev_t(X, torch.float32)
+    idx = torch.empty((n, k), dtype=torch.int32, device="cuda")
+    dist = torch.empty((n, k), dtype=torch.float32, device="cuda")
+    info = torch.zeros(_lib.INFO_WORDS, dtype=torch.int32, device="cuda")
+    wsb = _lib.lib.gll_knn_workspace_bytes(n, d, k)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.lib.gll_knn(Xc.data_ptr(), n, d, k, idx.data_ptr(), dist.data_ptr(), info.data_ptr(), ws.data_ptr(), wsb,
+                                torch.cuda.current_stream().cuda_stream), "gll_knn")
+    torch.cuda.synchronize()
+    return idx, dist, info
+
+
+def run_graph(_lib, idx, dist):
+    n, k = idx.shape
+    emax = _lib.lib.gll_max_edges(n, k)
+    row_ptr = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    col = torch.empty(emax, dtype=torch.int32, device="cuda")
+    dd = torch.empty(emax, dtype=torch.float32, device="cuda")
+    info = torch.zeros(_lib.INFO_WORDS, dtype=torch.int32, device="cuda")
+    wsb = _lib.lib.gll_graph_workspace_bytes(n, k)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.lib.gll_graph_build(idx.data_ptr(), dist.data_ptr(), n, k, row_ptr.data_ptr(), col.data_ptr(), dd.data_ptr(),
+                                        info.data_ptr(), ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream),
+               "gll_graph_build")
+    torch.cuda.synchronize()
+    E = int(row_ptr[-1].item())
+    assert int(info[_lib.INFO_NNZ].item()) == E
+    return row_ptr, col, dd, E
+
+
+def run_weights(_lib, idx, dist, row_ptr, col, dd, Y, eps, tau):
+    n, k = idx.shape
+    k_lab, l = Y.shape
+    m = n - k_lab
+    lp = _lib.lib.gll_padded_classes(l)
+    emax = _lib.lib.gll_max_edges(n, k)
+    f32, i32 = torch.float32, torch.int32
+    Yc = dev_t(Y, f32)
+    o = dict(eps=torch.empty(n, dtype=f32, device="cuda"), kappa=torch.empty(n, dtype=i32, device="cuda"),
+             w=torch.empty(emax, dtype=f32, device="cuda"), deg=torch.empty(n, dtype=f32, device="cuda"),
+             uu_ptr=torch.empty(m + 1, dtype=i32, device="cuda"), uu_col=torch.empty(emax, dtype=i32, device="cuda"),
+             uu_val=torch.empty(emax, dtype=f32, device="cuda"), diag=torch.empty(m, dtype=f32, device="cuda"),
+             rhs=torch.empty((m, lp), dtype=f32, device="cuda"), ut=torch.zeros((n, lp), dtype=f32, device="cuda"),
+             info=torch.zeros(_lib.INFO_WORDS, dtype=i32, device="cuda"))
+    wsb = _lib.lib.gll_weights_workspace_bytes(n, k)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    auto = isinstance(eps, str)
+    _lib.check(_lib.lib.gll_edge_weights(idx.data_ptr(), dist.data_ptr(), row_ptr.data_ptr(), col.data_ptr(), dd.data_ptr(),
+                                         Yc.data_ptr(), n, k, l, k_lab, int(auto), 0.0 if auto else float(eps), float(tau),
+                                         o["eps"].data_ptr(), o["kappa"].data_ptr(), o["w"].data_ptr(), o["deg"].data_ptr(),
+                                         o["uu_ptr"].data_ptr(), o["uu_col"].data_ptr(), o["uu_val"].data_ptr(),
+                                         o["diag"].data_ptr(), o["rhs"].data_ptr(), o["ut"].data_ptr(), o["info"].data_ptr(),
+                                         ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream), "gll_edge_weights")
+    torch.cuda.synchronize()
+    return o
+
+
+def run_cg(_lib, Luu: sp.csr_matrix, B: np.ndarray, tol=1e-7, max_iter=5000):
+    """Feeds an oracle-built system to gll_cg_solve: diag + negated off-diagonal."""
+    m, l = B.shape
+    lp = _lib.lib.gll_padded_classes(l)
+    dg = Luu.diagonal()
+    off = (Luu - sp.diags(dg)).tocsr()
+    off.eliminate_zeros()
+    off.sort_indices()
+    ptr = dev_t(off.indptr, torch.int32)
+    col = dev_t(off.indices, torch.int32)
+    val = dev_t(-off.data, torch.float32)
+    diag = dev_t(dg, torch.float32)
+    rhs = torch.zeros((m, lp), dtype=torch.float32, device="cuda")
+    rhs[:, :l] = dev_t(B, torch.float32)
+    x = torch.empty((m, lp), dtype=torch.float32, device="cuda")
+    stat = torch.zeros(4, dtype=torch.int32, device="cuda")
+    wsb = _lib.lib.gll_cg_workspace_bytes(m, l)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.lib.gll_cg_solve(ptr.data_ptr(), col.data_ptr(), val.data_ptr(), diag.data_ptr(), rhs.data_ptr(), m, l, tol,
+                                     max_iter, x.data_ptr(), stat.data_ptr(), stat[1:].data_ptr(), stat[2:].data_ptr(),
+                                     ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream), "gll_cg_solve")
+    torch.cuda.synchronize()
+    s = stat.cpu().numpy()
+    return x[:, :l].double().cpu().numpy(), int(s[0]), float(s[1:2].view(np.float32)[0]), int(s[2])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# K1: kNN
+# ----------------------------------------------------------------------------------------------------------------
+KNN_SHAPES = [(0, 300, 500, 64, 10, 2.0), (3, 37, 91, 19, 3, 1.0), (1, 1000, 1000, 128, 10, 3.0),
+              (4, 2048, 1024, 512, 10, 4.5), (6, 10, 20, 7, 2, 0.5), (8, 500, 700, 130, 5, 2.0)]
+
+
+@pytest.mark.parametrize("seed,k_lab,m,d,l,sigma", KNN_SHAPES)
+def test_knn_bit_exact_vs_oracle(gll, seed, k_lab, m, d, l, sigma):
+    _, _lib = gll
+    X, *_ = O.synth_inputs(seed, k_lab, m, d, l, sigma)
+    ref_ind, ref_dist = O.exact_knn(X, 25)
+    idx, dist, info = run_knn(_lib, X)
+    ind = idx.cpu().numpy().astype(np.int64)
+    exact, tie, bad = O.knn_sets_match(ind, ref_ind, ref_dist)
+    assert bad == 0, (exact, tie, bad)
+    assert np.array_equal(ind[:, 0], np.arange(X.shape[0]))  # self first (GLL.py:183 contract)
+    same = np.all(ind == ref_ind, axis=1)
+    assert same.mean() > 0.999  # order (distance, index); only exact-distance ties computed differently may differ
+    d_gpu = dist.cpu().numpy()
+    assert np.array_equal(d_gpu[same], ref_dist[same].astype(np.float32))  # fp64 direct differences rounded to fp32
+
+
+def test_knn_duplicates_and_tiny_n(gll):
+    _, _lib = gll
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((60, 16)).astype(np.float32)
+    X[10:40] = X[10]  # 30 identical points: zero distances, ties broken by index
+    idx, dist, _ = run_knn(_lib, X)
+    ind, dd = idx.cpu().numpy(), dist.cpu().numpy()
+    ref_ind, ref_dist = O.exact_knn(X, 25)
+    assert np.array_equal(np.sort(dd, axis=1), np.sort(ref_dist.astype(np.float32), axis=1))
+    assert (dd[10:40, :25] == 0).all()
+    # n == k edge: every row lists every node
+    X2 = rng.standard_normal((25, 8)).astype(np.float32)
+    idx2, _, _ = run_knn(_lib, X2)
+    assert np.array_equal(np.sort(idx2.cpu().numpy(), axis=1), np.tile(np.arange(25), (25, 1)))
+
+
+def test_knn_full_size_properties(gll):
+    """C4 size (n=16384, d=512): properties that need no oracle: self first, sorted distances, symmetric distances on
+    mutual pairs, distances equal to a torch fp64 recomputation on the chosen pairs, and k-th distance <= any
+    non-neighbour distance on sampled rows."""
+    _, _lib = gll
+    X, *_ = O.synth_inputs(2, 2048, 14336, 512, 10, 4.5)
+    idx, dist, info = run_knn(_lib, X)
+    ind = idx.long()
+    n = X.shape[0]
+    assert torch.equal(ind[:, 0].cpu(), torch.arange(n))
+    assert bool((dist[:, 1:] >= dist[:, :-1]).all())
+    Xd = torch.as_tensor(X).cuda().double()
+    rows = torch.arange(0, n, 97, device="cuda")
+    ref = torch.cdist(Xd[rows], Xd, compute_mode="donot_use_mm_for_euclid_dist")
+    ref[torch.arange(len(rows)), rows] = -1.0
+    kth = torch.sort(ref, dim=1).values[:, :25]
+    kth[:, 0] = 0
+    assert torch.equal(kth.float(), dist[rows])
+    got = torch.gather(ref, 1, ind[rows])
+    got[:, 0] = 0
+    assert torch.equal(got.float(), dist[rows])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# K2 + K3: graph and weights
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("eps,tau", [("auto", 0.0), (1.0, 0.07)])
+@pytest.mark.parametrize("seed,k_lab,m,d,l,sigma", [(0, 300, 500, 64, 10, 2.0), (3, 37, 91, 19, 3, 1.0)])
+def test_graph_and_weights_vs_oracle(gll, seed, k_lab, m, d, l, sigma, eps, tau):
+    _, _lib = gll
+    X, Y, *_ = O.synth_inputs(seed, k_lab, m, d, l, sigma)
+    f = O.forward(X, Y, tau, eps, solver="lu")
+    g = f.graph
+    idx = dev_t(g.knn_ind, torch.int32)
+    dist = dev_t(g.knn_dist, torch.float32)
+    row_ptr, col, dd, E = run_graph(_lib, idx, dist)
+    assert np.array_equal(row_ptr.cpu().numpy(), g.dist.indptr)          # bit-exact integer work
+    assert np.array_equal(col[:E].cpu().numpy(), g.dist.indices)
+    assert np.array_equal(dd[:E].cpu().numpy(), g.dist.data.astype(np.float32))
+    o = run_weights(_lib, idx, dist, row_ptr, col, dd, Y, eps, tau)
+    assert np.array_equal(o["eps"].cpu().numpy(), g.eps.astype(np.float32))
+    if eps == "auto":
+        assert np.array_equal(o["kappa"].cpu().numpy(), g.kappa)
+    assert O.max_rel(o["w"][:E].cpu().numpy(), g.W.data) < 1e-6
+    assert O.max_rel(o["deg"].cpu().numpy(), f.deg) < 1e-6
+    assert O.max_rel(o["diag"].cpu().numpy(), f.Luu.diagonal()) < 1e-6
+    assert O.max_rel(o["rhs"][:, :l].cpu().numpy(), f.B) < 1e-6
+    off = (f.Luu - sp.diags(f.Luu.diagonal())).tocsr()
+    off.eliminate_zeros()
+    off.sort_indices()
+    nuu = int(o["uu_ptr"][-1].item())
+    assert np.array_equal(o["uu_ptr"].cpu().numpy(), off.indptr)
+    assert np.array_equal(o["uu_col"][:nuu].cpu().numpy(), off.indices)
+    assert O.max_rel(o["uu_val"][:nuu].cpu().numpy(), -off.data) < 1e-6
+    assert np.array_equal(o["ut"][:k_lab, :l].cpu().numpy(), Y)
+
+
+def test_graph_drops_zero_distance_edges(gll):
+    """sparse.find at GLL.py:198 drops exact zeros: duplicate points are not edges."""
+    _, _lib = gll
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((80, 12)).astype(np.float32)
+    X[5] = X[6]
+    ind, dist = O.exact_knn(X, 25)
+    g = O.build_graph(X, 25, 1.0, knn=(ind, dist))
+    row_ptr, col, dd, E = run_graph(_lib, dev_t(ind, torch.int32), dev_t(dist, torch.float32))
+    assert np.array_equal(row_ptr.cpu().numpy(), g.dist.indptr)
+    assert np.array_equal(col[:E].cpu().numpy(), g.dist.indices)
+    assert 6 not in col[row_ptr[5]:row_ptr[6]].cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# K4: CG
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("l", [1, 3, 10, 37, 100])
+def test_cg_vs_direct_solve(gll, l):
+    _, _lib = gll
+    X, Y, *_ = O.synth_inputs(3, 160, 1500, 24, l, 1.5)
+    f = O.forward(X, Y, 0.02, 1.0, solver="lu")
+    x, iters, resid, status = run_cg(_lib, f.Luu, f.B, tol=1e-7)
+    assert status == 0 and 0 < iters < 2000 and resid <= 1e-7
+    assert O.max_rel(x, f.pred) < TOL
+    true_res = np.sqrt(((f.Luu @ x - f.B) ** 2).sum(axis=0)).max()
+    assert true_res < 5e-5  # fp32 storage of A and x bounds the true residual
+
+
+def test_cg_zero_rhs_column_and_maxiter(gll):
+    _, _lib = gll
+    X, Y, *_ = O.synth_inputs(5, 100, 900, 16, 4, 1.5)
+    f = O.forward(X, Y, 0.05, 1.0, solver="lu")
+    B = f.B.copy()
+    B[:, 2] = 0.0  # a frozen column from the start (the per-column mask of GLL.py:262-263 must not divide 0/0)
+    x, iters, resid, status = run_cg(_lib, f.Luu, B, tol=1e-7)
+    assert status == 0 and np.all(x[:, 2] == 0) and np.isfinite(x).all()
+    ref = O.solve(f.Luu, B, "lu")
+    assert O.max_rel(x, ref) < TOL
+    x2, it2, _, status2 = run_cg(_lib, f.Luu, f.B, tol=1e-12, max_iter=3)
+    assert it2 == 3 and status2 & 1  # GLL_STATUS_CG_NOT_CONVERGED <-> 'max iter reached' (GLL.py:273-274)
+
+
+def test_cg_relative_tolerance(gll):
+    _, _lib = gll
+    X, Y, *_ = O.synth_inputs(5, 100, 900, 16, 4, 1.5)
+    f = O.forward(X, Y, 0.05, 1.0, solver="lu")
+    B = f.B * 1e4
+    x, iters, resid, status = run_cg(_lib, f.Luu, B, tol=-1e-7)
+    assert status == 0
+    assert O.max_rel(x, f.pred * 1e4) < TOL
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# end to end through the autograd Function (gll_forward / gll_backward)
+# ----------------------------------------------------------------------------------------------------------------
+def layer_fwd_bwd(pkg, X, Y, yq, tau, eps):
+    Xt = torch.as_tensor(X).cuda().requires_grad_(True)
+    Yt = torch.as_tensor(Y).cuda()
+    pred = pkg.LaplaceLearningSparseHard.apply(Xt, Yt, tau, eps)
+    tgt = torch.nn.functional.one_hot(torch.as_tensor(yq).cuda(), pred.shape[1]).to(pred.dtype)
+    loss = -torch.sum(tgt * torch.log(pred + 1e-8)) / pred.shape[0]  # custom_ce_loss, losses.py:128-136
+    loss.backward()
+    torch.cuda.synchronize()
+    return pred, loss, Xt.grad
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_layer_matches_reference_fixture(gll, name):
+    """Fixtures were produced by the UNMODIFIED /root/reference/GLL.py (oracle/make_golden.py)."""
+    pkg, _lib = gll
+    g, X, Y, yq = load_golden(name)
+    pred, loss, dX = layer_fwd_bwd(pkg, X, Y, yq, g["tau_arg"], g["eps_arg"])
+    assert pred.dtype == torch.float64 and dX.dtype == torch.float32  # GLL.py:66,154
+    assert O.max_rel(pred.cpu().numpy(), g["pred"]) < TOL
+    assert abs(loss.item() - float(g["loss"])) < 1e-5 * max(1.0, abs(float(g["loss"])))
+    s = int(g["dX_stride"])
+    dXn = dX.cpu().numpy()
+    assert np.abs(dXn[::s] - g["dX"]).max() <= TOL * float(g["dX_absmax"])
+    assert abs(np.linalg.norm(dXn.astype(np.float64)) / float(g["dX_fro"]) - 1) < TOL
+    assert np.abs(dXn.astype(np.float64).sum(axis=0) - g["dX_colsum"]).max() <= 10 * TOL * float(g["dX_absmax"])
+    info = pkg.last_info()
+    assert info["status"] & ~_lib.STATUS_KNN_FALLBACK == 0, info
+
+
+@pytest.mark.parametrize("eps,tau", [("auto", 0.0), (1.0, 0.07), ("auto", 0.07)])
+def test_layer_vs_oracle_mid_size(gll, eps, tau):
+    """n = 6144 (above the LU fixtures, oracle solves by fp64 CG to 1e-13)."""
+    pkg, _ = gll
+    X, Y, _, yq = O.synth_inputs(21, 1024, 5120, 256, 10, 3.0)
+    f, loss_ref, gout, bw = O.fwd_bwd(X, Y, yq, tau, eps, solver="cg")
+    pred, loss, dX = layer_fwd_bwd(pkg, X, Y, yq, tau, eps)
+    assert O.max_rel(pred.cpu().numpy(), f.pred) < TOL
+    assert O.max_rel(dX.cpu().numpy(), bw.dX) < TOL
+
+
+def test_layer_full_size_properties(gll):
+    """C4 size (2048 + 14336, d=512): invariants of SURVEY 4 that need no oracle."""
+    pkg, _lib = gll
+    X, Y, _, yq = O.synth_inputs(2, 2048, 14336, 512, 10, 4.5)
+    pred, loss, dX = layer_fwd_bwd(pkg, X, Y, yq, 0.0, "auto")
+    p = pred.cpu().numpy()
+    assert np.abs(p.sum(axis=1) - 1.0).max() < 2e-5      # tau = 0: harmonic extension of one-hot rows sums to 1
+    assert p.min() > -1e-5 and p.max() < 1 + 1e-5        # discrete maximum principle
+    g = dX.cpu().numpy().astype(np.float64)
+    assert np.isfinite(g).all()
+    assert np.abs(g.sum(axis=0)).max() <= 1e-4 * np.abs(g).sum(axis=0).max()  # sum_i dX_i = 0: loss is translation invariant
+    assert np.linalg.norm(g[:2048]) > 0.01 * np.linalg.norm(g)               # base rows get gradient too
+    info = pkg.last_info()
+    assert info["status"] & ~_lib.STATUS_KNN_FALLBACK == 0 and info["cg_iters_fwd"] > 0 and info["cg_iters_bwd"] > 0
+    # linearity of the backward in grad_output: bwd(2 g) = 2 bwd(g)
+    Xt = torch.as_tensor(X).cuda().requires_grad_(True)
+    pr = pkg.LaplaceLearningSparseHard.apply(Xt, torch.as_tensor(Y).cuda(), 0.0, "auto")
+    gsel = torch.randn(pr.shape, dtype=pr.dtype, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+    (g1,) = torch.autograd.grad((pr * gsel).sum(), Xt, retain_graph=True)
+    (g2,) = torch.autograd.grad((pr * (2 * gsel)).sum(), Xt)
+    assert torch.allclose(g2, 2 * g1, rtol=0, atol=2e-5 * g1.abs().max().item())
+
+
+def test_layer_api_contract(gll):
+    pkg, _ = gll
+    X, Y, _, yq = O.synth_inputs(9, 100, 200, 32, 5, 1.5)
+    Xt = torch.as_tensor(X).cuda()
+    # two-argument call: tau = 0, epsilon = 'auto', int64 labels (train_and_adversarial.py:545,552)
+    p2 = pkg.LaplaceLearningSparseHard.apply(Xt, torch.as_tensor(Y).long().cuda())
+    p4 = pkg.LaplaceLearningSparseHard.apply(Xt, torch.as_tensor(Y).cuda(), 0, "auto")
+    assert torch.equal(p2, p4) and p2.shape == (200, 5) and p2.dtype == torch.float64 and p2.is_cuda
+    with torch.no_grad():  # train_and_adversarial.py:579-595
+        p3 = pkg.LaplaceLearningSparseHard.apply(Xt, torch.as_tensor(Y).cuda())
+    assert torch.equal(p3, p2)
+    # callers mutate the output in place (adversarial.py:691) and then still backpropagate
+    Xg = Xt.clone().requires_grad_(True)
+    out = pkg.LaplaceLearningSparseHard.apply(Xg, torch.as_tensor(Y).cuda(), 0.07, 1.0)
+    ref = O.forward(X, Y, 0.07, 1.0)
+    out2 = out.clone()
+    out2[0, 0] = -1000000
+    out2.sum().backward()
+    assert Xg.grad is not None and Xg.grad.shape == Xg.shape and torch.isfinite(Xg.grad).all()
+    assert O.max_rel(out.detach().cpu().numpy(), ref.pred) < TOL
+    with pytest.raises(RuntimeError):  # no CPU path by design
+        pkg.LaplaceLearningSparseHard.apply(torch.as_tensor(X), torch.as_tensor(Y))
+    with pytest.raises(ValueError):
+        pkg.LaplaceLearningSparseHard.apply(Xt, torch.as_tensor(Y).cuda(), 0, "banana")
+
+
+def test_layer_is_deterministic(gll):
+    pkg, _ = gll
+    X, Y, _, yq = O.synth_inputs(1, 1000, 1000, 128, 10, 3.0)
+    a = layer_fwd_bwd(pkg, X, Y, yq, 0.0, "auto")
+    b = layer_fwd_bwd(pkg, X, Y, yq, 0.0, "auto")
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])  # no floating-point atomics anywhere
+
+
+def test_eps_tiny_warns(gll, monkeypatch):
+    pkg, _ = gll
+    monkeypatch.setenv("GLL_B200_CHECK", "1")
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((80, 8)).astype(np.float32)
+    X[30:60] = X[30]  # >= 24 duplicates: epsilon_i = 0 (GLL.py:240-241 warns)
+    Y = np.eye(4, dtype=np.float32)[np.arange(20) % 4]
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        pkg.LaplaceLearningSparseHard.apply(torch.as_tensor(X).cuda(), torch.as_tensor(Y).cuda())
+        torch.cuda.synchronize()
+    assert any("Epsilon in KNN" in str(x.message) for x in w)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# numpy / scipy wrappers (utils.py:570-593 call sites)
+# ----------------------------------------------------------------------------------------------------------------
+def test_knn_sym_dist_wrapper(gll):
+    pkg, _ = gll
+    X, *_ = O.synth_inputs(0, 300, 500, 64, 10, 2.0)
+    g = O.build_graph(X, 25, "auto")
+    W, V, mod_V, Cm, knn_ind = pkg.knn_sym_dist(X, 25, "auto")
+    assert sp.issparse(W) and W.shape == (800, 800)
+    assert np.array_equal(W.indptr, g.W.indptr) and np.array_equal(W.indices, g.W.indices)
+    assert O.max_rel(W.data, g.W.data) < 1e-6 and O.max_rel(V.data, g.V.data) < 1e-6
+    assert O.max_rel(mod_V.data, g.modV.data) < 1e-6
+    assert np.array_equal(np.asarray(Cm.argmax(axis=0)).ravel(), g.kappa)
+    assert np.array_equal(knn_ind, g.knn_ind)
+    W50, V50, mv, cc, ki = pkg.knn_sym_dist(X, 30, 1.0)  # a different k (utils.py:651 uses 50 at eval; kernel max is 33)
+    assert mv is None and cc is None and ki.shape == (800, 30)
+    g30 = O.build_graph(X, 30, 1.0)
+    assert np.array_equal(W50.indices, g30.W.indices) and O.max_rel(W50.data, g30.W.data) < 1e-6
+
+
+def test_stable_conjgrad_wrapper(gll, capsys):
+    pkg, _ = gll
+    X, Y, *_ = O.synth_inputs(3, 150, 1450, 16, 6, 1.0)
+    f = O.forward(X, Y, 0.05, 1.0, solver="lu")
+    # the live call site (utils.py:586-591): Jacobi-scaled system, default tol = 1e-10
+    Mh = sp.diags(1.0 / np.sqrt(f.Luu.diagonal() + 1e-10))
+    A = (Mh @ f.Luu @ Mh).tocsr()
+    b = Mh @ f.B
+    y = pkg.stable_conjgrad(A, b)
+    assert np.sqrt(((A @ y - b) ** 2).sum(axis=0)).max() <= 1e-10
+    assert O.max_rel(Mh @ y, f.pred) < 1e-8
+    y1 = pkg.stable_conjgrad(A, b[:, 0], tol=1e-8)  # 1-D right-hand side
+    assert y1.shape == (1450,) and np.abs(A @ y1 - b[:, 0]).max() < 1e-8
+    pkg.stable_conjgrad(A, b, max_iter=2, tol=1e-12)
+    assert "max iter reached" in capsys.readouterr().out
