@@ -281,7 +281,7 @@ def layer_fwd_bwd(pkg, X, Y, yq, tau, eps):
     loss = -torch.sum(tgt * torch.log(pred + 1e-8)) / pred.shape[0]  # custom_ce_loss, losses.py:128-136
     loss.backward()
     torch.cuda.synchronize()
-    return pred, loss, Xt.grad
+    return pred.detach(), loss.detach(), Xt.grad
 
 
 @pytest.mark.parametrize("name", golden_names())
