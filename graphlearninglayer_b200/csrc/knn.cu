@@ -241,7 +241,7 @@ __device__ __forceinline__ double exact_d2(const float* __restrict__ xi_s, const
 template <bool VEC4>
 __global__ void __launch_bounds__(RERANK_WARPS * 32)
 knn_rerank_kernel(const float* __restrict__ X, const float* __restrict__ sq, const unsigned* __restrict__ sqmax_bits,
-                  int n, int d, int k, int splits, const u64* __restrict__ cand, float err_coef,
+                  int n, int d, int k, CandLayout lay, const u64* __restrict__ cand, float err_coef,
                   int* __restrict__ knn_idx, float* __restrict__ knn_dist, int* __restrict__ flag_count,
                   int* __restrict__ flag_rows) {
   extern __shared__ __align__(16) float xs[];
@@ -252,11 +252,18 @@ knn_rerank_kernel(const float* __restrict__ X, const float* __restrict__ sq, con
   for (int t = lane; t < d; t += 32) xi[t] = X[(size_t)i * d + t];
 
   u64 mine = KEY_INF;
+  int splits = lay.stride;
+  if (lay.tc) {  // lists written for this row's tile: one per CTA that touched it (knn_tc.cu)
+    const long long rt = i / lay.row_tile;
+    const int b0 = (int)(((rt * lay.col_tiles + 1) * lay.grid - 1) / lay.units);
+    const int b1 = (int)((((rt + 1) * lay.col_tiles) * lay.grid - 1) / lay.units);
+    splits = b1 - b0 + 1;
+  }
   if (splits == 1) {
-    mine = cand[(size_t)i * KC + lane];
+    mine = cand[(size_t)i * lay.stride * KC + lane];
   } else {
     for (int s = 0; s < splits; ++s) {
-      u64 c = cand[((size_t)i * splits + s) * KC + lane];
+      u64 c = cand[((size_t)i * lay.stride + s) * KC + lane];
       for (int t = 0; t < KC; ++t) {
         u64 x = __shfl_sync(FULL, c, t);
         if (x == KEY_INF) break;
@@ -375,7 +382,7 @@ knn_fallback_kernel(const float* __restrict__ X, int n, int d, int k, const int*
 
 }  // namespace
 
-int knn_finish(const float* X, const float* sq, const unsigned* sqmax_bits, int n, int d, int k, int splits,
+int knn_finish(const float* X, const float* sq, const unsigned* sqmax_bits, int n, int d, int k, CandLayout lay,
                const u64* cand, float err_coef, int* knn_idx, float* knn_dist, int* flag_count, int* flag_rows,
                int* info, cudaStream_t st) {
   const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
@@ -386,7 +393,7 @@ int knn_finish(const float* X, const float* sq, const unsigned* sqmax_bits, int 
       GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
       GLL_PROF(KID_RERANK, st);
-      knn_rerank_kernel<true><<<blocks, RERANK_WARPS * 32, smem, st>>>(X, sq, sqmax_bits, n, d, k, splits, cand,
+      knn_rerank_kernel<true><<<blocks, RERANK_WARPS * 32, smem, st>>>(X, sq, sqmax_bits, n, d, k, lay, cand,
                                                                       err_coef, knn_idx, knn_dist, flag_count, flag_rows);
     }
   } else {
@@ -394,7 +401,7 @@ int knn_finish(const float* X, const float* sq, const unsigned* sqmax_bits, int 
       GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
       GLL_PROF(KID_RERANK, st);
-      knn_rerank_kernel<false><<<blocks, RERANK_WARPS * 32, smem, st>>>(X, sq, sqmax_bits, n, d, k, splits, cand,
+      knn_rerank_kernel<false><<<blocks, RERANK_WARPS * 32, smem, st>>>(X, sq, sqmax_bits, n, d, k, lay, cand,
                                                                        err_coef, knn_idx, knn_dist, flag_count, flag_rows);
     }
   }
@@ -422,13 +429,13 @@ static int simt_splits(int n, int* cols_per_split) {
 }
 
 size_t knn_ws_bytes(int n, int d, int k) {
-  (void)d;
   (void)k;
   size_t b = 0;
   b += align_up(sizeof(float) * (size_t)n, 256);                        // sq
   b += 256;                                                             // sqmax + flag_count
   b += align_up(sizeof(u64) * (size_t)n * KNN_MAX_SPLITS * KC, 256);    // cand
   b += align_up(sizeof(int) * (size_t)n, 256);                          // flag_rows
+  b += knn_tc_ws_upper(n, d);                                           // bf16 hi / lo copies for the tensor-core path
   return b + 1024;
 }
 
@@ -448,6 +455,7 @@ int knn_run(const float* X, int n, int d, int k, int* knn_idx, float* knn_dist, 
   int* flag_count = reinterpret_cast<int*>(small + 1);
   u64* cand = cv.take<u64>((size_t)n * KNN_MAX_SPLITS * KC);
   int* flag_rows = cv.take<int>(n);
+  char* tc_ws = cv.take<char>(knn_tc_ws_upper(n, d));
 
   GLL_CUDA_CHECK(cudaMemsetAsync(small, 0, 256, st));
   {
@@ -456,17 +464,22 @@ int knn_run(const float* X, int n, int d, int k, int* knn_idx, float* knn_dist, 
   }
   GLL_LAUNCH_CHECK();
 
-  int rc = knn_tc_candidates(X, sq, n, d, cand, st);  // tensor-core path when the shape allows it
-  int splits;
+  CandLayout lay;
   float err_coef;
-  if (rc > 0) {
-    splits = rc;
+  const TcPlan plan = knn_tc_plan(n, d);
+  if (plan.ok) {  // tcgen05 / TMA Gram GEMM with the fused top-k epilogue
+    int rc = knn_tc_candidates(X, sq, n, d, plan, tc_ws, cand, st);
+    if (rc) return rc;
+    lay.stride = plan.max_splits;
+    lay.tc = 1;
+    lay.row_tile = 128;
+    lay.col_tiles = plan.col_tiles;
+    lay.grid = plan.grid;
+    lay.units = plan.units;
     err_coef = knn_tc_err_coef(d);
-  } else if (rc < 0) {
-    return rc;
-  } else {
+  } else {  // fp32 SIMT Gram (tiny graphs, or forced by GLL_B200_KNN_PATH=simt)
     int cps;
-    splits = simt_splits(n, &cps);
+    const int splits = simt_splits(n, &cps);
     const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
     dim3 grid(ceil_div(n, BM), splits);
     size_t smem = gemm_smem_bytes();
@@ -484,11 +497,15 @@ int knn_run(const float* X, int n, int d, int k, int* knn_idx, float* knn_dist, 
       }
     }
     GLL_LAUNCH_CHECK();
+    lay.stride = splits;
+    lay.tc = 0;
+    lay.row_tile = lay.col_tiles = lay.grid = 0;
+    lay.units = 0;
     // |fl(d~^2) - d^2| <= (gamma_d + 4u)(|x_i|^2 + |x_j|^2), gamma_d = d u/(1 - d u), u = 2^-24 (sequential fp32 FMA chain)
     const double u = 5.9604644775390625e-8;
     err_coef = (float)(((double)d * u / (1.0 - (double)d * u) + 4.0 * u) * 1.0001);
   }
-  return knn_finish(X, sq, sqmax_bits, n, d, k, splits, cand, err_coef, knn_idx, knn_dist, flag_count, flag_rows, info, st);
+  return knn_finish(X, sq, sqmax_bits, n, d, k, lay, cand, err_coef, knn_idx, knn_dist, flag_count, flag_rows, info, st);
 }
 
 }  // namespace gll

@@ -1,7 +1,453 @@
-// Tensor-core (tcgen05 + TMA) candidate generation for K1 -- placeholder until the UMMA kernel lands.
+// K1 on the tensor cores: candidate generation for the exact kNN search as a tcgen05 / TMA Gram GEMM with a fused
+// per-row top-KC epilogue (replaces the annoy search behind gl.weightmatrix.knnsearch, GLL.py:181-189).
+//
+// Arithmetic.  bf16 alone (8 mantissa bits) cannot order neighbours whose squared distances differ by ~1e-3, so every
+// feature is split x = hi + lo (+ e, |e| <= 2^-18 |x|) into two bf16 numbers and the Gram entry is accumulated in fp32
+// TMEM as  hi.hi + lo.hi + hi.lo  (the dropped lo.lo term is O(2^-18)): three bf16 MMA passes that share operand
+// tiles.  The result is only used to pick KC = 32 candidates per row; knn_finish() (knn.cu) recomputes the survivors
+// exactly, proves that no true neighbour was missed (error budget knn_tc_err_coef) and redoes unprovable rows by brute
+// force, so the emitted neighbour lists do not depend on tensor-core rounding.
+//
+// Kernel (one persistent CTA per SM, 6 warps, warp-specialised):
+//   warp 0   TMA producer: per 64-wide K block one stage = {A_hi, A_lo (128 rows), B_hi, B_lo (192 rows)}, 128B swizzle
+//   warp 1   MMA issuer: one elected lane issues 12 tcgen05.mma (3 operand pairs x 4 K=16 steps) per stage into one of
+//            two 128 x 192 fp32 accumulators in TMEM (double buffered against the epilogue)
+//   warps 2-5 epilogue: tcgen05.ld gives each thread ONE row of the tile; d~^2 = |xi|^2 + |xj|^2 - 2 acc is compared
+//            with the row's running 32nd-best; survivors go to a 16-entry per-row pending buffer in shared memory and
+//            are merged warp-cooperatively into the row's sorted list.  The n x n matrix never leaves the SM.
+// Work = (row tile, column tile) units in row-major order, split evenly and contiguously over the CTAs, so a CTA keeps
+// one row tile's lists on chip for many column tiles; lists are flushed to cand[row][slot][KC] when the row tile changes.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cudaTypedefs.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "knn_common.cuh"
 
 namespace gll {
-int knn_tc_candidates(const float*, const float*, int, int, u64*, cudaStream_t) { return 0; }
-float knn_tc_err_coef(int) { return 0.f; }
+namespace {
+
+constexpr int TC_BM = 128, TC_BN = 192, TC_BK = 64, TC_STAGES = 2;
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;          // 24 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // 80 KB
+constexpr int TC_CHUNK = 16;                           // columns per tcgen05.ld, == pending capacity per row
+constexpr int TC_TMEM_COLS = 512, TC_ACC_STRIDE = 256;
+
+constexpr size_t TC_OFF_LISTS = (size_t)TC_STAGES * TC_STAGE_BYTES;          // u64 [4][32][KC]
+constexpr size_t TC_OFF_PEND = TC_OFF_LISTS + 4 * 32 * KC * 8;               // u64 [4][32][TC_CHUNK]
+constexpr size_t TC_OFF_SQJ = TC_OFF_PEND + 4 * 32 * TC_CHUNK * 8;           // float [4][TC_BN]
+constexpr size_t TC_OFF_BAR = TC_OFF_SQJ + 4 * TC_BN * 4;                    // mbarriers + tmem pointer
+constexpr size_t TC_SMEM_BYTES = TC_OFF_BAR + 128 + 1024;                    // + slack for manual 1024 B alignment
+
+// M = 128, N = 192, A/B bf16 K-major, D fp32 (layout: cute::UMMA::InstrDescriptor)
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch (error code), never as a hung GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (uint32_t spin = 1; !mbar_try_wait(bar, parity); ++spin) {
+    if ((spin & 1023u) == 0) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 4000000000ull) __trap();  // 4 s
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major operand tile, rows of 128 B (64 bf16), 128B swizzle, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[TC_CHUNK]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[c]);
+}
+
+struct TcParams {
+  int n, kblocks, col_tiles, max_splits;
+  long long units;
+  const float* sq;
+  u64* cand;
+};
+
+// CTA that owns unit u when `units` units are dealt contiguously to G CTAs (CTA b owns [b*units/G, (b+1)*units/G))
+__host__ __device__ inline int tc_cta_of_unit(long long u, int G, long long units) { return (int)(((u + 1) * G - 1) / units); }
+
+// ---------------------------------------------------------------------------------------------- split X = hi + lo
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ X, int n, int d, int d_pad, __nv_bfloat16* __restrict__ H, __nv_bfloat16* __restrict__ L) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per pair of columns
+  const int half = d_pad >> 1;
+  if (t >= (long long)n * half) return;
+  const int i = (int)(t / half), c = (int)(t % half) * 2;
+  const float x0 = (c < d) ? X[(size_t)i * d + c] : 0.f;
+  const float x1 = (c + 1 < d) ? X[(size_t)i * d + c + 1] : 0.f;
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+  const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+  __nv_bfloat162 hv, lv;
+  hv.x = h0; hv.y = h1; lv.x = l0; lv.y = l1;
+  *reinterpret_cast<__nv_bfloat162*>(H + (size_t)i * d_pad + c) = hv;
+  *reinterpret_cast<__nv_bfloat162*>(L + (size_t)i * d_pad + c) = lv;
+}
+
+// ---------------------------------------------------------------------------------------------- the GEMM + top-k kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_constant__ CUtensorMap mapAL,
+                        const __grid_constant__ CUtensorMap mapBH, const __grid_constant__ CUtensorMap mapBL, TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // 128B-swizzled operand tiles need 1024 B alignment
+  uint8_t* smem = smem_raw + (base - raw);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x, b = blockIdx.x;
+  const long long u_begin = (long long)b * P.units / G, u_end = (long long)(b + 1) * P.units / G;
+  const int C = P.col_tiles, KB = P.kblocks;
+
+  const uint32_t bar_full = base + (uint32_t)TC_OFF_BAR;        // [TC_STAGES]
+  const uint32_t bar_empty = bar_full + 8 * TC_STAGES;          // [TC_STAGES]
+  const uint32_t bar_tfull = bar_empty + 8 * TC_STAGES;         // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;                   // [2]
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + TC_OFF_BAR + 96);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapAH);
+    tma_prefetch_desc(&mapAL);
+    tma_prefetch_desc(&mapBH);
+    tma_prefetch_desc(&mapBL);
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + (uint32_t)TC_OFF_BAR + 96),
+                 "r"((uint32_t)TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================= TMA producer =================================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long u = u_begin; u < u_end; ++u) {
+        const int rt = (int)(u / C), ct = (int)(u % C);
+        for (int kk = 0; kk < KB; ++kk) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+          const uint32_t full = bar_full + 8 * stage;
+          const uint32_t s0 = base + (uint32_t)stage * TC_STAGE_BYTES;
+          mbar_arrive_expect_tx(full, TC_STAGE_BYTES);
+          tma_load_2d(s0, &mapAH, full, kk * TC_BK, rt * TC_BM);
+          tma_load_2d(s0 + TC_A_BYTES, &mapAL, full, kk * TC_BK, rt * TC_BM);
+          tma_load_2d(s0 + 2 * TC_A_BYTES, &mapBH, full, kk * TC_BK, ct * TC_BN);
+          tma_load_2d(s0 + 2 * TC_A_BYTES + TC_B_BYTES, &mapBL, full, kk * TC_BK, ct * TC_BN);
+          if (++stage == TC_STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================= MMA issuer ===================================================
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (long long u = u_begin; u < u_end; ++u) {
+      mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);  // the epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_ACC_STRIDE;
+      for (int kk = 0; kk < KB; ++kk) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t s0 = base + (uint32_t)stage * TC_STAGE_BYTES;
+          const uint64_t dAH = tc_smem_desc(s0), dAL = tc_smem_desc(s0 + TC_A_BYTES);
+          const uint64_t dBH = tc_smem_desc(s0 + 2 * TC_A_BYTES), dBL = tc_smem_desc(s0 + 2 * TC_A_BYTES + TC_B_BYTES);
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            const uint64_t da = (g == 1) ? dAL : dAH, db = (g == 2) ? dBL : dBH;  // hi.hi, lo.hi, hi.lo
+#pragma unroll
+            for (int k4 = 0; k4 < TC_BK / 16; ++k4)  // +32 B (two 16 B units) per K=16 step inside the swizzle atom
+              tc_mma_bf16(d_tmem, da + (uint64_t)(2 * k4), db + (uint64_t)(2 * k4), TC_IDESC, (uint32_t)((kk | g | k4) != 0));
+          }
+          tc_commit(bar_empty + 8 * stage);                 // frees the smem stage when these MMAs retire
+          if (kk == KB - 1) tc_commit(bar_tfull + 8 * acc);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == TC_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  } else {
+    // ================================================= epilogue =====================================================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may read
+    u64* lists = reinterpret_cast<u64*>(smem + TC_OFF_LISTS) + (size_t)quarter * 32 * KC;
+    u64* pend = reinterpret_cast<u64*>(smem + TC_OFF_PEND) + (size_t)quarter * 32 * TC_CHUNK;
+    float* sqj_s = reinterpret_cast<float*>(smem + TC_OFF_SQJ) + (size_t)quarter * TC_BN;
+    int acc = 0, cur_rt = -1, cnt = 0, gi = 0;
+    uint32_t acc_phase = 0;
+    float thr = INFINITY, sqi = 0.f;
+
+    auto flush = [&](int rt) {
+      const long long first_unit = (long long)rt * C;
+      const int slot = b - tc_cta_of_unit(first_unit, G, P.units);
+      for (int r = 0; r < 32; ++r) {
+        const int row = rt * TC_BM + quarter * 32 + r;
+        if (row < P.n) P.cand[((size_t)row * P.max_splits + slot) * KC + lane] = lists[r * KC + lane];
+      }
+    };
+
+    for (long long u = u_begin; u < u_end; ++u) {
+      const int rt = (int)(u / C), ct = (int)(u % C);
+      if (rt != cur_rt) {
+        if (cur_rt >= 0) flush(cur_rt);
+        __syncwarp();
+        for (int r = 0; r < 32; ++r) lists[r * KC + lane] = KEY_INF;
+        cur_rt = rt;
+        thr = INFINITY;
+        gi = rt * TC_BM + quarter * 32 + lane;
+        sqi = (gi < P.n) ? __ldg(P.sq + gi) : 0.f;
+      }
+      const int c_begin = ct * TC_BN;
+      for (int t = lane; t < TC_BN; t += 32) sqj_s[t] = (c_begin + t < P.n) ? __ldg(P.sq + c_begin + t) : INFINITY;
+      __syncwarp();
+      const bool diag = (c_begin < rt * TC_BM + TC_BM) && (c_begin + TC_BN > rt * TC_BM);
+
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * TC_ACC_STRIDE;
+      u64* my_pend = pend + lane * TC_CHUNK;
+#pragma unroll 1
+      for (int q = 0; q < TC_BN / TC_CHUNK; ++q) {
+        float v[TC_CHUNK];
+        tc_ld16(taddr + q * TC_CHUNK, v);
+#pragma unroll
+        for (int c = 0; c < TC_CHUNK; ++c) {
+          const int j = c_begin + q * TC_CHUNK + c;
+          float dist = fmaf(-2.f, v[c], sqi + sqj_s[q * TC_CHUNK + c]);  // +inf for columns beyond n
+          if (diag && j == gi) dist = INFINITY;                           // self is slot 0 by construction (knn_finish)
+          if (dist < thr) my_pend[cnt++] = make_key(dist, j);
+        }
+        // ---- merge the survivors: the warp walks the rows that have pending entries ----
+        unsigned active = __ballot_sync(FULL, cnt > 0);
+        if (active) {
+          __syncwarp();
+          while (active) {
+            const int r = __ffs(active) - 1;
+            active &= active - 1;
+            const int nr = __shfl_sync(FULL, cnt, r);
+            u64 mine = lists[r * KC + lane];
+            for (int t = 0; t < nr; ++t) list_insert(mine, pend[r * TC_CHUNK + t], lane);
+            lists[r * KC + lane] = mine;
+            const u64 last = __shfl_sync(FULL, mine, KC - 1);
+            if (lane == r) {
+              thr = (last == KEY_INF) ? INFINITY : key_dist(last);
+              cnt = 0;
+            }
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);  // accumulator may be overwritten
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (cur_rt >= 0) flush(cur_rt);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+PFN_cuTensorMapEncodeTiled get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap* m, const void* base, int n, int d_pad, int box_rows) {
+  PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return GLL_ERR_CUDA;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)d_pad, (cuuint64_t)n};
+  const cuuint64_t gstride[1] = {(cuuint64_t)d_pad * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (n=%d d_pad=%d box_rows=%d)", (int)r, n, d_pad, box_rows);
+    return GLL_ERR_CUDA;
+  }
+  return GLL_OK;
+}
+
+}  // namespace
+
+TcPlan knn_tc_plan(int n, int d) {
+  TcPlan p;
+  memset(&p, 0, sizeof(p));
+  const char* force = getenv("GLL_B200_KNN_PATH");  // "simt" or "tc": testing knob, both paths are exact
+  if (force && strcmp(force, "simt") == 0) return p;
+  if (n < 2 * TC_BM && !(force && strcmp(force, "tc") == 0)) return p;  // tiny graphs: the SIMT kernel is enough
+  p.d_pad = ceil_div(d, TC_BK) * TC_BK;
+  p.kblocks = p.d_pad / TC_BK;
+  p.row_tiles = ceil_div(n, TC_BM);
+  p.col_tiles = ceil_div(n, TC_BN);
+  p.units = (long long)p.row_tiles * p.col_tiles;
+  p.grid = (int)((p.units < (long long)device_info().sms) ? p.units : (long long)device_info().sms);
+  int ms = 1;
+  for (int rt = 0; rt < p.row_tiles; ++rt) {  // exact: CTAs touching each row tile
+    const int b0 = tc_cta_of_unit((long long)rt * p.col_tiles, p.grid, p.units);
+    const int b1 = tc_cta_of_unit((long long)(rt + 1) * p.col_tiles - 1, p.grid, p.units);
+    ms = max(ms, b1 - b0 + 1);
+  }
+  p.max_splits = ms;
+  p.ws_bytes = 2 * align_up((size_t)n * p.d_pad * 2, 256);
+  p.ok = (ms <= KNN_MAX_SPLITS) ? 1 : 0;
+  return p;
+}
+
+size_t knn_tc_ws_upper(int n, int d) { return 2 * align_up((size_t)n * (size_t)(ceil_div(d, TC_BK) * TC_BK) * 2, 256) + 512; }
+
+int knn_tc_splits_of_row(const TcPlan& p, int row) {
+  const int rt = row / TC_BM;
+  return tc_cta_of_unit((long long)(rt + 1) * p.col_tiles - 1, p.grid, p.units) - tc_cta_of_unit((long long)rt * p.col_tiles, p.grid, p.units) + 1;
+}
+
+// |d~^2 - d^2| <= coef * (|xi|^2 + |xj|^2): split residual 3*2^-18, fp32 accumulation over 3*d/16 MMA steps of unknown
+// internal rounding (budgeted at 2^-21 per step and per 16-term tree), final fp32 expression 4u; then a 4x margin.
+float knn_tc_err_coef(int d) {
+  const double steps = 3.0 * ceil_div(d, 16) + 8.0;
+  const double e = 3.0 / 262144.0 + steps * 4.76837158203125e-7 + 4.0 * 5.9604644775390625e-8;
+  return (float)(4.0 * e);
+}
+
+int knn_tc_candidates(const float* X, const float* sq, int n, int d, const TcPlan& plan, void* tc_ws, u64* cand, cudaStream_t st) {
+  __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(tc_ws);
+  __nv_bfloat16* L = reinterpret_cast<__nv_bfloat16*>((char*)tc_ws + align_up((size_t)n * plan.d_pad * 2, 256));
+  {
+    GLL_PROF(KID_CONVERT, st);
+    const long long work = (long long)n * (plan.d_pad / 2);
+    split_bf16_kernel<<<ceil_div(work, 256), 256, 0, st>>>(X, n, d, plan.d_pad, H, L);
+  }
+  GLL_LAUNCH_CHECK();
+  CUtensorMap mAH, mAL, mBH, mBL;
+  int rc;
+  if ((rc = make_map(&mAH, H, n, plan.d_pad, TC_BM))) return rc;
+  if ((rc = make_map(&mAL, L, n, plan.d_pad, TC_BM))) return rc;
+  if ((rc = make_map(&mBH, H, n, plan.d_pad, TC_BN))) return rc;
+  if ((rc = make_map(&mBL, L, n, plan.d_pad, TC_BN))) return rc;
+  TcParams P;
+  P.n = n;
+  P.kblocks = plan.kblocks;
+  P.col_tiles = plan.col_tiles;
+  P.max_splits = plan.max_splits;
+  P.units = plan.units;
+  P.sq = sq;
+  P.cand = cand;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_gram_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  {
+    GLL_PROF(KID_GRAM_TOPK_TC, st);
+    knn_gram_topk_tc_kernel<<<plan.grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mAH, mAL, mBH, mBL, P);
+  }
+  GLL_LAUNCH_CHECK();
+  return GLL_OK;
+}
+
 }  // namespace gll

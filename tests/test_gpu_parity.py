@@ -128,9 +128,11 @@ KNN_SHAPES = [(0, 300, 500, 64, 10, 2.0), (3, 37, 91, 19, 3, 1.0), (1, 1000, 100
               (4, 2048, 1024, 512, 10, 4.5), (6, 10, 20, 7, 2, 0.5), (8, 500, 700, 130, 5, 2.0)]
 
 
+@pytest.mark.parametrize("path", ["simt", "tc"])  # fp32 SIMT Gram / tcgen05 bf16x3 Gram: both must give the exact lists
 @pytest.mark.parametrize("seed,k_lab,m,d,l,sigma", KNN_SHAPES)
-def test_knn_bit_exact_vs_oracle(gll, seed, k_lab, m, d, l, sigma):
+def test_knn_bit_exact_vs_oracle(gll, monkeypatch, path, seed, k_lab, m, d, l, sigma):
     _, _lib = gll
+    monkeypatch.setenv("GLL_B200_KNN_PATH", path)
     X, *_ = O.synth_inputs(seed, k_lab, m, d, l, sigma)
     ref_ind, ref_dist = O.exact_knn(X, 25)
     idx, dist, info = run_knn(_lib, X)
@@ -144,8 +146,10 @@ def test_knn_bit_exact_vs_oracle(gll, seed, k_lab, m, d, l, sigma):
     assert np.array_equal(d_gpu[same], ref_dist[same].astype(np.float32))  # fp64 direct differences rounded to fp32
 
 
-def test_knn_duplicates_and_tiny_n(gll):
+@pytest.mark.parametrize("path", ["simt", "tc"])
+def test_knn_duplicates_and_tiny_n(gll, monkeypatch, path):
     _, _lib = gll
+    monkeypatch.setenv("GLL_B200_KNN_PATH", path)
     rng = np.random.default_rng(0)
     X = rng.standard_normal((60, 16)).astype(np.float32)
     X[10:40] = X[10]  # 30 identical points: zero distances, ties broken by index
@@ -158,6 +162,24 @@ def test_knn_duplicates_and_tiny_n(gll):
     X2 = rng.standard_normal((25, 8)).astype(np.float32)
     idx2, _, _ = run_knn(_lib, X2)
     assert np.array_equal(np.sort(idx2.cpu().numpy(), axis=1), np.tile(np.arange(25), (25, 1)))
+
+
+def test_knn_paths_agree_and_tc_is_used(gll, monkeypatch):
+    """Default dispatch takes the tensor-core kernel at this size; its lists are identical to the SIMT kernel's."""
+    _, _lib = gll
+    X, *_ = O.synth_inputs(12, 3000, 1777, 200, 10, 3.5)  # n, d not multiples of the tile sizes
+    names = _lib.kernel_names()
+    tc_id, simt_id = names.index("knn_gram_topk_tcgen05"), names.index("knn_gram_topk_simt")
+    monkeypatch.delenv("GLL_B200_KNN_PATH", raising=False)
+    before = _lib.launch_count(tc_id)
+    i_tc, d_tc, info = run_knn(_lib, X)
+    assert _lib.launch_count(tc_id) == before + 1
+    monkeypatch.setenv("GLL_B200_KNN_PATH", "simt")
+    before = _lib.launch_count(simt_id)
+    i_s, d_s, _ = run_knn(_lib, X)
+    assert _lib.launch_count(simt_id) == before + 1
+    assert torch.equal(i_tc, i_s) and torch.equal(d_tc, d_s)
+    assert int(info[_lib.INFO_KNN_FALLBACK_ROWS].item()) < 0.02 * X.shape[0]
 
 
 def test_knn_full_size_properties(gll):
