@@ -259,15 +259,14 @@ knn_rerank_kernel(const float* __restrict__ X, const float* __restrict__ sq, con
     const int b1 = (int)((((rt + 1) * lay.col_tiles) * lay.grid - 1) / lay.units);
     splits = b1 - b0 + 1;
   }
-  if (splits == 1) {
-    mine = cand[(size_t)i * lay.stride * KC + lane];
+  if (splits == 1 && !lay.tc) {
+    mine = cand[(size_t)i * lay.stride * KC + lane];  // SIMT lists are sorted
   } else {
-    for (int s = 0; s < splits; ++s) {
+    for (int s = 0; s < splits; ++s) {  // tensor-core lists are unsorted sets: merge by insertion
       u64 c = cand[((size_t)i * lay.stride + s) * KC + lane];
       for (int t = 0; t < KC; ++t) {
         u64 x = __shfl_sync(FULL, c, t);
-        if (x == KEY_INF) break;
-        list_insert(mine, x, lane);
+        if (x != KEY_INF) list_insert(mine, x, lane);
       }
     }
   }

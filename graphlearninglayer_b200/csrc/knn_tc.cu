@@ -9,12 +9,15 @@
 // force, so the emitted neighbour lists do not depend on tensor-core rounding.
 //
 // Kernel (one persistent CTA per SM, 6 warps, warp-specialised):
-//   warp 0   TMA producer: per 64-wide K block one stage = {A_hi, A_lo (128 rows), B_hi, B_lo (192 rows)}, 128B swizzle
+//   warp 0   TMA producer: per 64-wide K block one stage = {A_hi, A_lo (128 rows), B_hi, B_lo (256 rows)}, 128B swizzle
 //   warp 1   MMA issuer: one elected lane issues 12 tcgen05.mma (3 operand pairs x 4 K=16 steps) per stage into one of
-//            two 128 x 192 fp32 accumulators in TMEM (double buffered against the epilogue)
-//   warps 2-5 epilogue: tcgen05.ld gives each thread ONE row of the tile; d~^2 = |xi|^2 + |xj|^2 - 2 acc is compared
-//            with the row's running 32nd-best; survivors go to a 16-entry per-row pending buffer in shared memory and
-//            are merged warp-cooperatively into the row's sorted list.  The n x n matrix never leaves the SM.
+//            two 128 x 256 fp32 accumulators in TMEM (all 512 columns; double buffered against the epilogue)
+//   warps 2-5 epilogue: tcgen05.ld gives each thread ONE row of the tile, 16 columns at a time; d~^2 = |xi|^2 + |xj|^2
+//            - 2 acc is compared with the row's running 32nd-best (a register).  A thread owns its row's candidate set:
+//            an unsorted 32-slot array in shared memory (slot-major, so the 32 threads of a warp never bank-conflict)
+//            in which a survivor replaces the current maximum, followed by a 32-load rescan for the new maximum.
+//            All rows of a warp insert concurrently, so a chunk costs max-over-rows(survivors) rescans, ~1 in steady
+//            state.  The n x n matrix never leaves the SM.
 // Work = (row tile, column tile) units in row-major order, split evenly and contiguously over the CTAs, so a CTA keeps
 // one row tile's lists on chip for many column tiles; lists are flushed to cand[row][slot][KC] when the row tile changes.
 #include <cuda.h>
@@ -29,21 +32,22 @@
 namespace gll {
 namespace {
 
-constexpr int TC_BM = 128, TC_BN = 192, TC_BK = 64, TC_STAGES = 2;
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 2;
 constexpr int TC_THREADS = 192;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
-constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;          // 24 KB
-constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // 80 KB
-constexpr int TC_CHUNK = 16;                           // columns per tcgen05.ld, == pending capacity per row
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;          // 32 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // 96 KB
+constexpr int TC_CHUNK = 16;                           // columns per tcgen05.ld
 constexpr int TC_TMEM_COLS = 512, TC_ACC_STRIDE = 256;
 
-constexpr size_t TC_OFF_LISTS = (size_t)TC_STAGES * TC_STAGE_BYTES;          // u64 [4][32][KC]
-constexpr size_t TC_OFF_PEND = TC_OFF_LISTS + 4 * 32 * KC * 8;               // u64 [4][32][TC_CHUNK]
-constexpr size_t TC_OFF_SQJ = TC_OFF_PEND + 4 * 32 * TC_CHUNK * 8;           // float [4][TC_BN]
-constexpr size_t TC_OFF_BAR = TC_OFF_SQJ + 4 * TC_BN * 4;                    // mbarriers + tmem pointer
+constexpr size_t TC_OFF_LD = (size_t)TC_STAGES * TC_STAGE_BYTES;             // float [4 warps][KC entries][32 rows]
+constexpr size_t TC_OFF_LI = TC_OFF_LD + 4 * KC * 32 * 4;                    // int   [4 warps][KC entries][32 rows]
+constexpr size_t TC_OFF_BAR = TC_OFF_LI + 4 * KC * 32 * 4;                   // mbarriers + tmem pointer
 constexpr size_t TC_SMEM_BYTES = TC_OFF_BAR + 128 + 1024;                    // + slack for manual 1024 B alignment
+static_assert(TC_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(2 * TC_BN <= TC_TMEM_COLS && TC_ACC_STRIDE >= TC_BN, "two accumulators must fit in TMEM");
 
-// M = 128, N = 192, A/B bf16 K-major, D fp32 (layout: cute::UMMA::InstrDescriptor)
+// M = 128, N = 256, A/B bf16 K-major, D fp32 (layout: cute::UMMA::InstrDescriptor)
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -254,71 +258,90 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
   } else {
     // ================================================= epilogue =====================================================
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may read
-    u64* lists = reinterpret_cast<u64*>(smem + TC_OFF_LISTS) + (size_t)quarter * 32 * KC;
-    u64* pend = reinterpret_cast<u64*>(smem + TC_OFF_PEND) + (size_t)quarter * 32 * TC_CHUNK;
-    float* sqj_s = reinterpret_cast<float*>(smem + TC_OFF_SQJ) + (size_t)quarter * TC_BN;
-    int acc = 0, cur_rt = -1, cnt = 0, gi = 0;
+    float* Ld = reinterpret_cast<float*>(smem + TC_OFF_LD) + (size_t)quarter * KC * 32 + lane;  // my row: Ld[e * 32]
+    int* Li = reinterpret_cast<int*>(smem + TC_OFF_LI) + (size_t)quarter * KC * 32 + lane;
+    int acc = 0, cur_rt = -1, gi = 0, maxpos = 0;
     uint32_t acc_phase = 0;
     float thr = INFINITY, sqi = 0.f;
 
     auto flush = [&](int rt) {
-      const long long first_unit = (long long)rt * C;
-      const int slot = b - tc_cta_of_unit(first_unit, G, P.units);
-      for (int r = 0; r < 32; ++r) {
+      __syncwarp();
+      const int slot = b - tc_cta_of_unit((long long)rt * C, G, P.units);
+      const float* wd = Ld - lane;
+      const int* wi = Li - lane;
+      for (int r = 0; r < 32; ++r) {  // lane = slot index e here; 256 B coalesced store per row
         const int row = rt * TC_BM + quarter * 32 + r;
-        if (row < P.n) P.cand[((size_t)row * P.max_splits + slot) * KC + lane] = lists[r * KC + lane];
+        const float dd = wd[lane * 32 + r];
+        const u64 key = (dd == INFINITY) ? KEY_INF : make_key(dd, wi[lane * 32 + r]);
+        if (row < P.n) P.cand[((size_t)row * P.max_splits + slot) * KC + lane] = key;
       }
+      __syncwarp();
     };
 
     for (long long u = u_begin; u < u_end; ++u) {
       const int rt = (int)(u / C), ct = (int)(u % C);
       if (rt != cur_rt) {
         if (cur_rt >= 0) flush(cur_rt);
-        __syncwarp();
-        for (int r = 0; r < 32; ++r) lists[r * KC + lane] = KEY_INF;
+#pragma unroll
+        for (int e = 0; e < KC; ++e) Ld[e * 32] = INFINITY;
         cur_rt = rt;
         thr = INFINITY;
+        maxpos = 0;
         gi = rt * TC_BM + quarter * 32 + lane;
         sqi = (gi < P.n) ? __ldg(P.sq + gi) : 0.f;
       }
       const int c_begin = ct * TC_BN;
-      for (int t = lane; t < TC_BN; t += 32) sqj_s[t] = (c_begin + t < P.n) ? __ldg(P.sq + c_begin + t) : INFINITY;
-      __syncwarp();
       const bool diag = (c_begin < rt * TC_BM + TC_BM) && (c_begin + TC_BN > rt * TC_BM);
+      // |x_j|^2 of the chunk's 16 columns sits in lanes 0..15 (and again in 16..31); +inf masks columns beyond n
+      auto load_sqj = [&](int q) {
+        const int j = c_begin + q * TC_CHUNK + (lane & (TC_CHUNK - 1));
+        return (j < P.n) ? __ldg(P.sq + j) : INFINITY;
+      };
+      float sqj_next = load_sqj(0);
 
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * TC_ACC_STRIDE;
-      u64* my_pend = pend + lane * TC_CHUNK;
 #pragma unroll 1
       for (int q = 0; q < TC_BN / TC_CHUNK; ++q) {
         float v[TC_CHUNK];
         tc_ld16(taddr + q * TC_CHUNK, v);
+        const float sqj_cur = sqj_next;
+        if (q + 1 < TC_BN / TC_CHUNK) sqj_next = load_sqj(q + 1);
+        const int j0 = c_begin + q * TC_CHUNK;
+        uint32_t hits = 0;
 #pragma unroll
         for (int c = 0; c < TC_CHUNK; ++c) {
-          const int j = c_begin + q * TC_CHUNK + c;
-          float dist = fmaf(-2.f, v[c], sqi + sqj_s[q * TC_CHUNK + c]);  // +inf for columns beyond n
-          if (diag && j == gi) dist = INFINITY;                           // self is slot 0 by construction (knn_finish)
-          if (dist < thr) my_pend[cnt++] = make_key(dist, j);
+          float dist = fmaf(-2.f, v[c], sqi + __shfl_sync(FULL, sqj_cur, c));
+          if (diag && j0 + c == gi) dist = INFINITY;  // self is slot 0 by construction (knn_finish)
+          v[c] = dist;
+          hits |= (dist < thr) ? (1u << c) : 0u;
         }
-        // ---- merge the survivors: the warp walks the rows that have pending entries ----
-        unsigned active = __ballot_sync(FULL, cnt > 0);
-        if (active) {
-          __syncwarp();
-          while (active) {
-            const int r = __ffs(active) - 1;
-            active &= active - 1;
-            const int nr = __shfl_sync(FULL, cnt, r);
-            u64 mine = lists[r * KC + lane];
-            for (int t = 0; t < nr; ++t) list_insert(mine, pend[r * TC_CHUNK + t], lane);
-            lists[r * KC + lane] = mine;
-            const u64 last = __shfl_sync(FULL, mine, KC - 1);
-            if (lane == r) {
-              thr = (last == KEY_INF) ? INFINITY : key_dist(last);
-              cnt = 0;
+        // ---- every row (thread) inserts its own survivors; rows proceed concurrently ----
+        while (__any_sync(FULL, hits != 0)) {
+          if (hits) {
+            const int c = __ffs(hits) - 1;
+            hits &= hits - 1;
+            float dsel = v[0];
+#pragma unroll
+            for (int t = 1; t < TC_CHUNK; ++t) dsel = (t == c) ? v[t] : dsel;
+            if (dsel < thr) {  // thr may have tightened since the scan
+              Ld[maxpos * 32] = dsel;
+              Li[maxpos * 32] = j0 + c;
+              float mx = -INFINITY;
+              int mp = 0;
+#pragma unroll
+              for (int e = 0; e < KC; ++e) {
+                const float t = Ld[e * 32];
+                if (t > mx) {
+                  mx = t;
+                  mp = e;
+                }
+              }
+              thr = mx;
+              maxpos = mp;
             }
           }
-          __syncwarp();
         }
       }
       tc_fence_before();
