@@ -2,9 +2,17 @@
 
     from graphlearninglayer_b200 import LaplaceLearningSparseHard, knn_sym_dist, stable_conjgrad
 
-Importing the package loads libgll_b200.so (built in-tree by ``python -m graphlearninglayer_b200.build``) and fails
-loudly if it is missing; there is no CPU or PyTorch fallback.
+The names resolve lazily so that ``python -m graphlearninglayer_b200.build`` can run before the shared library
+exists; the first access loads libgll_b200.so through ctypes and fails loudly if it is missing or stale.  There is no
+CPU or PyTorch fallback.
 """
-from .GLL import LaplaceLearningSparseHard, knn_sym_dist, stable_conjgrad, last_info  # noqa: F401
+__all__ = ["LaplaceLearningSparseHard", "knn_sym_dist", "stable_conjgrad", "last_info", "GLL"]
 
-__all__ = ["LaplaceLearningSparseHard", "knn_sym_dist", "stable_conjgrad", "last_info"]
+
+def __getattr__(name):
+    if name in __all__:
+        import importlib
+
+        mod = importlib.import_module(".GLL", __name__)
+        return mod if name == "GLL" else getattr(mod, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

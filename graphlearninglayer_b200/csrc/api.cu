@@ -6,6 +6,7 @@
 #include <mutex>
 #include <vector>
 
+#include "cg_common.cuh"
 #include "common.cuh"
 
 namespace gll {
@@ -165,6 +166,7 @@ long long gll_launch_count(int id) {
   for (int i = 0; i < KID_COUNT; ++i) t += g_launches[i].load();
   return t;
 }
+void gll_debug_cg_trace(void* device_buf) { cg_set_trace(device_buf); }
 void gll_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
 int gll_profile_collect(double* ms_sum, long long* count) {
   std::vector<ProfRec*> recs;

@@ -14,34 +14,13 @@
 // Vectors written by other CTAs are read with ld.global.cg (L2), never through a possibly stale L1 line.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
-#include "common.cuh"
+#include "cg_common.cuh"
 
 namespace gll {
 namespace {
-
-constexpr int CG_THREADS = 1024;
-constexpr int CG_WARPS = CG_THREADS / 32;
-constexpr int CG_MAX_LP = 128;
-
-struct CgParams {
-  const int* ptr;
-  const int* col;
-  const float* val;
-  const float* diag;
-  const float* rhs;
-  float* x;
-  float* r;
-  float* p;
-  float* ap;
-  double* partial;    // [2 buffers][2*lp columns][grid]
-  unsigned* barrier;  // zeroed before launch
-  int m, lp, rows_per_block, max_iter;
-  float tol;
-  int* iters_out;
-  float* resid_out;
-  int* status_out;
-};
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
@@ -301,7 +280,8 @@ int cg_grid(int m) {
 size_t cg_ws_bytes(int m, int l) {
   const int lp = padded_classes(l);
   size_t v = align_up(sizeof(float) * (size_t)m * lp, 256);
-  return 3 * v + align_up(sizeof(double) * 2 * (2 * CG_MAX_LP) * (size_t)device_info().sms, 256) + 256 + 1024;
+  return 3 * v + align_up(sizeof(double) * 2 * (2 * CG_MAX_LP) * (size_t)device_info().sms, 256) + 256 + 1024 +
+         cg_resident_ws_bytes(m, lp);
 }
 
 int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, const float* rhs, int m, int l,
@@ -329,12 +309,23 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
   P.partial = cv.take<double>((size_t)2 * (2 * CG_MAX_LP) * device_info().sms);
   P.barrier = cv.take<unsigned>(64);
   P.m = m;
+  P.l = l;
   P.lp = lp;
   P.max_iter = max_iter;
   P.tol = tol;
   P.iters_out = iters_out;
   P.resid_out = resid_out;
   P.status_out = status_out;
+  P.rows_per_block = 0;
+  {  // systems that fit on chip (every config except the sharded 1M-node graph) take the shared-memory-resident kernel
+    const char* force = getenv("GLL_B200_CG_PATH");  // "streaming": testing knob
+    if (!(force && strcmp(force, "streaming") == 0)) {
+      void* scratch = cv.take<char>(cg_resident_ws_bytes(m, lp));
+      const int rc = cg_resident_try(P, scratch, st);
+      if (rc < 0) return rc;
+      if (rc == 1) return GLL_OK;
+    }
+  }
   const int grid = cg_grid(m);
   const int S = 32 / (lp / 4);
   int rpb = ceil_div(m, grid);

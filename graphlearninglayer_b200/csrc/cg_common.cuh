@@ -1,0 +1,37 @@
+// Shared by the two CG kernels: cg.cu (streaming: vectors in global memory, any size) and cg_resident.cu
+// (vectors and the CSR slice of every CTA stay in shared memory across iterations).
+#pragma once
+#include "common.cuh"
+
+namespace gll {
+
+constexpr int CG_THREADS = 1024;
+constexpr int CG_WARPS = CG_THREADS / 32;
+constexpr int CG_MAX_LP = 128;
+
+struct CgParams {
+  const int* ptr;
+  const int* col;
+  const float* val;
+  const float* diag;
+  const float* rhs;
+  float* x;
+  float* r;
+  float* p;
+  float* ap;
+  double* partial;    // [2 buffers][2*lp columns][grid]
+  unsigned* barrier;  // zeroed before launch
+  int m, l, lp, rows_per_block, max_iter;
+  float tol;
+  int* iters_out;
+  float* resid_out;
+  int* status_out;
+};
+
+// Resident variant (cg_resident.cu): returns 1 if it took the solve, 0 if the system does not fit on chip, <0 on error.
+// scratch must hold cg_resident_ws_bytes(m, lp) bytes.
+size_t cg_resident_ws_bytes(int m, int lp);
+int cg_resident_try(const CgParams& P, void* scratch, cudaStream_t st);
+void cg_set_trace(void* buf);
+
+}  // namespace gll

@@ -59,6 +59,9 @@ const char* gll_kernel_name(int id);
 long long gll_launch_count(int id);
 void gll_profile_enable(int on);
 int gll_profile_collect(double* ms_sum, long long* count);
+/* Debug aid: when device_buf != NULL the on-chip CG kernel writes %globaltimer stamps [cta][16 passes][8 phases]
+ * (uint64) into it; NULL switches the trace off.  Not for production use. */
+void gll_debug_cg_trace(void* device_buf);
 
 /* Class columns are padded to a multiple of 4 so that every class row is float4-addressable. */
 int gll_padded_classes(int l);

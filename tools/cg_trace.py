@@ -1,0 +1,29 @@
+"""Debug tool: per-phase timeline of the on-chip CG kernel on the C4-size system (run on the GPU box)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import graphlearninglayer_b200 as pkg
+from graphlearninglayer_b200 import _lib
+from oracle.gll_oracle import synth_inputs
+
+k_lab, m, d, l = 2048, 14336, 512, 10
+X, Y, _, yq = synth_inputs(2000, k_lab, m, d, l, 4.5)
+Xd = torch.as_tensor(X).cuda(); Yd = torch.as_tensor(Y).cuda()
+for _ in range(2): pkg.LaplaceLearningSparseHard.apply(Xd, Yd, 0.0, "auto")
+G = 148
+trace = torch.zeros(G * 16 * 8, dtype=torch.int64, device="cuda")
+_lib.lib.gll_debug_cg_trace(trace.data_ptr())
+pkg.LaplaceLearningSparseHard.apply(Xd, Yd, 0.0, "auto")
+torch.cuda.synchronize()
+_lib.lib.gll_debug_cg_trace(None)
+t = trace.cpu().numpy().reshape(G, 16, 8).astype(np.float64)
+t0 = t[:, 0, 0]  # per-CTA origin: clock64 is a per-SM counter
+t = t - t0[:, None, None]
+t0 = 0.0
+names = ["loop top", "E1 done", "spmv done", "dots done", "results rcvd", "scalars done", "  (stop known)", "  (alpha/beta)"]
+for p in range(0, 6):
+    print("pass", p)
+    for ph in (0, 1, 2, 3, 4, 6, 7, 5):
+        v = (t[:, p, ph] - t0) / 1965.0  # cycles -> us at 1965 MHz
+        print(f"   {names[ph]:14s} min {v.min():8.2f} us  median {np.median(v):8.2f}  max {v.max():8.2f}")
+print(pkg.last_info())
