@@ -14,8 +14,9 @@
 //            two 128 x 256 fp32 accumulators in TMEM (all 512 columns; double buffered against the epilogue)
 //   warps 2-5 epilogue: tcgen05.ld gives each thread ONE row of the tile, 16 columns at a time; d~^2 = |xi|^2 + |xj|^2
 //            - 2 acc is compared with the row's running 32nd-best (a register).  A thread owns its row's candidate set:
-//            an unsorted 32-slot array in shared memory (slot-major, so the 32 threads of a warp never bank-conflict)
-//            in which a survivor replaces the current maximum, followed by a 32-load rescan for the new maximum.
+//            an unsorted 32-slot array in shared memory (slot-major, so the 32 threads of a warp never bank-conflict),
+//            4 groups of 8 slots whose maxima are cached in registers; a survivor replaces the overall maximum and only
+//            that group is rescanned.
 //            All rows of a warp insert concurrently, so a chunk costs max-over-rows(survivors) rescans, ~1 in steady
 //            state.  The n x n matrix never leaves the SM.
 // Work = (row tile, column tile) units in row-major order, split evenly and contiguously over the CTAs, so a CTA keeps
@@ -42,7 +43,8 @@ constexpr int TC_TMEM_COLS = 512, TC_ACC_STRIDE = 256;
 
 constexpr size_t TC_OFF_LD = (size_t)TC_STAGES * TC_STAGE_BYTES;             // float [4 warps][KC entries][32 rows]
 constexpr size_t TC_OFF_LI = TC_OFF_LD + 4 * KC * 32 * 4;                    // int   [4 warps][KC entries][32 rows]
-constexpr size_t TC_OFF_BAR = TC_OFF_LI + 4 * KC * 32 * 4;                   // mbarriers + tmem pointer
+constexpr size_t TC_OFF_SQJ = TC_OFF_LI + 4 * KC * 32 * 4;                   // float [TC_BN]  |x_j|^2 of the unit's columns
+constexpr size_t TC_OFF_BAR = TC_OFF_SQJ + TC_BN * 4;                        // mbarriers + tmem pointer
 constexpr size_t TC_SMEM_BYTES = TC_OFF_BAR + 128 + 1024;                    // + slack for manual 1024 B alignment
 static_assert(TC_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(2 * TC_BN <= TC_TMEM_COLS && TC_ACC_STRIDE >= TC_BN, "two accumulators must fit in TMEM");
@@ -112,18 +114,24 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[TC_CHUNK]) {
-  uint32_t r[16];
+// Asynchronous TMEM -> register load of 16 consecutive columns of this thread's row; the registers are valid only after
+// tc_ld_wait(), which names them as in/out operands so that no use can be scheduled ahead of the wait.
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[TC_CHUNK]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[c]);
 }
+__device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[TC_CHUNK]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
 
 struct TcParams {
   int n, kblocks, col_tiles, max_splits;
@@ -260,9 +268,14 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may read
     float* Ld = reinterpret_cast<float*>(smem + TC_OFF_LD) + (size_t)quarter * KC * 32 + lane;  // my row: Ld[e * 32]
     int* Li = reinterpret_cast<int*>(smem + TC_OFF_LI) + (size_t)quarter * KC * 32 + lane;
-    int acc = 0, cur_rt = -1, gi = 0, maxpos = 0;
+    int acc = 0, cur_rt = -1, gi = 0;
+    float gm[4];  // maximum of slots [8t, 8t+8) of my row's candidate set
+    int gp[4];    // ... and where it sits
     uint32_t acc_phase = 0;
-    float thr = INFINITY, sqi = 0.f;
+    // Ranking inside a row only needs key = |x_j|^2 - 2 x_i.x_j; |x_i|^2 is added when the set is flushed.
+    float thr = INFINITY;
+    float* sqj_s = reinterpret_cast<float*>(smem + TC_OFF_SQJ);
+    const int et = (warp - 2) * 32 + lane;  // 0..127 over the epilogue warps
 
     auto flush = [&](int rt) {
       __syncwarp();
@@ -272,7 +285,8 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
       for (int r = 0; r < 32; ++r) {  // lane = slot index e here; 256 B coalesced store per row
         const int row = rt * TC_BM + quarter * 32 + r;
         const float dd = wd[lane * 32 + r];
-        const u64 key = (dd == INFINITY) ? KEY_INF : make_key(dd, wi[lane * 32 + r]);
+        const float sqr = (row < P.n) ? __ldg(P.sq + row) : 0.f;
+        const u64 key = (dd == INFINITY) ? KEY_INF : make_key(dd + sqr, wi[lane * 32 + r]);
         if (row < P.n) P.cand[((size_t)row * P.max_splits + slot) * KC + lane] = key;
       }
       __syncwarp();
@@ -286,37 +300,46 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
         for (int e = 0; e < KC; ++e) Ld[e * 32] = INFINITY;
         cur_rt = rt;
         thr = INFINITY;
-        maxpos = 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          gm[t] = INFINITY;
+          gp[t] = 8 * t;
+        }
         gi = rt * TC_BM + quarter * 32 + lane;
-        sqi = (gi < P.n) ? __ldg(P.sq + gi) : 0.f;
       }
       const int c_begin = ct * TC_BN;
-      const bool diag = (c_begin < rt * TC_BM + TC_BM) && (c_begin + TC_BN > rt * TC_BM);
-      // |x_j|^2 of the chunk's 16 columns sits in lanes 0..15 (and again in 16..31); +inf masks columns beyond n
-      auto load_sqj = [&](int q) {
-        const int j = c_begin + q * TC_CHUNK + (lane & (TC_CHUNK - 1));
-        return (j < P.n) ? __ldg(P.sq + j) : INFINITY;
-      };
-      float sqj_next = load_sqj(0);
+      // stage |x_j|^2 of the unit's 256 columns for all four epilogue warps (+inf masks columns beyond n)
+      epi_bar_sync();  // everybody is done with the previous unit's values
+      sqj_s[et] = (c_begin + et < P.n) ? __ldg(P.sq + c_begin + et) : INFINITY;
+      sqj_s[et + 128] = (c_begin + et + 128 < P.n) ? __ldg(P.sq + c_begin + et + 128) : INFINITY;
+      epi_bar_sync();
+      // does this warp's row range meet this unit's column range?  (only then can a column be the row itself)
+      const int wrow0 = rt * TC_BM + quarter * 32;
+      const bool diag = (c_begin < wrow0 + 32) && (c_begin + TC_BN > wrow0);
 
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * TC_ACC_STRIDE;
-#pragma unroll 1
-      for (int q = 0; q < TC_BN / TC_CHUNK; ++q) {
-        float v[TC_CHUNK];
-        tc_ld16(taddr + q * TC_CHUNK, v);
-        const float sqj_cur = sqj_next;
-        if (q + 1 < TC_BN / TC_CHUNK) sqj_next = load_sqj(q + 1);
+      uint32_t rawA[TC_CHUNK], rawB[TC_CHUNK];
+      auto process = [&](const uint32_t (&raw)[TC_CHUNK], int q) {
         const int j0 = c_begin + q * TC_CHUNK;
+        float v[TC_CHUNK];
         uint32_t hits = 0;
 #pragma unroll
-        for (int c = 0; c < TC_CHUNK; ++c) {
-          float dist = fmaf(-2.f, v[c], sqi + __shfl_sync(FULL, sqj_cur, c));
-          if (diag && j0 + c == gi) dist = INFINITY;  // self is slot 0 by construction (knn_finish)
-          v[c] = dist;
-          hits |= (dist < thr) ? (1u << c) : 0u;
+        for (int c4 = 0; c4 < TC_CHUNK / 4; ++c4) {
+          const float4 s4 = *reinterpret_cast<const float4*>(sqj_s + q * TC_CHUNK + 4 * c4);  // warp-wide broadcast
+          v[4 * c4 + 0] = fmaf(-2.f, __uint_as_float(raw[4 * c4 + 0]), s4.x);
+          v[4 * c4 + 1] = fmaf(-2.f, __uint_as_float(raw[4 * c4 + 1]), s4.y);
+          v[4 * c4 + 2] = fmaf(-2.f, __uint_as_float(raw[4 * c4 + 2]), s4.z);
+          v[4 * c4 + 3] = fmaf(-2.f, __uint_as_float(raw[4 * c4 + 3]), s4.w);
         }
+        if (diag && j0 < wrow0 + 32 && j0 + TC_CHUNK > wrow0) {  // warp-uniform, true for at most 3 chunks of one unit
+#pragma unroll
+          for (int c = 0; c < TC_CHUNK; ++c)
+            if (j0 + c == gi) v[c] = INFINITY;  // self is slot 0 by construction (knn_finish)
+        }
+#pragma unroll
+        for (int c = 0; c < TC_CHUNK; ++c) hits |= (v[c] < thr) ? (1u << c) : 0u;
         // ---- every row (thread) inserts its own survivors; rows proceed concurrently ----
         while (__any_sync(FULL, hits != 0)) {
           if (hits) {
@@ -326,27 +349,58 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
 #pragma unroll
             for (int t = 1; t < TC_CHUNK; ++t) dsel = (t == c) ? v[t] : dsel;
             if (dsel < thr) {  // thr may have tightened since the scan
-              Ld[maxpos * 32] = dsel;
-              Li[maxpos * 32] = j0 + c;
+              // the row's 32 slots are 4 groups of 8 with the group maxima (value, slot) cached in registers: replace
+              // the overall maximum, rescan only its group (8 shared-memory loads instead of 32)
+              int g = 0;
+              float gmax = gm[0];
+#pragma unroll
+              for (int t = 1; t < 4; ++t)
+                if (gm[t] > gmax) {
+                  gmax = gm[t];
+                  g = t;
+                }
+              int pos = gp[0];
+#pragma unroll
+              for (int t = 1; t < 4; ++t) pos = (t == g) ? gp[t] : pos;
+              Ld[pos * 32] = dsel;
+              Li[pos * 32] = j0 + c;
               float mx = -INFINITY;
               int mp = 0;
 #pragma unroll
-              for (int e = 0; e < KC; ++e) {
-                const float t = Ld[e * 32];
+              for (int e = 0; e < 8; ++e) {
+                const float t = Ld[(g * 8 + e) * 32];
                 if (t > mx) {
                   mx = t;
-                  mp = e;
+                  mp = g * 8 + e;
                 }
               }
-              thr = mx;
-              maxpos = mp;
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                gm[t] = (t == g) ? mx : gm[t];
+                gp[t] = (t == g) ? mp : gp[t];
+              }
+              thr = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
             }
           }
         }
+      };
+      // two register sets: the TMEM load of the next 16 columns is in flight while the current ones are processed
+      tc_ld16_issue(taddr, rawA);
+#pragma unroll 1
+      for (int q = 0; q < TC_BN / TC_CHUNK; q += 2) {
+        tc_ld_wait(rawA);
+        tc_ld16_issue(taddr + (q + 1) * TC_CHUNK, rawB);
+        process(rawA, q);
+        tc_ld_wait(rawB);
+        if (q + 2 < TC_BN / TC_CHUNK) {
+          tc_ld16_issue(taddr + (q + 2) * TC_CHUNK, rawA);
+        } else {  // the whole accumulator is in registers or consumed: hand it back to the MMA warp early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        }
+        process(rawB, q + 1);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);  // accumulator may be overwritten
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
