@@ -186,7 +186,7 @@ def run_b200(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
     import graphlearninglayer_b200 as pkg
-    from graphlearninglayer_b200 import _lib
+    from graphlearninglayer_b200 import _lib, ranks
     from oracle.gll_oracle import synth_inputs  # input generator only (shared with the tests); not on the timed path
 
     torch.cuda.set_device(local_rank)
@@ -254,13 +254,11 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
         tot_ms = sum(a.elapsed_time(b) for a, b in ev)
-        if dist is not None:
-            t = torch.tensor([tot_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            tot_ms = float(t.item())
+        # whole-job time = max over ranks (graphlearninglayer_b200.ranks: all_reduce MAX; no data-path collective)
+        _, tot_ms, _ = ranks.aggregate_throughput(steps, tot_ms, device=str(dev))
         return tot_ms
 
-    resident, e2e, shp, h2d, d2h = step_fn(args.workload, 1000 + rank)
+    resident, e2e, shp, h2d, d2h = step_fn(args.workload, ranks.rank_seed(1000, rank))
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
