@@ -238,6 +238,29 @@ __device__ __forceinline__ double exact_d2(const float* __restrict__ xi_s, const
   return warp_sum(part);  // xor butterfly: identical on all lanes, and exact_d2(i,j) == exact_d2(j,i) bitwise
 }
 
+// Row x_i held in registers as doubles (d <= 512, 16-byte aligned rows): lane owns float4 chunks lane, lane+32, lane+64,
+// lane+96.  One fp32->fp64 conversion per element in the candidate loop (the conversion unit bounds this kernel) and no
+// shared-memory traffic.  Same summation order as exact_d2, so the two are bitwise interchangeable.
+__device__ __forceinline__ double exact_d2_reg(const double (&xr)[16], const float* __restrict__ xj, int q, int lane) {
+  const float4* b = reinterpret_cast<const float4*>(xj);
+  float4 v[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) v[t] = (lane + 32 * t < q) ? __ldg(b + lane + 32 * t) : make_float4(0.f, 0.f, 0.f, 0.f);
+  double part = 0.0;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    if (lane + 32 * t < q) {
+      const double d0 = xr[4 * t + 0] - (double)v[t].x, d1 = xr[4 * t + 1] - (double)v[t].y;
+      const double d2 = xr[4 * t + 2] - (double)v[t].z, d3 = xr[4 * t + 3] - (double)v[t].w;
+      part += d0 * d0;
+      part += d1 * d1;
+      part += d2 * d2;
+      part += d3 * d3;
+    }
+  }
+  return warp_sum(part);
+}
+
 template <bool VEC4>
 __global__ void __launch_bounds__(RERANK_WARPS * 32)
 knn_rerank_kernel(const float* __restrict__ X, const float* __restrict__ sq, const unsigned* __restrict__ sqmax_bits,
@@ -249,7 +272,21 @@ knn_rerank_kernel(const float* __restrict__ X, const float* __restrict__ sq, con
   const int i = blockIdx.x * RERANK_WARPS + warp;
   if (i >= n) return;
   float* xi = xs + (size_t)warp * d;
-  for (int t = lane; t < d; t += 32) xi[t] = X[(size_t)i * d + t];
+  const bool use_reg = VEC4 && d <= 512;
+  double xr[16];
+  if (use_reg) {
+    const float4* xrow = reinterpret_cast<const float4*>(X + (size_t)i * d);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float4 u = (lane + 32 * t < (d >> 2)) ? __ldg(xrow + lane + 32 * t) : make_float4(0.f, 0.f, 0.f, 0.f);
+      xr[4 * t + 0] = (double)u.x;
+      xr[4 * t + 1] = (double)u.y;
+      xr[4 * t + 2] = (double)u.z;
+      xr[4 * t + 3] = (double)u.w;
+    }
+  } else {
+    for (int t = lane; t < d; t += 32) xi[t] = X[(size_t)i * d + t];
+  }
 
   u64 mine = KEY_INF;
   int splits = lay.stride;
@@ -280,7 +317,7 @@ knn_rerank_kernel(const float* __restrict__ X, const float* __restrict__ sq, con
     u64 kc = __shfl_sync(FULL, mine, c);
     if (kc == KEY_INF) break;
     int j = key_idx(kc);
-    double v = exact_d2<VEC4>(xi, X + (size_t)j * d, d, lane);
+    double v = use_reg ? exact_d2_reg(xr, X + (size_t)j * d, d >> 2, lane) : exact_d2<VEC4>(xi, X + (size_t)j * d, d, lane);
     if (lane == c) {
       myd2 = v;
       myj = j;
