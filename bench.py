@@ -39,11 +39,18 @@ WORKLOADS = {
     "c2": (10000, 512, 512, 10, 4.5, 0.0, "auto"),
     "c3": (4096, 512, 512, 10, 4.5, 0.0, "auto"),
     "c4": (2048, 14336, 512, 10, 4.5, 0.0, "auto"),
+    "c5": (65536, 983040, 256, 100, 3.0, 0.0, "auto"),   # ONE graph sharded over the ranks (strong scaling)
+    "c5s": (8192, 122880, 256, 100, 3.0, 0.0, "auto"),   # 1/8-size version of c5 for quick runs
 }
+SHARDED = ("c5", "c5s")
 WORKLOAD_DESC = {
     "c2": "GLL classifier head, 10000 base + 512 batch, d=512, l=10, eps='auto', tau=0, k=25",
     "c3": "data-parallel GLL step, 4096 base + 512 batch per rank, d=512, l=10, eps='auto', tau=0, k=25",
     "c4": "large single graph, 2048 base + 14336 unlabeled, d=512, l=10, eps='auto', tau=0, k=25, CG tol 1e-7",
+    "c5": "sharded Laplace learning, ONE graph of n=2^20 nodes (65536 labeled), d=256, l=100, eps='auto', tau=0, k=25; "
+          "kNN/backward row-sharded, CG column-sharded, NCCL all-gathers",
+    "c5s": "sharded Laplace learning, ONE graph of n=131072 nodes (8192 labeled), d=256, l=100, eps='auto', tau=0, k=25; "
+           "kNN/backward row-sharded, CG column-sharded, NCCL all-gathers",
 }
 METRIC = "gll_fwd_bwd_calls_per_sec"
 UNIT = "calls/s"
@@ -199,6 +206,12 @@ def run_b200(args, rank, world, local_rank):
 
     def step_fn(shape_name, seed):
         k_lab, m, d, l, sigma, tau, eps = WORKLOADS[shape_name]
+        if shape_name in SHARDED:
+            from graphlearninglayer_b200.sharded import ShardedLaplaceLearning
+
+            layer = ShardedLaplaceLearning.apply  # every rank passes the same graph, collectives inside
+        else:
+            layer = pkg.LaplaceLearningSparseHard.apply
         X, Y, _, yq = synth_inputs(seed, k_lab, m, d, l, sigma)
         Xh = torch.as_tensor(X).pin_memory()
         Yh = torch.as_tensor(Y).pin_memory()
@@ -212,7 +225,7 @@ def run_b200(args, rank, world, local_rank):
 
         def resident():
             Xd.grad = None
-            pred = pkg.LaplaceLearningSparseHard.apply(Xd, Yd, tau, eps)
+            pred = layer(Xd, Yd, tau, eps)
             loss = -torch.sum(tgt * torch.log(pred + 1e-8)) / m  # custom_ce_loss, losses.py:128-136
             loss.backward()
             return loss
@@ -222,7 +235,7 @@ def run_b200(args, rank, world, local_rank):
             with torch.no_grad():
                 Xe.copy_(Xh, non_blocking=True)
                 Ye.copy_(Yh, non_blocking=True)
-            pred = pkg.LaplaceLearningSparseHard.apply(Xe, Ye, tau, eps)
+            pred = layer(Xe, Ye, tau, eps)
             loss = -torch.sum(tgt * torch.log(pred + 1e-8)) / m
             loss.backward()
             predh.copy_(pred.detach(), non_blocking=True)
@@ -258,7 +271,9 @@ def run_b200(args, rank, world, local_rank):
         _, tot_ms, _ = ranks.aggregate_throughput(steps, tot_ms, device=str(dev))
         return tot_ms
 
-    resident, e2e, shp, h2d, d2h = step_fn(args.workload, ranks.rank_seed(1000, rank))
+    sharded = args.workload in SHARDED
+    resident, e2e, shp, h2d, d2h = step_fn(args.workload, 1000 if sharded else ranks.rank_seed(1000, rank))
+    jobs = 1 if sharded else world  # graphs finished per step by the whole job
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -267,7 +282,12 @@ def run_b200(args, rank, world, local_rank):
     launches = (_lib.launch_count() - l0) * args.steps // (args.steps + args.warmup)
     clocks = sampler.stop() if sampler else None
     e2e_ms = timed(e2e, args.steps, args.warmup)
-    info = pkg.last_info()
+    if sharded:
+        from graphlearninglayer_b200 import sharded as sharded_mod
+
+        info = sharded_mod.last_info()
+    else:
+        info = pkg.last_info()
 
     # per-kernel pass (instrumented; not the pass `value` comes from)
     _lib.lib.gll_profile_enable(1)
@@ -280,7 +300,7 @@ def run_b200(args, rank, world, local_rank):
     _lib.lib.gll_profile_enable(0)
 
     extra = {}
-    if rank == 0 and world == 1 and args.workload != "c4" and not args.no_large_graph:
+    if rank == 0 and world == 1 and args.workload not in ("c4",) + SHARDED and not args.no_large_graph:
         # the CG roofline study (BASELINE.json configs[3]); reported beside the headline, not instead of it
         r4, _, shp4, _, _ = step_fn("c4", 2000)
         ms4 = timed(r4, 5, 3)
@@ -304,7 +324,12 @@ def run_b200(args, rank, world, local_rank):
             kern[nm] = {"ms_per_launch": ms / cnt, "launches_per_step": cnt / args.steps,
                         "share_of_kernel_time": (ms / args.steps) / step_kernel_ms}
         top = max(prof.items(), key=lambda kv: kv[1][0])[0]
+        if sharded:
+            top = "knn_gram_topk_tcgen05" if "knn_gram_topk_tcgen05" in prof else top
+            shp = dict(shp, n_rows_this_rank=-(-shp["n"] // world))
         bound, work, unit = algorithmic_work(top, shp, info)
+        if sharded and bound == "tensor":
+            work = work / world  # each rank searches n/world rows against all n columns
         t_s = prof[top][0] / prof[top][1] * 1e-3
         if bound == "tensor":
             ach, peak, u = work / t_s / 1e12, peaks["tflops"], "TFLOP/s"
@@ -314,20 +339,22 @@ def run_b200(args, rank, world, local_rank):
                     "frac": (ach / peak if ach else None), "traffic": None, "peak_source": peaks["source"],
                     "algorithmic_work_per_launch": work, "work_unit": unit, "launch_ms": t_s * 1e3}
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not sharded:
             times = cpu_calls(args.workload, 1000, 4, 25.0)
             cpu = {"value": len(times) / float(np.sum(times)), "unit": UNIT, "cores": host_threads(), "kind": "port",
                    "sample": f"{len(times)} full fwd+bwd calls of the same workload through oracle/gll_oracle.py (fp64)"}
         line = {
-            "metric": METRIC, "value": world * 1e3 / per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": jobs * 1e3 / per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per_step, "higher_is_better": True,
+            "scaling": "strong" if sharded else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic gaussian clusters (oracle.synth_inputs), L2-normalised, one graph per rank",
             "config": {"workload": args.workload + ": " + WORKLOAD_DESC[args.workload], "l2": "flushed between timed steps "
-                       "(256 MiB memset outside the event pairs)", "parallelism": f"independent graphs x{world}",
+                       "(256 MiB memset outside the event pairs)", "parallelism": (f"one graph over {world} rank(s): rows (kNN, backward) + class columns (CG)" if sharded
+                                       else f"independent graphs x{world}"),
                        "cg_tol": 1e-7, "graph": {"nnz": info["nnz"], "nnz_uu": info["nnz_uu"],
                                                  "cg_iters_fwd": info["cg_iters_fwd"], "cg_iters_bwd": info["cg_iters_bwd"],
                                                  "knn_fallback_rows": info["knn_fallback_rows"], "status": info["status"]}},
-            "e2e": {"value": world * 1e3 / (e2e_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "e2e": {"value": jobs * 1e3 / (e2e_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kern,
             "cpu_baseline": cpu,

@@ -70,6 +70,13 @@ def _load():
                                   vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp])
     sig("gll_cg_solve", i32, [vp, vp, vp, vp, vp, i32, i32, f32, i32, vp, vp, vp, vp, vp, sz, vp])
     sig("gll_backward_edges", i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
+    sig("gll_knn_rows_workspace_bytes", sz, [i32, i32, i32, i32, i32])
+    sig("gll_knn_rows", i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp])
+    sig("gll_backward_edges_rows", i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp])
+    sig("gll_pack_columns", i32, [vp, i32, i32, i32, i32, vp, i32, vp])
+    sig("gll_unpack_columns", i32, [vp, i32, i32, i32, i32, vp, i32, vp])
+    sig("gll_unpack_pred", i32, [vp, i32, i32, vp, i32, vp])
+    sig("gll_pack_grad", i32, [vp, i32, i32, i32, vp, vp])
     sig("gll_forward", i32, [vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, f32, i32, vp, vp, i32, vp, sz, vp])
     sig("gll_backward", i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, i32, vp, vp, vp, sz, vp])
     return lib
@@ -82,7 +89,8 @@ EXPORTS = ["gll_last_error", "gll_version", "gll_device_sm_count", "gll_kernel_c
            "gll_launch_count", "gll_profile_enable", "gll_profile_collect", "gll_debug_cg_trace", "gll_padded_classes", "gll_max_edges",
            "gll_state_layout", "gll_workspace_bytes", "gll_knn_workspace_bytes", "gll_graph_workspace_bytes",
            "gll_weights_workspace_bytes", "gll_cg_workspace_bytes", "gll_knn", "gll_graph_build", "gll_edge_weights",
-           "gll_cg_solve", "gll_backward_edges", "gll_forward", "gll_backward"]
+           "gll_cg_solve", "gll_backward_edges", "gll_forward", "gll_backward", "gll_knn_rows_workspace_bytes", "gll_knn_rows",
+           "gll_backward_edges_rows", "gll_pack_columns", "gll_unpack_columns", "gll_unpack_pred", "gll_pack_grad"]
 
 
 def check(rc: int, what: str) -> None:

@@ -98,7 +98,38 @@ __global__ void unpack_pred_kernel(const float* __restrict__ u, int m, int l, in
     ((float*)pred)[t] = v;
 }
 
+__global__ void pack_columns_kernel(const float* __restrict__ src, int rows, int lp_src, int c0, int cnt, float* __restrict__ dst,
+                                    int lp_dst) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)rows * lp_dst) return;
+  int r = (int)(t / lp_dst), c = (int)(t % lp_dst);
+  dst[t] = (c < cnt) ? src[(size_t)r * lp_src + c0 + c] : 0.f;
+}
+
+__global__ void unpack_columns_kernel(const float* __restrict__ src, int rows, int lp_src, int c0, int cnt, float* __restrict__ dst,
+                                      int lp_dst) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)rows * cnt) return;
+  int r = (int)(t / cnt), c = (int)(t % cnt);
+  dst[(size_t)r * lp_dst + c0 + c] = src[(size_t)r * lp_src + c];
+}
+
 }  // namespace
+
+int pack_columns(const float* src, int rows, int lp_src, int c0, int cnt, float* dst, int lp_dst, cudaStream_t st) {
+  GLL_PROF(KID_PACK, st);
+  pack_columns_kernel<<<ceil_div((long long)rows * lp_dst, 256), 256, 0, st>>>(src, rows, lp_src, c0, cnt, dst, lp_dst);
+  GLL_LAUNCH_CHECK();
+  return GLL_OK;
+}
+
+int unpack_columns(const float* src, int rows, int lp_src, int c0, int cnt, float* dst, int lp_dst, cudaStream_t st) {
+  if (cnt <= 0) return GLL_OK;
+  GLL_PROF(KID_PACK, st);
+  unpack_columns_kernel<<<ceil_div((long long)rows * cnt, 256), 256, 0, st>>>(src, rows, lp_src, c0, cnt, dst, lp_dst);
+  GLL_LAUNCH_CHECK();
+  return GLL_OK;
+}
 
 int pack_grad(const void* g, int is_f64, int m, int l, int lp, float* rhs, cudaStream_t st) {
   GLL_PROF(KID_PACK, st);
@@ -201,13 +232,16 @@ int gll_state_layout(int n, int k, int l, int k_lab, gll_layout* out) {
   return rc;
 }
 
-size_t gll_knn_workspace_bytes(int n, int d, int k) { return knn_ws_bytes(n, d, k); }
+size_t gll_knn_workspace_bytes(int n, int d, int k) { return knn_ws_bytes(n, d, k, 0, n); }
+size_t gll_knn_rows_workspace_bytes(int n, int d, int k, int row_begin, int row_end) {
+  return knn_ws_bytes(n, d, k, row_begin, row_end);
+}
 size_t gll_graph_workspace_bytes(int n, int k) { return graph_ws_bytes(n, k); }
 size_t gll_weights_workspace_bytes(int n, int k) { return weights_ws_bytes(n, k); }
 size_t gll_cg_workspace_bytes(int m, int l) { return cg_ws_bytes(m, l); }
 
 size_t gll_workspace_bytes(int n, int d, int k, int l, int k_lab) {
-  size_t b = knn_ws_bytes(n, d, k);
+  size_t b = knn_ws_bytes(n, d, k, 0, n);
   size_t t = graph_ws_bytes(n, k);
   if (t > b) b = t;
   t = weights_ws_bytes(n, k);
@@ -219,7 +253,12 @@ size_t gll_workspace_bytes(int n, int d, int k, int l, int k_lab) {
 
 int gll_knn(const float* X, int n, int d, int k, int* knn_idx, float* knn_dist, int* info, void* workspace,
             size_t workspace_bytes, void* stream) {
-  return knn_run(X, n, d, k, knn_idx, knn_dist, info, workspace, workspace_bytes, (cudaStream_t)stream);
+  return knn_run(X, n, d, k, 0, n, knn_idx, knn_dist, info, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gll_knn_rows(const float* X, int n, int d, int k, int row_begin, int row_end, int* knn_idx, float* knn_dist, int* info,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+  return knn_run(X, n, d, k, row_begin, row_end, knn_idx, knn_dist, info, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int gll_graph_build(const int* knn_idx, const float* knn_dist, int n, int k, int* row_ptr, int* col, float* dist, int* info,
@@ -245,8 +284,36 @@ int gll_cg_solve(const int* uu_ptr, const int* uu_col, const float* uu_val, cons
 int gll_backward_edges(const float* X, int n, int d, int l, int k_lab, int eps_auto, const int* row_ptr, const int* col,
                        const float* dist, const float* w, const float* eps, const int* kappa, const float* ut,
                        const float* wt, float* gv, float* bvec, float* dX, void* stream) {
-  return backward_edges_run(X, n, d, l, k_lab, eps_auto, row_ptr, col, dist, w, eps, kappa, ut, wt, gv, bvec, dX,
+  return backward_edges_run(X, n, d, l, k_lab, eps_auto, row_ptr, col, dist, w, eps, kappa, ut, wt, gv, bvec, dX, 0, n, 3,
                             (cudaStream_t)stream);
+}
+
+int gll_backward_edges_rows(const float* X, int n, int d, int l, int k_lab, int eps_auto, const int* row_ptr, const int* col,
+                            const float* dist, const float* w, const float* eps, const int* kappa, const float* ut,
+                            const float* wt, float* gv, float* bvec, float* dX, int row_begin, int row_end, int phases,
+                            void* stream) {
+  return backward_edges_run(X, n, d, l, k_lab, eps_auto, row_ptr, col, dist, w, eps, kappa, ut, wt, gv, bvec, dX, row_begin,
+                            row_end, phases, (cudaStream_t)stream);
+}
+
+int gll_pack_columns(const float* src, int rows, int lp_src, int c0, int cnt, float* dst, int lp_dst, void* stream) {
+  GLL_REQUIRE(src && dst && rows >= 1 && c0 >= 0 && cnt >= 0 && c0 + cnt <= lp_src && cnt <= lp_dst, "bad column slice");
+  return pack_columns(src, rows, lp_src, c0, cnt, dst, lp_dst, (cudaStream_t)stream);
+}
+
+int gll_unpack_columns(const float* src, int rows, int lp_src, int c0, int cnt, float* dst, int lp_dst, void* stream) {
+  GLL_REQUIRE(src && dst && rows >= 1 && c0 >= 0 && cnt >= 0 && cnt <= lp_src && c0 + cnt <= lp_dst, "bad column slice");
+  return unpack_columns(src, rows, lp_src, c0, cnt, dst, lp_dst, (cudaStream_t)stream);
+}
+
+int gll_unpack_pred(const float* u, int m, int l, void* pred, int pred_is_f64, void* stream) {
+  GLL_REQUIRE(u && pred && m >= 1 && l >= 1, "bad arguments");
+  return unpack_pred(u, m, l, padded_classes(l), pred, pred_is_f64, (cudaStream_t)stream);
+}
+
+int gll_pack_grad(const void* grad_out, int grad_is_f64, int m, int l, float* rhs, void* stream) {
+  GLL_REQUIRE(grad_out && rhs && m >= 1 && l >= 1, "bad arguments");
+  return pack_grad(grad_out, grad_is_f64, m, l, padded_classes(l), rhs, (cudaStream_t)stream);
 }
 
 int gll_forward(const float* X, const float* Y, int n, int d, int k, int l, int k_lab, int eps_auto, float eps_fixed,
@@ -264,7 +331,7 @@ int gll_forward(const float* X, const float* Y, int n, int d, int k, int l, int 
   int* info = (int*)(S + L.info);
   const int m = n - k_lab, lp = padded_classes(l);
   GLL_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int) * GLL_INFO_WORDS, st));
-  int rc = knn_run(X, n, d, k, (int*)(S + L.knn_idx), (float*)(S + L.knn_dist), info, workspace, workspace_bytes, st);
+  int rc = knn_run(X, n, d, k, 0, n, (int*)(S + L.knn_idx), (float*)(S + L.knn_dist), info, workspace, workspace_bytes, st);
   if (rc) return rc;
   rc = graph_run((int*)(S + L.knn_idx), (float*)(S + L.knn_dist), n, k, (int*)(S + L.row_ptr), (int*)(S + L.col),
                  (float*)(S + L.dist), info, workspace, workspace_bytes, st);
@@ -307,7 +374,7 @@ int gll_backward(const float* X, const void* grad_out, int grad_is_f64, int n, i
   if (rc) return rc;
   return backward_edges_run(X, n, d, l, k_lab, eps_auto, (int*)(S + L.row_ptr), (int*)(S + L.col), (float*)(S + L.dist),
                             (float*)(S + L.w), (float*)(S + L.eps), (int*)(S + L.kappa), (float*)(S + L.ut), wt,
-                            (float*)(S + L.gv), (float*)(S + L.bvec), dX, st);
+                            (float*)(S + L.gv), (float*)(S + L.bvec), dX, 0, n, 3, st);
 }
 
 }  // extern "C"

@@ -11,12 +11,12 @@ namespace gll {
 namespace {
 
 __global__ void __launch_bounds__(256)
-edge_grad_kernel(int n, int lp, int k_lab, int eps_auto, const int* __restrict__ row_ptr, const int* __restrict__ col,
+edge_grad_kernel(int row_begin, int row_end, int lp, int k_lab, int eps_auto, const int* __restrict__ row_ptr, const int* __restrict__ col,
                  const float* __restrict__ dist, const float* __restrict__ w, const float* __restrict__ eps,
                  const float* __restrict__ ut, const float* __restrict__ wt, float* __restrict__ gv,
                  float* __restrict__ bvec) {
-  const int i = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  if (i >= n) return;
+  const int i = row_begin + (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (i >= row_end) return;
   const int e0 = row_ptr[i], e1 = row_ptr[i + 1];
   const double ei = (double)eps[i];
   const float4* ui = reinterpret_cast<const float4*>(ut + (size_t)i * lp);
@@ -66,12 +66,12 @@ __device__ __forceinline__ void load_chunk(const float* __restrict__ base, int c
 // block per row; a thread owns up to 4 feature chunks (W floats each) per pass and keeps them in registers
 template <int W>
 __global__ void __launch_bounds__(256)
-row_gather_kernel(const float* __restrict__ X, int n, int d, int eps_auto, const int* __restrict__ row_ptr,
+row_gather_kernel(const float* __restrict__ X, int row_begin, int d, int eps_auto, const int* __restrict__ row_ptr,
                   const int* __restrict__ col, const int* __restrict__ kappa, const float* __restrict__ gv,
                   const float* __restrict__ bvec, float* __restrict__ dX) {
   __shared__ int sj[ROW_CHUNK];
   __shared__ float stc[ROW_CHUNK];
-  const int i = blockIdx.x;
+  const int i = row_begin + blockIdx.x;
   const int e0 = row_ptr[i], e1 = row_ptr[i + 1];
   const int ki = eps_auto ? kappa[i] : -1;
   const float bi = eps_auto ? bvec[i] : 0.f;
@@ -136,25 +136,29 @@ row_gather_kernel(const float* __restrict__ X, int n, int d, int eps_auto, const
 
 int backward_edges_run(const float* X, int n, int d, int l, int k_lab, int eps_auto, const int* row_ptr, const int* col,
                        const float* dist, const float* w, const float* eps, const int* kappa, const float* ut,
-                       const float* wt, float* gv, float* bvec, float* dX, cudaStream_t st) {
+                       const float* wt, float* gv, float* bvec, float* dX, int row_begin, int row_end, int phases,
+                       cudaStream_t st) {
   GLL_REQUIRE(X && row_ptr && col && dist && w && eps && ut && wt && gv && bvec && dX, "null pointer");
   GLL_REQUIRE(!eps_auto || kappa, "kappa missing");
+  GLL_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= n, "bad row range");
+  const int rows = row_end - row_begin;
+  if (rows == 0) return GLL_OK;
   const int lp = padded_classes(l);
-  {
+  if (phases & 1) {  // K5: gv for the rows' edges, b for the rows
     GLL_PROF(KID_EDGE_GRAD, st);
-    edge_grad_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(n, lp, k_lab, eps_auto, row_ptr, col, dist, w, eps,
-                                                                     ut, wt, gv, bvec);
+    edge_grad_kernel<<<ceil_div((long long)rows * 32, 256), 256, 0, st>>>(row_begin, row_end, lp, k_lab, eps_auto, row_ptr, col,
+                                                                          dist, w, eps, ut, wt, gv, bvec);
   }
   GLL_LAUNCH_CHECK();
-  const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dX) & 15) == 0);
-  const int cols = vec4 ? d / 4 : d;
-  int threads = min(256, max(32, ceil_div(cols, 32) * 32));
-  {
+  if (phases & 2) {  // K6: needs b of ALL rows (neighbours j with kappa(j) = i)
+    const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dX) & 15) == 0);
+    const int cols = vec4 ? d / 4 : d;
+    int threads = min(256, max(32, ceil_div(cols, 32) * 32));
     GLL_PROF(KID_ROW_GATHER, st);
     if (vec4)
-      row_gather_kernel<4><<<n, threads, 0, st>>>(X, n, d, eps_auto, row_ptr, col, kappa, gv, bvec, dX);
+      row_gather_kernel<4><<<rows, threads, 0, st>>>(X, row_begin, d, eps_auto, row_ptr, col, kappa, gv, bvec, dX);
     else
-      row_gather_kernel<1><<<n, threads, 0, st>>>(X, n, d, eps_auto, row_ptr, col, kappa, gv, bvec, dX);
+      row_gather_kernel<1><<<rows, threads, 0, st>>>(X, row_begin, d, eps_auto, row_ptr, col, kappa, gv, bvec, dX);
   }
   GLL_LAUNCH_CHECK();
   return GLL_OK;

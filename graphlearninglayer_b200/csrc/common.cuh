@@ -105,9 +105,9 @@ struct ProfScope {
 #define GLL_PROF(id, st) gll::ProfScope _prof_scope_##id(gll::id, st)
 
 // ---- internal launchers (one per stage), implemented in the .cu files ----
-int knn_run(const float* X, int n, int d, int k, int* knn_idx, float* knn_dist, int* info, void* ws,
-            size_t ws_bytes, cudaStream_t st);
-size_t knn_ws_bytes(int n, int d, int k);
+int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int* knn_idx, float* knn_dist, int* info,
+            void* ws, size_t ws_bytes, cudaStream_t st);
+size_t knn_ws_bytes(int n, int d, int k, int row_begin, int row_end);
 
 int graph_run(const int* knn_idx, const float* knn_dist, int n, int k, int* row_ptr, int* col, float* dist,
               int* info, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -126,7 +126,12 @@ size_t cg_ws_bytes(int m, int l);
 
 int backward_edges_run(const float* X, int n, int d, int l, int k_lab, int eps_auto, const int* row_ptr,
                        const int* col, const float* dist, const float* w, const float* eps, const int* kappa,
-                       const float* ut, const float* wt, float* gv, float* bvec, float* dX, cudaStream_t st);
+                       const float* ut, const float* wt, float* gv, float* bvec, float* dX, int row_begin, int row_end,
+                       int phases, cudaStream_t st);
+
+// column slices of m x lp class matrices (sharded solves): dst[r][c] = src[r][c0 + c] for c < cnt (zero padding), and back
+int pack_columns(const float* src, int rows, int lp_src, int c0, int cnt, float* dst, int lp_dst, cudaStream_t st);
+int unpack_columns(const float* src, int rows, int lp_src, int c0, int cnt, float* dst, int lp_dst, cudaStream_t st);
 
 // exclusive prefix sum of int32 counts[0..n) into out[0..n] (out[n] = total). scratch: scan_ws_bytes(n).
 size_t scan_ws_bytes(int n);

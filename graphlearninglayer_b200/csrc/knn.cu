@@ -88,7 +88,7 @@ __device__ __forceinline__ void store_tile_smem(float* __restrict__ S, int lds, 
 template <bool VEC4>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 knn_gemm_topk_kernel(const float* __restrict__ X, const float* __restrict__ sq, int n, int d, int cols_per_split,
-                     int splits, u64* __restrict__ cand) {
+                     int splits, u64* __restrict__ cand, int row_begin, int row_end) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* As = reinterpret_cast<float*>(smem_raw);
   float* Bs = As + 2 * BK * LDS_A;
@@ -99,7 +99,7 @@ knn_gemm_topk_kernel(const float* __restrict__ X, const float* __restrict__ sq, 
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid & 15, ty = tid >> 4;
-  const int row0 = blockIdx.x * BM;
+  const int row0 = row_begin + blockIdx.x * BM;
   const int split = blockIdx.y;
   const int c_begin = split * cols_per_split;
   const int c_end = min(n, c_begin + cols_per_split);
@@ -166,7 +166,7 @@ knn_gemm_topk_kernel(const float* __restrict__ X, const float* __restrict__ sq, 
     for (int i = 0; i < 8; ++i) {
       int rr = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
       int gi = row0 + rr;
-      if (gi >= n) continue;
+      if (gi >= row_end) continue;
       float t = thr[rr];
       float sqi = __ldg(sq + gi);
 #pragma unroll
@@ -197,7 +197,7 @@ knn_gemm_topk_kernel(const float* __restrict__ X, const float* __restrict__ sq, 
 
   for (int rr = warp * (BM / 8); rr < (warp + 1) * (BM / 8); ++rr) {
     int gi = row0 + rr;
-    if (gi < n) cand[((size_t)gi * splits + split) * KC + lane] = topk[rr * KC + lane];
+    if (gi < row_end) cand[((size_t)gi * splits + split) * KC + lane] = topk[rr * KC + lane];
   }
 }
 
@@ -264,13 +264,13 @@ __device__ __forceinline__ double exact_d2_reg(const double (&xr)[16], const flo
 template <bool VEC4>
 __global__ void __launch_bounds__(RERANK_WARPS * 32)
 knn_rerank_kernel(const float* __restrict__ X, const float* __restrict__ sq, const unsigned* __restrict__ sqmax_bits,
-                  int n, int d, int k, CandLayout lay, const u64* __restrict__ cand, float err_coef,
+                  int n, int d, int k, int row_end, CandLayout lay, const u64* __restrict__ cand, float err_coef,
                   int* __restrict__ knn_idx, float* __restrict__ knn_dist, int* __restrict__ flag_count,
                   int* __restrict__ flag_rows) {
   extern __shared__ __align__(16) float xs[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = blockIdx.x * RERANK_WARPS + warp;
-  if (i >= n) return;
+  const int i = lay.row_begin + blockIdx.x * RERANK_WARPS + warp;
+  if (i >= row_end) return;
   float* xi = xs + (size_t)warp * d;
   const bool use_reg = VEC4 && d <= 512;
   double xr[16];
@@ -290,13 +290,13 @@ knn_rerank_kernel(const float* __restrict__ X, const float* __restrict__ sq, con
 
   u64 mine = KEY_INF;
   int splits = lay.stride;
-  if (lay.tc) {  // lists written for this row's tile: one per CTA that touched it (knn_tc.cu)
-    const long long rt = i / lay.row_tile;
+  if (lay.tc == 1) {  // lists written for this row's tile: one per CTA that touched it (knn_tc.cu)
+    const long long rt = (i - lay.row_begin) / lay.row_tile;
     const int b0 = (int)(((rt * lay.col_tiles + 1) * lay.grid - 1) / lay.units);
     const int b1 = (int)((((rt + 1) * lay.col_tiles) * lay.grid - 1) / lay.units);
     splits = b1 - b0 + 1;
   }
-  if (splits == 1 && !lay.tc) {
+  if (splits == 1 && lay.tc == 0) {
     mine = cand[(size_t)i * lay.stride * KC + lane];  // SIMT lists are sorted
   } else {
     for (int s = 0; s < splits; ++s) {  // tensor-core lists are unsorted sets: merge by insertion
@@ -418,18 +418,19 @@ knn_fallback_kernel(const float* __restrict__ X, int n, int d, int k, const int*
 
 }  // namespace
 
-int knn_finish(const float* X, const float* sq, const unsigned* sqmax_bits, int n, int d, int k, CandLayout lay,
-               const u64* cand, float err_coef, int* knn_idx, float* knn_dist, int* flag_count, int* flag_rows,
+int knn_finish(const float* X, const float* sq, const unsigned* sqmax_bits, int n, int d, int k, int row_begin, int row_end,
+               CandLayout lay, const u64* cand, float err_coef, int* knn_idx, float* knn_dist, int* flag_count, int* flag_rows,
                int* info, cudaStream_t st) {
   const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
   size_t smem = sizeof(float) * (size_t)RERANK_WARPS * d;
-  int blocks = ceil_div(n, RERANK_WARPS);
+  lay.row_begin = row_begin;
+  int blocks = ceil_div(row_end - row_begin, RERANK_WARPS);
   if (vec4) {
     if (smem > 48 * 1024)
       GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
       GLL_PROF(KID_RERANK, st);
-      knn_rerank_kernel<true><<<blocks, RERANK_WARPS * 32, smem, st>>>(X, sq, sqmax_bits, n, d, k, lay, cand,
+      knn_rerank_kernel<true><<<blocks, RERANK_WARPS * 32, smem, st>>>(X, sq, sqmax_bits, n, d, k, row_end, lay, cand,
                                                                       err_coef, knn_idx, knn_dist, flag_count, flag_rows);
     }
   } else {
@@ -437,7 +438,7 @@ int knn_finish(const float* X, const float* sq, const unsigned* sqmax_bits, int 
       GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
       GLL_PROF(KID_RERANK, st);
-      knn_rerank_kernel<false><<<blocks, RERANK_WARPS * 32, smem, st>>>(X, sq, sqmax_bits, n, d, k, lay, cand,
+      knn_rerank_kernel<false><<<blocks, RERANK_WARPS * 32, smem, st>>>(X, sq, sqmax_bits, n, d, k, row_end, lay, cand,
                                                                        err_coef, knn_idx, knn_dist, flag_count, flag_rows);
     }
   }
@@ -455,8 +456,8 @@ int knn_finish(const float* X, const float* sq, const unsigned* sqmax_bits, int 
   return GLL_OK;
 }
 
-static int simt_splits(int n, int* cols_per_split) {
-  int row_tiles = ceil_div(n, BM), col_tiles = ceil_div(n, BN);
+static int simt_splits(int n, int rows, int* cols_per_split) {
+  int row_tiles = ceil_div(rows, BM), col_tiles = ceil_div(n, BN);
   int want = ceil_div(2 * device_info().sms, row_tiles);
   want = max(1, min(want, min(col_tiles, KNN_MAX_SPLITS)));
   int tiles_per = ceil_div(col_tiles, want);
@@ -464,33 +465,47 @@ static int simt_splits(int n, int* cols_per_split) {
   return ceil_div(col_tiles, tiles_per);
 }
 
-size_t knn_ws_bytes(int n, int d, int k) {
+// candidate sets per row the chosen Gram path will write for this row range
+static int cand_stride(int n, int d, int row_begin, int row_end) {
+  const TcPlan plan = knn_tc_plan(n, d, row_begin, row_end);
+  if (plan.ok) return plan.max_splits;
+  int cps;
+  return simt_splits(n, row_end - row_begin, &cps);
+}
+
+size_t knn_ws_bytes(int n, int d, int k, int row_begin, int row_end) {
   (void)k;
+  const size_t rows = (size_t)(row_end - row_begin);
   size_t b = 0;
-  b += align_up(sizeof(float) * (size_t)n, 256);                        // sq
-  b += 256;                                                             // sqmax + flag_count
-  b += align_up(sizeof(u64) * (size_t)n * KNN_MAX_SPLITS * KC, 256);    // cand
-  b += align_up(sizeof(int) * (size_t)n, 256);                          // flag_rows
+  b += align_up(sizeof(float) * (size_t)n, 256);                                                   // sq
+  b += 256;                                                                                        // sqmax + flag_count
+  b += align_up(sizeof(u64) * rows * (size_t)cand_stride(n, d, row_begin, row_end) * KC, 256);     // cand
+  b += align_up(sizeof(int) * rows, 256);                                                          // flag_rows
   b += knn_tc_ws_upper(n, d);                                           // bf16 hi / lo copies for the tensor-core path
   return b + 1024;
 }
 
-int knn_run(const float* X, int n, int d, int k, int* knn_idx, float* knn_dist, int* info, void* ws,
-            size_t ws_bytes, cudaStream_t st) {
+int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int* knn_idx, float* knn_dist, int* info,
+            void* ws, size_t ws_bytes, cudaStream_t st) {
   GLL_REQUIRE(X && knn_idx && knn_dist && ws, "null pointer");
   GLL_REQUIRE(n >= k && k >= 2 && k <= KC + 1, "need n >= k and 2 <= k <= 33");
   GLL_REQUIRE(d >= 1, "d must be positive");
-  if (ws_bytes < knn_ws_bytes(n, d, k)) {
-    set_error("kNN workspace too small: %zu < %zu", ws_bytes, knn_ws_bytes(n, d, k));
+  GLL_REQUIRE(0 <= row_begin && row_begin < row_end && row_end <= n, "bad row range");
+  if (ws_bytes < knn_ws_bytes(n, d, k, row_begin, row_end)) {
+    set_error("kNN workspace too small: %zu < %zu", ws_bytes, knn_ws_bytes(n, d, k, row_begin, row_end));
     return GLL_ERR_WORKSPACE;
   }
+  const int rows = row_end - row_begin;
+  const int stride = cand_stride(n, d, row_begin, row_end);
   Carver cv(ws, ws_bytes);
   float* sq = cv.take<float>(n);
   unsigned* small = cv.take<unsigned>(64);
   unsigned* sqmax_bits = small;
   int* flag_count = reinterpret_cast<int*>(small + 1);
-  u64* cand = cv.take<u64>((size_t)n * KNN_MAX_SPLITS * KC);
-  int* flag_rows = cv.take<int>(n);
+  u64* cand_store = cv.take<u64>((size_t)rows * stride * KC);
+  // kernels index candidate sets by GLOBAL row: hand them the pointer where row 0 would live
+  u64* cand = cand_store - (size_t)row_begin * stride * KC;
+  int* flag_rows = cv.take<int>(rows);
   char* tc_ws = cv.take<char>(knn_tc_ws_upper(n, d));
 
   GLL_CUDA_CHECK(cudaMemsetAsync(small, 0, 256, st));
@@ -502,12 +517,12 @@ int knn_run(const float* X, int n, int d, int k, int* knn_idx, float* knn_dist, 
 
   CandLayout lay;
   float err_coef;
-  const TcPlan plan = knn_tc_plan(n, d);
+  const TcPlan plan = knn_tc_plan(n, d, row_begin, row_end);
   if (plan.ok) {  // tcgen05 / TMA Gram GEMM with the fused top-k epilogue
-    int rc = knn_tc_candidates(X, sq, n, d, plan, tc_ws, cand, st);
+    int rc = knn_tc_candidates(X, sq, n, d, row_end, plan, tc_ws, cand, st);
     if (rc) return rc;
     lay.stride = plan.max_splits;
-    lay.tc = 1;
+    lay.tc = plan.aligned ? 2 : 1;
     lay.row_tile = 128;
     lay.col_tiles = plan.col_tiles;
     lay.grid = plan.grid;
@@ -515,21 +530,21 @@ int knn_run(const float* X, int n, int d, int k, int* knn_idx, float* knn_dist, 
     err_coef = knn_tc_err_coef(d);
   } else {  // fp32 SIMT Gram (tiny graphs, or forced by GLL_B200_KNN_PATH=simt)
     int cps;
-    const int splits = simt_splits(n, &cps);
+    const int splits = simt_splits(n, rows, &cps);
     const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
-    dim3 grid(ceil_div(n, BM), splits);
+    dim3 grid(ceil_div(rows, BM), splits);
     size_t smem = gemm_smem_bytes();
     if (vec4) {
       GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       {
         GLL_PROF(KID_GRAM_TOPK, st);
-        knn_gemm_topk_kernel<true><<<grid, GEMM_THREADS, smem, st>>>(X, sq, n, d, cps, splits, cand);
+        knn_gemm_topk_kernel<true><<<grid, GEMM_THREADS, smem, st>>>(X, sq, n, d, cps, splits, cand, row_begin, row_end);
       }
     } else {
       GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       {
         GLL_PROF(KID_GRAM_TOPK, st);
-        knn_gemm_topk_kernel<false><<<grid, GEMM_THREADS, smem, st>>>(X, sq, n, d, cps, splits, cand);
+        knn_gemm_topk_kernel<false><<<grid, GEMM_THREADS, smem, st>>>(X, sq, n, d, cps, splits, cand, row_begin, row_end);
       }
     }
     GLL_LAUNCH_CHECK();
@@ -541,7 +556,8 @@ int knn_run(const float* X, int n, int d, int k, int* knn_idx, float* knn_dist, 
     const double u = 5.9604644775390625e-8;
     err_coef = (float)(((double)d * u / (1.0 - (double)d * u) + 4.0 * u) * 1.0001);
   }
-  return knn_finish(X, sq, sqmax_bits, n, d, k, lay, cand, err_coef, knn_idx, knn_dist, flag_count, flag_rows, info, st);
+  return knn_finish(X, sq, sqmax_bits, n, d, k, row_begin, row_end, lay, cand, err_coef, knn_idx, knn_dist, flag_count, flag_rows,
+                    info, st);
 }
 
 }  // namespace gll

@@ -28,26 +28,28 @@ __device__ __forceinline__ void list_insert(u64& mine, u64 x, int lane) {
 
 // Tensor-core candidate generation (knn_tc.cu).  plan.ok == 0: shape or configuration not handled, use the SIMT path.
 struct TcPlan {
-  int ok, d_pad, kblocks, row_tiles, col_tiles, grid, max_splits;
+  int ok, d_pad, kblocks, row_tiles, col_tiles, grid, max_splits, rt0, aligned;
   long long units;
   size_t ws_bytes;  // bf16 hi / lo copies of X
 };
-TcPlan knn_tc_plan(int n, int d);
+TcPlan knn_tc_plan(int n, int d, int row_begin, int row_end);
 size_t knn_tc_ws_upper(int n, int d);
-int knn_tc_splits_of_row(const TcPlan& p, int row);
-int knn_tc_candidates(const float* X, const float* sq, int n, int d, const TcPlan& plan, void* tc_ws, u64* cand, cudaStream_t st);
+int knn_tc_candidates(const float* X, const float* sq, int n, int d, int row_end, const TcPlan& plan, void* tc_ws, u64* cand,
+                      cudaStream_t st);
 float knn_tc_err_coef(int d);
 
 // How the candidate lists of a row are laid out in cand[n][stride][KC]: uniform (SIMT: every row has `stride` lists)
 // or the tensor-core work split (row tile rt was touched by CTAs b0(rt)..b1(rt); slot = b - b0).
 struct CandLayout {
   int stride;      // lists allocated per row
-  int tc;          // 0: every row has `stride` lists
+  int tc;          // 0: every row has `stride` sorted lists; 1: tensor-core work split; 2: one unsorted set per row
+  int row_begin;   // first row of this call's row range (row tiles are counted from it)
   int row_tile, col_tiles, grid;
   long long units;
 };
 
-int knn_finish(const float* X, const float* sq, const unsigned* sqmax_bits, int n, int d, int k, CandLayout lay,
+int knn_finish(const float* X, const float* sq, const unsigned* sqmax_bits, int n, int d, int k, int row_begin, int row_end,
+               CandLayout lay,
                const u64* cand, float err_coef, int* knn_idx, float* knn_dist, int* flag_count, int* flag_rows,
                int* info, cudaStream_t st);
 

@@ -135,6 +135,9 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 
 struct TcParams {
   int n, kblocks, col_tiles, max_splits;
+  int rt0, row_end;   // first row tile of this call's row range, one past its last row
+  int aligned;        // 1: every CTA owns whole row tiles (all CTAs sweep the column tiles in lockstep: B tiles hit in L2)
+  int row_tiles;
   long long units;
   const float* sq;
   u64* cand;
@@ -171,8 +174,15 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x, b = blockIdx.x;
-  const long long u_begin = (long long)b * P.units / G, u_end = (long long)(b + 1) * P.units / G;
   const int C = P.col_tiles, KB = P.kblocks;
+  long long u_begin, u_end;
+  if (P.aligned) {
+    u_begin = ((long long)b * P.row_tiles / G) * C;
+    u_end = ((long long)(b + 1) * P.row_tiles / G) * C;
+  } else {
+    u_begin = (long long)b * P.units / G;
+    u_end = (long long)(b + 1) * P.units / G;
+  }
 
   const uint32_t bar_full = base + (uint32_t)TC_OFF_BAR;        // [TC_STAGES]
   const uint32_t bar_empty = bar_full + 8 * TC_STAGES;          // [TC_STAGES]
@@ -212,7 +222,7 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
       int stage = 0;
       uint32_t phase = 0;
       for (long long u = u_begin; u < u_end; ++u) {
-        const int rt = (int)(u / C), ct = (int)(u % C);
+        const int rt = P.rt0 + (int)(u / C), ct = (int)(u % C);
         for (int kk = 0; kk < KB; ++kk) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
           const uint32_t full = bar_full + 8 * stage;
@@ -279,7 +289,7 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
 
     auto flush = [&](int rt) {
       __syncwarp();
-      const int slot = b - tc_cta_of_unit((long long)rt * C, G, P.units);
+      const int slot = P.aligned ? 0 : b - tc_cta_of_unit((long long)(rt - P.rt0) * C, G, P.units);
       const float* wd = Ld - lane;
       const int* wi = Li - lane;
       for (int r = 0; r < 32; ++r) {  // lane = slot index e here; 256 B coalesced store per row
@@ -287,13 +297,13 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
         const float dd = wd[lane * 32 + r];
         const float sqr = (row < P.n) ? __ldg(P.sq + row) : 0.f;
         const u64 key = (dd == INFINITY) ? KEY_INF : make_key(dd + sqr, wi[lane * 32 + r]);
-        if (row < P.n) P.cand[((size_t)row * P.max_splits + slot) * KC + lane] = key;
+        if (row < P.row_end) P.cand[((size_t)row * P.max_splits + slot) * KC + lane] = key;
       }
       __syncwarp();
     };
 
     for (long long u = u_begin; u < u_end; ++u) {
-      const int rt = (int)(u / C), ct = (int)(u % C);
+      const int rt = P.rt0 + (int)(u / C), ct = (int)(u % C);
       if (rt != cur_rt) {
         if (cur_rt >= 0) flush(cur_rt);
 #pragma unroll
@@ -452,36 +462,39 @@ int make_map(CUtensorMap* m, const void* base, int n, int d_pad, int box_rows) {
 
 }  // namespace
 
-TcPlan knn_tc_plan(int n, int d) {
+TcPlan knn_tc_plan(int n, int d, int row_begin, int row_end) {
   TcPlan p;
   memset(&p, 0, sizeof(p));
   const char* force = getenv("GLL_B200_KNN_PATH");  // "simt" or "tc": testing knob, both paths are exact
   if (force && strcmp(force, "simt") == 0) return p;
   if (n < 2 * TC_BM && !(force && strcmp(force, "tc") == 0)) return p;  // tiny graphs: the SIMT kernel is enough
+  if (row_begin % TC_BM != 0) return p;                                   // row ranges start on a tile boundary
   p.d_pad = ceil_div(d, TC_BK) * TC_BK;
   p.kblocks = p.d_pad / TC_BK;
-  p.row_tiles = ceil_div(n, TC_BM);
+  p.rt0 = row_begin / TC_BM;
+  p.row_tiles = ceil_div(row_end - row_begin, TC_BM);
   p.col_tiles = ceil_div(n, TC_BN);
   p.units = (long long)p.row_tiles * p.col_tiles;
-  p.grid = (int)((p.units < (long long)device_info().sms) ? p.units : (long long)device_info().sms);
-  int ms = 1;
-  for (int rt = 0; rt < p.row_tiles; ++rt) {  // exact: CTAs touching each row tile
-    const int b0 = tc_cta_of_unit((long long)rt * p.col_tiles, p.grid, p.units);
-    const int b1 = tc_cta_of_unit((long long)(rt + 1) * p.col_tiles - 1, p.grid, p.units);
-    ms = max(ms, b1 - b0 + 1);
+  const int sms = device_info().sms;
+  p.grid = (int)((p.units < (long long)sms) ? p.units : (long long)sms);
+  if (p.row_tiles >= 4 * sms) {  // big graphs: whole row tiles per CTA, one candidate set per row
+    p.aligned = 1;
+    p.max_splits = 1;
+  } else {
+    int ms = 1;
+    for (int rt = 0; rt < p.row_tiles; ++rt) {  // exact: CTAs touching each row tile
+      const int b0 = tc_cta_of_unit((long long)rt * p.col_tiles, p.grid, p.units);
+      const int b1 = tc_cta_of_unit((long long)(rt + 1) * p.col_tiles - 1, p.grid, p.units);
+      ms = max(ms, b1 - b0 + 1);
+    }
+    p.max_splits = ms;
   }
-  p.max_splits = ms;
   p.ws_bytes = 2 * align_up((size_t)n * p.d_pad * 2, 256);
-  p.ok = (ms <= KNN_MAX_SPLITS) ? 1 : 0;
+  p.ok = (p.max_splits <= KNN_MAX_SPLITS) ? 1 : 0;
   return p;
 }
 
 size_t knn_tc_ws_upper(int n, int d) { return 2 * align_up((size_t)n * (size_t)(ceil_div(d, TC_BK) * TC_BK) * 2, 256) + 512; }
-
-int knn_tc_splits_of_row(const TcPlan& p, int row) {
-  const int rt = row / TC_BM;
-  return tc_cta_of_unit((long long)(rt + 1) * p.col_tiles - 1, p.grid, p.units) - tc_cta_of_unit((long long)rt * p.col_tiles, p.grid, p.units) + 1;
-}
 
 // |d~^2 - d^2| <= coef * (|xi|^2 + |xj|^2): split residual 3*2^-18, fp32 accumulation over 3*d/16 MMA steps of unknown
 // internal rounding (budgeted at 2^-21 per step and per 16-term tree), final fp32 expression 4u; then a 4x margin.
@@ -491,7 +504,8 @@ float knn_tc_err_coef(int d) {
   return (float)(4.0 * e);
 }
 
-int knn_tc_candidates(const float* X, const float* sq, int n, int d, const TcPlan& plan, void* tc_ws, u64* cand, cudaStream_t st) {
+int knn_tc_candidates(const float* X, const float* sq, int n, int d, int row_end, const TcPlan& plan, void* tc_ws, u64* cand,
+                      cudaStream_t st) {
   __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(tc_ws);
   __nv_bfloat16* L = reinterpret_cast<__nv_bfloat16*>((char*)tc_ws + align_up((size_t)n * plan.d_pad * 2, 256));
   {
@@ -512,6 +526,10 @@ int knn_tc_candidates(const float* X, const float* sq, int n, int d, const TcPla
   P.col_tiles = plan.col_tiles;
   P.max_splits = plan.max_splits;
   P.units = plan.units;
+  P.rt0 = plan.rt0;
+  P.row_end = row_end;
+  P.aligned = plan.aligned;
+  P.row_tiles = plan.row_tiles;
   P.sq = sq;
   P.cand = cand;
   static bool attr_set = false;

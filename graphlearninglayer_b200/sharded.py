@@ -1,0 +1,262 @@
+"""One large graph on N GPUs (BASELINE.json configs[4]: n = 1M nodes, d = 256, 100 classes).
+
+    pred = ShardedLaplaceLearning.apply(X, label_matrix, tau, epsilon)        # same call as the single-GPU layer
+
+Every rank holds the full feature matrix X (the encoder output is all-gathered by the trainer, like the reference's
+nn.DataParallel gather, utils.py:547-548).  Inside the layer the path is cut along its natural shards:
+
+  rows      kNN search (K1) and the backward gather (K5/K6): rank r owns a block of nodes                [NCCL all-gather]
+  columns   both CG solves (K4): rank r owns a block of the l class columns.  Columns of the multi-RHS CG are independent
+            (per-column alpha/beta, GLL.py:262-269), so there is NO communication inside the solver      [NCCL all-gather]
+  replicated graph symmetrisation and weights (K2, K3): O(E) integer/byte work, a few ms at 1M nodes
+
+Collectives per call: forward 2 all-gathers (kNN lists; U column blocks), backward 3 (w column blocks; b; dX row blocks).
+`world` virtual ranks can also be executed one after the other in ONE process (`emulate=N`): that is how the slicing is
+tested on a single GPU; the arithmetic is identical to the N-process run.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import lib
+from .GLL import K_NEIGHBOURS, _bytes, _cg_maxit, _cg_tol, _require_cuda, _stream_ptr
+
+ROW_ALIGN = 128  # row blocks start on a tensor-core row tile
+
+
+def row_block(n: int, rank: int, world: int):
+    """Rows owned by `rank`: equal blocks of ceil(n/world) rounded up to ROW_ALIGN (the last blocks may be short/empty)."""
+    per = -(-n // world)
+    per = -(-per // ROW_ALIGN) * ROW_ALIGN
+    lo = min(n, rank * per)
+    hi = min(n, lo + per)
+    return lo, hi, per
+
+
+def col_block(l: int, rank: int, world: int):
+    """Class columns owned by `rank`: equal blocks of ceil(l/world)."""
+    per = -(-l // world)
+    lo = min(l, rank * per)
+    hi = min(l, lo + per)
+    return lo, hi, per
+
+
+class _Comm:
+    """all_gather over real ranks (torch.distributed, NCCL) or over virtual ranks executed in this process."""
+
+    def __init__(self, group=None, emulate: int = 0):
+        self.group = group
+        if emulate:
+            self.world, self.ranks, self.real = emulate, list(range(emulate)), False
+        elif dist.is_available() and dist.is_initialized():
+            self.world, self.ranks, self.real = dist.get_world_size(group), [dist.get_rank(group)], True
+        else:
+            self.world, self.ranks, self.real = 1, [0], False
+
+    def all_gather(self, parts: dict, like: torch.Tensor) -> List[torch.Tensor]:
+        """parts: {rank: equally shaped tensor} for the ranks executed here -> list over all ranks."""
+        if not self.real:
+            return [parts[r] for r in range(self.world)]
+        (mine,) = parts.values()
+        out = torch.empty((self.world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+        dist.all_gather_into_tensor(out, mine.contiguous(), group=self.group)
+        return list(out.unbind(0))
+
+
+class _Graph:
+    pass
+
+
+def _forward(X: torch.Tensor, Y: torch.Tensor, tau: float, epsilon, comm: _Comm, k: int = K_NEIGHBOURS):
+    dev = X.device
+    n, d = X.shape
+    k_lab, l = Y.shape
+    m = n - k_lab
+    i32, f32 = torch.int32, torch.float32
+    s = _stream_ptr(dev)
+    g = _Graph()
+    g.n, g.d, g.k, g.l, g.k_lab, g.m = n, d, k, l, k_lab, m
+    g.lp = lib.gll_padded_classes(l)
+    emax = lib.gll_max_edges(n, k)
+    eps_auto = isinstance(epsilon, str)
+    if eps_auto and epsilon != "auto":
+        raise ValueError("epsilon must be a float or 'auto'")
+    g.eps_auto = int(eps_auto)
+    info = torch.zeros(_lib.INFO_WORDS, dtype=i32, device=dev)
+    g.info = info
+
+    # ---- K1, rows: every rank searches its block of nodes against all n columns ----
+    _, _, per = row_block(n, 0, comm.world)
+    idx_parts, dist_parts = {}, {}
+    knn_idx = torch.empty((comm.world * per, k), dtype=i32, device=dev)
+    knn_dist = torch.empty((comm.world * per, k), dtype=f32, device=dev)
+    for r in comm.ranks:
+        lo, hi, _ = row_block(n, r, comm.world)
+        if hi > lo:
+            wsb = lib.gll_knn_rows_workspace_bytes(n, d, k, lo, hi)
+            ws = _bytes(wsb, dev)
+            _lib.check(lib.gll_knn_rows(X.data_ptr(), n, d, k, lo, hi, knn_idx.data_ptr(), knn_dist.data_ptr(), info.data_ptr(),
+                                        ws.data_ptr(), wsb, s), "gll_knn_rows")
+        idx_parts[r] = knn_idx[r * per:(r + 1) * per]
+        dist_parts[r] = knn_dist[r * per:(r + 1) * per]
+    if comm.real:  # (emulation wrote every block into the shared arrays already)
+        knn_idx = torch.cat(comm.all_gather(idx_parts, knn_idx), 0)
+        knn_dist = torch.cat(comm.all_gather(dist_parts, knn_dist), 0)
+    g.knn_idx, g.knn_dist = knn_idx, knn_dist  # rows >= n are padding and never read
+
+    # ---- K2, K3 replicated ----
+    g.row_ptr = torch.empty(n + 1, dtype=i32, device=dev)
+    g.col = torch.empty(emax, dtype=i32, device=dev)
+    g.dist = torch.empty(emax, dtype=f32, device=dev)
+    wsb = max(lib.gll_graph_workspace_bytes(n, k), lib.gll_weights_workspace_bytes(n, k))
+    ws = _bytes(wsb, dev)
+    _lib.check(lib.gll_graph_build(knn_idx.data_ptr(), knn_dist.data_ptr(), n, k, g.row_ptr.data_ptr(), g.col.data_ptr(),
+                                   g.dist.data_ptr(), info.data_ptr(), ws.data_ptr(), wsb, s), "gll_graph_build")
+    g.eps = torch.empty(n, dtype=f32, device=dev)
+    g.kappa = torch.empty(n, dtype=i32, device=dev)
+    g.w = torch.empty(emax, dtype=f32, device=dev)
+    g.deg = torch.empty(n, dtype=f32, device=dev)
+    g.uu_ptr = torch.empty(m + 1, dtype=i32, device=dev)
+    g.uu_col = torch.empty(emax, dtype=i32, device=dev)
+    g.uu_val = torch.empty(emax, dtype=f32, device=dev)
+    g.diag = torch.empty(m, dtype=f32, device=dev)
+    rhs = torch.empty((m, g.lp), dtype=f32, device=dev)
+    g.ut = torch.zeros((n, g.lp), dtype=f32, device=dev)
+    _lib.check(lib.gll_edge_weights(knn_idx.data_ptr(), knn_dist.data_ptr(), g.row_ptr.data_ptr(), g.col.data_ptr(),
+                                    g.dist.data_ptr(), Y.data_ptr(), n, k, l, k_lab, g.eps_auto,
+                                    0.0 if eps_auto else float(epsilon), float(tau), g.eps.data_ptr(), g.kappa.data_ptr(),
+                                    g.w.data_ptr(), g.deg.data_ptr(), g.uu_ptr.data_ptr(), g.uu_col.data_ptr(),
+                                    g.uu_val.data_ptr(), g.diag.data_ptr(), rhs.data_ptr(), g.ut.data_ptr(), info.data_ptr(),
+                                    ws.data_ptr(), wsb, s), "gll_edge_weights")
+
+    # ---- K4, columns: each rank solves its block of class columns ----
+    g.iters_fwd = torch.zeros(comm.world, dtype=i32, device=dev)
+    _solve_columns(g, rhs, g.ut[k_lab:], _cg_tol(), comm, g.iters_fwd)
+    pred64 = os.environ.get("GLL_B200_PRED_DTYPE", "float64") != "float32"
+    pred = torch.empty((m, l), dtype=torch.float64 if pred64 else f32, device=dev)
+    _lib.check(lib.gll_unpack_pred(g.ut[k_lab:].data_ptr(), m, l, pred.data_ptr(), int(pred64), s), "gll_unpack_pred")
+    return pred, g
+
+
+def _solve_columns(g, rhs: torch.Tensor, out: torch.Tensor, tol: float, comm: _Comm, iters: torch.Tensor):
+    """out[:, cols] = A^-1 rhs[:, cols], cols split over the ranks; out and rhs are m x lp."""
+    dev = rhs.device
+    f32 = torch.float32
+    s = _stream_ptr(dev)
+    _, _, cper = col_block(g.l, 0, comm.world)
+    lp_loc = lib.gll_padded_classes(cper)
+    parts = {}
+    for r in comm.ranks:
+        c0, c1, _ = col_block(g.l, r, comm.world)
+        cnt = c1 - c0
+        x_loc = torch.zeros((g.m, lp_loc), dtype=f32, device=dev)
+        if cnt > 0:
+            b_loc = torch.empty((g.m, lp_loc), dtype=f32, device=dev)
+            _lib.check(lib.gll_pack_columns(rhs.data_ptr(), g.m, g.lp, c0, cnt, b_loc.data_ptr(), lp_loc, s), "gll_pack_columns")
+            # always solve `cper` columns (layout m x padded(cper)); columns beyond cnt have a zero right-hand side and
+            # are frozen from the first iteration (GLL.py:262-263)
+            wsb = lib.gll_cg_workspace_bytes(g.m, cper)
+            ws = _bytes(wsb, dev)
+            _lib.check(lib.gll_cg_solve(g.uu_ptr.data_ptr(), g.uu_col.data_ptr(), g.uu_val.data_ptr(), g.diag.data_ptr(),
+                                        b_loc.data_ptr(), g.m, cper, tol, _cg_maxit(), x_loc.data_ptr(), iters[r:].data_ptr(), 0,
+                                        g.info[_lib.INFO_STATUS:].data_ptr(), ws.data_ptr(), wsb, s), "gll_cg_solve")
+        parts[r] = x_loc
+    blocks = comm.all_gather(parts, out)
+    for r, xb in enumerate(blocks):
+        c0, c1, _ = col_block(g.l, r, comm.world)
+        if c1 > c0:
+            _lib.check(lib.gll_unpack_columns(xb.data_ptr(), g.m, lp_loc, c0, c1 - c0, out.data_ptr(), g.lp, s),
+                       "gll_unpack_columns")
+
+
+def _backward(g, X: torch.Tensor, grad_output: torch.Tensor, comm: _Comm) -> torch.Tensor:
+    dev = X.device
+    f32 = torch.float32
+    s = _stream_ptr(dev)
+    n, d, l, m, k_lab = g.n, g.d, g.l, g.m, g.k_lab
+    gout = grad_output.detach().to(dev)
+    if gout.dtype not in (torch.float32, torch.float64):
+        gout = gout.float()
+    gout = gout.contiguous()
+    rhs = torch.empty((m, g.lp), dtype=f32, device=dev)
+    _lib.check(lib.gll_pack_grad(gout.data_ptr(), int(gout.dtype == torch.float64), m, l, rhs.data_ptr(), s), "gll_pack_grad")
+    wt = torch.zeros((n, g.lp), dtype=f32, device=dev)  # GLL.py:104: zero rows for the labeled nodes
+    g.iters_bwd = torch.zeros(comm.world, dtype=torch.int32, device=dev)
+    _solve_columns(g, rhs, wt[k_lab:], -_cg_tol(), comm, g.iters_bwd)
+
+    # ---- K5 rows -> all-gather b -> K6 rows -> all-gather dX ----
+    _, _, per = row_block(n, 0, comm.world)
+    emax = g.col.numel()
+    gv = torch.empty(emax, dtype=f32, device=dev)
+    bvec = torch.zeros(comm.world * per, dtype=f32, device=dev)
+    dX = torch.empty((comm.world * per, d), dtype=f32, device=dev)
+
+    def edges(r, phases):
+        lo, hi, _ = row_block(n, r, comm.world)
+        _lib.check(lib.gll_backward_edges_rows(X.data_ptr(), n, d, l, k_lab, g.eps_auto, g.row_ptr.data_ptr(), g.col.data_ptr(),
+                                               g.dist.data_ptr(), g.w.data_ptr(), g.eps.data_ptr(), g.kappa.data_ptr(),
+                                               g.ut.data_ptr(), wt.data_ptr(), gv.data_ptr(), bvec.data_ptr(), dX.data_ptr(),
+                                               lo, hi, phases, s), "gll_backward_edges_rows")
+
+    for r in comm.ranks:
+        edges(r, 1)
+    if comm.real and g.eps_auto:
+        parts = {r: bvec[r * per:(r + 1) * per] for r in comm.ranks}
+        bvec.copy_(torch.cat(comm.all_gather(parts, bvec), 0))
+    for r in comm.ranks:
+        edges(r, 2)
+    if comm.real:
+        parts = {r: dX[r * per:(r + 1) * per] for r in comm.ranks}
+        dX = torch.cat(comm.all_gather(parts, dX), 0)
+    return dX[:n]
+
+
+class ShardedLaplaceLearning(torch.autograd.Function):
+    """`LaplaceLearningSparseHard` (GLL.py:10-177) for ONE graph spread over the ranks of a process group.
+
+    forward(X, label_matrix, tau=0, epsilon='auto', group=None, emulate=0): every rank passes the SAME X and labels and
+    receives the same full prediction; backward returns the full dX on every rank."""
+
+    @staticmethod
+    def forward(ctx, X, label_matrix, tau=0, epsilon="auto", group=None, emulate=0):
+        _require_cuda(X, "features")
+        Xc = X.detach().float().contiguous()
+        Y = label_matrix.detach().to(device=X.device, dtype=torch.float32).contiguous()
+        if not (0 < Y.shape[0] < Xc.shape[0]):
+            raise ValueError("need 0 < k_lab < n; labeled rows come first (GLL.py:11)")
+        comm = _Comm(group, emulate)
+        with torch.cuda.device(X.device):
+            pred, g = _forward(Xc, Y, float(tau), epsilon, comm)
+        global _last_graph
+        _last_graph = g
+        ctx.gll_graph, ctx.gll_comm, ctx.x_dtype = g, comm, X.dtype
+        ctx.save_for_backward(Xc)
+        return pred
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        (Xc,) = ctx.saved_tensors
+        with torch.cuda.device(Xc.device):
+            dX = _backward(ctx.gll_graph, Xc, grad_output, ctx.gll_comm)
+        return dX.to(ctx.x_dtype), None, None, None, None, None
+
+
+_last_graph = None
+
+
+def last_info() -> dict:
+    """Status block of the most recent sharded call on this rank (synchronises); same keys as GLL.last_info()."""
+    g = _last_graph
+    if g is None:
+        return {}
+    v = g.info.cpu().numpy()
+    return dict(status=int(v[_lib.INFO_STATUS]), nnz=int(v[_lib.INFO_NNZ]), nnz_uu=int(v[_lib.INFO_NNZ_UU]),
+                cg_iters_fwd=int(g.iters_fwd.max().item()),
+                cg_iters_bwd=int(g.iters_bwd.max().item()) if hasattr(g, "iters_bwd") else 0,
+                knn_fallback_rows=int(v[_lib.INFO_KNN_FALLBACK_ROWS]), cg_resid_fwd=float("nan"), cg_resid_bwd=float("nan"))

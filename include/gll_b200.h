@@ -147,6 +147,31 @@ int gll_backward_edges(const float* X, int n, int d, int l, int k_lab, int eps_a
                        const float* ut, const float* wt, float* gv, float* bvec, float* dX, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Row-range and column-slice variants: the building blocks of the sharded (one graph on N GPUs) path, see
+ * graphlearninglayer_b200/sharded.py.  Nodes are sharded by ROWS for the kNN search and the backward gather (results are
+ * all-gathered by the host with NCCL); the two CG solves are sharded by CLASS COLUMNS (columns of the multi-RHS CG are
+ * independent, GLL.py:262-269, so no communication happens inside the solver).
+ * ------------------------------------------------------------------------------------------- */
+/* gll_knn for rows [row_begin, row_end) against all n columns; writes rows [row_begin, row_end) of the full n x k
+ * arrays.  row_begin should be a multiple of 128 (otherwise the SIMT Gram path is taken). */
+size_t gll_knn_rows_workspace_bytes(int n, int d, int k, int row_begin, int row_end);
+int gll_knn_rows(const float* X, int n, int d, int k, int row_begin, int row_end, int* knn_idx, float* knn_dist, int* info,
+                 void* workspace, size_t workspace_bytes, void* stream);
+/* gll_backward_edges restricted to rows [row_begin, row_end); phases bit 0: K5 (gv of the rows' edges, b of the rows),
+ * bit 1: K6 (dX rows; reads b of ALL rows, i.e. after the host has gathered bvec). */
+int gll_backward_edges_rows(const float* X, int n, int d, int l, int k_lab, int eps_auto, const int* row_ptr, const int* col,
+                            const float* dist, const float* w, const float* eps, const int* kappa, const float* ut,
+                            const float* wt, float* gv, float* bvec, float* dX, int row_begin, int row_end, int phases,
+                            void* stream);
+/* dst[r][c] = src[r][c0 + c] for c < cnt, zero for cnt <= c < lp_dst (rows x lp_src -> rows x lp_dst), and the inverse
+ * (dst[r][c0 + c] = src[r][c], c < cnt). */
+int gll_pack_columns(const float* src, int rows, int lp_src, int c0, int cnt, float* dst, int lp_dst, void* stream);
+int gll_unpack_columns(const float* src, int rows, int lp_src, int c0, int cnt, float* dst, int lp_dst, void* stream);
+/* m x lp fp32 -> m x l float64/fp32 (GLL.py:66) and m x l float64/fp32 grad_output -> m x lp fp32 (GLL.py:90). */
+int gll_unpack_pred(const float* u, int m, int l, void* pred, int pred_is_f64, void* stream);
+int gll_pack_grad(const void* grad_out, int grad_is_f64, int m, int l, float* rhs, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused drivers: what LaplaceLearningSparseHard.forward / .backward call (GLL.py:13-73, 75-177).
  * `state` is a buffer of gll_state_layout(...).total bytes that must stay alive (and untouched) between the
  * two calls; `workspace` may be reused by anybody in between.

@@ -441,3 +441,60 @@ def test_stable_conjgrad_wrapper(gll, capsys):
     assert y1.shape == (1450,) and np.abs(A @ y1 - b[:, 0]).max() < 1e-8
     pkg.stable_conjgrad(A, b, max_iter=2, tol=1e-12)
     assert "max iter reached" in capsys.readouterr().out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# one graph over several ranks (sharded.py), executed as virtual ranks on this single GPU
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("eps,tau", [("auto", 0.0), (1.0, 0.07)])
+def test_sharded_layer_matches_single_gpu_layer(gll, world, eps, tau):
+    pkg, _ = gll
+    from graphlearninglayer_b200.sharded import ShardedLaplaceLearning, last_info
+
+    X, Y, _, yq = O.synth_inputs(31, 700, 2300, 96, 13, 2.5)  # l = 13: uneven column blocks; n = 3000: ragged row blocks
+    ref_pred, ref_loss, ref_dX = layer_fwd_bwd(pkg, X, Y, yq, tau, eps)
+    Xt = torch.as_tensor(X).cuda().requires_grad_(True)
+    pred = ShardedLaplaceLearning.apply(Xt, torch.as_tensor(Y).cuda(), tau, eps, None, world)
+    tgt = torch.nn.functional.one_hot(torch.as_tensor(yq).cuda(), pred.shape[1]).to(pred.dtype)
+    loss = -torch.sum(tgt * torch.log(pred + 1e-8)) / pred.shape[0]
+    loss.backward()
+    torch.cuda.synchronize()
+    assert pred.dtype == torch.float64 and Xt.grad.dtype == torch.float32
+    # column blocks are solved independently of each other (GLL.py:262-269): same answer as the unsharded solve
+    assert O.max_rel(pred.detach().cpu().numpy(), ref_pred.cpu().numpy()) < 2e-6
+    assert O.max_rel(Xt.grad.cpu().numpy(), ref_dX.cpu().numpy()) < 2e-6
+    info = last_info()
+    assert info["status"] & ~8 == 0 and info["cg_iters_fwd"] > 0 and info["cg_iters_bwd"] > 0
+
+
+def test_sharded_layer_vs_oracle(gll):
+    pkg, _ = gll
+    from graphlearninglayer_b200.sharded import ShardedLaplaceLearning
+
+    X, Y, _, yq = O.synth_inputs(21, 1024, 5120, 256, 10, 3.0)
+    f, loss_ref, gout, bw = O.fwd_bwd(X, Y, yq, 0.0, "auto", solver="cg")
+    Xt = torch.as_tensor(X).cuda().requires_grad_(True)
+    pred = ShardedLaplaceLearning.apply(Xt, torch.as_tensor(Y).cuda(), 0.0, "auto", None, 4)
+    tgt = torch.nn.functional.one_hot(torch.as_tensor(yq).cuda(), pred.shape[1]).to(pred.dtype)
+    (-torch.sum(tgt * torch.log(pred + 1e-8)) / pred.shape[0]).backward()
+    assert O.max_rel(pred.detach().cpu().numpy(), f.pred) < TOL
+    assert O.max_rel(Xt.grad.cpu().numpy(), bw.dX) < TOL
+
+
+def test_knn_row_blocks_equal_full_search(gll):
+    _, _lib = gll
+    X, *_ = O.synth_inputs(12, 3000, 1777, 200, 10, 3.5)
+    n, d = X.shape
+    full_i, full_d, _ = run_knn(_lib, X)
+    Xc = dev_t(X, torch.float32)
+    idx = torch.full((n, 25), -1, dtype=torch.int32, device="cuda")
+    dd = torch.zeros((n, 25), dtype=torch.float32, device="cuda")
+    info = torch.zeros(_lib.INFO_WORDS, dtype=torch.int32, device="cuda")
+    for lo, hi in [(0, 1664), (1664, 3328), (3328, n)]:  # blocks start on multiples of 128
+        wsb = _lib.lib.gll_knn_rows_workspace_bytes(n, d, 25, lo, hi)
+        ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+        _lib.check(_lib.lib.gll_knn_rows(Xc.data_ptr(), n, d, 25, lo, hi, idx.data_ptr(), dd.data_ptr(), info.data_ptr(),
+                                         ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream), "gll_knn_rows")
+    torch.cuda.synchronize()
+    assert torch.equal(idx, full_i) and torch.equal(dd, full_d)

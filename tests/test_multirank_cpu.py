@@ -63,3 +63,28 @@ def test_single_process_degenerates():
     assert ranks.aggregate_throughput(3, 6.0) == (3, 6.0, 500.0)
     assert list(ranks.units_for_rank(5, 0, 1)) == [0, 1, 2, 3, 4]
     assert ranks.rank_seed(1000, 0) == 1000 and ranks.rank_seed(1000, 3) != ranks.rank_seed(1001, 2)
+
+
+def test_row_and_column_blocks_partition():
+    """Slicing rules of the sharded (one graph on N GPUs) path: blocks are disjoint, complete, tile-aligned."""
+    sys.path.insert(0, ROOT)
+    from graphlearninglayer_b200.sharded import col_block, row_block
+
+    for n, world in [(3000, 3), (1 << 20, 8), (130, 4), (4608, 2)]:
+        rows = []
+        for r in range(world):
+            lo, hi, per = row_block(n, r, world)
+            assert per % 128 == 0 and lo % 128 == 0 or lo == n
+            assert hi - lo <= per
+            rows += list(range(lo, hi)) if n <= 5000 else [lo, hi]
+        if n <= 5000:
+            assert rows == list(range(n))
+        else:
+            assert rows[0] == 0 and rows[-1] == n and all(rows[2 * i + 1] == rows[2 * i + 2] for i in range(world - 1))
+    for l, world in [(100, 8), (10, 4), (13, 3), (3, 8)]:
+        cols = []
+        for r in range(world):
+            lo, hi, per = col_block(l, r, world)
+            assert hi - lo <= per
+            cols += list(range(lo, hi))
+        assert cols == list(range(l))
