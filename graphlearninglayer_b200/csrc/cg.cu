@@ -175,14 +175,26 @@ __global__ void __launch_bounds__(CG_THREADS, 1) cg_persistent_kernel(CgParams P
       const int e0 = __ldg(P.ptr + i), e1 = __ldg(P.ptr + i + 1);
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
       if (active) {
-        for (int e = e0 + s; e < e1; e += S) {
-          const int j = __ldg(P.col + e);
-          const float wv = __ldg(P.val + e);
-          const float4 pj = ldcg4(P.p + (size_t)j * lp + 4 * q);
-          a.x = fmaf(wv, pj.x, a.x);
-          a.y = fmaf(wv, pj.y, a.y);
-          a.z = fmaf(wv, pj.z, a.z);
-          a.w = fmaf(wv, pj.w, a.w);
+        // four neighbours per trip: the four 128-bit gathers are independent, so a row of ~26 neighbours costs ~7 memory
+        // round trips instead of 26 (with many class columns a warp has a single neighbour slot, S = 1)
+        for (int e = e0 + s; e < e1; e += 4 * S) {
+          float wv[4];
+          float4 pj[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int et = e + t * S;
+            const bool ok = et < e1;
+            const int j = ok ? __ldg(P.col + et) : 0;
+            wv[t] = ok ? __ldg(P.val + et) : 0.f;
+            pj[t] = ldcg4(P.p + (size_t)j * lp + 4 * q);
+          }
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            a.x = fmaf(wv[t], pj[t].x, a.x);
+            a.y = fmaf(wv[t], pj[t].y, a.y);
+            a.z = fmaf(wv[t], pj[t].z, a.z);
+            a.w = fmaf(wv[t], pj[t].w, a.w);
+          }
         }
       }
       a = reduce_over_s(a, s, S, Q);
