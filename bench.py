@@ -335,8 +335,12 @@ def run_b200(args, rank, world, local_rank):
             ach, peak, u = work / t_s / 1e12, peaks["tflops"], "TFLOP/s"
         else:
             ach, peak, u = (work / t_s / 1e9 if work else None), peaks["hbm_gbs"], "GB/s"
+        traffic = None  # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same workload)
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(args.workload, {}).get(top)
         roofline = {"kernel": top, "bound": bound, "achieved": ach, "peak": peak, "unit": u,
-                    "frac": (ach / peak if ach else None), "traffic": None, "peak_source": peaks["source"],
+                    "frac": (ach / peak if ach else None), "traffic": traffic, "peak_source": peaks["source"],
                     "algorithmic_work_per_launch": work, "work_unit": unit, "launch_ms": t_s * 1e3}
         cpu = None
         if world == 1 and not args.no_cpu_baseline and not sharded:

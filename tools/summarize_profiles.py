@@ -41,10 +41,25 @@ def launches(path, out):
     print("wrote", out)
 
 
+NAME_MAP = {"knn_gram_topk_tc_kernel": "knn_gram_topk_tcgen05", "knn_rerank_kernel": "knn_rerank", "cg_resident_kernel": "cg_persistent",
+            "cg_persistent_kernel": "cg_persistent", "row_gather_kernel": "row_gather", "edge_grad_kernel": "edge_grad"}
+TRAFFIC = {}
+
+
+def to_bytes(v, unit):
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+    return float(v.replace(",", "")) * scale
+
+
 def full(rep, out):
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr, units = rows[0], rows[1]
+    wl = "c4" if "_c4_" in os.path.basename(rep) else "c2"
+    for r in rows[2:]:
+        nm = short(r[hdr.index("Kernel Name")]).split("<")[0]
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        TRAFFIC.setdefault(wl, {}).setdefault(NAME_MAP.get(nm, nm), []).append(to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]))
     with open(out, "w") as f:
         f.write(f"# ncu --set full summary of {os.path.basename(rep)} (one row block per captured launch)\n\n")
         for r in rows[2:]:
@@ -64,3 +79,10 @@ if __name__ == "__main__":
             launches(os.path.join(GO, nm), os.path.join(OUT, nm[:-4] + ".md"))
         if nm.startswith(TAG) and nm.endswith(".ncu-rep"):
             full(os.path.join(GO, nm), os.path.join(OUT, nm[:-8] + "_ncu_full.md"))
+    if TRAFFIC:
+        import json
+
+        out = {wl: {k: sum(v) / len(v) for k, v in d.items()} for wl, d in TRAFFIC.items()}
+        out["_source"] = f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full captures tagged {TAG}"
+        json.dump(out, open(os.path.join(OUT, "ncu_traffic.json"), "w"), indent=1)
+        print("wrote ncu_traffic.json", out)
