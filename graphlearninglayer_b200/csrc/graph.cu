@@ -134,54 +134,58 @@ namespace {
 // ------------------------------------------------------------------------------------------------ graph
 __device__ __forceinline__ bool is_edge(int i, int j, float dd, int n) { return dd > 0.f && j != i && j >= 0 && j < n; }
 
-// Does row j list i as a valid (non-zero) neighbour?  Also returns the number of valid entries of row j.
+// Does row j list i as a valid (non-zero) neighbour?
 __device__ __forceinline__ bool lists(const int* __restrict__ knn_idx, const float* __restrict__ knn_dist, int n, int k,
-                                      int j, int i, int* valid_in_j) {
+                                      int j, int i) {
   bool found = false;
-  int cnt = 0;
   const int* ri = knn_idx + (size_t)j * k;
   const float* rd = knn_dist + (size_t)j * k;
   for (int t = 0; t < k; ++t) {
     int c = __ldg(ri + t);
     float dd = __ldg(rd + t);
-    bool v = is_edge(j, c, dd, n);
-    cnt += v;
-    found |= (v && c == i);
+    found |= (is_edge(j, c, dd, n) && c == i);
   }
-  *valid_in_j = cnt;
   return found;
 }
 
+// flag per kNN entry: 0 not an edge, 1 edge listed by both ends, 2 edge listed only by i (the reverse edge j->i must be
+// created).  The (expensive) membership scan is done once here and reused by the fill kernel.
 __global__ void graph_count_kernel(const int* __restrict__ knn_idx, const float* __restrict__ knn_dist, int n, int k,
-                                   int* __restrict__ len) {
+                                   int* __restrict__ len, unsigned char* __restrict__ flag) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)n * k) return;
   int i = (int)(t / k);
   int j = knn_idx[t];
   float dd = knn_dist[t];
-  if (!is_edge(i, j, dd, n)) return;
+  if (!is_edge(i, j, dd, n)) {
+    flag[t] = 0;
+    return;
+  }
   atomicAdd(&len[i], 1);
-  int dummy;
-  if (!lists(knn_idx, knn_dist, n, k, j, i, &dummy)) atomicAdd(&len[j], 1);
+  const bool mutual = lists(knn_idx, knn_dist, n, k, j, i);
+  if (!mutual) atomicAdd(&len[j], 1);
+  flag[t] = mutual ? 1 : 2;
 }
 
+// forward edges of row i fill the head of the row in kNN order (deterministic slots); reverse edges fill the tail through an
+// integer cursor (their order is fixed afterwards by the per-row sort)
 __global__ void graph_fill_kernel(const int* __restrict__ knn_idx, const float* __restrict__ knn_dist, int n, int k,
-                                  const int* __restrict__ row_ptr, int* __restrict__ cursor, int* __restrict__ col_tmp,
-                                  float* __restrict__ dist_tmp) {
+                                  const int* __restrict__ row_ptr, const unsigned char* __restrict__ flag,
+                                  int* __restrict__ cursor, int* __restrict__ col_tmp, float* __restrict__ dist_tmp) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)n * k) return;
+  const unsigned char f = flag[t];
+  if (f == 0) return;
   int i = (int)(t / k), s = (int)(t % k);
   int j = knn_idx[t];
   float dd = knn_dist[t];
-  if (!is_edge(i, j, dd, n)) return;
   int before = 0;
-  for (int u = 0; u < s; ++u) before += is_edge(i, __ldg(knn_idx + (size_t)i * k + u), __ldg(knn_dist + (size_t)i * k + u), n);
+  for (int u = 0; u < s; ++u) before += (flag[(size_t)i * k + u] != 0);
   int p = row_ptr[i] + before;
   col_tmp[p] = j;
   dist_tmp[p] = dd;
-  int valid_j;
-  if (!lists(knn_idx, knn_dist, n, k, j, i, &valid_j)) {
-    int q = row_ptr[j] + valid_j + atomicAdd(&cursor[j], 1);
+  if (f == 2) {
+    int q = row_ptr[j + 1] - 1 - atomicAdd(&cursor[j], 1);
     col_tmp[q] = i;
     dist_tmp[q] = dd;
   }
@@ -209,7 +213,7 @@ __global__ void graph_sort_rows_kernel(const int* __restrict__ row_ptr, int n, c
 size_t graph_ws_bytes(int n, int k) {
   size_t emax = gll_max_edges(n, k);
   return align_up(sizeof(int) * (size_t)(n + 1), 256) * 2 + align_up(sizeof(int) * emax, 256) +
-         align_up(sizeof(float) * emax, 256) + scan_ws_bytes(n + 1) + 1024;
+         align_up(sizeof(float) * emax, 256) + scan_ws_bytes(n + 1) + align_up((size_t)n * k, 256) + 1024;
 }
 
 int graph_run(const int* knn_idx, const float* knn_dist, int n, int k, int* row_ptr, int* col, float* dist, int* info,
@@ -227,20 +231,21 @@ int graph_run(const int* knn_idx, const float* knn_dist, int n, int k, int* row_
   int* col_tmp = cv.take<int>(emax);
   float* dist_tmp = cv.take<float>(emax);
   void* scan_ws = cv.take<char>(scan_ws_bytes(n + 1));
+  unsigned char* flag = cv.take<unsigned char>((size_t)n * k);
   // len and cursor are adjacent 256-aligned blocks: clear both with one memset
   GLL_CUDA_CHECK(cudaMemsetAsync(len, 0, (size_t)((char*)cursor - (char*)len) + sizeof(int) * (size_t)(n + 1), st));
   long long total = (long long)n * k;
   int blocks = ceil_div(total, 256);
   {
     GLL_PROF(KID_GRAPH_COUNT, st);
-    graph_count_kernel<<<blocks, 256, 0, st>>>(knn_idx, knn_dist, n, k, len);
+    graph_count_kernel<<<blocks, 256, 0, st>>>(knn_idx, knn_dist, n, k, len, flag);
   }
   GLL_LAUNCH_CHECK();
   int rc = exclusive_scan(len, n, row_ptr, scan_ws, st);
   if (rc) return rc;
   {
     GLL_PROF(KID_GRAPH_FILL, st);
-    graph_fill_kernel<<<blocks, 256, 0, st>>>(knn_idx, knn_dist, n, k, row_ptr, cursor, col_tmp, dist_tmp);
+    graph_fill_kernel<<<blocks, 256, 0, st>>>(knn_idx, knn_dist, n, k, row_ptr, flag, cursor, col_tmp, dist_tmp);
   }
   GLL_LAUNCH_CHECK();
   {

@@ -15,6 +15,8 @@
 // lives in knn_tc.cu and reuses the rerank / fallback kernels through knn_finish().
 #include <math.h>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "knn_common.cuh"
 
@@ -30,20 +32,36 @@ constexpr size_t gemm_smem_bytes() {
          sizeof(float) * BM + sizeof(int) * BM;
 }
 
-__global__ void sqnorm_kernel(const float* __restrict__ X, int n, int d, float* __restrict__ sq,
-                              unsigned* __restrict__ sqmax_bits) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= n) return;
-  const float* x = X + (size_t)warp * d;
+// |x_i|^2 (fp64 accumulate -> fp32) and the global maximum; when H/L are given also the bf16 split x = hi + lo that
+// feeds the tensor-core Gram kernel (row stride d_pad, zero padded), so X is read once.
+__global__ void __launch_bounds__(256)
+sqnorm_split_kernel(const float* __restrict__ X, int n, int d, int d_pad, float* __restrict__ sq, unsigned* __restrict__ sqmax_bits,
+                    __nv_bfloat16* __restrict__ H, __nv_bfloat16* __restrict__ L) {
+  const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* x = X + (size_t)row * d;
   double s = 0.0;
-  for (int t = lane; t < d; t += 32) {
-    double v = (double)x[t];
-    s += v * v;
+  const int cend = (H != nullptr) ? d_pad : d;
+  for (int c = 2 * lane; c < cend; c += 64) {
+    const float x0 = (c < d) ? __ldg(x + c) : 0.f;
+    const float x1 = (c + 1 < d) ? __ldg(x + c + 1) : 0.f;
+    s += (double)x0 * (double)x0;
+    s += (double)x1 * (double)x1;
+    if (H != nullptr) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+      __nv_bfloat162 hv, lv;
+      hv.x = h0;
+      hv.y = h1;
+      lv.x = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+      lv.y = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+      *reinterpret_cast<__nv_bfloat162*>(H + (size_t)row * d_pad + c) = hv;
+      *reinterpret_cast<__nv_bfloat162*>(L + (size_t)row * d_pad + c) = lv;
+    }
   }
   s = warp_sum(s);
   if (lane == 0) {
     float f = (float)s;
-    sq[warp] = f;
+    sq[row] = f;
     if (f == f) atomicMax(sqmax_bits, __float_as_uint(f));  // non-negative floats order like their bits
   }
 }
@@ -508,16 +526,21 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
   int* flag_rows = cv.take<int>(rows);
   char* tc_ws = cv.take<char>(knn_tc_ws_upper(n, d));
 
-  GLL_CUDA_CHECK(cudaMemsetAsync(small, 0, 256, st));
-  {
-    GLL_PROF(KID_SQNORM, st);
-    sqnorm_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(X, n, d, sq, sqmax_bits);
-  }
-  GLL_LAUNCH_CHECK();
-
   CandLayout lay;
   float err_coef;
   const TcPlan plan = knn_tc_plan(n, d, row_begin, row_end);
+  __nv_bfloat16 *H = nullptr, *L = nullptr;
+  if (plan.ok) {
+    H = reinterpret_cast<__nv_bfloat16*>(tc_ws);
+    L = reinterpret_cast<__nv_bfloat16*>(tc_ws + align_up((size_t)n * plan.d_pad * 2, 256));
+  }
+  GLL_CUDA_CHECK(cudaMemsetAsync(small, 0, 256, st));
+  {
+    GLL_PROF(KID_SQNORM, st);
+    sqnorm_split_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(X, n, d, plan.ok ? plan.d_pad : d, sq, sqmax_bits, H, L);
+  }
+  GLL_LAUNCH_CHECK();
+
   if (plan.ok) {  // tcgen05 / TMA Gram GEMM with the fused top-k epilogue
     int rc = knn_tc_candidates(X, sq, n, d, row_end, plan, tc_ws, cand, st);
     if (rc) return rc;

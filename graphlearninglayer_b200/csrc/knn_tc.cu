@@ -146,23 +146,6 @@ struct TcParams {
 // CTA that owns unit u when `units` units are dealt contiguously to G CTAs (CTA b owns [b*units/G, (b+1)*units/G))
 __host__ __device__ inline int tc_cta_of_unit(long long u, int G, long long units) { return (int)(((u + 1) * G - 1) / units); }
 
-// ---------------------------------------------------------------------------------------------- split X = hi + lo
-__global__ void __launch_bounds__(256)
-split_bf16_kernel(const float* __restrict__ X, int n, int d, int d_pad, __nv_bfloat16* __restrict__ H, __nv_bfloat16* __restrict__ L) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per pair of columns
-  const int half = d_pad >> 1;
-  if (t >= (long long)n * half) return;
-  const int i = (int)(t / half), c = (int)(t % half) * 2;
-  const float x0 = (c < d) ? X[(size_t)i * d + c] : 0.f;
-  const float x1 = (c + 1 < d) ? X[(size_t)i * d + c + 1] : 0.f;
-  const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-  const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-  __nv_bfloat162 hv, lv;
-  hv.x = h0; hv.y = h1; lv.x = l0; lv.y = l1;
-  *reinterpret_cast<__nv_bfloat162*>(H + (size_t)i * d_pad + c) = hv;
-  *reinterpret_cast<__nv_bfloat162*>(L + (size_t)i * d_pad + c) = lv;
-}
-
 // ---------------------------------------------------------------------------------------------- the GEMM + top-k kernel
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_constant__ CUtensorMap mapAL,
@@ -508,12 +491,7 @@ int knn_tc_candidates(const float* X, const float* sq, int n, int d, int row_end
                       cudaStream_t st) {
   __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(tc_ws);
   __nv_bfloat16* L = reinterpret_cast<__nv_bfloat16*>((char*)tc_ws + align_up((size_t)n * plan.d_pad * 2, 256));
-  {
-    GLL_PROF(KID_CONVERT, st);
-    const long long work = (long long)n * (plan.d_pad / 2);
-    split_bf16_kernel<<<ceil_div(work, 256), 256, 0, st>>>(X, n, d, plan.d_pad, H, L);
-  }
-  GLL_LAUNCH_CHECK();
+  // H and L (bf16 hi / lo split of X, row stride d_pad) were written by sqnorm_split_kernel (knn.cu)
   CUtensorMap mAH, mAL, mBH, mBL;
   int rc;
   if ((rc = make_map(&mAH, H, n, plan.d_pad, TC_BM))) return rc;
