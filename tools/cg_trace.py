@@ -6,11 +6,12 @@ import graphlearninglayer_b200 as pkg
 from graphlearninglayer_b200 import _lib
 from oracle.gll_oracle import synth_inputs
 
-k_lab, m, d, l = 2048, 14336, 512, 10
+shape = sys.argv[1] if len(sys.argv) > 1 else 'c4'
+k_lab, m, d, l = (2048, 14336, 512, 10) if shape == 'c4' else (10000, 512, 512, 10)
 X, Y, _, yq = synth_inputs(2000, k_lab, m, d, l, 4.5)
 Xd = torch.as_tensor(X).cuda(); Yd = torch.as_tensor(Y).cuda()
 for _ in range(2): pkg.LaplaceLearningSparseHard.apply(Xd, Yd, 0.0, "auto")
-G = 148
+G = 148 if shape == 'c4' else 1
 trace = torch.zeros(G * 16 * 8, dtype=torch.int64, device="cuda")
 _lib.lib.gll_debug_cg_trace(trace.data_ptr())
 pkg.LaplaceLearningSparseHard.apply(Xd, Yd, 0.0, "auto")
