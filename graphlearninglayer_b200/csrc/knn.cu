@@ -546,7 +546,7 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
     if (rc) return rc;
     lay.stride = plan.max_splits;
     lay.tc = plan.aligned ? 2 : 1;
-    lay.row_tile = 128;
+    lay.row_tile = 128 * plan.rstep;  // rows per row group
     lay.col_tiles = plan.col_tiles;
     lay.grid = plan.grid;
     lay.units = plan.units;

@@ -28,7 +28,7 @@ __device__ __forceinline__ void list_insert(u64& mine, u64 x, int lane) {
 
 // Tensor-core candidate generation (knn_tc.cu).  plan.ok == 0: shape or configuration not handled, use the SIMT path.
 struct TcPlan {
-  int ok, d_pad, kblocks, row_tiles, col_tiles, grid, max_splits, rt0, aligned;
+  int ok, d_pad, kblocks, row_tiles, col_tiles, grid, max_splits, rt0, aligned, rstep;  // row_tiles counts row GROUPS of rstep tiles
   long long units;
   size_t ws_bytes;  // bf16 hi / lo copies of X
 };

@@ -93,6 +93,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
       : "memory");
 }
+// Same load delivered to the CTAs of the cluster selected by `mask` (same shared-memory offset and barrier offset in each)
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -100,6 +116,11 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at the same offset in every CTA of `mask` once the MMAs issued so far have retired
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -147,6 +168,10 @@ struct TcParams {
 __host__ __device__ inline int tc_cta_of_unit(long long u, int G, long long units) { return (int)(((u + 1) * G - 1) / units); }
 
 // ---------------------------------------------------------------------------------------------- the GEMM + top-k kernel
+// PAIR: launched as clusters of two CTAs that process the SAME column tile for two adjacent row tiles; each CTA fetches
+// half of the B tiles and multicasts it to both, so the L2 -> shared-memory operand traffic per CTA drops from 96 to 64 KB
+// per stage (this kernel is bound by that traffic on mid-size graphs).  The MMAs stay per-CTA (cta_group::1).
+template <bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_constant__ CUtensorMap mapAL,
                         const __grid_constant__ CUtensorMap mapBH, const __grid_constant__ CUtensorMap mapBL, TcParams P) {
@@ -156,7 +181,10 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
   uint8_t* smem = smem_raw + (base - raw);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int G = gridDim.x, b = blockIdx.x;
+  // work is dealt to CTAs, or to CTA pairs: G owners, this CTA belongs to owner b and is rank `crank` inside it
+  const int crank = PAIR ? (int)cluster_ctarank() : 0;
+  const int G = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x, b = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int RSTEP = PAIR ? 2 : 1;  // row tiles per unit
   const int C = P.col_tiles, KB = P.kblocks;
   long long u_begin, u_end;
   if (P.aligned) {
@@ -180,7 +208,7 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     tma_prefetch_desc(&mapBL);
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, PAIR ? 2 : 1);  // PAIR: both CTAs' MMAs must have consumed the stage
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
@@ -195,7 +223,10 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR)
+    cluster_sync_all();  // the peer's barriers must exist before anything is multicast into this CTA
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -205,7 +236,7 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
       int stage = 0;
       uint32_t phase = 0;
       for (long long u = u_begin; u < u_end; ++u) {
-        const int rt = P.rt0 + (int)(u / C), ct = (int)(u % C);
+        const int rt = P.rt0 + RSTEP * (int)(u / C) + crank, ct = (int)(u % C);
         for (int kk = 0; kk < KB; ++kk) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
           const uint32_t full = bar_full + 8 * stage;
@@ -213,8 +244,14 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
           mbar_arrive_expect_tx(full, TC_STAGE_BYTES);
           tma_load_2d(s0, &mapAH, full, kk * TC_BK, rt * TC_BM);
           tma_load_2d(s0 + TC_A_BYTES, &mapAL, full, kk * TC_BK, rt * TC_BM);
-          tma_load_2d(s0 + 2 * TC_A_BYTES, &mapBH, full, kk * TC_BK, ct * TC_BN);
-          tma_load_2d(s0 + 2 * TC_A_BYTES + TC_B_BYTES, &mapBL, full, kk * TC_BK, ct * TC_BN);
+          if (PAIR) {  // my half of the B tiles (128 of the 256 rows), delivered to both CTAs (128-row boxes: the A maps)
+            const uint32_t half = (uint32_t)crank * (TC_B_BYTES / 2);
+            tma_load_2d_mc(s0 + 2 * TC_A_BYTES + half, &mapAH, full, kk * TC_BK, ct * TC_BN + crank * (TC_BN / 2), 3);
+            tma_load_2d_mc(s0 + 2 * TC_A_BYTES + TC_B_BYTES + half, &mapAL, full, kk * TC_BK, ct * TC_BN + crank * (TC_BN / 2), 3);
+          } else {
+            tma_load_2d(s0 + 2 * TC_A_BYTES, &mapBH, full, kk * TC_BK, ct * TC_BN);
+            tma_load_2d(s0 + 2 * TC_A_BYTES + TC_B_BYTES, &mapBL, full, kk * TC_BK, ct * TC_BN);
+          }
           if (++stage == TC_STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -244,7 +281,10 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
             for (int k4 = 0; k4 < TC_BK / 16; ++k4)  // +32 B (two 16 B units) per K=16 step inside the swizzle atom
               tc_mma_bf16(d_tmem, da + (uint64_t)(2 * k4), db + (uint64_t)(2 * k4), TC_IDESC, (uint32_t)((kk | g | k4) != 0));
           }
-          tc_commit(bar_empty + 8 * stage);                 // frees the smem stage when these MMAs retire
+          if (PAIR)
+            tc_commit_mc(bar_empty + 8 * stage, 3);  // frees the stage in BOTH CTAs (the peer multicasts into mine)
+          else
+            tc_commit(bar_empty + 8 * stage);      // frees the smem stage when these MMAs retire
           if (kk == KB - 1) tc_commit(bar_tfull + 8 * acc);  // accumulator complete
         }
         __syncwarp();
@@ -272,7 +312,7 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
 
     auto flush = [&](int rt) {
       __syncwarp();
-      const int slot = P.aligned ? 0 : b - tc_cta_of_unit((long long)(rt - P.rt0) * C, G, P.units);
+      const int slot = P.aligned ? 0 : b - tc_cta_of_unit((long long)((rt - P.rt0) / RSTEP) * C, G, P.units);
       const float* wd = Ld - lane;
       const int* wi = Li - lane;
       for (int r = 0; r < 32; ++r) {  // lane = slot index e here; 256 B coalesced store per row
@@ -286,7 +326,7 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     };
 
     for (long long u = u_begin; u < u_end; ++u) {
-      const int rt = P.rt0 + (int)(u / C), ct = (int)(u % C);
+      const int rt = P.rt0 + RSTEP * (int)(u / C) + crank, ct = (int)(u % C);
       if (rt != cur_rt) {
         if (cur_rt >= 0) flush(cur_rt);
 #pragma unroll
@@ -401,7 +441,10 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR)
+    cluster_sync_all();  // nobody exits while the peer may still multicast into it or signal its barriers
+  else
+    __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS) : "memory");
@@ -455,17 +498,24 @@ TcPlan knn_tc_plan(int n, int d, int row_begin, int row_end) {
   p.d_pad = ceil_div(d, TC_BK) * TC_BK;
   p.kblocks = p.d_pad / TC_BK;
   p.rt0 = row_begin / TC_BM;
-  p.row_tiles = ceil_div(row_end - row_begin, TC_BM);
-  p.col_tiles = ceil_div(n, TC_BN);
-  p.units = (long long)p.row_tiles * p.col_tiles;
+  const int row_tiles = ceil_div(row_end - row_begin, TC_BM);
   const int sms = device_info().sms;
-  p.grid = (int)((p.units < (long long)sms) ? p.units : (long long)sms);
-  if (p.row_tiles >= 4 * sms) {  // big graphs: whole row tiles per CTA, one candidate set per row
-    p.aligned = 1;
+  p.col_tiles = ceil_div(n, TC_BN);
+  p.aligned = (row_tiles >= 4 * sms) ? 1 : 0;  // big graphs: whole row tiles per CTA, one candidate set per row
+  // mid-size graphs: CTA pairs (clusters of 2) that share the B tiles by TMA multicast; GLL_B200_KNN_PAIR=0/1 overrides
+  const char* pr = getenv("GLL_B200_KNN_PAIR");
+  p.rstep = (!p.aligned && row_tiles >= 2) ? 2 : 1;
+  if (pr && pr[0] == '0') p.rstep = 1;
+  if (pr && pr[0] == '1' && row_tiles >= 2) p.rstep = 2;
+  p.row_tiles = ceil_div(row_tiles, p.rstep);  // row groups: the unit of work is (row group, column tile)
+  p.units = (long long)p.row_tiles * p.col_tiles;
+  const int owners = sms / p.rstep;
+  p.grid = (int)((p.units < (long long)owners) ? p.units : (long long)owners);  // owners (CTAs or CTA pairs)
+  if (p.aligned) {
     p.max_splits = 1;
   } else {
     int ms = 1;
-    for (int rt = 0; rt < p.row_tiles; ++rt) {  // exact: CTAs touching each row tile
+    for (int rt = 0; rt < p.row_tiles; ++rt) {  // exact: owners touching each row group
       const int b0 = tc_cta_of_unit((long long)rt * p.col_tiles, p.grid, p.units);
       const int b1 = tc_cta_of_unit((long long)(rt + 1) * p.col_tiles - 1, p.grid, p.units);
       ms = max(ms, b1 - b0 + 1);
@@ -512,12 +562,30 @@ int knn_tc_candidates(const float* X, const float* sq, int n, int d, int row_end
   P.cand = cand;
   static bool attr_set = false;
   if (!attr_set) {
-    GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_gram_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_gram_topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_gram_topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
     attr_set = true;
   }
   {
     GLL_PROF(KID_GRAM_TOPK_TC, st);
-    knn_gram_topk_tc_kernel<<<plan.grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mAH, mAL, mBH, mBL, P);
+    if (plan.rstep == 2) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(2 * plan.grid);
+      cfg.blockDim = dim3(TC_THREADS);
+      cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      GLL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, knn_gram_topk_tc_kernel<true>, mAH, mAL, mBH, mBL, P));
+    } else {
+      knn_gram_topk_tc_kernel<false><<<plan.grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mAH, mAL, mBH, mBL, P);
+    }
   }
   GLL_LAUNCH_CHECK();
   return GLL_OK;
