@@ -182,6 +182,18 @@ def test_knn_paths_agree_and_tc_is_used(gll, monkeypatch):
     assert int(info[_lib.INFO_KNN_FALLBACK_ROWS].item()) < 0.02 * X.shape[0]
 
 
+def test_knn_cta_pair_multicast_variant(gll, monkeypatch):
+    """Opt-in cluster-of-2 variant of the tensor-core kernel (TMA multicast of the B tiles): identical lists."""
+    _, _lib = gll
+    X, *_ = O.synth_inputs(12, 3000, 1777, 200, 10, 3.5)
+    monkeypatch.setenv("GLL_B200_KNN_PATH", "tc")
+    monkeypatch.setenv("GLL_B200_KNN_PAIR", "0")
+    i0, d0, _ = run_knn(_lib, X)
+    monkeypatch.setenv("GLL_B200_KNN_PAIR", "1")
+    i1, d1, _ = run_knn(_lib, X)
+    assert torch.equal(i0, i1) and torch.equal(d0, d1)
+
+
 def test_knn_full_size_properties(gll):
     """C4 size (n=16384, d=512): properties that need no oracle: self first, sorted distances, symmetric distances on
     mutual pairs, distances equal to a torch fp64 recomputation on the chosen pairs, and k-th distance <= any
