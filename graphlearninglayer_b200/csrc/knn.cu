@@ -404,33 +404,145 @@ knn_fallback_kernel(const float* __restrict__ X, int n, int d, int k, const int*
     const int i = flag_rows[f];
     for (int t = threadIdx.x; t < d; t += blockDim.x) xs[t] = X[(size_t)i * d + t];
     __syncthreads();
-    double md = INFINITY;
-    int mj = 0x7fffffff;
-    for (int j = warp; j < n; j += FB_WARPS) {
-      if (j == i) continue;
-      double v = exact_d2<VEC4>(xs, X + (size_t)j * d, d, lane);
-      list_insert_d(md, mj, v, j, lane);
-    }
-    sd[warp][lane] = md;
-    sj[warp][lane] = mj;
-    __syncthreads();
-    if (warp == 0) {
-      for (int w = 1; w < FB_WARPS; ++w)
-        for (int t = 0; t < 32; ++t) {
-          int xj = sj[w][t];
-          if (xj == 0x7fffffff) break;
-          list_insert_d(md, mj, sd[w][t], xj, lane);
+    // k - 1 <= 32 neighbours fit one 32-wide list; larger k takes a second scan that only admits pairs beyond the 32nd
+    // (distance, index) of the first scan
+    double ex_d = -1.0;
+    int ex_j = -1;
+    for (int pass = 0; pass * 32 < k - 1; ++pass) {
+      double md = INFINITY;
+      int mj = 0x7fffffff;
+      for (int j = warp; j < n; j += FB_WARPS) {
+        if (j == i) continue;
+        double v = exact_d2<VEC4>(xs, X + (size_t)j * d, d, lane);
+        if (v > ex_d || (v == ex_d && j > ex_j)) list_insert_d(md, mj, v, j, lane);
+      }
+      sd[warp][lane] = md;
+      sj[warp][lane] = mj;
+      __syncthreads();
+      if (warp == 0) {
+        for (int w = 1; w < FB_WARPS; ++w)
+          for (int t = 0; t < 32; ++t) {
+            int xj = sj[w][t];
+            if (xj == 0x7fffffff) break;
+            list_insert_d(md, mj, sd[w][t], xj, lane);
+          }
+        const int slot = pass * 32 + lane;
+        if (slot < k - 1 && mj != 0x7fffffff) {
+          knn_idx[(size_t)i * k + 1 + slot] = mj;
+          knn_dist[(size_t)i * k + 1 + slot] = (float)sqrt(md);
         }
-      if (lane < k - 1 && mj != 0x7fffffff) {
-        knn_idx[(size_t)i * k + 1 + lane] = mj;
-        knn_dist[(size_t)i * k + 1 + lane] = (float)sqrt(md);
+        if (lane == 0 && pass == 0) {
+          knn_idx[(size_t)i * k] = i;
+          knn_dist[(size_t)i * k] = 0.f;
+        }
+        if (lane == 31) {  // threshold for the next scan
+          sd[0][0] = md;
+          sj[0][0] = mj;
+        }
       }
-      if (lane == 0) {
-        knn_idx[(size_t)i * k] = i;
-        knn_dist[(size_t)i * k] = 0.f;
-      }
+      __syncthreads();
+      ex_d = sd[0][0];
+      ex_j = sj[0][0];
+      __syncthreads();
     }
     __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k in (33, 64]: two candidate rounds of 32 (the second excludes the first by key), merged and re-ranked together.
+// Used by the evaluation path (utils.laplace asks for k = 50, utils.py:651); the layer itself uses k = 25.
+// ---------------------------------------------------------------------------------------------------------
+// one warp per row: union of the row's candidate sets of one round -> one sorted 32-list; optionally its last key
+__global__ void __launch_bounds__(RERANK_WARPS * 32)
+knn_merge_kernel(int row_end, CandLayout lay, const u64* __restrict__ cand, u64* __restrict__ merged, u64* __restrict__ excl) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = lay.row_begin + blockIdx.x * RERANK_WARPS + warp;
+  if (i >= row_end) return;
+  int splits = lay.stride;
+  if (lay.tc == 1) {
+    const long long rt = (i - lay.row_begin) / lay.row_tile;
+    const int b0 = (int)(((rt * lay.col_tiles + 1) * lay.grid - 1) / lay.units);
+    const int b1 = (int)((((rt + 1) * lay.col_tiles) * lay.grid - 1) / lay.units);
+    splits = b1 - b0 + 1;
+  }
+  u64 mine = KEY_INF;
+  for (int s = 0; s < splits; ++s) {
+    u64 c = cand[((size_t)i * lay.stride + s) * KC + lane];
+    for (int t = 0; t < KC; ++t) {
+      u64 x = __shfl_sync(FULL, c, t);
+      if (x != KEY_INF) list_insert(mine, x, lane);
+    }
+  }
+  merged[(size_t)(i - lay.row_begin) * KC + lane] = mine;
+  if (excl != nullptr && lane == KC - 1) excl[i] = mine;  // KEY_INF if fewer than 32 columns exist: round 2 finds nothing
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(RERANK_WARPS * 32)
+knn_rerank64_kernel(const float* __restrict__ X, const float* __restrict__ sq, const unsigned* __restrict__ sqmax_bits, int n, int d,
+                    int k, int row_begin, int row_end, const u64* __restrict__ m1, const u64* __restrict__ m2, float err_coef,
+                    int* __restrict__ knn_idx, float* __restrict__ knn_dist, int* __restrict__ flag_count,
+                    int* __restrict__ flag_rows) {
+  extern __shared__ __align__(16) float xs[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = row_begin + blockIdx.x * RERANK_WARPS + warp;
+  if (i >= row_end) return;
+  float* xi = xs + (size_t)warp * d;
+  for (int t = lane; t < d; t += 32) xi[t] = X[(size_t)i * d + t];
+  __syncwarp();
+  const u64 ca = m1[(size_t)(i - row_begin) * KC + lane], cb = m2[(size_t)(i - row_begin) * KC + lane];
+  const u64 last = __shfl_sync(FULL, cb, KC - 1);
+  const float lower = (last == KEY_INF) ? INFINITY : key_dist(last);  // every non-candidate has d~^2 >= lower
+  double da = INFINITY, db = INFINITY;
+  int ja = -1, jb = -1;
+  for (int c = 0; c < 2 * KC; ++c) {
+    const u64 kc = __shfl_sync(FULL, (c < KC) ? ca : cb, c & (KC - 1));
+    if (kc == KEY_INF) continue;
+    const int j = key_idx(kc);
+    const double v = exact_d2<VEC4>(xi, X + (size_t)j * d, d, lane);
+    if (lane == (c & (KC - 1))) {
+      if (c < KC) {
+        da = v;
+        ja = j;
+      } else {
+        db = v;
+        jb = j;
+      }
+    }
+  }
+  int ra = 0, rb = 0;
+  for (int c = 0; c < 2 * KC; ++c) {
+    const double od = __shfl_sync(FULL, (c < KC) ? da : db, c & (KC - 1));
+    const int oj = __shfl_sync(FULL, (c < KC) ? ja : jb, c & (KC - 1));
+    if (oj < 0) continue;
+    ra += (od < da || (od == da && oj < ja)) ? 1 : 0;
+    rb += (od < db || (od == db && oj < jb)) ? 1 : 0;
+  }
+  if (ja >= 0 && ra < k - 1) {
+    knn_idx[(size_t)i * k + 1 + ra] = ja;
+    knn_dist[(size_t)i * k + 1 + ra] = (float)sqrt(da);
+  }
+  if (jb >= 0 && rb < k - 1) {
+    knn_idx[(size_t)i * k + 1 + rb] = jb;
+    knn_dist[(size_t)i * k + 1 + rb] = (float)sqrt(db);
+  }
+  if (lane == 0) {
+    knn_idx[(size_t)i * k] = i;
+    knn_dist[(size_t)i * k] = 0.f;
+  }
+  // completeness proof against the (k-1)-th exact distance
+  const unsigned wa = __ballot_sync(FULL, ja >= 0 && ra == k - 2), wb = __ballot_sync(FULL, jb >= 0 && rb == k - 2);
+  bool ok = false;
+  if (wa | wb) {
+    const double dk = wa ? __shfl_sync(FULL, da, __ffs(wa) - 1) : __shfl_sync(FULL, db, __ffs(wb) - 1);
+    const float sqm = __uint_as_float(*sqmax_bits);
+    const double errb = (double)err_coef * ((double)sq[i] + (double)sqm);
+    ok = ((double)lower - errb > dk) || (lower == INFINITY);
+  }
+  if (!ok && lane == 0) {
+    int p = atomicAdd(flag_count, 1);
+    flag_rows[p] = i;
   }
 }
 
@@ -474,6 +586,40 @@ int knn_finish(const float* X, const float* sq, const unsigned* sqmax_bits, int 
   return GLL_OK;
 }
 
+static int knn_finish64(const float* X, const float* sq, const unsigned* sqmax_bits, int n, int d, int k, int row_begin, int row_end,
+                       const u64* m1, const u64* m2, float err_coef, int* knn_idx, float* knn_dist, int* flag_count,
+                       int* flag_rows, int* info, cudaStream_t st) {
+  const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  const size_t smem = sizeof(float) * (size_t)RERANK_WARPS * d;
+  const int blocks = ceil_div(row_end - row_begin, RERANK_WARPS);
+  {
+    GLL_PROF(KID_RERANK, st);
+    if (vec4) {
+      if (smem > 48 * 1024)
+        GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_rerank64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      knn_rerank64_kernel<true><<<blocks, RERANK_WARPS * 32, smem, st>>>(X, sq, sqmax_bits, n, d, k, row_begin, row_end, m1, m2,
+                                                                          err_coef, knn_idx, knn_dist, flag_count, flag_rows);
+    } else {
+      if (smem > 48 * 1024)
+        GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_rerank64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      knn_rerank64_kernel<false><<<blocks, RERANK_WARPS * 32, smem, st>>>(X, sq, sqmax_bits, n, d, k, row_begin, row_end, m1, m2,
+                                                                           err_coef, knn_idx, knn_dist, flag_count, flag_rows);
+    }
+  }
+  GLL_LAUNCH_CHECK();
+  const size_t fsmem = sizeof(float) * (size_t)d;
+  const int fblocks = device_info().sms * 2;
+  {
+    GLL_PROF(KID_KNN_FALLBACK, st);
+    if (vec4)
+      knn_fallback_kernel<true><<<fblocks, FB_WARPS * 32, fsmem, st>>>(X, n, d, k, flag_count, flag_rows, knn_idx, knn_dist, info);
+    else
+      knn_fallback_kernel<false><<<fblocks, FB_WARPS * 32, fsmem, st>>>(X, n, d, k, flag_count, flag_rows, knn_idx, knn_dist, info);
+  }
+  GLL_LAUNCH_CHECK();
+  return GLL_OK;
+}
+
 static int simt_splits(int n, int rows, int* cols_per_split) {
   int row_tiles = ceil_div(rows, BM), col_tiles = ceil_div(n, BN);
   int want = ceil_div(2 * device_info().sms, row_tiles);
@@ -500,13 +646,14 @@ size_t knn_ws_bytes(int n, int d, int k, int row_begin, int row_end) {
   b += align_up(sizeof(u64) * rows * (size_t)cand_stride(n, d, row_begin, row_end) * KC, 256);     // cand
   b += align_up(sizeof(int) * rows, 256);                                                          // flag_rows
   b += knn_tc_ws_upper(n, d);                                           // bf16 hi / lo copies for the tensor-core path
+  if (k > KC + 1) b += 2 * align_up(sizeof(u64) * rows * KC, 256) + align_up(sizeof(u64) * (size_t)n, 256);  // merged lists, excl
   return b + 1024;
 }
 
 int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int* knn_idx, float* knn_dist, int* info,
             void* ws, size_t ws_bytes, cudaStream_t st) {
   GLL_REQUIRE(X && knn_idx && knn_dist && ws, "null pointer");
-  GLL_REQUIRE(n >= k && k >= 2 && k <= KC + 1, "need n >= k and 2 <= k <= 33");
+  GLL_REQUIRE(n >= k && k >= 2 && k <= 2 * KC, "need n >= k and 2 <= k <= 64");
   GLL_REQUIRE(d >= 1, "d must be positive");
   GLL_REQUIRE(0 <= row_begin && row_begin < row_end && row_end <= n, "bad row range");
   if (ws_bytes < knn_ws_bytes(n, d, k, row_begin, row_end)) {
@@ -541,8 +688,39 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
   }
   GLL_LAUNCH_CHECK();
 
+  if (k > KC + 1) {
+    // ---- k in (33, 64]: two rounds of the tensor-core search, the second admits only keys beyond the first round's 32nd ----
+    GLL_REQUIRE(plan.ok, "k > 33 needs the tensor-core path (n >= 256, row range starting on a multiple of 128)");
+    u64* merged1 = cv.take<u64>((size_t)rows * KC);
+    u64* merged2 = cv.take<u64>((size_t)rows * KC);
+    u64* excl = cv.take<u64>(n);
+    lay.stride = plan.max_splits;
+    lay.tc = plan.aligned ? 2 : 1;
+    lay.row_tile = 128 * plan.rstep;
+    lay.col_tiles = plan.col_tiles;
+    lay.grid = plan.grid;
+    lay.units = plan.units;
+    lay.row_begin = row_begin;
+    const int mblocks = ceil_div(rows, RERANK_WARPS);
+    int rc = knn_tc_candidates(X, sq, n, d, row_end, plan, tc_ws, cand, nullptr, st);
+    if (rc) return rc;
+    {
+      GLL_PROF(KID_RERANK, st);
+      knn_merge_kernel<<<mblocks, RERANK_WARPS * 32, 0, st>>>(row_end, lay, cand, merged1, excl);
+    }
+    GLL_LAUNCH_CHECK();
+    rc = knn_tc_candidates(X, sq, n, d, row_end, plan, tc_ws, cand, excl, st);
+    if (rc) return rc;
+    {
+      GLL_PROF(KID_RERANK, st);
+      knn_merge_kernel<<<mblocks, RERANK_WARPS * 32, 0, st>>>(row_end, lay, cand, merged2, nullptr);
+    }
+    GLL_LAUNCH_CHECK();
+    return knn_finish64(X, sq, sqmax_bits, n, d, k, row_begin, row_end, merged1, merged2, knn_tc_err_coef(d), knn_idx, knn_dist,
+                        flag_count, flag_rows, info, st);
+  }
   if (plan.ok) {  // tcgen05 / TMA Gram GEMM with the fused top-k epilogue
-    int rc = knn_tc_candidates(X, sq, n, d, row_end, plan, tc_ws, cand, st);
+    int rc = knn_tc_candidates(X, sq, n, d, row_end, plan, tc_ws, cand, nullptr, st);
     if (rc) return rc;
     lay.stride = plan.max_splits;
     lay.tc = plan.aligned ? 2 : 1;

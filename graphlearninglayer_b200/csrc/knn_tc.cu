@@ -162,6 +162,7 @@ struct TcParams {
   long long units;
   const float* sq;
   u64* cand;
+  const u64* excl;    // optional [n]: per row, only keys > excl[row] are candidates (second round of a k > 33 search)
 };
 
 // CTA that owns unit u when `units` units are dealt contiguously to G CTAs (CTA b owns [b*units/G, (b+1)*units/G))
@@ -307,6 +308,8 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     uint32_t acc_phase = 0;
     // Ranking inside a row only needs key = |x_j|^2 - 2 x_i.x_j; |x_i|^2 is added when the set is flushed.
     float thr = INFINITY;
+    u64 excl_row = 0ull;   // second-round searches: skip everything the first round already holds
+    float sqi_row = 0.f;
     float* sqj_s = reinterpret_cast<float*>(smem + TC_OFF_SQJ);
     const int et = (warp - 2) * 32 + lane;  // 0..127 over the epilogue warps
 
@@ -339,6 +342,10 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
           gp[t] = 8 * t;
         }
         gi = rt * TC_BM + quarter * 32 + lane;
+        if (P.excl != nullptr) {
+          excl_row = (gi < P.n) ? __ldg(P.excl + gi) : 0ull;
+          sqi_row = (gi < P.n) ? __ldg(P.sq + gi) : 0.f;
+        }
       }
       const int c_begin = ct * TC_BN;
       // stage |x_j|^2 of the unit's 256 columns for all four epilogue warps (+inf masks columns beyond n)
@@ -381,7 +388,10 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
             float dsel = v[0];
 #pragma unroll
             for (int t = 1; t < TC_CHUNK; ++t) dsel = (t == c) ? v[t] : dsel;
-            if (dsel < thr) {  // thr may have tightened since the scan
+            // second round: the key is rebuilt exactly as the first round flushed it (dd + |x_i|^2, index), so the
+            // lexicographic test excludes precisely the first round's set
+            const bool fresh = (P.excl == nullptr) || (make_key(dsel + sqi_row, j0 + c) > excl_row);
+            if (dsel < thr && fresh) {  // thr may have tightened since the scan
               // the row's 32 slots are 4 groups of 8 with the group maxima (value, slot) cached in registers: replace
               // the overall maximum, rescan only its group (8 shared-memory loads instead of 32)
               int g = 0;
@@ -538,7 +548,7 @@ float knn_tc_err_coef(int d) {
 }
 
 int knn_tc_candidates(const float* X, const float* sq, int n, int d, int row_end, const TcPlan& plan, void* tc_ws, u64* cand,
-                      cudaStream_t st) {
+                      const u64* excl, cudaStream_t st) {
   __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(tc_ws);
   __nv_bfloat16* L = reinterpret_cast<__nv_bfloat16*>((char*)tc_ws + align_up((size_t)n * plan.d_pad * 2, 256));
   // H and L (bf16 hi / lo split of X, row stride d_pad) were written by sqnorm_split_kernel (knn.cu)
@@ -560,6 +570,7 @@ int knn_tc_candidates(const float* X, const float* sq, int n, int d, int row_end
   P.row_tiles = plan.row_tiles;
   P.sq = sq;
   P.cand = cand;
+  P.excl = excl;
   static bool attr_set = false;
   if (!attr_set) {
     GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_gram_topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));

@@ -102,7 +102,7 @@ size_t gll_workspace_bytes(int n, int d, int k, int l, int k_lab);
  * Stage entry points (each is also what the parity tests call)
  * ------------------------------------------------------------------------------------------- */
 
-/* K1. Exact k nearest neighbours of every row of X (n x d), Euclidean, self in slot 0 with distance 0,
+/* K1. Exact k nearest neighbours (2 <= k <= 64; k > 33 runs two candidate rounds and needs n >= 256) of every row of X (n x d), Euclidean, self in slot 0 with distance 0,
  * remaining slots ordered by (distance, index).  Replaces gl.weightmatrix.knnsearch(...,'annoy') at
  * GLL.py:181-189.  Candidate selection runs as a tiled Gram GEMM with a fused per-row top-k epilogue (the
  * n x n matrix never reaches HBM); kept distances are recomputed as sqrt(sum (x_i-x_j)^2) in fp64 and

@@ -510,3 +510,62 @@ def test_knn_row_blocks_equal_full_search(gll):
                                          ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream), "gll_knn_rows")
     torch.cuda.synchronize()
     assert torch.equal(idx, full_i) and torch.equal(dd, full_d)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# evaluation path: utils.laplace uses k = 50 neighbours and the Jacobi-scaled stable_conjgrad
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [34, 50, 64])
+def test_knn_large_k_two_round_search(gll, k):
+    _, _lib = gll
+    X, *_ = O.synth_inputs(17, 900, 2100, 128, 10, 3.0)
+    ref_ind, ref_dist = O.exact_knn(X, k)
+    idx, dist, info = run_knn(_lib, X, k)
+    ind = idx.cpu().numpy().astype(np.int64)
+    exact, tie, bad = O.knn_sets_match(ind, ref_ind, ref_dist)
+    assert bad == 0, (exact, tie, bad)
+    same = np.all(ind == ref_ind, axis=1)
+    assert same.mean() > 0.999
+    assert np.array_equal(dist.cpu().numpy()[same], ref_dist[same].astype(np.float32))
+
+
+def test_knn_large_k_with_duplicates(gll):
+    _, _lib = gll
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((400, 24)).astype(np.float32)
+    X[50:120] = X[50]  # 70 identical points: more zero-distance ties than one round of 32 can hold
+    ref_ind, ref_dist = O.exact_knn(X, 50, slack=40)
+    idx, dist, _ = run_knn(_lib, X, 50)
+    assert np.array_equal(np.sort(dist.cpu().numpy(), axis=1), np.sort(ref_dist.astype(np.float32), axis=1))
+    assert np.array_equal(idx.cpu().numpy()[50:120, :50], ref_ind[50:120])  # ties resolved by index in both
+
+
+def test_eval_path_like_utils_laplace(gll):
+    """The reference's evaluation routine (utils.py:570-593) run on our drop-in wrappers: k = 50 graph, Jacobi-scaled
+    system, stable_conjgrad to 1e-10, argmax accuracy -- against the same steps on the fp64 oracle."""
+    import scipy.sparse as sparse
+
+    pkg, _ = gll
+    X, Y, y_base, yq = O.synth_inputs(23, 500, 2500, 64, 10, 2.0)
+    k_lab, tau, eps = 500, 1e-8, "auto"
+
+    def laplace(knn_sym_dist, stable_conjgrad):          # utils.py:570-593, condensed
+        W = knn_sym_dist(X, 50, eps)[0]
+        L = (sparse.diags(np.asarray(W.sum(axis=0)).ravel()) - W).tocsr()
+        Luu = (L[k_lab:, k_lab:] + tau * sparse.identity(X.shape[0] - k_lab)).tocsr()
+        Lul = L[k_lab:, :k_lab]
+        M = sparse.diags(1.0 / np.sqrt(Luu.diagonal() + 1e-10))
+        Pred = stable_conjgrad(M @ Luu @ M, -(M @ (Lul @ Y.astype(np.float64))))
+        return M @ Pred
+
+    def oracle_knn_sym_dist(data, k, epsilon):
+        g = O.build_graph(data, k, epsilon)
+        return g.W, g.V, g.modV, None, g.knn_ind
+
+    def oracle_cg(A, b):
+        return O.textbook_cg(sparse.csr_matrix(A), b, tol=1e-12)[0]
+
+    ours = laplace(pkg.knn_sym_dist, pkg.stable_conjgrad)
+    ref = laplace(oracle_knn_sym_dist, oracle_cg)
+    assert O.max_rel(ours, ref) < 1e-6
+    assert np.array_equal(ours.argmax(axis=1), ref.argmax(axis=1))
