@@ -353,11 +353,15 @@ def run_b200(args, rank, world, local_rank):
             "scaling": "strong" if sharded else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic gaussian clusters (oracle.synth_inputs), L2-normalised, one graph per rank",
             "config": {"workload": args.workload + ": " + WORKLOAD_DESC[args.workload], "l2": "flushed between timed steps "
-                       "(256 MiB memset outside the event pairs)", "parallelism": (f"one graph over {world} rank(s): rows (kNN, backward) + class columns (CG)" if sharded
+                       "(256 MiB memset outside the event pairs)", "parallelism": (f"one graph over {world} rank(s): rows (kNN, backward) + "
+                                       + ("class columns (CG, no per-iteration collective)" if args.cg_partition == "columns" else
+                                          "rows (CG: NCCL all-gather of the iterate + all-reduce of the dot products per iteration)")
+                                       if sharded
                                        else f"independent graphs x{world}"),
                        "cg_tol": 1e-7, "graph": {"nnz": info["nnz"], "nnz_uu": info["nnz_uu"],
                                                  "cg_iters_fwd": info["cg_iters_fwd"], "cg_iters_bwd": info["cg_iters_bwd"],
-                                                 "knn_fallback_rows": info["knn_fallback_rows"], "status": info["status"]}},
+                                                 "knn_fallback_rows": info["knn_fallback_rows"], "status": info["status"],
+                                                 **({"cg_solve_ms_fwd_bwd": info.get("cg_solve_ms")} if sharded else {})}},
             "e2e": {"value": jobs * 1e3 / (e2e_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kern,
@@ -397,10 +401,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--cg-partition", choices=["columns", "rows"], default="columns",
+                    help="sharded workloads: split the CG solves by class columns (no per-iteration collective) or by rows "
+                         "(all-gather + all-reduce per iteration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-large-graph", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    os.environ["GLL_B200_SHARD_CG"] = args.cg_partition
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -53,7 +53,7 @@ std::atomic<long long> g_launches[KID_COUNT];
 const char* const g_kernel_names[KID_COUNT] = {
     "sqnorm", "knn_gram_topk_simt", "knn_gram_topk_tcgen05", "knn_rerank", "knn_fallback", "graph_count", "scan",
     "graph_fill", "graph_sort_rows", "edge_weights", "uu_fill", "cg_persistent", "pack_unpack", "edge_grad",
-    "row_gather", "convert"};
+    "row_gather", "convert", "cg_rows"};
 }  // namespace
 
 ProfScope::ProfScope(int id_, cudaStream_t st_) : id(id_), st(st_), slot(nullptr) {
@@ -294,6 +294,26 @@ int gll_backward_edges_rows(const float* X, int n, int d, int l, int k_lab, int 
                             void* stream) {
   return backward_edges_run(X, n, d, l, k_lab, eps_auto, row_ptr, col, dist, w, eps, kappa, ut, wt, gv, bvec, dX, row_begin,
                             row_end, phases, (cudaStream_t)stream);
+}
+
+size_t gll_cg_rows_workspace_bytes(int rows_local, int l) { return cg_rows_ws_bytes(rows_local, l); }
+
+int gll_cg_rows_init(const float* diag, const float* rhs, int m, int l, int row_lo, int row_hi, float* x, float* u_full,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  return cg_rows_init(diag, rhs, m, l, row_lo, row_hi, x, u_full, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gll_cg_rows_spmv(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, int m, int l, int row_lo,
+                     int row_hi, const float* u_full, double* sums, void* workspace, size_t workspace_bytes, void* stream) {
+  return cg_rows_spmv(uu_ptr, uu_col, uu_val, diag, m, l, row_lo, row_hi, u_full, sums, workspace, workspace_bytes,
+                      (cudaStream_t)stream);
+}
+
+int gll_cg_rows_update(const float* diag, int m, int l, int row_lo, int row_hi, const double* sums, int iter, int max_iter,
+                       float tol, float* x, float* u_full, int* ctrl, float* resid_out, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  return cg_rows_update(diag, m, l, row_lo, row_hi, sums, iter, max_iter, tol, x, u_full, ctrl, resid_out, workspace,
+                        workspace_bytes, (cudaStream_t)stream);
 }
 
 int gll_pack_columns(const float* src, int rows, int lp_src, int c0, int cnt, float* dst, int lp_dst, void* stream) {

@@ -92,7 +92,7 @@ __device__ __forceinline__ float ordered_to_float(uint32_t u) {
 enum KernelId {
   KID_SQNORM = 0, KID_GRAM_TOPK, KID_GRAM_TOPK_TC, KID_RERANK, KID_KNN_FALLBACK, KID_GRAPH_COUNT, KID_SCAN,
   KID_GRAPH_FILL, KID_GRAPH_SORT, KID_WEIGHTS, KID_UU_FILL, KID_CG, KID_PACK, KID_EDGE_GRAD, KID_ROW_GATHER,
-  KID_CONVERT, KID_COUNT
+  KID_CONVERT, KID_CG_ROWS, KID_COUNT
 };
 // RAII: counts the launch; when profiling is on, brackets it with two events on the launch stream.
 struct ProfScope {
@@ -123,6 +123,15 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
            int l, float tol, int max_iter, float* x, int* iters_out, float* resid_out, int* status_out, void* ws,
            size_t ws_bytes, cudaStream_t st);
 size_t cg_ws_bytes(int m, int l);
+
+// row-partitioned CG (cg_rows.cu): stage launchers, the host runs the NCCL collectives between them
+size_t cg_rows_ws_bytes(int rows_local, int l);
+int cg_rows_init(const float* diag, const float* rhs, int m, int l, int row_lo, int row_hi, float* x, float* u_full, void* ws,
+                 size_t ws_bytes, cudaStream_t st);
+int cg_rows_spmv(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, int m, int l, int row_lo, int row_hi,
+                 const float* u_full, double* sums, void* ws, size_t ws_bytes, cudaStream_t st);
+int cg_rows_update(const float* diag, int m, int l, int row_lo, int row_hi, const double* sums, int iter, int max_iter, float tol,
+                   float* x, float* u_full, int* ctrl, float* resid_out, void* ws, size_t ws_bytes, cudaStream_t st);
 
 int backward_edges_run(const float* X, int n, int d, int l, int k_lab, int eps_auto, const int* row_ptr,
                        const int* col, const float* dist, const float* w, const float* eps, const int* kappa,

@@ -6,8 +6,12 @@ Every rank holds the full feature matrix X (the encoder output is all-gathered b
 nn.DataParallel gather, utils.py:547-548).  Inside the layer the path is cut along its natural shards:
 
   rows      kNN search (K1) and the backward gather (K5/K6): rank r owns a block of nodes                [NCCL all-gather]
-  columns   both CG solves (K4): rank r owns a block of the l class columns.  Columns of the multi-RHS CG are independent
-            (per-column alpha/beta, GLL.py:262-269), so there is NO communication inside the solver      [NCCL all-gather]
+  columns   both CG solves (K4), default: rank r owns a block of the l class columns.  Columns of the multi-RHS CG are
+            independent (per-column alpha/beta, GLL.py:262-269), so there is NO communication inside the solver
+                                                                                                         [NCCL all-gather]
+  rows      both CG solves, `cg_partition="rows"` (or GLL_B200_SHARD_CG=rows) -- the partition BASELINE.json's north star
+            names: rank r owns a block of the unlabeled rows of x, r, p, s; every iteration exchanges the iterate with one
+            all-gather and the three dot products with one all-reduce        [NCCL all-gather + all-reduce per iteration]
   replicated graph symmetrisation and weights (K2, K3): O(E) integer/byte work, a few ms at 1M nodes
 
 Collectives per call: forward 2 all-gathers (kNN lists; U column blocks), backward 3 (w column blocks; b; dX row blocks).
@@ -68,11 +72,31 @@ class _Comm:
         return list(out.unbind(0))
 
 
+    def all_gather_blocks_(self, full: torch.Tensor, per: int) -> None:
+        """In place: block r of `full` (rows [r*per, (r+1)*per)) is rank r's contribution.  Virtual ranks share `full`."""
+        if self.real:
+            r = self.ranks[0]
+            dist.all_gather_into_tensor(full, full[r * per:(r + 1) * per], group=self.group)
+
+    def all_reduce_sum_(self, parts: dict) -> None:
+        """parts: {rank: tensor}; every tensor becomes the sum over all ranks (fixed rank order when emulated)."""
+        if self.real:
+            (mine,) = parts.values()
+            dist.all_reduce(mine, op=dist.ReduceOp.SUM, group=self.group)
+        elif self.world > 1:
+            total = parts[0].clone()
+            for r in range(1, self.world):
+                total += parts[r]
+            for r in range(self.world):
+                parts[r].copy_(total)
+
+
 class _Graph:
     pass
 
 
-def _forward(X: torch.Tensor, Y: torch.Tensor, tau: float, epsilon, comm: _Comm, k: int = K_NEIGHBOURS):
+def _forward(X: torch.Tensor, Y: torch.Tensor, tau: float, epsilon, comm: _Comm, k: int = K_NEIGHBOURS,
+             cg_partition: str = "columns"):
     dev = X.device
     n, d = X.shape
     k_lab, l = Y.shape
@@ -81,6 +105,7 @@ def _forward(X: torch.Tensor, Y: torch.Tensor, tau: float, epsilon, comm: _Comm,
     s = _stream_ptr(dev)
     g = _Graph()
     g.n, g.d, g.k, g.l, g.k_lab, g.m = n, d, k, l, k_lab, m
+    g.cg_partition = cg_partition
     g.lp = lib.gll_padded_classes(l)
     emax = lib.gll_max_edges(n, k)
     eps_auto = isinstance(epsilon, str)
@@ -136,7 +161,7 @@ def _forward(X: torch.Tensor, Y: torch.Tensor, tau: float, epsilon, comm: _Comm,
 
     # ---- K4, columns: each rank solves its block of class columns ----
     g.iters_fwd = torch.zeros(comm.world, dtype=i32, device=dev)
-    _solve_columns(g, rhs, g.ut[k_lab:], _cg_tol(), comm, g.iters_fwd)
+    _solve(g, rhs, g.ut[k_lab:], _cg_tol(), comm, g.iters_fwd)
     pred64 = os.environ.get("GLL_B200_PRED_DTYPE", "float64") != "float32"
     pred = torch.empty((m, l), dtype=torch.float64 if pred64 else f32, device=dev)
     _lib.check(lib.gll_unpack_pred(g.ut[k_lab:].data_ptr(), m, l, pred.data_ptr(), int(pred64), s), "gll_unpack_pred")
@@ -174,6 +199,75 @@ def _solve_columns(g, rhs: torch.Tensor, out: torch.Tensor, tol: float, comm: _C
                        "gll_unpack_columns")
 
 
+def m_block(m: int, rank: int, world: int):
+    """Unlabeled rows owned by `rank` in the row-partitioned CG: equal blocks of ceil(m/world) rounded up to 32."""
+    per = -(-m // world)
+    per = -(-per // 32) * 32
+    lo = min(m, rank * per)
+    hi = min(m, lo + per)
+    return lo, hi, per
+
+
+def _solve_rows(g, rhs: torch.Tensor, out: torch.Tensor, tol: float, comm: _Comm, iters: torch.Tensor):
+    """out = A^-1 rhs with the ROWS of the system split over the ranks (csrc/cg_rows.cu): per iteration one all-gather of
+    the iterate u (m x lp fp32) and one all-reduce of 3*lp fp64 dot products; out and rhs are m x lp."""
+    dev = rhs.device
+    s = _stream_ptr(dev)
+    _, _, per = m_block(g.m, 0, comm.world)
+    u_full = torch.zeros((comm.world * per, g.lp), dtype=torch.float32, device=dev)
+    x_full = torch.zeros((comm.world * per, g.lp), dtype=torch.float32, device=dev)
+    resid = torch.zeros(1, dtype=torch.float32, device=dev)
+    st = {}
+    for r in comm.ranks:
+        lo, hi, _ = m_block(g.m, r, comm.world)
+        wsb = lib.gll_cg_rows_workspace_bytes(max(hi - lo, 1), g.l)
+        ws = _bytes(wsb, dev)
+        sums = torch.zeros(3 * g.lp, dtype=torch.float64, device=dev)
+        ctrl = torch.zeros(4, dtype=torch.int32, device=dev)
+        st[r] = (lo, hi, ws, wsb, sums, ctrl)
+        _lib.check(lib.gll_cg_rows_init(g.diag.data_ptr(), rhs.data_ptr(), g.m, g.l, lo, hi, x_full.data_ptr(), u_full.data_ptr(),
+                                        ws.data_ptr(), wsb, s), "gll_cg_rows_init")
+    maxit = _cg_maxit()
+    check_every = max(1, int(os.environ.get("GLL_B200_ROWS_CHECK_EVERY", "2")))
+    first = comm.ranks[0]
+    for it in range(maxit + 1):
+        comm.all_gather_blocks_(u_full, per)
+        for r in comm.ranks:
+            lo, hi, ws, wsb, sums, ctrl = st[r]
+            _lib.check(lib.gll_cg_rows_spmv(g.uu_ptr.data_ptr(), g.uu_col.data_ptr(), g.uu_val.data_ptr(), g.diag.data_ptr(), g.m,
+                                            g.l, lo, hi, u_full.data_ptr(), sums.data_ptr(), ws.data_ptr(), wsb, s),
+                       "gll_cg_rows_spmv")
+        comm.all_reduce_sum_({r: st[r][4] for r in comm.ranks})
+        for r in comm.ranks:
+            lo, hi, ws, wsb, sums, ctrl = st[r]
+            _lib.check(lib.gll_cg_rows_update(g.diag.data_ptr(), g.m, g.l, lo, hi, sums.data_ptr(), it, maxit, tol,
+                                              x_full.data_ptr(), u_full.data_ptr(), ctrl.data_ptr(), resid.data_ptr(),
+                                              ws.data_ptr(), wsb, s), "gll_cg_rows_update")
+        # the stop flag is identical on every rank (same reduced sums); reading it synchronises, so not every iteration --
+        # iterations after the stop are no-ops on the device
+        if (it + 1) % check_every == 0 or it == maxit:
+            if int(st[first][5][0].item()) != 0:
+                break
+    comm.all_gather_blocks_(x_full, per)
+    out.copy_(x_full[:g.m])
+    ctrl = st[first][5]
+    for r in comm.ranks:
+        iters[r:r + 1].copy_(ctrl[1:2])
+    g.info[_lib.INFO_STATUS:_lib.INFO_STATUS + 1] |= ctrl[2:3]
+    g.cg_rows_resid = resid
+
+
+def _solve(g, rhs, out, tol, comm, iters):
+    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))  # solve incl. its collectives
+    ev[0].record()
+    if g.cg_partition == "rows":
+        _solve_rows(g, rhs, out, tol, comm, iters)
+    else:
+        _solve_columns(g, rhs, out, tol, comm, iters)
+    ev[1].record()
+    g.solve_events = getattr(g, "solve_events", []) + [ev]
+
+
 def _backward(g, X: torch.Tensor, grad_output: torch.Tensor, comm: _Comm) -> torch.Tensor:
     dev = X.device
     f32 = torch.float32
@@ -187,7 +281,7 @@ def _backward(g, X: torch.Tensor, grad_output: torch.Tensor, comm: _Comm) -> tor
     _lib.check(lib.gll_pack_grad(gout.data_ptr(), int(gout.dtype == torch.float64), m, l, rhs.data_ptr(), s), "gll_pack_grad")
     wt = torch.zeros((n, g.lp), dtype=f32, device=dev)  # GLL.py:104: zero rows for the labeled nodes
     g.iters_bwd = torch.zeros(comm.world, dtype=torch.int32, device=dev)
-    _solve_columns(g, rhs, wt[k_lab:], -_cg_tol(), comm, g.iters_bwd)
+    _solve(g, rhs, wt[k_lab:], -_cg_tol(), comm, g.iters_bwd)
 
     # ---- K5 rows -> all-gather b -> K6 rows -> all-gather dX ----
     _, _, per = row_block(n, 0, comm.world)
@@ -219,19 +313,23 @@ def _backward(g, X: torch.Tensor, grad_output: torch.Tensor, comm: _Comm) -> tor
 class ShardedLaplaceLearning(torch.autograd.Function):
     """`LaplaceLearningSparseHard` (GLL.py:10-177) for ONE graph spread over the ranks of a process group.
 
-    forward(X, label_matrix, tau=0, epsilon='auto', group=None, emulate=0): every rank passes the SAME X and labels and
-    receives the same full prediction; backward returns the full dX on every rank."""
+    forward(X, label_matrix, tau=0, epsilon='auto', group=None, emulate=0, cg_partition=None): every rank passes the SAME X
+    and labels and receives the same full prediction; backward returns the full dX on every rank.  cg_partition: "columns"
+    (default; or GLL_B200_SHARD_CG) / "rows" -- how the two CG solves are split (module docstring)."""
 
     @staticmethod
-    def forward(ctx, X, label_matrix, tau=0, epsilon="auto", group=None, emulate=0):
+    def forward(ctx, X, label_matrix, tau=0, epsilon="auto", group=None, emulate=0, cg_partition=None):
         _require_cuda(X, "features")
         Xc = X.detach().float().contiguous()
         Y = label_matrix.detach().to(device=X.device, dtype=torch.float32).contiguous()
         if not (0 < Y.shape[0] < Xc.shape[0]):
             raise ValueError("need 0 < k_lab < n; labeled rows come first (GLL.py:11)")
         comm = _Comm(group, emulate)
+        part = cg_partition or os.environ.get("GLL_B200_SHARD_CG", "columns")
+        if part not in ("columns", "rows"):
+            raise ValueError("cg_partition must be 'columns' or 'rows'")
         with torch.cuda.device(X.device):
-            pred, g = _forward(Xc, Y, float(tau), epsilon, comm)
+            pred, g = _forward(Xc, Y, float(tau), epsilon, comm, cg_partition=part)
         global _last_graph
         _last_graph = g
         ctx.gll_graph, ctx.gll_comm, ctx.x_dtype = g, comm, X.dtype
@@ -244,7 +342,7 @@ class ShardedLaplaceLearning(torch.autograd.Function):
         (Xc,) = ctx.saved_tensors
         with torch.cuda.device(Xc.device):
             dX = _backward(ctx.gll_graph, Xc, grad_output, ctx.gll_comm)
-        return dX.to(ctx.x_dtype), None, None, None, None, None
+        return dX.to(ctx.x_dtype), None, None, None, None, None, None
 
 
 _last_graph = None
@@ -256,7 +354,9 @@ def last_info() -> dict:
     if g is None:
         return {}
     v = g.info.cpu().numpy()
-    return dict(status=int(v[_lib.INFO_STATUS]), nnz=int(v[_lib.INFO_NNZ]), nnz_uu=int(v[_lib.INFO_NNZ_UU]),
+    solve_ms = [a.elapsed_time(b) for a, b in getattr(g, "solve_events", [])]
+    return dict(cg_partition=g.cg_partition, cg_solve_ms=solve_ms,
+                status=int(v[_lib.INFO_STATUS]), nnz=int(v[_lib.INFO_NNZ]), nnz_uu=int(v[_lib.INFO_NNZ_UU]),
                 cg_iters_fwd=int(g.iters_fwd.max().item()),
                 cg_iters_bwd=int(g.iters_bwd.max().item()) if hasattr(g, "iters_bwd") else 0,
                 knn_fallback_rows=int(v[_lib.INFO_KNN_FALLBACK_ROWS]), cg_resid_fwd=float("nan"), cg_resid_bwd=float("nan"))

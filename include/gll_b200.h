@@ -167,6 +167,25 @@ int gll_backward_edges_rows(const float* X, int n, int d, int l, int k_lab, int 
  * (dst[r][c0 + c] = src[r][c], c < cnt). */
 int gll_pack_columns(const float* src, int rows, int lp_src, int c0, int cnt, float* dst, int lp_dst, void* stream);
 int gll_unpack_columns(const float* src, int rows, int lp_src, int c0, int cnt, float* dst, int lp_dst, void* stream);
+/* K4 for ONE graph whose unlabeled rows are partitioned over ranks (BASELINE north star: "row-block partitioned, CG
+ * iterate exchanged by all-gather, dot products by all-reduce").  The library does not link NCCL: these are the three
+ * per-rank stages and the host runs the two collectives between them on the same stream
+ * (graphlearninglayer_b200/sharded.py: torch.distributed all_gather_into_tensor / all_reduce):
+ *     init;  repeat { all-gather u_full;  spmv -> sums[3*lp] (fp64: <r,u>, <w,u>, <r,r> over own rows);
+ *                     all-reduce(sum) sums;  update(iter) }  until ctrl[0] != 0.
+ * Arithmetic: Jacobi-preconditioned Chronopoulos-Gear CG, per-column freeze / stop test of stable_conjgrad
+ * (GLL.py:247-276), identical on every rank because every rank sees the same reduced sums.
+ * x, u_full: m' x lp with m' >= m (rows [row_lo,row_hi) are written; u_full is the all-gather buffer).
+ * ctrl: int[4] zeroed by the caller: [0] stop flag, [1] iterations, [2] GLL_STATUS_* bits.  The workspace keeps r, p, s, w
+ * of the own rows between calls and must not be touched while a solve is running. */
+size_t gll_cg_rows_workspace_bytes(int rows_local, int l);
+int gll_cg_rows_init(const float* diag, const float* rhs, int m, int l, int row_lo, int row_hi, float* x, float* u_full,
+                     void* workspace, size_t workspace_bytes, void* stream);
+int gll_cg_rows_spmv(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, int m, int l, int row_lo,
+                     int row_hi, const float* u_full, double* sums, void* workspace, size_t workspace_bytes, void* stream);
+int gll_cg_rows_update(const float* diag, int m, int l, int row_lo, int row_hi, const double* sums, int iter, int max_iter,
+                       float tol, float* x, float* u_full, int* ctrl, float* resid_out, void* workspace, size_t workspace_bytes,
+                       void* stream);
 /* m x lp fp32 -> m x l float64/fp32 (GLL.py:66) and m x l float64/fp32 grad_output -> m x lp fp32 (GLL.py:90). */
 int gll_unpack_pred(const float* u, int m, int l, void* pred, int pred_is_f64, void* stream);
 int gll_pack_grad(const void* grad_out, int grad_is_f64, int m, int l, float* rhs, void* stream);

@@ -494,6 +494,84 @@ def test_sharded_layer_vs_oracle(gll):
     assert O.max_rel(Xt.grad.cpu().numpy(), bw.dX) < TOL
 
 
+@pytest.mark.parametrize("world", [1, 2, 5])
+@pytest.mark.parametrize("eps,tau", [("auto", 0.0), (1.0, 0.07)])
+def test_sharded_layer_row_partitioned_cg(gll, world, eps, tau):
+    """The north star's partition of the solve: rows of x, r, p, s split over the ranks, iterate all-gathered and dot
+    products all-reduced every iteration (csrc/cg_rows.cu), here with virtual ranks on one GPU."""
+    pkg, _ = gll
+    from graphlearninglayer_b200.sharded import ShardedLaplaceLearning, last_info
+
+    X, Y, _, yq = O.synth_inputs(33, 700, 2300, 96, 13, 2.5)  # m = 2300: ragged row blocks (last one short)
+    f, loss_ref, gout, bw = O.fwd_bwd(X, Y, yq, tau, eps, solver="lu")
+    Xt = torch.as_tensor(X).cuda().requires_grad_(True)
+    pred = ShardedLaplaceLearning.apply(Xt, torch.as_tensor(Y).cuda(), tau, eps, None, world, "rows")
+    tgt = torch.nn.functional.one_hot(torch.as_tensor(yq).cuda(), pred.shape[1]).to(pred.dtype)
+    (-torch.sum(tgt * torch.log(pred + 1e-8)) / pred.shape[0]).backward()
+    torch.cuda.synchronize()
+    assert pred.dtype == torch.float64 and Xt.grad.dtype == torch.float32
+    assert O.max_rel(pred.detach().cpu().numpy(), f.pred) < TOL
+    assert O.max_rel(Xt.grad.cpu().numpy(), bw.dX) < TOL
+    info = last_info()
+    assert info["status"] & ~8 == 0 and 0 < info["cg_iters_fwd"] < 200 and 0 < info["cg_iters_bwd"] < 200
+
+
+def test_cg_rows_stages_solve_to_tolerance(gll):
+    """gll_cg_rows_* through the C ABI on a hand-built SPD system, 3 virtual ranks, 100 class columns; fp64 direct solve
+    as the checker; zero right-hand-side columns are frozen from the start (GLL.py:262-263)."""
+    import scipy.sparse as sparse
+    import scipy.sparse.linalg as spla
+
+    _, _lib = gll
+    lib = _lib.lib
+    rng = np.random.default_rng(3)
+    m, l = 1500, 100
+    A = sparse.random(m, m, density=0.01, random_state=7, format="csr")
+    A = (A + A.T).tocsr()
+    A.setdiag(0)
+    A.eliminate_zeros()
+    A.sort_indices()
+    diag = np.asarray(A.sum(axis=1)).ravel() + 0.05 + rng.random(m)
+    B = rng.standard_normal((m, l))
+    B[:, 17] = 0.0
+    lp = lib.gll_padded_classes(l)
+    rhs = np.zeros((m, lp), np.float32)
+    rhs[:, :l] = B
+    ref = spla.spsolve((sparse.diags(diag) - A).tocsc(), rhs.astype(np.float64))
+    ptr, col, val = dev_t(A.indptr, torch.int32), dev_t(A.indices, torch.int32), dev_t(A.data, torch.float32)
+    dg, b = dev_t(diag, torch.float32), dev_t(rhs, torch.float32)
+    world, per = 3, 512
+    s = torch.cuda.current_stream().cuda_stream
+    x = torch.zeros((world * per, lp), dtype=torch.float32, device="cuda")
+    u = torch.zeros_like(x)
+    st = []
+    for r in range(world):
+        lo, hi = min(m, r * per), min(m, (r + 1) * per)
+        wsb = lib.gll_cg_rows_workspace_bytes(hi - lo, l)
+        st.append((lo, hi, torch.empty(wsb, dtype=torch.uint8, device="cuda"), wsb, torch.zeros(3 * lp, dtype=torch.float64, device="cuda"),
+                   torch.zeros(4, dtype=torch.int32, device="cuda")))
+        _lib.check(lib.gll_cg_rows_init(dg.data_ptr(), b.data_ptr(), m, l, lo, hi, x.data_ptr(), u.data_ptr(), st[r][2].data_ptr(),
+                                        wsb, s), "init")
+    for it in range(400):
+        for lo, hi, ws, wsb, sums, ctrl in st:
+            _lib.check(lib.gll_cg_rows_spmv(ptr.data_ptr(), col.data_ptr(), val.data_ptr(), dg.data_ptr(), m, l, lo, hi, u.data_ptr(),
+                                            sums.data_ptr(), ws.data_ptr(), wsb, s), "spmv")
+        tot = st[0][4] + st[1][4] + st[2][4]
+        for lo, hi, ws, wsb, sums, ctrl in st:
+            sums.copy_(tot)
+            _lib.check(lib.gll_cg_rows_update(dg.data_ptr(), m, l, lo, hi, sums.data_ptr(), it, 400, 1e-6, x.data_ptr(), u.data_ptr(),
+                                              ctrl.data_ptr(), 0, ws.data_ptr(), wsb, s), "update")
+        if st[0][5][0].item():
+            break
+    ctrls = torch.stack([c for *_, c in st]).cpu().numpy()
+    assert (ctrls[:, 0] == 1).all() and (ctrls[:, 1] == ctrls[0, 1]).all() and (ctrls[:, 2] == 0).all() and 0 < ctrls[0, 1] < 400
+    got = x[:m].cpu().numpy().astype(np.float64)
+    assert np.all(got[:, 17] == 0.0)
+    assert O.max_rel(got, ref) < 1e-5
+    resid = (sparse.diags(diag) - A) @ got - rhs
+    assert np.sqrt((resid ** 2).sum(axis=0)).max() < 1e-6 * np.sqrt((rhs.astype(np.float64) ** 2).sum(axis=0)).max()  # fp32 floor
+
+
 def test_knn_row_blocks_equal_full_search(gll):
     _, _lib = gll
     X, *_ = O.synth_inputs(12, 3000, 1777, 200, 10, 3.5)
