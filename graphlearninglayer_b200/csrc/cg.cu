@@ -330,7 +330,12 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
   P.status_out = status_out;
   P.rows_per_block = 0;
   {  // systems that fit on chip (every config except the sharded 1M-node graph) take the shared-memory-resident kernel
-    const char* force = getenv("GLL_B200_CG_PATH");  // "streaming": testing knob
+    const char* force = getenv("GLL_B200_CG_PATH");  // "streaming" / "resident": testing knobs
+    if (force == nullptr || force[0] == 0) {  // minibatch-sized systems: the one-CTA, register-resident kernel
+      const int rc = cg_small_try(P, st);
+      if (rc < 0) return rc;
+      if (rc == 1) return GLL_OK;
+    }
     if (!(force && strcmp(force, "streaming") == 0)) {
       void* scratch = cv.take<char>(cg_resident_ws_bytes(m, lp));
       const int rc = cg_resident_try(P, scratch, st);

@@ -33,5 +33,8 @@ struct CgParams {
 size_t cg_resident_ws_bytes(int m, int lp);
 int cg_resident_try(const CgParams& P, void* scratch, cudaStream_t st);
 void cg_set_trace(void* buf);
+void* cg_get_trace();
+// One-CTA kernel for minibatch-sized systems (cg_small.cu): 1 = took the solve, 0 = not small, < 0 = error.
+int cg_small_try(const CgParams& P, cudaStream_t st);
 
 }  // namespace gll

@@ -542,6 +542,7 @@ CrPlan plan(int m, int lp) {
 
 static unsigned long long* g_cg_trace = nullptr;
 void cg_set_trace(void* buf) { g_cg_trace = (unsigned long long*)buf; }
+void* cg_get_trace() { return g_cg_trace; }
 
 size_t cg_resident_ws_bytes(int m, int lp) {
   const size_t sms = (size_t)device_info().sms;

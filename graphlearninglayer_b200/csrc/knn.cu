@@ -312,28 +312,30 @@ knn_rerank_kernel(const float* __restrict__ X, const float* __restrict__ sq, con
     const long long rt = (i - lay.row_begin) / lay.row_tile;
     const int b0 = (int)(((rt * lay.col_tiles + 1) * lay.grid - 1) / lay.units);
     const int b1 = (int)((((rt + 1) * lay.col_tiles) * lay.grid - 1) / lay.units);
-    splits = b1 - b0 + 1;
+    splits = 2 * (b1 - b0 + 1);  // every CTA writes two lists per row (the column halves of its epilogue)
   }
   if (splits == 1 && lay.tc == 0) {
     mine = cand[(size_t)i * lay.stride * KC + lane];  // SIMT lists are sorted
   } else {
     for (int s = 0; s < splits; ++s) {  // tensor-core lists are unsorted sets: merge by insertion
-      u64 c = cand[((size_t)i * lay.stride + s) * KC + lane];
-      for (int t = 0; t < KC; ++t) {
-        u64 x = __shfl_sync(FULL, c, t);
-        if (x != KEY_INF) list_insert(mine, x, lane);
-      }
+      list_merge_set(mine, cand[((size_t)i * lay.stride + s) * KC + lane], lane);
     }
   }
   u64 last = __shfl_sync(FULL, mine, KC - 1);
   const float lower = (last == KEY_INF) ? INFINITY : key_dist(last);  // every non-candidate has d~^2 >= lower
   __syncwarp();
 
+  // Candidates whose approximate distance exceeds the (k-1)-th approximate distance by more than twice the error bound
+  // cannot be among the k-1 nearest (k-1 others are provably closer): their exact distance is not needed.
+  const double errb = (double)err_coef * ((double)sq[i] + (double)__uint_as_float(*sqmax_bits));
+  const u64 kth = __shfl_sync(FULL, mine, k - 2);
+  const float cutoff = (kth == KEY_INF) ? INFINITY : (float)((double)key_dist(kth) + 2.0 * errb + 1e-30) * (1.f + 1e-6f);
   double myd2 = INFINITY;
   int myj = -1;
   for (int c = 0; c < KC; ++c) {
     u64 kc = __shfl_sync(FULL, mine, c);
     if (kc == KEY_INF) break;
+    if (c > k - 2 && key_dist(kc) > cutoff) break;  // sorted: everything behind is farther still
     int j = key_idx(kc);
     double v = use_reg ? exact_d2_reg(xr, X + (size_t)j * d, d >> 2, lane) : exact_d2<VEC4>(xi, X + (size_t)j * d, d, lane);
     if (lane == c) {
@@ -360,8 +362,6 @@ knn_rerank_kernel(const float* __restrict__ X, const float* __restrict__ sq, con
   bool ok = false;
   if (who) {
     double dk = __shfl_sync(FULL, myd2, __ffs(who) - 1);
-    float sqm = __uint_as_float(*sqmax_bits);
-    double errb = (double)err_coef * ((double)sq[i] + (double)sqm);
     ok = ((double)lower - errb > dk) || (lower == INFINITY);
   }
   if (!ok && lane == 0) {
@@ -464,15 +464,11 @@ knn_merge_kernel(int row_end, CandLayout lay, const u64* __restrict__ cand, u64*
     const long long rt = (i - lay.row_begin) / lay.row_tile;
     const int b0 = (int)(((rt * lay.col_tiles + 1) * lay.grid - 1) / lay.units);
     const int b1 = (int)((((rt + 1) * lay.col_tiles) * lay.grid - 1) / lay.units);
-    splits = b1 - b0 + 1;
+    splits = 2 * (b1 - b0 + 1);  // every CTA writes two lists per row (the column halves of its epilogue)
   }
   u64 mine = KEY_INF;
   for (int s = 0; s < splits; ++s) {
-    u64 c = cand[((size_t)i * lay.stride + s) * KC + lane];
-    for (int t = 0; t < KC; ++t) {
-      u64 x = __shfl_sync(FULL, c, t);
-      if (x != KEY_INF) list_insert(mine, x, lane);
-    }
+    list_merge_set(mine, cand[((size_t)i * lay.stride + s) * KC + lane], lane);
   }
   merged[(size_t)(i - lay.row_begin) * KC + lane] = mine;
   if (excl != nullptr && lane == KC - 1) excl[i] = mine;  // KEY_INF if fewer than 32 columns exist: round 2 finds nothing

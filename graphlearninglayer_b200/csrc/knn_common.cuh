@@ -6,7 +6,7 @@ namespace gll {
 
 typedef unsigned long long u64;
 constexpr int KC = 32;               // candidates kept per row (one per lane)
-constexpr int KNN_MAX_SPLITS = 16;   // column-range splits per row tile
+constexpr int KNN_MAX_SPLITS = 32;   // candidate lists per row: two per CTA that touches the row tile
 constexpr u64 KEY_INF = ~0ull;
 
 // key = (order-preserving bits of the approximate squared distance, column index): u64 compare == (dist, idx) compare
@@ -24,6 +24,18 @@ __device__ __forceinline__ void list_insert(u64& mine, u64 x, int lane) {
     mine = prev;
   else if (lane == pos)
     mine = x;
+}
+
+// Merge one unsorted 32-set (one key per lane, KEY_INF = empty) into the sorted list `mine`: only keys below the list's
+// current last entry can enter, and those are found with one ballot instead of 32 trial insertions.
+__device__ __forceinline__ void list_merge_set(u64& mine, u64 c, int lane) {
+  unsigned m = __ballot_sync(FULL, c < __shfl_sync(FULL, mine, KC - 1));
+  while (m) {
+    const int t = __ffs(m) - 1;
+    m &= m - 1;
+    const u64 x = __shfl_sync(FULL, c, t);
+    if (x < __shfl_sync(FULL, mine, KC - 1)) list_insert(mine, x, lane);  // the last entry may have tightened meanwhile
+  }
 }
 
 // Tensor-core candidate generation (knn_tc.cu).  plan.ok == 0: shape or configuration not handled, use the SIMT path.

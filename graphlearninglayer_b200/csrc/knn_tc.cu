@@ -33,17 +33,21 @@
 namespace gll {
 namespace {
 
-constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 2;
-constexpr int TC_THREADS = 192;
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
-constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;          // 32 KB
-constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // 96 KB
+// Stage = one K block of {A_hi, A_lo, B_hi, B_lo}: 48 KB at a K block of 32 (64-byte swizzle).  Three stages already run
+// the MMA pipe at 98 % of the cuBLAS peak when the epilogue does nothing (GLL_B200_KNN_DEBUG=2: 0.22 ms at 10k nodes), and
+// leave room for the candidate sets of EIGHT epilogue warps.
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 32, TC_STAGES = 3;
+constexpr int TC_EPI_WARPS = 8;                        // two per TMEM lane quarter: each takes one half of the 256 columns
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 8 KB
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;          // 16 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // 48 KB
 constexpr int TC_CHUNK = 16;                           // columns per tcgen05.ld
 constexpr int TC_TMEM_COLS = 512, TC_ACC_STRIDE = 256;
 
-constexpr size_t TC_OFF_LD = (size_t)TC_STAGES * TC_STAGE_BYTES;             // float [4 warps][KC entries][32 rows]
-constexpr size_t TC_OFF_LI = TC_OFF_LD + 4 * KC * 32 * 4;                    // int   [4 warps][KC entries][32 rows]
-constexpr size_t TC_OFF_SQJ = TC_OFF_LI + 4 * KC * 32 * 4;                   // float [TC_BN]  |x_j|^2 of the unit's columns
+constexpr size_t TC_OFF_LD = (size_t)TC_STAGES * TC_STAGE_BYTES;             // float [8 warps][KC entries][32 rows]
+constexpr size_t TC_OFF_LI = TC_OFF_LD + TC_EPI_WARPS * KC * 32 * 4;         // int   [8 warps][KC entries][32 rows]
+constexpr size_t TC_OFF_SQJ = TC_OFF_LI + TC_EPI_WARPS * KC * 32 * 4;        // float [TC_BN]  |x_j|^2 of the unit's columns
 constexpr size_t TC_OFF_BAR = TC_OFF_SQJ + TC_BN * 4;                        // mbarriers + tmem pointer
 constexpr size_t TC_SMEM_BYTES = TC_OFF_BAR + 128 + 1024;                    // + slack for manual 1024 B alignment
 static_assert(TC_SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -130,10 +134,11 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// K-major operand tile, rows of 128 B (64 bf16), 128B swizzle, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+// K-major operand tile whose rows are one swizzle atom wide (TC_BK bf16 = 64 B), 8-row groups 8 rows apart
+// (cute::UMMA::SmemDescriptor; layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
+  constexpr uint64_t sbo = (uint64_t)(8 * TC_BK * 2) >> 4, layout = (TC_BK == 64) ? 2 : 4;
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | (sbo << 32) | ((uint64_t)1 << 46) | (layout << 61);
 }
 // Asynchronous TMEM -> register load of 16 consecutive columns of this thread's row; the registers are valid only after
 // tc_ld_wait(), which names them as in/out operands so that no use can be scheduled ahead of the wait.
@@ -152,7 +157,7 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[TC_CHUNK]) {
                :
                : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory"); }  // the epilogue warps
 
 struct TcParams {
   int n, kblocks, col_tiles, max_splits;
@@ -162,6 +167,7 @@ struct TcParams {
   long long units;
   const float* sq;
   u64* cand;
+  int debug;          // GLL_B200_KNN_DEBUG (timing experiments only, results are wrong): 1 no insertions, 2 no TMEM drain
   const u64* excl;    // optional [n]: per row, only keys > excl[row] are candidates (second round of a k > 33 search)
 };
 
@@ -213,7 +219,7 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 4);  // one arrival per epilogue warp
+      mbar_init(bar_tempty + 8 * a, TC_EPI_WARPS);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -299,9 +305,14 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     }
   } else {
     // ================================================= epilogue =====================================================
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may read
-    float* Ld = reinterpret_cast<float*>(smem + TC_OFF_LD) + (size_t)quarter * KC * 32 + lane;  // my row: Ld[e * 32]
-    int* Li = reinterpret_cast<int*>(smem + TC_OFF_LI) + (size_t)quarter * KC * 32 + lane;
+    // Every SM sub-partition hosts TWO epilogue warps (w and w + 4: same TMEM lane quarter, i.e. the same 32 rows); each
+    // scans one half of the unit's 256 columns into its OWN candidate set, so a row has two sets per CTA.  The insertion
+    // path is one long dependent chain (ncu: 0.18 IPC with a single warp per sub-partition): the second warp fills the gaps.
+    const int quarter = warp & 3;          // TMEM lanes [32*quarter, +32) are the ones this warp may read
+    const int half = (warp - 2) >> 2;      // which 128 columns of the unit
+    const int eset = half * 4 + quarter;   // the warp's block of candidate sets
+    float* Ld = reinterpret_cast<float*>(smem + TC_OFF_LD) + (size_t)eset * KC * 32 + lane;  // my row: Ld[e * 32]
+    int* Li = reinterpret_cast<int*>(smem + TC_OFF_LI) + (size_t)eset * KC * 32 + lane;
     int acc = 0, cur_rt = -1, gi = 0;
     float gm[4];  // maximum of slots [8t, 8t+8) of my row's candidate set
     int gp[4];    // ... and where it sits
@@ -311,11 +322,11 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     u64 excl_row = 0ull;   // second-round searches: skip everything the first round already holds
     float sqi_row = 0.f;
     float* sqj_s = reinterpret_cast<float*>(smem + TC_OFF_SQJ);
-    const int et = (warp - 2) * 32 + lane;  // 0..127 over the epilogue warps
+    const int et = (warp - 2) * 32 + lane;  // 0..255 over the epilogue warps
 
     auto flush = [&](int rt) {
       __syncwarp();
-      const int slot = P.aligned ? 0 : b - tc_cta_of_unit((long long)((rt - P.rt0) / RSTEP) * C, G, P.units);
+      const int slot = 2 * (P.aligned ? 0 : b - tc_cta_of_unit((long long)((rt - P.rt0) / RSTEP) * C, G, P.units)) + half;
       const float* wd = Ld - lane;
       const int* wi = Li - lane;
       for (int r = 0; r < 32; ++r) {  // lane = slot index e here; 256 B coalesced store per row
@@ -351,7 +362,6 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
       // stage |x_j|^2 of the unit's 256 columns for all four epilogue warps (+inf masks columns beyond n)
       epi_bar_sync();  // everybody is done with the previous unit's values
       sqj_s[et] = (c_begin + et < P.n) ? __ldg(P.sq + c_begin + et) : INFINITY;
-      sqj_s[et + 128] = (c_begin + et + 128 < P.n) ? __ldg(P.sq + c_begin + et + 128) : INFINITY;
       epi_bar_sync();
       // does this warp's row range meet this unit's column range?  (only then can a column be the row itself)
       const int wrow0 = rt * TC_BM + quarter * 32;
@@ -380,6 +390,7 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
         }
 #pragma unroll
         for (int c = 0; c < TC_CHUNK; ++c) hits |= (v[c] < thr) ? (1u << c) : 0u;
+        if (P.debug >= 1) hits = 0;
         // ---- every row (thread) inserts its own survivors; rows proceed concurrently ----
         while (__any_sync(FULL, hits != 0)) {
           if (hits) {
@@ -428,16 +439,23 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
         }
       };
       // two register sets: the TMEM load of the next 16 columns is in flight while the current ones are processed
-      tc_ld16_issue(taddr, rawA);
+      constexpr int QH = TC_BN / TC_CHUNK / 2;  // chunks per warp (its half of the columns)
+      const int q0 = half * QH;
+      if (P.debug >= 2) {  // timing experiment: hand the accumulator back untouched
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      } else
+        tc_ld16_issue(taddr + q0 * TC_CHUNK, rawA);
 #pragma unroll 1
-      for (int q = 0; q < TC_BN / TC_CHUNK; q += 2) {
+      for (int q = q0; q < ((P.debug >= 2) ? 0 : q0 + QH); q += 2) {
         tc_ld_wait(rawA);
         tc_ld16_issue(taddr + (q + 1) * TC_CHUNK, rawB);
         process(rawA, q);
         tc_ld_wait(rawB);
-        if (q + 2 < TC_BN / TC_CHUNK) {
+        if (q + 2 < q0 + QH) {
           tc_ld16_issue(taddr + (q + 2) * TC_CHUNK, rawA);
-        } else {  // the whole accumulator is in registers or consumed: hand it back to the MMA warp early
+        } else {  // this warp's half of the accumulator is in registers or consumed: hand it back to the MMA warp early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
@@ -487,7 +505,7 @@ int make_map(CUtensorMap* m, const void* base, int n, int d_pad, int box_rows) {
   const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, (TC_BK == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (n=%d d_pad=%d box_rows=%d)", (int)r, n, d_pad, box_rows);
@@ -522,7 +540,7 @@ TcPlan knn_tc_plan(int n, int d, int row_begin, int row_end) {
   const int owners = sms / p.rstep;
   p.grid = (int)((p.units < (long long)owners) ? p.units : (long long)owners);  // owners (CTAs or CTA pairs)
   if (p.aligned) {
-    p.max_splits = 1;
+    p.max_splits = 2;  // the two column halves of the epilogue (knn_tc.cu: `half`)
   } else {
     int ms = 1;
     for (int rt = 0; rt < p.row_tiles; ++rt) {  // exact: owners touching each row group
@@ -530,7 +548,7 @@ TcPlan knn_tc_plan(int n, int d, int row_begin, int row_end) {
       const int b1 = tc_cta_of_unit((long long)(rt + 1) * p.col_tiles - 1, p.grid, p.units);
       ms = max(ms, b1 - b0 + 1);
     }
-    p.max_splits = ms;
+    p.max_splits = 2 * ms;  // two candidate sets (column halves) per CTA and row
   }
   p.ws_bytes = 2 * align_up((size_t)n * p.d_pad * 2, 256);
   p.ok = (p.max_splits <= KNN_MAX_SPLITS) ? 1 : 0;
@@ -571,6 +589,10 @@ int knn_tc_candidates(const float* X, const float* sq, int n, int d, int row_end
   P.sq = sq;
   P.cand = cand;
   P.excl = excl;
+  {
+    const char* dbg = getenv("GLL_B200_KNN_DEBUG");
+    P.debug = dbg ? atoi(dbg) : 0;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_gram_topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));

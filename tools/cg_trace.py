@@ -1,5 +1,6 @@
 """Debug tool: per-phase timeline of the on-chip CG kernel on the C4-size system (run on the GPU box)."""
 import os, sys
+os.environ.setdefault("GLL_B200_CG_PATH", "resident")  # the trace instruments cg_resident.cu, not the one-CTA cg_small.cu
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import graphlearninglayer_b200 as pkg
