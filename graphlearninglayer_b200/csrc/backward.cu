@@ -132,6 +132,100 @@ row_gather_kernel(const float* __restrict__ X, int row_begin, int d, int eps_aut
   }
 }
 
+// Warp per row (vectorised path, d % 4 == 0): a lane owns NV float4 chunks of the feature row (chunk = lane + 32 u), so one
+// neighbour row is NV coalesced 512-byte loads.  Edge metadata (column, t_ij) is prepared 32 edges at a time, one edge per
+// lane; edges with t_ij == 0 (both ends labeled: most edges of a minibatch graph) are dropped with a ballot; the row of
+// the NEXT surviving edge is already in flight while the current one is accumulated (fp64 accumulators).
+// Four rows per CTA: many more rows in flight per SM than the block-per-row kernel, whose CTAs spent their life waiting on
+// five dependent loads.
+template <int NV>
+__global__ void __launch_bounds__(128)
+row_gather_warp_kernel(const float* __restrict__ X, int row_begin, int row_end, int d, int eps_auto, const int* __restrict__ row_ptr,
+                       const int* __restrict__ col, const int* __restrict__ kappa, const float* __restrict__ gv,
+                       const float* __restrict__ bvec, float* __restrict__ dX) {
+  const int lane = threadIdx.x & 31;
+  const int i = row_begin + blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (i >= row_end) return;
+  const int cols = d >> 2;
+  const int e0 = __ldg(row_ptr + i), e1 = __ldg(row_ptr + i + 1);
+  const int ki = eps_auto ? __ldg(kappa + i) : -1;
+  const float bi = eps_auto ? __ldg(bvec + i) : 0.f;
+  const float4* xrow = reinterpret_cast<const float4*>(X + (size_t)i * d);
+  for (int cbase = 0; cbase < cols; cbase += 32 * NV) {
+    float4 xi[NV];
+    double acc[NV][4];
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int c = cbase + lane + 32 * u;
+      xi[u] = (c < cols) ? __ldg(xrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.0;
+    }
+    auto fetch = [&](int j, float4 (&v)[NV]) {
+      const float4* xj = reinterpret_cast<const float4*>(X + (size_t)j * d);
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        const int c = cbase + lane + 32 * u;
+        v[u] = (c < cols) ? __ldg(xj + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto accumulate = [&](float tc, const float4 (&v)[NV]) {
+      const double t = (double)tc;
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {  // the difference is exact enough in fp32 (one rounding); products and sums in fp64
+        acc[u][0] = fma(t, (double)(xi[u].x - v[u].x), acc[u][0]);
+        acc[u][1] = fma(t, (double)(xi[u].y - v[u].y), acc[u][1]);
+        acc[u][2] = fma(t, (double)(xi[u].z - v[u].z), acc[u][2]);
+        acc[u][3] = fma(t, (double)(xi[u].w - v[u].w), acc[u][3]);
+      }
+    };
+    for (int eb = e0; eb < e1; eb += 32) {
+      const int e = eb + lane;
+      int j = 0;
+      float tc = 0.f;
+      if (e < e1) {
+        j = __ldg(col + e);
+        tc = __ldg(gv + e);
+        if (eps_auto) {
+          if (j == ki) tc -= bi;
+          if (__ldg(kappa + j) == i) tc -= __ldg(bvec + j);
+        }
+      }
+      unsigned live = __ballot_sync(FULL, tc != 0.f);
+      if (live == 0) continue;
+      float4 va[NV], vb[NV];
+      int t = __ffs(live) - 1;
+      live &= live - 1;
+      fetch(__shfl_sync(FULL, j, t), va);
+      while (true) {
+        const float tca = __shfl_sync(FULL, tc, t);
+        if (live == 0) {
+          accumulate(tca, va);
+          break;
+        }
+        t = __ffs(live) - 1;
+        live &= live - 1;
+        fetch(__shfl_sync(FULL, j, t), vb);
+        accumulate(tca, va);
+        const float tcb = __shfl_sync(FULL, tc, t);
+        if (live == 0) {
+          accumulate(tcb, vb);
+          break;
+        }
+        t = __ffs(live) - 1;
+        live &= live - 1;
+        fetch(__shfl_sync(FULL, j, t), va);
+        accumulate(tcb, vb);
+      }
+    }
+    float4* out = reinterpret_cast<float4*>(dX + (size_t)i * d);
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int c = cbase + lane + 32 * u;
+      if (c < cols) out[c] = make_float4((float)acc[u][0], (float)acc[u][1], (float)acc[u][2], (float)acc[u][3]);
+    }
+  }
+}
+
 }  // namespace
 
 int backward_edges_run(const float* X, int n, int d, int l, int k_lab, int eps_auto, const int* row_ptr, const int* col,
@@ -155,9 +249,15 @@ int backward_edges_run(const float* X, int n, int d, int l, int k_lab, int eps_a
     const int cols = vec4 ? d / 4 : d;
     int threads = min(256, max(32, ceil_div(cols, 32) * 32));
     GLL_PROF(KID_ROW_GATHER, st);
-    if (vec4)
-      row_gather_kernel<4><<<rows, threads, 0, st>>>(X, row_begin, d, eps_auto, row_ptr, col, kappa, gv, bvec, dX);
-    else
+    if (vec4) {
+      const int grid = ceil_div(rows, 4);
+      if (cols <= 32)
+        row_gather_warp_kernel<1><<<grid, 128, 0, st>>>(X, row_begin, row_end, d, eps_auto, row_ptr, col, kappa, gv, bvec, dX);
+      else if (cols <= 64)
+        row_gather_warp_kernel<2><<<grid, 128, 0, st>>>(X, row_begin, row_end, d, eps_auto, row_ptr, col, kappa, gv, bvec, dX);
+      else
+        row_gather_warp_kernel<4><<<grid, 128, 0, st>>>(X, row_begin, row_end, d, eps_auto, row_ptr, col, kappa, gv, bvec, dX);
+    } else
       row_gather_kernel<1><<<rows, threads, 0, st>>>(X, row_begin, d, eps_auto, row_ptr, col, kappa, gv, bvec, dX);
   }
   GLL_LAUNCH_CHECK();
