@@ -647,3 +647,32 @@ def test_eval_path_like_utils_laplace(gll):
     ref = laplace(oracle_knn_sym_dist, oracle_cg)
     assert O.max_rel(ours, ref) < 1e-6
     assert np.array_equal(ours.argmax(axis=1), ref.argmax(axis=1))
+
+
+def test_host_pipeline_matches_plain_calls(gll):
+    """HostPipeline (H2D / kernels / D2H of neighbouring calls overlapped on three streams) returns, for every call, exactly
+    what the plain layer call returns on the same inputs -- several different graphs in flight, slots reused."""
+    pkg, _ = gll
+    from graphlearninglayer_b200.hostpipe import HostPipeline
+
+    k_lab, m, d, l = 300, 200, 64, 7
+    batches = []
+    for seed in range(5):
+        X, Y, _, yq = O.synth_inputs(40 + seed, k_lab, m, d, l, 2.0)
+        batches.append((torch.as_tensor(X).pin_memory(), torch.as_tensor(Y).pin_memory(), yq))
+    tgts = [torch.nn.functional.one_hot(torch.as_tensor(yq), l).to(torch.float64).cuda() for *_, yq in batches]
+    order = []
+    pipe = HostPipeline(k_lab + m, d, k_lab, l, "cuda", tau=0.0, epsilon="auto",
+                        loss_fn=lambda pred, slot: -torch.sum(tgts[order[-1]] * torch.log(pred + 1e-8)) / m)
+    got = []
+    for i, (Xh, Yh, _) in enumerate(batches):
+        if pipe.outstanding == pipe.depth:
+            p, g = pipe.collect()
+            got.append((p.clone(), g.clone()))
+        order.append(i)
+        pipe.submit(Xh, Yh)
+    got += [(p.clone(), g.clone()) for p, g in pipe.drain()]
+    assert len(got) == len(batches)
+    for i, (Xh, Yh, yq) in enumerate(batches):
+        ref_pred, _, ref_dX = layer_fwd_bwd(pkg, Xh.numpy(), Yh.numpy(), yq, 0.0, "auto")
+        assert torch.equal(got[i][0], ref_pred.cpu()) and torch.equal(got[i][1], ref_dX.cpu())
