@@ -217,7 +217,17 @@ def run_b200(args, rank, world, local_rank):
         Yh = torch.as_tensor(Y).pin_memory()
         Xd = Xh.to(dev).requires_grad_(True)
         Yd = Yh.to(dev)
-        tgt = torch.nn.functional.one_hot(torch.as_tensor(yq), l).to(torch.float64).to(dev)
+        yq_d = torch.as_tensor(yq).to(dev)
+        if args.loss == "torch":   # the reference function body, op by op (losses.py:128-136)
+            tgt = torch.nn.functional.one_hot(yq_d, l).to(torch.float64)
+
+            def ce(pred):
+                return -torch.sum(tgt * torch.log(pred + 1e-8)) / m
+        else:                      # the same function as one kernel (graphlearninglayer_b200/losses.py)
+            from graphlearninglayer_b200.losses import custom_ce_loss
+
+            def ce(pred):
+                return custom_ce_loss(pred, yq_d)
         predh = torch.empty((m, l), dtype=torch.float64).pin_memory()
         dXh = torch.empty((k_lab + m, d), dtype=torch.float32).pin_memory()
         Xe = torch.empty_like(Xd).requires_grad_(True)
@@ -226,7 +236,7 @@ def run_b200(args, rank, world, local_rank):
         def resident():
             Xd.grad = None
             pred = layer(Xd, Yd, tau, eps)
-            loss = -torch.sum(tgt * torch.log(pred + 1e-8)) / m  # custom_ce_loss, losses.py:128-136
+            loss = ce(pred)  # custom_ce_loss, losses.py:128-136
             loss.backward()
             return loss
 
@@ -236,7 +246,7 @@ def run_b200(args, rank, world, local_rank):
                 Xe.copy_(Xh, non_blocking=True)
                 Ye.copy_(Yh, non_blocking=True)
             pred = layer(Xe, Ye, tau, eps)
-            loss = -torch.sum(tgt * torch.log(pred + 1e-8)) / m
+            loss = ce(pred)
             loss.backward()
             predh.copy_(pred.detach(), non_blocking=True)
             dXh.copy_(Xe.grad, non_blocking=True)
@@ -248,7 +258,7 @@ def run_b200(args, rank, world, local_rank):
             from graphlearninglayer_b200.hostpipe import HostPipeline
 
             pipe = HostPipeline(k_lab + m, d, k_lab, l, dev, tau=tau, epsilon=eps, layer=layer, depth=3,
-                                loss_fn=lambda pred, slot: -torch.sum(tgt * torch.log(pred + 1e-8)) / m)
+                                loss_fn=lambda pred, slot: ce(pred))
             for _ in range(warmup):
                 if pipe.outstanding == pipe.depth:
                     pipe.collect()
@@ -392,7 +402,10 @@ def run_b200(args, rank, world, local_rank):
                                           "rows (CG: NCCL all-gather of the iterate + all-reduce of the dot products per iteration)")
                                        if sharded
                                        else f"independent graphs x{world}"),
-                       "cg_tol": 1e-7, "graph": {"nnz": info["nnz"], "nnz_uu": info["nnz_uu"],
+                       "cg_tol": 1e-7,
+                       "loss": ("custom_ce_loss as one kernel (graphlearninglayer_b200.losses; formula of losses.py:128-136)"
+                                if args.loss == "fused" else "custom_ce_loss with the reference's PyTorch ops (losses.py:128-136)"),
+                       "graph": {"nnz": info["nnz"], "nnz_uu": info["nnz_uu"],
                                                  "cg_iters_fwd": info["cg_iters_fwd"], "cg_iters_bwd": info["cg_iters_bwd"],
                                                  "knn_fallback_rows": info["knn_fallback_rows"], "status": info["status"],
                                                  **({"cg_solve_ms_fwd_bwd": info.get("cg_solve_ms")} if sharded else {})}},
@@ -446,6 +459,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--loss", choices=["fused", "torch"], default="fused",
+                    help="custom_ce_loss of the step: graphlearninglayer_b200.losses (one kernel) or the reference's PyTorch ops")
     ap.add_argument("--cg-partition", choices=["columns", "rows"], default="columns",
                     help="sharded workloads: split the CG solves by class columns (no per-iteration collective) or by rows "
                          "(all-gather + all-reduce per iteration)")

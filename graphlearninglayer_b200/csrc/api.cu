@@ -87,6 +87,33 @@ __global__ void pack_grad_kernel(const void* __restrict__ g, int is_f64, int m, 
   rhs[t] = v;
 }
 
+// custom_ce_loss (losses.py:128-136): loss = -sum_i log(p[i, t_i] + 1e-8) / m and, in the same pass, its gradient
+// d loss / d p[i, c] = -[c == t_i] / (m (p[i, t_i] + 1e-8)).  One CTA; fixed summation order.
+template <typename T>
+__global__ void __launch_bounds__(1024) ce_loss_kernel(const T* __restrict__ p, const long long* __restrict__ tgt, int m, int l,
+                                                        T* __restrict__ loss, T* __restrict__ grad, int* __restrict__ status) {
+  __shared__ double part[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double acc = 0.0;
+  const double inv_m = 1.0 / (double)m;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const long long t = tgt[i];
+    const bool ok = t >= 0 && t < l;
+    if (!ok && status) atomicOr(status, GLL_STATUS_NONFINITE);
+    const double q = ok ? (double)p[(size_t)i * l + t] + 1e-8 : 1.0;
+    acc += log(q);
+    for (int c = 0; c < l; ++c) grad[(size_t)i * l + c] = (T)((ok && c == t) ? -inv_m / q : 0.0);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) part[warp] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    double v = (lane < (int)(blockDim.x >> 5)) ? part[lane] : 0.0;
+    v = warp_sum(v);
+    if (lane == 0) *loss = (T)(-v * inv_m);
+  }
+}
+
 __global__ void unpack_pred_kernel(const float* __restrict__ u, int m, int l, int lp, void* __restrict__ pred, int is_f64) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)m * l) return;
@@ -314,6 +341,19 @@ int gll_cg_rows_update(const float* diag, int m, int l, int row_lo, int row_hi, 
                        void* stream) {
   return cg_rows_update(diag, m, l, row_lo, row_hi, sums, iter, max_iter, tol, x, u_full, ctrl, resid_out, workspace,
                         workspace_bytes, (cudaStream_t)stream);
+}
+
+int gll_ce_loss(const void* pred, int pred_is_f64, const long long* targets, int m, int l, void* loss_out, void* grad_out,
+                int* status, void* stream) {
+  GLL_REQUIRE(pred && targets && loss_out && grad_out && m >= 1 && l >= 1, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  GLL_PROF(KID_PACK, st);
+  if (pred_is_f64)
+    ce_loss_kernel<double><<<1, 1024, 0, st>>>((const double*)pred, targets, m, l, (double*)loss_out, (double*)grad_out, status);
+  else
+    ce_loss_kernel<float><<<1, 1024, 0, st>>>((const float*)pred, targets, m, l, (float*)loss_out, (float*)grad_out, status);
+  GLL_LAUNCH_CHECK();
+  return GLL_OK;
 }
 
 int gll_pack_columns(const float* src, int rows, int lp_src, int c0, int cnt, float* dst, int lp_dst, void* stream) {

@@ -1,0 +1,47 @@
+"""`custom_ce_loss(softmax_logits, targets)` of the reference (losses.py:128-136; pasted again at
+train_and_adversarial.py:458 and adversarial.py:453) as ONE kernel: the loss and its gradient with respect to the
+layer's output come out of the same launch (the reference spends a dozen small PyTorch kernels on one_hot / add / log / mul /
+sum / neg / div and their backward).  Same name, arguments and result as the reference function; CUDA tensors only.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import lib
+
+__all__ = ["custom_ce_loss"]
+
+
+class _CELoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, softmax_logits, targets):
+        if not softmax_logits.is_cuda:
+            raise RuntimeError("graphlearninglayer_b200.losses.custom_ce_loss needs CUDA tensors (no CPU path)")
+        p = softmax_logits.detach()
+        if p.dtype not in (torch.float32, torch.float64):
+            p = p.float()
+        p = p.contiguous()
+        m, l = p.shape
+        t = targets.detach().to(device=p.device, dtype=torch.int64).contiguous()
+        if t.numel() != m:
+            raise ValueError("targets must hold one class index per row of softmax_logits")
+        loss = torch.empty((), dtype=p.dtype, device=p.device)
+        grad = torch.empty_like(p)
+        with torch.cuda.device(p.device):
+            _lib.check(lib.gll_ce_loss(p.data_ptr(), int(p.dtype == torch.float64), t.data_ptr(), m, l, loss.data_ptr(),
+                                       grad.data_ptr(), None, torch.cuda.current_stream(p.device).cuda_stream), "gll_ce_loss")
+        ctx.save_for_backward(grad)
+        ctx.in_dtype = softmax_logits.dtype
+        return loss.to(softmax_logits.dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        (grad,) = ctx.saved_tensors
+        return (grad * grad_output.to(grad.dtype)).to(ctx.in_dtype), None
+
+
+def custom_ce_loss(softmax_logits: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+    """-sum(one_hot(targets) * log(softmax_logits + 1e-8)) / batch_size  (losses.py:128-136)."""
+    return _CELoss.apply(softmax_logits, targets)

@@ -190,6 +190,14 @@ int gll_cg_rows_update(const float* diag, int m, int l, int row_lo, int row_hi, 
 int gll_unpack_pred(const float* u, int m, int l, void* pred, int pred_is_f64, void* stream);
 int gll_pack_grad(const void* grad_out, int grad_is_f64, int m, int l, float* rhs, void* stream);
 
+/* The loss every caller of the layer applies to its output (custom_ce_loss, losses.py:128-136; also pasted at
+ * train_and_adversarial.py:458 and adversarial.py:453): loss = -sum_i log(pred[i, targets[i]] + 1e-8) / m, and in the same
+ * launch d loss / d pred (m x l, same dtype as pred).  pred: m x l float64 (pred_is_f64 != 0) or fp32; targets: m int64;
+ * loss_out: one element of pred's dtype.  status (optional, device int): GLL_STATUS_NONFINITE is or-ed in when a target
+ * is outside [0, l). */
+int gll_ce_loss(const void* pred, int pred_is_f64, const long long* targets, int m, int l, void* loss_out, void* grad_out,
+                int* status, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused drivers: what LaplaceLearningSparseHard.forward / .backward call (GLL.py:13-73, 75-177).
  * `state` is a buffer of gll_state_layout(...).total bytes that must stay alive (and untouched) between the

@@ -676,3 +676,26 @@ def test_host_pipeline_matches_plain_calls(gll):
     for i, (Xh, Yh, yq) in enumerate(batches):
         ref_pred, _, ref_dX = layer_fwd_bwd(pkg, Xh.numpy(), Yh.numpy(), yq, 0.0, "auto")
         assert torch.equal(got[i][0], ref_pred.cpu()) and torch.equal(got[i][1], ref_dX.cpu())
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_fused_ce_loss_matches_reference_formula(gll, dtype):
+    """graphlearninglayer_b200.losses.custom_ce_loss vs the reference function body (losses.py:128-136), value and gradient."""
+    from graphlearninglayer_b200.losses import custom_ce_loss
+
+    g = torch.Generator().manual_seed(3)
+    m, l = 777, 10
+    p = torch.softmax(torch.randn(m, l, generator=g, dtype=torch.float64), dim=1).to(dtype).cuda()
+    p[5] = 0.0                                   # exact zeros are what the 1e-8 is for
+    t = torch.randint(0, l, (m,), generator=g).cuda()
+    a = p.clone().requires_grad_(True)
+    one_hot = torch.nn.functional.one_hot(t, num_classes=l).to(a.dtype)
+    ref = -torch.sum(one_hot * torch.log(a + 1e-8)) / m
+    (3.0 * ref).backward()
+    b = p.clone().requires_grad_(True)
+    ours = custom_ce_loss(b, t)
+    (3.0 * ours).backward()
+    tol = 1e-12 if dtype == torch.float64 else 2e-6
+    assert ours.dtype == dtype and ours.shape == ref.shape
+    assert abs(ours.item() - ref.item()) <= tol * abs(ref.item())
+    assert torch.allclose(b.grad, a.grad, rtol=tol, atol=0.0)
