@@ -14,6 +14,7 @@
 // This file holds the fp32 SIMT Gram path (any d, any alignment).  The tcgen05/TMA Gram path for d % 64 == 0
 // lives in knn_tc.cu and reuses the rerank / fallback kernels through knn_finish().
 #include <math.h>
+#include <stdlib.h>
 
 #include <cuda_bf16.h>
 
@@ -36,7 +37,7 @@ constexpr size_t gemm_smem_bytes() {
 // feeds the tensor-core Gram kernel (row stride d_pad, zero padded), so X is read once.
 __global__ void __launch_bounds__(256)
 sqnorm_split_kernel(const float* __restrict__ X, int n, int d, int d_pad, float* __restrict__ sq, unsigned* __restrict__ sqmax_bits,
-                    __nv_bfloat16* __restrict__ H, __nv_bfloat16* __restrict__ L) {
+                    __nv_bfloat16* __restrict__ H, __nv_bfloat16* __restrict__ L, unsigned* __restrict__ thr_g) {
   const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (row >= n) return;
   const float* x = X + (size_t)row * d;
@@ -62,6 +63,7 @@ sqnorm_split_kernel(const float* __restrict__ X, int n, int d, int d_pad, float*
   if (lane == 0) {
     float f = (float)s;
     sq[row] = f;
+    if (thr_g != nullptr) thr_g[row] = 0xFF800000u;  // float_to_ordered(+inf): the row's shared threshold (knn_tc.cu)
     if (f == f) atomicMax(sqmax_bits, __float_as_uint(f));  // non-negative floats order like their bits
   }
 }
@@ -642,6 +644,7 @@ size_t knn_ws_bytes(int n, int d, int k, int row_begin, int row_end) {
   b += align_up(sizeof(u64) * rows * (size_t)cand_stride(n, d, row_begin, row_end) * KC, 256);     // cand
   b += align_up(sizeof(int) * rows, 256);                                                          // flag_rows
   b += knn_tc_ws_upper(n, d);                                           // bf16 hi / lo copies for the tensor-core path
+  b += align_up(sizeof(unsigned) * (size_t)n, 256);                     // per-row shared thresholds
   if (k > KC + 1) b += 2 * align_up(sizeof(u64) * rows * KC, 256) + align_up(sizeof(u64) * (size_t)n, 256);  // merged lists, excl
   return b + 1024;
 }
@@ -668,6 +671,11 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
   u64* cand = cand_store - (size_t)row_begin * stride * KC;
   int* flag_rows = cv.take<int>(rows);
   char* tc_ws = cv.take<char>(knn_tc_ws_upper(n, d));
+  unsigned* thr_g = cv.take<unsigned>(n);
+  {
+    const char* sh = getenv("GLL_B200_KNN_SHARE");  // "0": every candidate set keeps its own threshold (experiments)
+    if (sh && sh[0] == '0') thr_g = nullptr;
+  }
 
   CandLayout lay;
   float err_coef;
@@ -680,7 +688,7 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
   GLL_CUDA_CHECK(cudaMemsetAsync(small, 0, 256, st));
   {
     GLL_PROF(KID_SQNORM, st);
-    sqnorm_split_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(X, n, d, plan.ok ? plan.d_pad : d, sq, sqmax_bits, H, L);
+    sqnorm_split_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(X, n, d, plan.ok ? plan.d_pad : d, sq, sqmax_bits, H, L, thr_g);
   }
   GLL_LAUNCH_CHECK();
 
@@ -698,14 +706,14 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
     lay.units = plan.units;
     lay.row_begin = row_begin;
     const int mblocks = ceil_div(rows, RERANK_WARPS);
-    int rc = knn_tc_candidates(X, sq, n, d, row_end, plan, tc_ws, cand, nullptr, st);
+    int rc = knn_tc_candidates(X, sq, n, d, row_end, plan, tc_ws, cand, nullptr, thr_g, st);
     if (rc) return rc;
     {
       GLL_PROF(KID_RERANK, st);
       knn_merge_kernel<<<mblocks, RERANK_WARPS * 32, 0, st>>>(row_end, lay, cand, merged1, excl);
     }
     GLL_LAUNCH_CHECK();
-    rc = knn_tc_candidates(X, sq, n, d, row_end, plan, tc_ws, cand, excl, st);
+    rc = knn_tc_candidates(X, sq, n, d, row_end, plan, tc_ws, cand, excl, nullptr, st);  // second round: own thresholds
     if (rc) return rc;
     {
       GLL_PROF(KID_RERANK, st);
@@ -716,7 +724,7 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
                         flag_count, flag_rows, info, st);
   }
   if (plan.ok) {  // tcgen05 / TMA Gram GEMM with the fused top-k epilogue
-    int rc = knn_tc_candidates(X, sq, n, d, row_end, plan, tc_ws, cand, nullptr, st);
+    int rc = knn_tc_candidates(X, sq, n, d, row_end, plan, tc_ws, cand, nullptr, thr_g, st);
     if (rc) return rc;
     lay.stride = plan.max_splits;
     lay.tc = plan.aligned ? 2 : 1;

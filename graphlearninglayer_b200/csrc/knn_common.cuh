@@ -47,7 +47,7 @@ struct TcPlan {
 TcPlan knn_tc_plan(int n, int d, int row_begin, int row_end);
 size_t knn_tc_ws_upper(int n, int d);
 int knn_tc_candidates(const float* X, const float* sq, int n, int d, int row_end, const TcPlan& plan, void* tc_ws, u64* cand,
-                      const u64* excl, cudaStream_t st);
+                      const u64* excl, unsigned* thr_g, cudaStream_t st);
 float knn_tc_err_coef(int d);
 
 // How the candidate lists of a row are laid out in cand[n][stride][KC]: uniform (SIMT: every row has `stride` lists)

@@ -167,6 +167,7 @@ struct TcParams {
   long long units;
   const float* sq;
   u64* cand;
+  unsigned* thr_g;    // [n] per-row threshold shared by every candidate set of the row (ordered-uint of the float), or NULL
   int debug;          // GLL_B200_KNN_DEBUG (timing experiments only, results are wrong): 1 no insertions, 2 no TMEM drain
   const u64* excl;    // optional [n]: per row, only keys > excl[row] are candidates (second round of a k > 33 search)
 };
@@ -318,7 +319,11 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     int gp[4];    // ... and where it sits
     uint32_t acc_phase = 0;
     // Ranking inside a row only needs key = |x_j|^2 - 2 x_i.x_j; |x_i|^2 is added when the set is flushed.
-    float thr = INFINITY;
+    // thr = min(smax, tlim): smax = largest entry of MY set (inf until it is full), tlim = what the row's other sets --
+    // the partner warp's column half, other CTAs working on the same row tile -- have published through thr_g (L2).
+    // Any set's 32nd-best bounds the row's overall 32nd-best from above, so entries >= tlim can never be needed; the
+    // union of the row's sets still holds the overall 32 best, and sets fill far more slowly (fewer insertions).
+    float thr = INFINITY, smax = INFINITY, tlim = INFINITY, published = INFINITY;
     u64 excl_row = 0ull;   // second-round searches: skip everything the first round already holds
     float sqi_row = 0.f;
     float* sqj_s = reinterpret_cast<float*>(smem + TC_OFF_SQJ);
@@ -346,7 +351,7 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
 #pragma unroll
         for (int e = 0; e < KC; ++e) Ld[e * 32] = INFINITY;
         cur_rt = rt;
-        thr = INFINITY;
+        thr = smax = tlim = published = INFINITY;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           gm[t] = INFINITY;
@@ -363,6 +368,11 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
       epi_bar_sync();  // everybody is done with the previous unit's values
       sqj_s[et] = (c_begin + et < P.n) ? __ldg(P.sq + c_begin + et) : INFINITY;
       epi_bar_sync();
+      // once per unit (sharing every 32 columns instead measured the same): take what the row's other sets have published
+      if (P.thr_g != nullptr && gi < P.n) {  // ordered + 1 = the next float up: ties with another set's bound stay admissible
+        tlim = fminf(tlim, ordered_to_float(__ldcg(P.thr_g + gi) + 1u));
+        thr = fminf(smax, tlim);
+      }
       // does this warp's row range meet this unit's column range?  (only then can a column be the row itself)
       const int wrow0 = rt * TC_BM + quarter * 32;
       const bool diag = (c_begin < wrow0 + 32) && (c_begin + TC_BN > wrow0);
@@ -433,7 +443,8 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
                 gm[t] = (t == g) ? mx : gm[t];
                 gp[t] = (t == g) ? mp : gp[t];
               }
-              thr = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+              smax = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+              thr = fminf(smax, tlim);
             }
           }
         }
@@ -461,6 +472,10 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
           if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         }
         process(rawB, q + 1);
+      }
+      if (P.thr_g != nullptr && gi < P.n && smax < published) {  // my set is full and its bound improved during this unit
+        atomicMin(P.thr_g + gi, float_to_ordered(smax));
+        published = smax;
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
@@ -566,7 +581,7 @@ float knn_tc_err_coef(int d) {
 }
 
 int knn_tc_candidates(const float* X, const float* sq, int n, int d, int row_end, const TcPlan& plan, void* tc_ws, u64* cand,
-                      const u64* excl, cudaStream_t st) {
+                      const u64* excl, unsigned* thr_g, cudaStream_t st) {
   __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(tc_ws);
   __nv_bfloat16* L = reinterpret_cast<__nv_bfloat16*>((char*)tc_ws + align_up((size_t)n * plan.d_pad * 2, 256));
   // H and L (bf16 hi / lo split of X, row stride d_pad) were written by sqnorm_split_kernel (knn.cu)
@@ -589,6 +604,7 @@ int knn_tc_candidates(const float* X, const float* sq, int n, int d, int row_end
   P.sq = sq;
   P.cand = cand;
   P.excl = excl;
+  P.thr_g = thr_g;
   {
     const char* dbg = getenv("GLL_B200_KNN_DEBUG");
     P.debug = dbg ? atoi(dbg) : 0;
