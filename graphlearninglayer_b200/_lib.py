@@ -77,7 +77,8 @@ def _load():
     sig("gll_cg_rows_init", i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, sz, vp])
     sig("gll_cg_rows_spmv", i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, sz, vp])
     sig("gll_cg_rows_update", i32, [vp, i32, i32, i32, i32, vp, i32, i32, f32, vp, vp, vp, vp, vp, sz, vp])
-    sig("gll_ce_loss", i32, [vp, i32, vp, i32, i32, vp, vp, vp, vp])
+    sig("gll_ce_loss_workspace_bytes", sz, [i32])
+    sig("gll_ce_loss", i32, [vp, i32, vp, i32, i32, vp, vp, vp, vp, sz, vp])
     sig("gll_pack_columns", i32, [vp, i32, i32, i32, i32, vp, i32, vp])
     sig("gll_unpack_columns", i32, [vp, i32, i32, i32, i32, vp, i32, vp])
     sig("gll_unpack_pred", i32, [vp, i32, i32, vp, i32, vp])
@@ -96,7 +97,7 @@ EXPORTS = ["gll_last_error", "gll_version", "gll_device_sm_count", "gll_kernel_c
            "gll_weights_workspace_bytes", "gll_cg_workspace_bytes", "gll_knn", "gll_graph_build", "gll_edge_weights",
            "gll_cg_solve", "gll_backward_edges", "gll_forward", "gll_backward", "gll_knn_rows_workspace_bytes", "gll_knn_rows",
            "gll_backward_edges_rows", "gll_pack_columns", "gll_unpack_columns", "gll_unpack_pred", "gll_pack_grad",
-           "gll_cg_rows_workspace_bytes", "gll_cg_rows_init", "gll_cg_rows_spmv", "gll_cg_rows_update", "gll_ce_loss"]
+           "gll_cg_rows_workspace_bytes", "gll_cg_rows_init", "gll_cg_rows_spmv", "gll_cg_rows_update", "gll_ce_loss", "gll_ce_loss_workspace_bytes"]
 
 
 def check(rc: int, what: str) -> None:

@@ -88,15 +88,18 @@ __global__ void pack_grad_kernel(const void* __restrict__ g, int is_f64, int m, 
 }
 
 // custom_ce_loss (losses.py:128-136): loss = -sum_i log(p[i, t_i] + 1e-8) / m and, in the same pass, its gradient
-// d loss / d p[i, c] = -[c == t_i] / (m (p[i, t_i] + 1e-8)).  One CTA; fixed summation order.
+// d loss / d p[i, c] = -[c == t_i] / (m (p[i, t_i] + 1e-8)).  Fixed summation order: per-CTA sums in CTA order.
+// One CTA writes the loss directly (minibatch sizes); with several CTAs each writes its partial sum and
+// ce_loss_finish_kernel adds them.
 template <typename T>
 __global__ void __launch_bounds__(1024) ce_loss_kernel(const T* __restrict__ p, const long long* __restrict__ tgt, int m, int l,
-                                                        T* __restrict__ loss, T* __restrict__ grad, int* __restrict__ status) {
+                                                        T* __restrict__ loss, T* __restrict__ grad, double* __restrict__ partial,
+                                                        int* __restrict__ status) {
   __shared__ double part[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double acc = 0.0;
   const double inv_m = 1.0 / (double)m;
-  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
     const long long t = tgt[i];
     const bool ok = t >= 0 && t < l;
     if (!ok && status) atomicOr(status, GLL_STATUS_NONFINITE);
@@ -110,8 +113,21 @@ __global__ void __launch_bounds__(1024) ce_loss_kernel(const T* __restrict__ p, 
   if (warp == 0) {
     double v = (lane < (int)(blockDim.x >> 5)) ? part[lane] : 0.0;
     v = warp_sum(v);
-    if (lane == 0) *loss = (T)(-v * inv_m);
+    if (lane == 0) {
+      if (gridDim.x == 1)
+        *loss = (T)(-v * inv_m);
+      else
+        partial[blockIdx.x] = v;
+    }
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32) ce_loss_finish_kernel(const double* __restrict__ partial, int blocks, int m, T* __restrict__ loss) {
+  double v = 0.0;
+  for (int b = threadIdx.x; b < blocks; b += 32) v += partial[b];
+  v = warp_sum(v);
+  if (threadIdx.x == 0) *loss = (T)(-v / (double)m);
 }
 
 __global__ void unpack_pred_kernel(const float* __restrict__ u, int m, int l, int lp, void* __restrict__ pred, int is_f64) {
@@ -343,16 +359,34 @@ int gll_cg_rows_update(const float* diag, int m, int l, int row_lo, int row_hi, 
                         workspace_bytes, (cudaStream_t)stream);
 }
 
+size_t gll_ce_loss_workspace_bytes(int m) { return (m <= 4096) ? 0 : sizeof(double) * 1024; }
+
 int gll_ce_loss(const void* pred, int pred_is_f64, const long long* targets, int m, int l, void* loss_out, void* grad_out,
-                int* status, void* stream) {
+                int* status, void* workspace, size_t workspace_bytes, void* stream) {
   GLL_REQUIRE(pred && targets && loss_out && grad_out && m >= 1 && l >= 1, "bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  GLL_PROF(KID_PACK, st);
-  if (pred_is_f64)
-    ce_loss_kernel<double><<<1, 1024, 0, st>>>((const double*)pred, targets, m, l, (double*)loss_out, (double*)grad_out, status);
-  else
-    ce_loss_kernel<float><<<1, 1024, 0, st>>>((const float*)pred, targets, m, l, (float*)loss_out, (float*)grad_out, status);
+  int blocks = 1;
+  if (m > 4096) {
+    blocks = min(1024, min(device_info().sms * 2, ceil_div(m, 1024)));
+    GLL_REQUIRE(workspace && workspace_bytes >= gll_ce_loss_workspace_bytes(m), "loss workspace too small");
+  }
+  double* partial = (double*)workspace;
+  {
+    GLL_PROF(KID_PACK, st);
+    if (pred_is_f64)
+      ce_loss_kernel<double><<<blocks, 1024, 0, st>>>((const double*)pred, targets, m, l, (double*)loss_out, (double*)grad_out, partial, status);
+    else
+      ce_loss_kernel<float><<<blocks, 1024, 0, st>>>((const float*)pred, targets, m, l, (float*)loss_out, (float*)grad_out, partial, status);
+  }
   GLL_LAUNCH_CHECK();
+  if (blocks > 1) {
+    GLL_PROF(KID_PACK, st);
+    if (pred_is_f64)
+      ce_loss_finish_kernel<double><<<1, 32, 0, st>>>(partial, blocks, m, (double*)loss_out);
+    else
+      ce_loss_finish_kernel<float><<<1, 32, 0, st>>>(partial, blocks, m, (float*)loss_out);
+    GLL_LAUNCH_CHECK();
+  }
   return GLL_OK;
 }
 

@@ -28,9 +28,12 @@ class _CELoss(torch.autograd.Function):
             raise ValueError("targets must hold one class index per row of softmax_logits")
         loss = torch.empty((), dtype=p.dtype, device=p.device)
         grad = torch.empty_like(p)
+        wsb = lib.gll_ce_loss_workspace_bytes(m)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=p.device) if wsb else None
         with torch.cuda.device(p.device):
             _lib.check(lib.gll_ce_loss(p.data_ptr(), int(p.dtype == torch.float64), t.data_ptr(), m, l, loss.data_ptr(),
-                                       grad.data_ptr(), None, torch.cuda.current_stream(p.device).cuda_stream), "gll_ce_loss")
+                                       grad.data_ptr(), None, ws.data_ptr() if wsb else None, wsb,
+                                       torch.cuda.current_stream(p.device).cuda_stream), "gll_ce_loss")
         ctx.save_for_backward(grad)
         ctx.in_dtype = softmax_logits.dtype
         return loss.to(softmax_logits.dtype)

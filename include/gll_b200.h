@@ -195,8 +195,9 @@ int gll_pack_grad(const void* grad_out, int grad_is_f64, int m, int l, float* rh
  * launch d loss / d pred (m x l, same dtype as pred).  pred: m x l float64 (pred_is_f64 != 0) or fp32; targets: m int64;
  * loss_out: one element of pred's dtype.  status (optional, device int): GLL_STATUS_NONFINITE is or-ed in when a target
  * is outside [0, l). */
+size_t gll_ce_loss_workspace_bytes(int m);  /* 0 for m <= 4096 (one CTA writes the loss directly) */
 int gll_ce_loss(const void* pred, int pred_is_f64, const long long* targets, int m, int l, void* loss_out, void* grad_out,
-                int* status, void* stream);
+                int* status, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused drivers: what LaplaceLearningSparseHard.forward / .backward call (GLL.py:13-73, 75-177).

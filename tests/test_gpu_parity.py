@@ -699,3 +699,21 @@ def test_fused_ce_loss_matches_reference_formula(gll, dtype):
     assert ours.dtype == dtype and ours.shape == ref.shape
     assert abs(ours.item() - ref.item()) <= tol * abs(ref.item())
     assert torch.allclose(b.grad, a.grad, rtol=tol, atol=0.0)
+
+
+def test_fused_ce_loss_many_rows(gll):
+    """More than 4096 rows: several CTAs, partial sums added by a second tiny launch (sharded 1M-node graph path)."""
+    from graphlearninglayer_b200.losses import custom_ce_loss
+
+    g = torch.Generator().manual_seed(4)
+    m, l = 50001, 100
+    p = torch.softmax(torch.randn(m, l, generator=g, dtype=torch.float64), dim=1).cuda()
+    t = torch.randint(0, l, (m,), generator=g).cuda()
+    a = p.clone().requires_grad_(True)
+    ref = -torch.sum(torch.nn.functional.one_hot(t, num_classes=l).to(a.dtype) * torch.log(a + 1e-8)) / m
+    ref.backward()
+    b = p.clone().requires_grad_(True)
+    ours = custom_ce_loss(b, t)
+    ours.backward()
+    assert abs(ours.item() - ref.item()) <= 1e-12 * abs(ref.item())
+    assert torch.allclose(b.grad, a.grad, rtol=1e-12, atol=0.0)
