@@ -26,10 +26,39 @@ __device__ __forceinline__ void list_insert(u64& mine, u64 x, int lane) {
     mine = x;
 }
 
-// Merge one unsorted 32-set (one key per lane, KEY_INF = empty) into the sorted list `mine`: only keys below the list's
-// current last entry can enter, and those are found with one ballot instead of 32 trial insertions.
+// compare-exchange with the lane at xor distance j: keep the smaller key if keep_min
+__device__ __forceinline__ void key_cmpx(u64& k, int j, bool keep_min) {
+  const u64 o = __shfl_xor_sync(FULL, k, j);
+  const bool less = k < o;
+  k = (less == keep_min) ? k : o;
+}
+// ascending bitonic sort of 32 keys, one per lane
+__device__ __forceinline__ void key_sort32(u64& k, int lane) {
+#pragma unroll
+  for (int w = 2; w <= 32; w <<= 1) {
+#pragma unroll
+    for (int j = w >> 1; j >= 1; j >>= 1) {
+      const bool up = (lane & w) == 0;  // w == 32: every lane ascending
+      key_cmpx(k, j, ((lane & j) == 0) == up);
+    }
+  }
+}
+// Merge one unsorted 32-set (one key per lane, KEY_INF = empty) into the sorted list `mine`.  Only keys below the list's
+// current last entry can enter: a handful are inserted one by one (one ballot finds them); many -- the first lists of a
+// row -- go through a sorting network: sort the set, take min(mine[i], set[31 - i]) (the 32 smallest of the union, a
+// bitonic sequence) and merge it back into ascending order.  The serial form alone was 40 % of the re-rank kernel's
+// instructions.
 __device__ __forceinline__ void list_merge_set(u64& mine, u64 c, int lane) {
   unsigned m = __ballot_sync(FULL, c < __shfl_sync(FULL, mine, KC - 1));
+  if (m == 0) return;
+  if (__popc(m) > 6) {
+    key_sort32(c, lane);
+    const u64 r = __shfl_sync(FULL, c, 31 - lane);
+    mine = (r < mine) ? r : mine;
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) key_cmpx(mine, j, (lane & j) == 0);
+    return;
+  }
   while (m) {
     const int t = __ffs(m) - 1;
     m &= m - 1;
