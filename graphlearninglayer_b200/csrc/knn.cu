@@ -572,7 +572,7 @@ int knn_finish(const float* X, const float* sq, const unsigned* sqmax_bits, int 
   }
   GLL_LAUNCH_CHECK();
   size_t fsmem = sizeof(float) * (size_t)d;
-  int fblocks = device_info().sms * 2;
+  int fblocks = device_info().sms;
   if (getenv("GLL_B200_KNN_DEBUG") != nullptr) return GLL_OK;  // timing experiments: every row would be "unproven"
   {
     GLL_PROF(KID_KNN_FALLBACK, st);
@@ -607,7 +607,7 @@ static int knn_finish64(const float* X, const float* sq, const unsigned* sqmax_b
   }
   GLL_LAUNCH_CHECK();
   const size_t fsmem = sizeof(float) * (size_t)d;
-  const int fblocks = device_info().sms * 2;
+  const int fblocks = device_info().sms;
   if (getenv("GLL_B200_KNN_DEBUG") != nullptr) return GLL_OK;  // timing experiments: every row would be "unproven"
   {
     GLL_PROF(KID_KNN_FALLBACK, st);
