@@ -399,7 +399,9 @@ def run_b200(args, rank, world, local_rank):
             "config": {"workload": args.workload + ": " + WORKLOAD_DESC[args.workload], "l2": "flushed between timed steps "
                        "(256 MiB memset outside the event pairs)", "parallelism": (f"one graph over {world} rank(s): rows (kNN, backward) + "
                                        + ("class columns (CG, no per-iteration collective)" if args.cg_partition == "columns" else
-                                          "rows (CG: NCCL all-gather of the iterate + all-reduce of the dot products per iteration)")
+                                          "rows (CG: NCCL all-gather of the iterate + all-reduce of the dot products per iteration)"
+                                          if args.cg_partition == "rows" else
+                                          "rows (CG: iterate and dot products exchanged INSIDE the kernels over NVLink peer memory)")
                                        if sharded
                                        else f"independent graphs x{world}"),
                        "cg_tol": 1e-7,
@@ -461,7 +463,7 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--loss", choices=["fused", "torch"], default="fused",
                     help="custom_ce_loss of the step: graphlearninglayer_b200.losses (one kernel) or the reference's PyTorch ops")
-    ap.add_argument("--cg-partition", choices=["columns", "rows"], default="columns",
+    ap.add_argument("--cg-partition", choices=["columns", "rows", "rows-p2p"], default="columns",
                     help="sharded workloads: split the CG solves by class columns (no per-iteration collective) or by rows "
                          "(all-gather + all-reduce per iteration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -26,6 +26,11 @@ class GllError(RuntimeError):
     pass
 
 
+class Peers(C.Structure):
+    """gll_peers (include/gll_b200.h): every rank's u array, mailbox and flag block as mapped in this process."""
+    _fields_ = [("u", C.c_void_p * 8), ("mail", C.c_void_p * 8), ("flags", C.c_void_p * 8), ("world", C.c_int), ("rank", C.c_int)]
+
+
 class Layout(C.Structure):
     """Mirror of ``gll_layout`` (include/gll_b200.h): byte offsets into the state buffer."""
     _names = ["knn_idx", "knn_dist", "row_ptr", "col", "dist", "w", "gv", "eps", "kappa", "deg", "bvec", "uu_ptr",
@@ -77,6 +82,12 @@ def _load():
     sig("gll_cg_rows_init", i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, sz, vp])
     sig("gll_cg_rows_spmv", i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, sz, vp])
     sig("gll_cg_rows_update", i32, [vp, i32, i32, i32, i32, vp, i32, i32, f32, vp, vp, vp, vp, vp, sz, vp])
+    sig("gll_cg_rows_peer_mail_bytes", sz, [])
+    sig("gll_cg_rows_peer_flag_bytes", sz, [])
+    u32, pp = C.c_uint, C.POINTER(Peers)
+    sig("gll_cg_rows_init_p2p", i32, [vp, vp, i32, i32, i32, i32, vp, pp, u32, vp, sz, vp])
+    sig("gll_cg_rows_spmv_p2p", i32, [vp, vp, vp, vp, i32, i32, i32, i32, pp, u32, vp, vp, sz, vp])
+    sig("gll_cg_rows_update_p2p", i32, [vp, i32, i32, i32, i32, i32, i32, f32, vp, pp, u32, vp, vp, vp, sz, vp])
     sig("gll_ce_loss_workspace_bytes", sz, [i32])
     sig("gll_ce_loss", i32, [vp, i32, vp, i32, i32, vp, vp, vp, vp, sz, vp])
     sig("gll_pack_columns", i32, [vp, i32, i32, i32, i32, vp, i32, vp])
@@ -97,7 +108,9 @@ EXPORTS = ["gll_last_error", "gll_version", "gll_device_sm_count", "gll_kernel_c
            "gll_weights_workspace_bytes", "gll_cg_workspace_bytes", "gll_knn", "gll_graph_build", "gll_edge_weights",
            "gll_cg_solve", "gll_backward_edges", "gll_forward", "gll_backward", "gll_knn_rows_workspace_bytes", "gll_knn_rows",
            "gll_backward_edges_rows", "gll_pack_columns", "gll_unpack_columns", "gll_unpack_pred", "gll_pack_grad",
-           "gll_cg_rows_workspace_bytes", "gll_cg_rows_init", "gll_cg_rows_spmv", "gll_cg_rows_update", "gll_ce_loss", "gll_ce_loss_workspace_bytes"]
+           "gll_cg_rows_workspace_bytes", "gll_cg_rows_init", "gll_cg_rows_spmv", "gll_cg_rows_update", "gll_ce_loss", "gll_ce_loss_workspace_bytes",
+           "gll_cg_rows_peer_mail_bytes", "gll_cg_rows_peer_flag_bytes", "gll_cg_rows_init_p2p", "gll_cg_rows_spmv_p2p",
+           "gll_cg_rows_update_p2p"]
 
 
 def check(rc: int, what: str) -> None:

@@ -343,23 +343,49 @@ size_t gll_cg_rows_workspace_bytes(int rows_local, int l) { return cg_rows_ws_by
 
 int gll_cg_rows_init(const float* diag, const float* rhs, int m, int l, int row_lo, int row_hi, float* x, float* u_full,
                      void* workspace, size_t workspace_bytes, void* stream) {
-  return cg_rows_init(diag, rhs, m, l, row_lo, row_hi, x, u_full, workspace, workspace_bytes, (cudaStream_t)stream);
+  return cg_rows_init(diag, rhs, m, l, row_lo, row_hi, x, u_full, workspace, workspace_bytes, nullptr, 0u, (cudaStream_t)stream);
 }
 
 int gll_cg_rows_spmv(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, int m, int l, int row_lo,
                      int row_hi, const float* u_full, double* sums, void* workspace, size_t workspace_bytes, void* stream) {
-  return cg_rows_spmv(uu_ptr, uu_col, uu_val, diag, m, l, row_lo, row_hi, u_full, sums, workspace, workspace_bytes,
-                      (cudaStream_t)stream);
+  return cg_rows_spmv(uu_ptr, uu_col, uu_val, diag, m, l, row_lo, row_hi, u_full, sums, workspace, workspace_bytes, nullptr, 0u,
+                      nullptr, (cudaStream_t)stream);
 }
 
 int gll_cg_rows_update(const float* diag, int m, int l, int row_lo, int row_hi, const double* sums, int iter, int max_iter,
                        float tol, float* x, float* u_full, int* ctrl, float* resid_out, void* workspace, size_t workspace_bytes,
                        void* stream) {
   return cg_rows_update(diag, m, l, row_lo, row_hi, sums, iter, max_iter, tol, x, u_full, ctrl, resid_out, workspace,
-                        workspace_bytes, (cudaStream_t)stream);
+                        workspace_bytes, nullptr, 0u, (cudaStream_t)stream);
 }
 
 size_t gll_ce_loss_workspace_bytes(int m) { return (m <= 4096) ? 0 : sizeof(double) * 1024; }
+
+size_t gll_cg_rows_peer_mail_bytes(void) { return cg_rows_peer_mail_bytes(); }
+size_t gll_cg_rows_peer_flag_bytes(void) { return cg_rows_peer_flag_bytes(); }
+
+int gll_cg_rows_init_p2p(const float* diag, const float* rhs, int m, int l, int row_lo, int row_hi, float* x,
+                         const gll_peers* peers, unsigned epoch, void* workspace, size_t workspace_bytes, void* stream) {
+  GLL_REQUIRE(peers != nullptr, "peer table missing");
+  return cg_rows_init(diag, rhs, m, l, row_lo, row_hi, x, (float*)peers->u[peers->rank], workspace, workspace_bytes, peers, epoch,
+                      (cudaStream_t)stream);
+}
+
+int gll_cg_rows_spmv_p2p(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, int m, int l, int row_lo,
+                         int row_hi, const gll_peers* peers, unsigned epoch, const int* ctrl, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  GLL_REQUIRE(peers != nullptr, "peer table missing");
+  return cg_rows_spmv(uu_ptr, uu_col, uu_val, diag, m, l, row_lo, row_hi, (const float*)peers->u[peers->rank], nullptr, workspace,
+                      workspace_bytes, peers, epoch, ctrl, (cudaStream_t)stream);
+}
+
+int gll_cg_rows_update_p2p(const float* diag, int m, int l, int row_lo, int row_hi, int iter, int max_iter, float tol, float* x,
+                           const gll_peers* peers, unsigned epoch, int* ctrl, float* resid_out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  GLL_REQUIRE(peers != nullptr, "peer table missing");
+  return cg_rows_update(diag, m, l, row_lo, row_hi, nullptr, iter, max_iter, tol, x, (float*)peers->u[peers->rank], ctrl, resid_out,
+                        workspace, workspace_bytes, peers, epoch, (cudaStream_t)stream);
+}
 
 int gll_ce_loss(const void* pred, int pred_is_f64, const long long* targets, int m, int l, void* loss_out, void* grad_out,
                 int* status, void* workspace, size_t workspace_bytes, void* stream) {

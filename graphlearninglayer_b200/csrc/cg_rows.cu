@@ -12,6 +12,19 @@
 //                    r -= alpha s; u = r/diag     (every CTA derives the same scalars from the same reduced sums)
 //
 // No floating-point atomics: per-CTA partials -> the last CTA to finish (integer ticket) adds them in CTA order.
+//
+// Peer-memory mode (gll_cg_rows_*_p2p): the two collectives are FUSED into the kernels over NVLink peer pointers
+// (symmetric memory) -- no NCCL call, no host round trip inside the loop:
+//   update / init   store the new u rows straight into EVERY rank's copy of the u array (P2P stores), then the last CTA
+//                   raises this rank's "u published" epoch flag on every peer (fence.sys, st.release.sys)
+//   spmv            waits (ld.acquire.sys on LOCAL flags, bounded spin) until every rank's u for this iteration has
+//                   landed; its last CTA writes this rank's 3*lp partial sums into a mailbox row on every peer and raises
+//                   the "sums published" flag
+//   update          waits for all ranks' sums, adds the mailbox rows in rank order (identical on every rank), proceeds
+// Every wait is for data produced by kernels that the peers launch EARLIER in the same sequence, so the scheme cannot
+// deadlock as long as every rank enqueues the same launches; a spin that lasts longer than 2 s traps (no hung GPU).
+#include <string.h>
+
 #include "cg_common.cuh"
 
 namespace gll {
@@ -23,7 +36,8 @@ constexpr int RW_WARPS = RW_THREADS / 32;
 struct RowsState {
   float *r, *p, *s, *w;      // [rows_local][lp]
   double* partial;           // [grid][3*lp]
-  unsigned* ticket;
+  unsigned* ticket;          // spmv: last-CTA election
+  unsigned* ticket2;         // init / update: last-CTA election for the "u published" flag (peer-memory mode)
   float* scal;               // [2 parities][3][lp]: 1/gamma_old, 1/alpha_old, frozen (0/1); launch `iter` reads parity
                              // iter&1 and CTA 0 writes the other one, so every CTA of a launch sees the same values
   double* tol2;              // resolved at iteration 0
@@ -43,6 +57,7 @@ RowsState carve(void* ws, size_t ws_bytes, int rows_local, int lp) {
   S.grid = rows_grid();
   S.partial = cv.take<double>((size_t)S.grid * 3 * lp);
   S.ticket = cv.take<unsigned>(64);
+  S.ticket2 = S.ticket + 32;
   S.scal = cv.take<float>(6 * (size_t)lp);
   S.tol2 = cv.take<double>(4);
   return S;
@@ -51,9 +66,53 @@ RowsState carve(void* ws, size_t ws_bytes, int rows_local, int lp) {
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// ---- peer-memory mode ----
+constexpr int MAX_PEERS = 8;
+constexpr int MAIL_ROW = 3 * CG_MAX_LP;  // doubles per (parity, source rank)
+struct Peers {
+  float* u[MAX_PEERS];      // every rank's u array (m' x lp), mine included
+  double* mail[MAX_PEERS];  // every rank's mailbox: [2 parities][MAX_PEERS sources][MAIL_ROW]
+  unsigned* flags[MAX_PEERS];  // every rank's flags: [0][src] = epoch of src's published u, [1][src] = of src's sums
+  int world, rank;          // world == 0: not in peer-memory mode
+};
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// one thread: until every rank's flag has reached `epoch` (flags only grow); bounded
+__device__ __forceinline__ void wait_all_flags(const unsigned* f, int world, unsigned epoch) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (int p = 0; p < world; ++p) {
+    unsigned spin = 0;
+    while ((int)(ld_acquire_sys(f + p) - epoch) < 0) {
+      if ((++spin & 1023u) == 0) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 2000000000ull) __trap();  // 2 s: a peer died or the launch sequences diverged
+      }
+    }
+  }
+}
+// whole CTA, at the end of a kernel whose threads stored into peer memory: the last CTA to get here raises flag `which`
+__device__ __forceinline__ void publish_epoch(const Peers& P, int which, unsigned epoch, unsigned* ticket) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();  // this CTA's peer stores (ordered before me by the barrier) are performed system-wide
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      __threadfence_system();
+      *ticket = 0u;
+      for (int p = 0; p < P.world; ++p) st_release_sys(P.flags[p] + which * MAX_PEERS + P.rank, epoch);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 rows_init_kernel(const float* __restrict__ diag, const float* __restrict__ rhs, int lp, int row_lo, int row_hi, float* __restrict__ x,
-                 float* __restrict__ u_full, RowsState S) {
+                 float* __restrict__ u_full, RowsState S, Peers PR, unsigned epoch) {
   const int Q = lp >> 2;
   const long long total = (long long)(row_hi - row_lo) * Q;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -67,7 +126,12 @@ rows_init_kernel(const float* __restrict__ diag, const float* __restrict__ rhs, 
     st4(S.r + lo, b);
     st4(S.p + lo, z);
     st4(S.s + lo, z);
-    st4(u_full + (size_t)i * lp + 4 * q, make_float4(b.x * dinv, b.y * dinv, b.z * dinv, b.w * dinv));
+    const float4 u4 = make_float4(b.x * dinv, b.y * dinv, b.z * dinv, b.w * dinv);
+    if (PR.world == 0) {
+      st4(u_full + (size_t)i * lp + 4 * q, u4);
+    } else {
+      for (int p = 0; p < PR.world; ++p) st4(PR.u[p] + (size_t)i * lp + 4 * q, u4);
+    }
   }
   if (blockIdx.x == 0) {
     for (int c = threadIdx.x; c < 6 * lp; c += blockDim.x) S.scal[c] = 0.f;
@@ -76,6 +140,7 @@ rows_init_kernel(const float* __restrict__ diag, const float* __restrict__ rhs, 
       *S.tol2 = 0.0;
     }
   }
+  if (PR.world > 0) publish_epoch(PR, 0, epoch, S.ticket2);
 }
 
 // sum over the neighbour-slot index s of lane = s*Q + q; valid on lanes < Q
@@ -103,9 +168,15 @@ __device__ __forceinline__ float4 reduce_slots(float4 a, int s, int S, int Q) {
 // w = A u on the rank's rows; lane = (neighbour slot s, class quad q), 128-bit gathers of u_j, four gathers in flight
 __global__ void __launch_bounds__(RW_THREADS)
 rows_spmv_kernel(const int* __restrict__ ptr, const int* __restrict__ col, const float* __restrict__ val, const float* __restrict__ diag,
-                 int lp, int row_lo, int row_hi, const float* __restrict__ u_full, RowsState S, double* __restrict__ sums) {
+                 int lp, int row_lo, int row_hi, const float* __restrict__ u_full, RowsState S, double* __restrict__ sums, Peers PR,
+                 unsigned epoch, const int* __restrict__ ctrl) {
   extern __shared__ double wpart[];  // [RW_WARPS][3*lp]
   __shared__ bool last;
+  if (PR.world > 0) {
+    if (ctrl[0] != 0) return;  // the solve has stopped on every rank (same decision everywhere): nothing to wait for
+    if (threadIdx.x == 0) wait_all_flags(PR.flags[PR.rank], PR.world, epoch);  // everybody's u of this iteration is here
+    __syncthreads();
+  }
   const int Q = lp >> 2, NS = 32 / Q;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int s = lane / Q, q = lane - s * Q;
@@ -172,22 +243,45 @@ rows_spmv_kernel(const int* __restrict__ ptr, const int* __restrict__ col, const
   for (int c = threadIdx.x; c < 3 * lp; c += RW_THREADS) {
     double t = 0.0;
     for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(S.partial + (size_t)b * 3 * lp + c);
-    sums[c] = t;
+    if (PR.world == 0) {
+      sums[c] = t;
+    } else {  // my partial sums into my mailbox row on every rank
+      for (int p = 0; p < PR.world; ++p) PR.mail[p][((size_t)(epoch & 1u) * MAX_PEERS + PR.rank) * MAIL_ROW + c] = t;
+    }
+  }
+  if (PR.world > 0) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int p = 0; p < PR.world; ++p) st_release_sys(PR.flags[p] + MAX_PEERS + PR.rank, epoch);
   }
   if (threadIdx.x == 0) *S.ticket = 0u;
 }
 
 // ctrl[0] = stop flag, ctrl[1] = iterations done, ctrl[2] = status bits
 __global__ void __launch_bounds__(256)
-rows_update_kernel(const float* __restrict__ diag, int lp, int row_lo, int row_hi, const double* __restrict__ sums, int iter,
+rows_update_kernel(const float* __restrict__ diag, int lp, int row_lo, int row_hi, const double* sums, int iter,
                    int max_iter, float tol, float* __restrict__ x, float* __restrict__ u_full, RowsState S, int* __restrict__ ctrl,
-                   float* __restrict__ resid_out) {
+                   float* __restrict__ resid_out, Peers PR, unsigned epoch) {
   __shared__ float alpha[CG_MAX_LP], beta[CG_MAX_LP];
+  __shared__ double ssum[MAIL_ROW];
   __shared__ int stop_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* sc_old = S.scal + (size_t)(iter & 1) * 3 * lp;
   float* sc_new = S.scal + (size_t)((iter + 1) & 1) * 3 * lp;
   if (ctrl[0] != 0) return;  // an earlier launch stopped the solve (written by that launch, so no race here)
+  if (PR.world > 0) {  // every rank's partial sums of this iteration: add the mailbox rows in rank order
+    if (threadIdx.x == 0) wait_all_flags(PR.flags[PR.rank] + MAX_PEERS, PR.world, epoch);
+    __syncthreads();
+    const double* mb = PR.mail[PR.rank] + (size_t)(epoch & 1u) * MAX_PEERS * MAIL_ROW;
+    for (int c = threadIdx.x; c < 3 * lp; c += blockDim.x) {
+      double t = 0.0;
+      for (int p = 0; p < PR.world; ++p) t += __ldcg(mb + (size_t)p * MAIL_ROW + c);
+      ssum[c] = t;
+    }
+    __syncthreads();
+    sums = ssum;
+  }
   if (warp == 0) {
     double tol2;
     if (iter == 0) {
@@ -272,8 +366,14 @@ rows_update_kernel(const float* __restrict__ diag, int lp, int row_lo, int row_h
     st4(S.s + lo, sv);
     st4(x + go, xv);
     st4(S.r + lo, r);
-    st4(u_full + go, make_float4(r.x * dinv, r.y * dinv, r.z * dinv, r.w * dinv));
+    const float4 un = make_float4(r.x * dinv, r.y * dinv, r.z * dinv, r.w * dinv);
+    if (PR.world == 0) {
+      st4(u_full + go, un);
+    } else {  // the fused all-gather: my rows of the new u into every rank's copy
+      for (int p = 0; p < PR.world; ++p) st4(PR.u[p] + go, un);
+    }
   }
+  if (PR.world > 0) publish_epoch(PR, 0, epoch + 1u, S.ticket2);
 }
 
 }  // namespace
@@ -284,8 +384,33 @@ size_t cg_rows_ws_bytes(int rows_local, int l) {
   return 4 * v + align_up(sizeof(double) * (size_t)rows_grid() * 3 * lp, 256) + 256 + align_up(sizeof(float) * 6 * lp, 256) + 256 + 2048;
 }
 
+static Peers make_peers(const gll_peers* pr) {
+  Peers P;
+  memset(&P, 0, sizeof(P));
+  if (pr != nullptr) {
+    P.world = pr->world;
+    P.rank = pr->rank;
+    for (int p = 0; p < pr->world && p < MAX_PEERS; ++p) {
+      P.u[p] = (float*)pr->u[p];
+      P.mail[p] = (double*)pr->mail[p];
+      P.flags[p] = (unsigned*)pr->flags[p];
+    }
+  }
+  return P;
+}
+static bool peers_ok(const gll_peers* pr) {
+  if (pr == nullptr) return true;
+  if (pr->world < 1 || pr->world > MAX_PEERS || pr->rank < 0 || pr->rank >= pr->world) return false;
+  for (int p = 0; p < pr->world; ++p)
+    if (!pr->u[p] || !pr->mail[p] || !pr->flags[p]) return false;
+  return true;
+}
+size_t cg_rows_peer_mail_bytes() { return sizeof(double) * 2 * MAX_PEERS * MAIL_ROW; }
+size_t cg_rows_peer_flag_bytes() { return sizeof(unsigned) * 2 * MAX_PEERS; }
+
 int cg_rows_init(const float* diag, const float* rhs, int m, int l, int row_lo, int row_hi, float* x, float* u_full, void* ws,
-                 size_t ws_bytes, cudaStream_t st) {
+                 size_t ws_bytes, const gll_peers* peers, unsigned epoch, cudaStream_t st) {
+  GLL_REQUIRE(peers_ok(peers), "bad peer table");
   GLL_REQUIRE(diag && rhs && x && u_full && ws, "null pointer");
   GLL_REQUIRE(m >= 1 && l >= 1 && 0 <= row_lo && row_lo <= row_hi && row_hi <= m, "bad sizes");
   const int lp = padded_classes(l);
@@ -297,15 +422,18 @@ int cg_rows_init(const float* diag, const float* rhs, int m, int l, int row_lo, 
   RowsState S = carve(ws, ws_bytes, row_hi - row_lo, lp);
   const long long total = (long long)(row_hi - row_lo) * (lp >> 2);
   const int grid = (int)max(1LL, min((long long)device_info().sms * 8, (total + 255) / 256));
+  GLL_CUDA_CHECK(cudaMemsetAsync(S.ticket, 0, 64 * sizeof(unsigned), st));  // both last-CTA tickets start at zero
   GLL_PROF(KID_CG_ROWS, st);
-  rows_init_kernel<<<grid, 256, 0, st>>>(diag, rhs, lp, row_lo, row_hi, x, u_full, S);
+  rows_init_kernel<<<grid, 256, 0, st>>>(diag, rhs, lp, row_lo, row_hi, x, u_full, S, make_peers(peers), epoch);
   GLL_LAUNCH_CHECK();
   return GLL_OK;
 }
 
 int cg_rows_spmv(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, int m, int l, int row_lo, int row_hi,
-                 const float* u_full, double* sums, void* ws, size_t ws_bytes, cudaStream_t st) {
-  GLL_REQUIRE(uu_ptr && uu_col && uu_val && diag && u_full && sums && ws, "null pointer");
+                 const float* u_full, double* sums, void* ws, size_t ws_bytes, const gll_peers* peers, unsigned epoch,
+                 const int* ctrl, cudaStream_t st) {
+  GLL_REQUIRE(uu_ptr && uu_col && uu_val && diag && u_full && ws && (sums || peers), "null pointer");
+  GLL_REQUIRE(peers_ok(peers) && (peers == nullptr || ctrl != nullptr), "bad peer table");
   GLL_REQUIRE(m >= 1 && l >= 1 && 0 <= row_lo && row_lo <= row_hi && row_hi <= m, "bad sizes");
   const int lp = padded_classes(l);
   GLL_REQUIRE(lp <= CG_MAX_LP, "at most 128 classes per solve");
@@ -318,21 +446,25 @@ int cg_rows_spmv(const int* uu_ptr, const int* uu_col, const float* uu_val, cons
     attr_set = true;
   }
   GLL_PROF(KID_CG_ROWS, st);
-  rows_spmv_kernel<<<S.grid, RW_THREADS, smem, st>>>(uu_ptr, uu_col, uu_val, diag, lp, row_lo, row_hi, u_full, S, sums);
+  rows_spmv_kernel<<<S.grid, RW_THREADS, smem, st>>>(uu_ptr, uu_col, uu_val, diag, lp, row_lo, row_hi, u_full, S, sums,
+                                                     make_peers(peers), epoch, ctrl);
   GLL_LAUNCH_CHECK();
   return GLL_OK;
 }
 
 int cg_rows_update(const float* diag, int m, int l, int row_lo, int row_hi, const double* sums, int iter, int max_iter, float tol,
-                   float* x, float* u_full, int* ctrl, float* resid_out, void* ws, size_t ws_bytes, cudaStream_t st) {
-  GLL_REQUIRE(diag && sums && x && u_full && ctrl && ws, "null pointer");
+                   float* x, float* u_full, int* ctrl, float* resid_out, void* ws, size_t ws_bytes, const gll_peers* peers,
+                   unsigned epoch, cudaStream_t st) {
+  GLL_REQUIRE(diag && (sums || peers) && x && u_full && ctrl && ws, "null pointer");
+  GLL_REQUIRE(peers_ok(peers), "bad peer table");
   GLL_REQUIRE(m >= 1 && l >= 1 && 0 <= row_lo && row_lo <= row_hi && row_hi <= m && iter >= 0, "bad sizes");
   const int lp = padded_classes(l);
   RowsState S = carve(ws, ws_bytes, row_hi - row_lo, lp);
   const long long total = (long long)(row_hi - row_lo) * (lp >> 2);
   const int grid = (int)max(1LL, min((long long)device_info().sms * 8, (total + 255) / 256));
   GLL_PROF(KID_CG_ROWS, st);
-  rows_update_kernel<<<grid, 256, 0, st>>>(diag, lp, row_lo, row_hi, sums, iter, max_iter, tol, x, u_full, S, ctrl, resid_out);
+  rows_update_kernel<<<grid, 256, 0, st>>>(diag, lp, row_lo, row_hi, sums, iter, max_iter, tol, x, u_full, S, ctrl, resid_out,
+                                           make_peers(peers), epoch);
   GLL_LAUNCH_CHECK();
   return GLL_OK;
 }

@@ -124,14 +124,19 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
            size_t ws_bytes, cudaStream_t st);
 size_t cg_ws_bytes(int m, int l);
 
-// row-partitioned CG (cg_rows.cu): stage launchers, the host runs the NCCL collectives between them
+// row-partitioned CG (cg_rows.cu): stage launchers.  peers == NULL: the host runs the NCCL collectives between them;
+// otherwise the exchanges are fused into the kernels over peer memory (epoch = flag value of this stage, see cg_rows.cu)
 size_t cg_rows_ws_bytes(int rows_local, int l);
+size_t cg_rows_peer_mail_bytes();
+size_t cg_rows_peer_flag_bytes();
 int cg_rows_init(const float* diag, const float* rhs, int m, int l, int row_lo, int row_hi, float* x, float* u_full, void* ws,
-                 size_t ws_bytes, cudaStream_t st);
+                 size_t ws_bytes, const gll_peers* peers, unsigned epoch, cudaStream_t st);
 int cg_rows_spmv(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, int m, int l, int row_lo, int row_hi,
-                 const float* u_full, double* sums, void* ws, size_t ws_bytes, cudaStream_t st);
+                 const float* u_full, double* sums, void* ws, size_t ws_bytes, const gll_peers* peers, unsigned epoch,
+                 const int* ctrl, cudaStream_t st);
 int cg_rows_update(const float* diag, int m, int l, int row_lo, int row_hi, const double* sums, int iter, int max_iter, float tol,
-                   float* x, float* u_full, int* ctrl, float* resid_out, void* ws, size_t ws_bytes, cudaStream_t st);
+                   float* x, float* u_full, int* ctrl, float* resid_out, void* ws, size_t ws_bytes, const gll_peers* peers,
+                   unsigned epoch, cudaStream_t st);
 
 int backward_edges_run(const float* X, int n, int d, int l, int k_lab, int eps_auto, const int* row_ptr,
                        const int* col, const float* dist, const float* w, const float* eps, const int* kappa,

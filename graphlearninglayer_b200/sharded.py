@@ -12,6 +12,8 @@ nn.DataParallel gather, utils.py:547-548).  Inside the layer the path is cut alo
   rows      both CG solves, `cg_partition="rows"` (or GLL_B200_SHARD_CG=rows) -- the partition BASELINE.json's north star
             names: rank r owns a block of the unlabeled rows of x, r, p, s; every iteration exchanges the iterate with one
             all-gather and the three dot products with one all-reduce        [NCCL all-gather + all-reduce per iteration]
+            `cg_partition="rows-p2p"`: the same partition with both exchanges fused into the kernels over NVLink peer
+            memory (torch symmetric memory for the mapping; P2P stores + epoch flags, no NCCL inside the loop)
   replicated graph symmetrisation and weights (K2, K3): O(E) integer/byte work, a few ms at 1M nodes
 
 Collectives per call: forward 2 all-gathers (kNN lists; U column blocks), backward 3 (w column blocks; b; dX row blocks).
@@ -257,10 +259,85 @@ def _solve_rows(g, rhs: torch.Tensor, out: torch.Tensor, tol: float, comm: _Comm
     g.cg_rows_resid = resid
 
 
+_P2P_BLOCKS = {}  # (device index, world, rows, lp) -> symmetric u array, mailbox / flag block, peer table, next epoch
+
+
+def _p2p_block(dev: torch.device, rows_total: int, lp: int, comm: _Comm):
+    """Symmetric-memory buffers of the peer-memory CG (allocated and exchanged once per shape, collectively)."""
+    import ctypes
+
+    import torch.distributed._symmetric_memory as symm_mem
+
+    key = (dev.index, comm.world, rows_total, lp)
+    blk = _P2P_BLOCKS.get(key)
+    if blk is None:
+        grp = comm.group if comm.group is not None else dist.group.WORLD
+        mail_b = lib.gll_cg_rows_peer_mail_bytes()
+        u = symm_mem.empty((rows_total, lp), dtype=torch.float32, device=dev)
+        ctl = symm_mem.empty((mail_b + lib.gll_cg_rows_peer_flag_bytes() + 256,), dtype=torch.uint8, device=dev)
+        u.zero_()
+        ctl.zero_()
+        hu, hc = symm_mem.rendezvous(u, grp), symm_mem.rendezvous(ctl, grp)
+        torch.cuda.synchronize(dev)
+        dist.barrier(grp)  # every rank's flags are zero before anybody can raise one
+        P = _lib.Peers()
+        P.world, P.rank = comm.world, comm.ranks[0]
+        for r in range(comm.world):
+            P.u[r] = ctypes.c_void_p(int(hu.buffer_ptrs[r]))
+            P.mail[r] = ctypes.c_void_p(int(hc.buffer_ptrs[r]))
+            P.flags[r] = ctypes.c_void_p(int(hc.buffer_ptrs[r]) + mail_b)
+        blk = dict(u=u, ctl=ctl, hu=hu, hc=hc, P=P, epoch=1)
+        _P2P_BLOCKS[key] = blk
+    return blk
+
+
+def _solve_rows_p2p(g, rhs: torch.Tensor, out: torch.Tensor, tol: float, comm: _Comm, iters: torch.Tensor):
+    """Row-partitioned CG with BOTH collectives fused into the kernels over NVLink peer memory (csrc/cg_rows.cu, peer-memory
+    mode): the update kernel stores the new iterate into every rank's copy, the SpMV kernel's last CTA stores the partial
+    dot products into every rank's mailbox; epoch flags in peer memory order the kernels across GPUs.  No NCCL call and no
+    host round trip inside the loop (the stop flag is read every second iteration, locally); one all-gather of x at the end."""
+    import ctypes
+
+    dev = rhs.device
+    s = _stream_ptr(dev)
+    rank = comm.ranks[0]
+    _, _, per = m_block(g.m, 0, comm.world)
+    blk = _p2p_block(dev, comm.world * per, g.lp, comm)
+    P = ctypes.byref(blk["P"])
+    x_full = torch.zeros((comm.world * per, g.lp), dtype=torch.float32, device=dev)
+    resid = torch.zeros(1, dtype=torch.float32, device=dev)
+    lo, hi, _ = m_block(g.m, rank, comm.world)
+    wsb = lib.gll_cg_rows_workspace_bytes(max(hi - lo, 1), g.l)
+    ws = _bytes(wsb, dev)
+    ctrl = torch.zeros(4, dtype=torch.int32, device=dev)
+    maxit = _cg_maxit()
+    e0 = blk["epoch"]
+    blk["epoch"] = e0 + maxit + 4  # flags only grow: the next solve starts above everything this one can publish
+    _lib.check(lib.gll_cg_rows_init_p2p(g.diag.data_ptr(), rhs.data_ptr(), g.m, g.l, lo, hi, x_full.data_ptr(), P, e0,
+                                        ws.data_ptr(), wsb, s), "gll_cg_rows_init_p2p")
+    check_every = max(1, int(os.environ.get("GLL_B200_ROWS_CHECK_EVERY", "2")))
+    for it in range(maxit + 1):
+        _lib.check(lib.gll_cg_rows_spmv_p2p(g.uu_ptr.data_ptr(), g.uu_col.data_ptr(), g.uu_val.data_ptr(), g.diag.data_ptr(), g.m,
+                                            g.l, lo, hi, P, e0 + it, ctrl.data_ptr(), ws.data_ptr(), wsb, s),
+                   "gll_cg_rows_spmv_p2p")
+        _lib.check(lib.gll_cg_rows_update_p2p(g.diag.data_ptr(), g.m, g.l, lo, hi, it, maxit, tol, x_full.data_ptr(), P, e0 + it,
+                                              ctrl.data_ptr(), resid.data_ptr(), ws.data_ptr(), wsb, s),
+                   "gll_cg_rows_update_p2p")
+        if (it + 1) % check_every == 0 or it == maxit:
+            if int(ctrl[0].item()) != 0:
+                break
+    comm.all_gather_blocks_(x_full, per)
+    out.copy_(x_full[:g.m])
+    iters[rank:rank + 1].copy_(ctrl[1:2])
+    g.info[_lib.INFO_STATUS:_lib.INFO_STATUS + 1] |= ctrl[2:3]
+
+
 def _solve(g, rhs, out, tol, comm, iters):
     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))  # solve incl. its collectives
     ev[0].record()
-    if g.cg_partition == "rows":
+    if g.cg_partition == "rows-p2p" and comm.real and comm.world > 1:
+        _solve_rows_p2p(g, rhs, out, tol, comm, iters)
+    elif g.cg_partition in ("rows", "rows-p2p"):   # rows-p2p needs real ranks with peer access; otherwise the NCCL form
         _solve_rows(g, rhs, out, tol, comm, iters)
     else:
         _solve_columns(g, rhs, out, tol, comm, iters)
@@ -326,8 +403,8 @@ class ShardedLaplaceLearning(torch.autograd.Function):
             raise ValueError("need 0 < k_lab < n; labeled rows come first (GLL.py:11)")
         comm = _Comm(group, emulate)
         part = cg_partition or os.environ.get("GLL_B200_SHARD_CG", "columns")
-        if part not in ("columns", "rows"):
-            raise ValueError("cg_partition must be 'columns' or 'rows'")
+        if part not in ("columns", "rows", "rows-p2p"):
+            raise ValueError("cg_partition must be 'columns', 'rows' or 'rows-p2p'")
         with torch.cuda.device(X.device):
             pred, g = _forward(Xc, Y, float(tau), epsilon, comm, cg_partition=part)
         global _last_graph

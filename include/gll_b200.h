@@ -186,6 +186,33 @@ int gll_cg_rows_spmv(const int* uu_ptr, const int* uu_col, const float* uu_val, 
 int gll_cg_rows_update(const float* diag, int m, int l, int row_lo, int row_hi, const double* sums, int iter, int max_iter,
                        float tol, float* x, float* u_full, int* ctrl, float* resid_out, void* workspace, size_t workspace_bytes,
                        void* stream);
+/* Peer-memory mode of the same three stages: the all-gather and the all-reduce are fused INTO the kernels over NVLink peer
+ * pointers (symmetric memory: every rank maps every rank's buffers), so the loop needs no NCCL call and no host round trip:
+ * update/init store the new u rows into every rank's u array and raise an epoch flag on every peer; spmv waits on its
+ * LOCAL flags for everybody's u, writes its partial sums into a mailbox row on every peer and raises a second flag; update
+ * waits for all sums and adds the mailbox rows in rank order.  Flags only grow: the caller supplies `epoch` values that
+ * increase monotonically over the life of the buffers (init: e; iteration it: spmv and update both e + it; the next solve
+ * starts above e + iterations + 1).  peers->u[p] / mail[p] / flags[p]: rank p's u array (m' x lp fp32), mailbox
+ * (gll_cg_rows_peer_mail_bytes()) and flag block (gll_cg_rows_peer_flag_bytes(), zeroed once before first use), as mapped
+ * in THIS process; p = 0..world-1 <= 8, own rank included.  Every rank must enqueue the same sequence of launches; a wait
+ * longer than 2 s traps the kernel instead of hanging the GPU. */
+typedef struct gll_peers {
+  void* u[8];
+  void* mail[8];
+  void* flags[8];
+  int world;
+  int rank;
+} gll_peers;
+size_t gll_cg_rows_peer_mail_bytes(void);
+size_t gll_cg_rows_peer_flag_bytes(void);
+int gll_cg_rows_init_p2p(const float* diag, const float* rhs, int m, int l, int row_lo, int row_hi, float* x,
+                         const gll_peers* peers, unsigned epoch, void* workspace, size_t workspace_bytes, void* stream);
+int gll_cg_rows_spmv_p2p(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, int m, int l, int row_lo,
+                         int row_hi, const gll_peers* peers, unsigned epoch, const int* ctrl, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int gll_cg_rows_update_p2p(const float* diag, int m, int l, int row_lo, int row_hi, int iter, int max_iter, float tol, float* x,
+                           const gll_peers* peers, unsigned epoch, int* ctrl, float* resid_out, void* workspace,
+                           size_t workspace_bytes, void* stream);
 /* m x lp fp32 -> m x l float64/fp32 (GLL.py:66) and m x l float64/fp32 grad_output -> m x lp fp32 (GLL.py:90). */
 int gll_unpack_pred(const float* u, int m, int l, void* pred, int pred_is_f64, void* stream);
 int gll_pack_grad(const void* grad_out, int grad_is_f64, int m, int l, float* rhs, void* stream);
