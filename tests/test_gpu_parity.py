@@ -717,3 +717,25 @@ def test_fused_ce_loss_many_rows(gll):
     ours.backward()
     assert abs(ours.item() - ref.item()) <= 1e-12 * abs(ref.item())
     assert torch.allclose(b.grad, a.grad, rtol=1e-12, atol=0.0)
+
+
+def test_knn_large_graph_mode_against_brute_force(gll):
+    """n = 80000: the tensor-core kernel runs with whole row tiles per CTA (one candidate set per row, four epilogue warps).
+    512 random rows are checked against a float64 brute-force search (the CPU oracle would take minutes at this size)."""
+    _, _lib = gll
+    g = torch.Generator().manual_seed(11)
+    n, d, k = 80000, 32, 25
+    X = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1).numpy()
+    idx, dist, info = run_knn(_lib, X, k)
+    assert int(info[_lib.INFO_KNN_FALLBACK_ROWS]) < n // 100
+    Xd = torch.as_tensor(X).cuda().double()
+    rows = torch.randperm(n, generator=g)[:512].cuda()
+    D = torch.cdist(Xd[rows], Xd)                       # 512 x n, float64
+    D[torch.arange(512, device="cuda"), rows] = -1.0    # self first
+    ref_d, ref_i = torch.topk(D, k, dim=1, largest=False)
+    got_i = idx[rows].long()
+    same = (got_i == ref_i).all(dim=1)
+    # float64 cdist and the kernel's exact distances can order two neighbours at ~1e-16 relative distance differently
+    assert same.float().mean().item() > 0.99
+    assert torch.equal(torch.sort(got_i, dim=1).values[same], torch.sort(ref_i, dim=1).values[same])
+    assert torch.allclose(dist[rows][:, 1:].double(), ref_d[:, 1:], rtol=1e-6, atol=0.0)
