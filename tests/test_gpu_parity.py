@@ -720,7 +720,7 @@ def test_fused_ce_loss_many_rows(gll):
 
 
 def test_knn_large_graph_mode_against_brute_force(gll):
-    """n = 80000: the tensor-core kernel runs with whole row tiles per CTA (one candidate set per row, four epilogue warps).
+    """n = 80000: the tensor-core kernel runs in its large-graph mode (whole row tiles per CTA, all CTAs sweeping the column tiles).
     512 random rows are checked against a float64 brute-force search (the CPU oracle would take minutes at this size)."""
     _, _lib = gll
     g = torch.Generator().manual_seed(11)
