@@ -233,11 +233,22 @@ def run_b200(args, rank, world, local_rank):
         Xe = torch.empty_like(Xd).requires_grad_(True)
         Ye = torch.empty_like(Yd)
 
+        split = {"ev": None}  # set to a list to have resident() record (start, after forward+loss, end) events
+
         def resident():
             Xd.grad = None
+            ev = None
+            if split["ev"] is not None:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                ev[0].record()
             pred = layer(Xd, Yd, tau, eps)
             loss = ce(pred)  # custom_ce_loss, losses.py:128-136
+            if ev is not None:
+                ev[1].record()
             loss.backward()
+            if ev is not None:
+                ev[2].record()
+                split["ev"].append(ev)
             return loss
 
         def e2e():
@@ -286,7 +297,7 @@ def run_b200(args, rank, world, local_rank):
         shp = dict(n=k_lab + m, d=d, l=l, m=m, k_lab=k_lab)
         h2d = Xh.numel() * 4 + Yh.numel() * 4
         d2h = predh.numel() * 8 + dXh.numel() * 4
-        return resident, e2e, shp, h2d, d2h, e2e_pipelined
+        return resident, e2e, shp, h2d, d2h, e2e_pipelined, split
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # 256 MiB > 126 MB L2
 
@@ -313,7 +324,7 @@ def run_b200(args, rank, world, local_rank):
         return tot_ms
 
     sharded = args.workload in SHARDED
-    resident, e2e, shp, h2d, d2h, e2e_pipelined = step_fn(args.workload, 1000 if sharded else ranks.rank_seed(1000, rank))
+    resident, e2e, shp, h2d, d2h, e2e_pipelined, split = step_fn(args.workload, 1000 if sharded else ranks.rank_seed(1000, rank))
     jobs = 1 if sharded else world  # graphs finished per step by the whole job
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -333,6 +344,16 @@ def run_b200(args, rank, world, local_rank):
     else:
         info = pkg.last_info()
 
+    # forward / backward split, its own pass: two extra events per step
+    split["ev"] = []
+    for _ in range(args.steps):
+        flush.zero_()
+        resident()
+    torch.cuda.synchronize()
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in split["ev"]) / args.steps
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in split["ev"]) / args.steps
+    split["ev"] = None
+
     # per-kernel pass (instrumented; not the pass `value` comes from)
     _lib.lib.gll_profile_enable(1)
     _lib.profile_collect()
@@ -346,7 +367,7 @@ def run_b200(args, rank, world, local_rank):
     extra = {}
     if rank == 0 and world == 1 and args.workload not in ("c4",) + SHARDED and not args.no_large_graph:
         # the CG roofline study (BASELINE.json configs[3]); reported beside the headline, not instead of it
-        r4, _, shp4, _, _, _ = step_fn("c4", 2000)
+        r4, _, shp4, _, _, _, _ = step_fn("c4", 2000)
         ms4 = timed(r4, 5, 3)
         info4 = pkg.last_info()
         _lib.lib.gll_profile_enable(1)
@@ -424,7 +445,9 @@ def run_b200(args, rank, world, local_rank):
                     if pipe_ms is not None else
                     {"value": jobs * 1e3 / (e2e_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
                      "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps}),
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kern,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "fwd_bwd_split_ms": {"forward_and_loss": fwd_ms, "backward": bwd_ms},
+            "kernels": kern,
             "cpu_baseline": cpu,
         }
         line.update(extra)

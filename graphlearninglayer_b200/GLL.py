@@ -287,7 +287,7 @@ def stable_conjgrad(A, b, x0=None, max_iter=1e5, tol=1e-10):
     (m,) or (m, l) -> numpy solution with max_c ||b_c - A x_c||_2 <= tol (absolute), or 'max iter reached'.
 
     The solves run in the persistent fp32 CG kernel (gll_cg_solve); tolerances below what fp32 can reach are met by
-    fp64 iterative refinement around it (residual b - A x in fp64 on the device, correction solved by the kernel), so
+    fp64 iterative refinement around it (residual b - A x by an fp64 CSR kernel, correction solved by the CG kernel), so
     the reference's default tol=1e-10 (utils.py:589-591) is honoured.  The ``p = r`` alias of GLL.py:254 is not
     reproduced (it only costs the reference iterations).
     """
@@ -309,9 +309,17 @@ def stable_conjgrad(A, b, x0=None, max_iter=1e5, tol=1e-10):
     col = torch.as_tensor(off.indices.astype(np.int32)).to(dev)
     val = torch.as_tensor((-off.data).astype(np.float32)).to(dev)  # kernel applies diag*p - sum val*p
     diag = torch.as_tensor(dg.astype(np.float32)).to(dev)
-    # fp64 copy for the refinement residual (torch sparse CSR @ dense: plumbing around the kernel, not the solver)
-    A64 = torch.sparse_csr_tensor(torch.as_tensor(A.indptr.astype(np.int64)), torch.as_tensor(A.indices.astype(np.int64)),
-                                  torch.as_tensor(A.data.astype(np.float64)), size=A.shape).to(dev)
+    # fp64 copy of the full matrix for the refinement residual r = b - A x (gll_csr_residual_f64)
+    a_ptr = torch.as_tensor(A.indptr.astype(np.int32)).to(dev)
+    a_col = torch.as_tensor(A.indices.astype(np.int32)).to(dev)
+    a_val = torch.as_tensor(A.data.astype(np.float64)).to(dev)
+
+    def residual(bb, x):
+        r = torch.empty_like(bb)
+        _lib.check(lib.gll_csr_residual_f64(a_ptr.data_ptr(), a_col.data_ptr(), a_val.data_ptr(), x.data_ptr(), bb.data_ptr(), m,
+                                            bb.shape[1], r.data_ptr(), _stream_ptr(dev)), "gll_csr_residual_f64")
+        return r
+
     X = np.zeros_like(B) if x0 is None else np.array(np.asarray(x0, dtype=np.float64).reshape(B.shape))
     maxit = int(max_iter)
     s = _stream_ptr(dev)
@@ -330,7 +338,7 @@ def stable_conjgrad(A, b, x0=None, max_iter=1e5, tol=1e-10):
         stat = torch.zeros(4, dtype=i32, device=dev)
         ok = False
         for _ in range(12):
-            r = bb - A64 @ x
+            r = residual(bb, x)
             rn = float(torch.linalg.vector_norm(r, dim=0).max().item())
             if rn <= tol or total_it >= maxit:
                 ok = rn <= tol
@@ -344,7 +352,7 @@ def stable_conjgrad(A, b, x0=None, max_iter=1e5, tol=1e-10):
             total_it += int(stat[0].item())
             x += corr[:, :l].to(f64) * scale
         else:
-            r = bb - A64 @ x
+            r = residual(bb, x)
             ok = float(torch.linalg.vector_norm(r, dim=0).max().item()) <= tol
         converged &= ok
         X[:, c0:c1] = x.cpu().numpy()

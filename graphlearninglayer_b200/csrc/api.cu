@@ -130,6 +130,21 @@ __global__ void __launch_bounds__(32) ce_loss_finish_kernel(const double* __rest
   if (threadIdx.x == 0) *loss = (T)(-v / (double)m);
 }
 
+// r = b - A x in fp64 (CSR with the diagonal included, int32 indices, m x l dense row-major): the refinement residual of
+// the stable_conjgrad wrapper (GLL.py:247-276 asks for ||b - A x|| <= 1e-10, below what the fp32 solver alone reaches).
+// One thread per (row, class column): lanes run along the contiguous class index.
+__global__ void __launch_bounds__(256)
+csr_residual_f64_kernel(const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val,
+                        const double* __restrict__ x, const double* __restrict__ b, int m, int l, double* __restrict__ r) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)m * l) return;
+  const int i = (int)(t / l), c = (int)(t - (long long)i * l);
+  double acc = b[t];
+  const int e1 = ptr[i + 1];
+  for (int e = ptr[i]; e < e1; ++e) acc = fma(-val[e], x[(size_t)col[e] * l + c], acc);
+  r[t] = acc;
+}
+
 __global__ void unpack_pred_kernel(const float* __restrict__ u, int m, int l, int lp, void* __restrict__ pred, int is_f64) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)m * l) return;
@@ -360,6 +375,16 @@ int gll_cg_rows_update(const float* diag, int m, int l, int row_lo, int row_hi, 
 }
 
 size_t gll_ce_loss_workspace_bytes(int m) { return (m <= 4096) ? 0 : sizeof(double) * 1024; }
+
+int gll_csr_residual_f64(const int* ptr, const int* col, const double* val, const double* x, const double* b, int m, int l,
+                         double* r, void* stream) {
+  GLL_REQUIRE(ptr && col && val && x && b && r && m >= 1 && l >= 1, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  GLL_PROF(KID_CONVERT, st);
+  csr_residual_f64_kernel<<<ceil_div((long long)m * l, 256), 256, 0, st>>>(ptr, col, val, x, b, m, l, r);
+  GLL_LAUNCH_CHECK();
+  return GLL_OK;
+}
 
 size_t gll_cg_rows_peer_mail_bytes(void) { return cg_rows_peer_mail_bytes(); }
 size_t gll_cg_rows_peer_flag_bytes(void) { return cg_rows_peer_flag_bytes(); }

@@ -217,6 +217,11 @@ int gll_cg_rows_update_p2p(const float* diag, int m, int l, int row_lo, int row_
 int gll_unpack_pred(const float* u, int m, int l, void* pred, int pred_is_f64, void* stream);
 int gll_pack_grad(const void* grad_out, int grad_is_f64, int m, int l, float* rhs, void* stream);
 
+/* r = b - A x in fp64: A in CSR (diagonal included, int32 indices, fp64 values, m x m), x, b, r dense m x l row-major fp64.
+ * The iterative-refinement residual of the stable_conjgrad wrapper (GLL.py:247-276, tol = 1e-10). */
+int gll_csr_residual_f64(const int* ptr, const int* col, const double* val, const double* x, const double* b, int m, int l,
+                         double* r, void* stream);
+
 /* The loss every caller of the layer applies to its output (custom_ce_loss, losses.py:128-136; also pasted at
  * train_and_adversarial.py:458 and adversarial.py:453): loss = -sum_i log(pred[i, targets[i]] + 1e-8) / m, and in the same
  * launch d loss / d pred (m x l, same dtype as pred).  pred: m x l float64 (pred_is_f64 != 0) or fp32; targets: m int64;
