@@ -8,19 +8,22 @@
 // exactly, proves that no true neighbour was missed (error budget knn_tc_err_coef) and redoes unprovable rows by brute
 // force, so the emitted neighbour lists do not depend on tensor-core rounding.
 //
-// Kernel (one persistent CTA per SM, 6 warps, warp-specialised):
-//   warp 0   TMA producer: per 64-wide K block one stage = {A_hi, A_lo (128 rows), B_hi, B_lo (256 rows)}, 128B swizzle
-//   warp 1   MMA issuer: one elected lane issues 12 tcgen05.mma (3 operand pairs x 4 K=16 steps) per stage into one of
+// Kernel (one persistent CTA per SM, 10 warps, warp-specialised):
+//   warp 0   TMA producer: per 32-wide K block one stage = {A_hi, A_lo (128 rows), B_hi, B_lo (256 rows)} = 48 KB,
+//            64-byte swizzle, 3 stages
+//   warp 1   MMA issuer: one elected lane issues 6 tcgen05.mma (3 operand pairs x 2 K=16 steps) per stage into one of
 //            two 128 x 256 fp32 accumulators in TMEM (all 512 columns; double buffered against the epilogue)
-//   warps 2-5 epilogue: tcgen05.ld gives each thread ONE row of the tile, 16 columns at a time; d~^2 = |xi|^2 + |xj|^2
-//            - 2 acc is compared with the row's running 32nd-best (a register).  A thread owns its row's candidate set:
-//            an unsorted 32-slot array in shared memory (slot-major, so the 32 threads of a warp never bank-conflict),
-//            4 groups of 8 slots whose maxima are cached in registers; a survivor replaces the overall maximum and only
-//            that group is rescanned.
-//            All rows of a warp insert concurrently, so a chunk costs max-over-rows(survivors) rescans, ~1 in steady
-//            state.  The n x n matrix never leaves the SM.
+//   warps 2-9 epilogue, two per SM sub-partition: warps w and w+4 read the same TMEM lane quarter (the same 32 rows) and
+//            take one half of the unit's 256 columns each.  tcgen05.ld gives each thread ONE row, 16 columns at a time;
+//            d~^2 = |xi|^2 + |xj|^2 - 2 acc is compared with the row's threshold (a register).  A thread owns its row's
+//            candidate set for its column half: an unsorted 32-slot array in shared memory (slot-major, so the 32 threads
+//            of a warp never bank-conflict), 4 groups of 8 slots whose maxima are cached in registers; a survivor replaces
+//            the overall maximum and only that group is rescanned.  All rows of a warp insert concurrently.  The insertion
+//            is one long dependent chain, which is why a sub-partition gets two warps.  The n x n matrix never leaves the SM.
+//   thresholds  a row's sets (column halves, other CTAs on the same row tile) publish their 32nd-best through a per-row
+//            word in L2 and prune against each other's bound: fewer insertions, same union of candidates.
 // Work = (row tile, column tile) units in row-major order, split evenly and contiguously over the CTAs, so a CTA keeps
-// one row tile's lists on chip for many column tiles; lists are flushed to cand[row][slot][KC] when the row tile changes.
+// one row tile's sets on chip for many column tiles; sets are flushed to cand[row][slot][KC] when the row tile changes.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cudaTypedefs.h>
