@@ -30,7 +30,7 @@ from ._lib import lib
 
 K_NEIGHBOURS = 25  # hard-coded in the reference at GLL.py:27
 
-__all__ = ["LaplaceLearningSparseHard", "knn_sym_dist", "stable_conjgrad", "last_info"]
+__all__ = ["LaplaceLearningSparseHard", "LaplaceLearningSparseHardNormalized", "knn_sym_dist", "stable_conjgrad", "last_info"]
 
 
 def _env_float(name: str, default: float) -> float:
@@ -191,6 +191,47 @@ class LaplaceLearningSparseHard(torch.autograd.Function):
         if dX.dtype != ctx.x_dtype:
             dX = dX.to(ctx.x_dtype)
         return dX, None, None, None
+
+
+class LaplaceLearningSparseHardNormalized(torch.autograd.Function):
+    """`LaplaceLearningSparseHard.apply(F.normalize(feat, dim=1), label_matrix, tau, epsilon)` in one autograd node
+    (SURVEY 8f-3): every caller normalises the encoder output right before the layer (networks/BuildNet.py:101,
+    FullySup.py:122,156).  The rows are normalised by one kernel and the normalisation's backward,
+    d feat = (d xn - xn <xn, d xn>) / |feat|, by another -- instead of PyTorch's ~10 small kernels for the pair."""
+
+    @staticmethod
+    def forward(ctx, feat, label_matrix, tau=0, epsilon="auto"):
+        _require_cuda(feat, "features")
+        f = feat.detach()
+        if f.dtype != torch.float32:
+            f = f.float()
+        f = f.contiguous()
+        n, d = f.shape
+        xn = torch.empty_like(f)
+        inv = torch.empty(n, dtype=torch.float32, device=f.device)
+        with torch.cuda.device(f.device):
+            _lib.check(lib.gll_normalize_rows(f.data_ptr(), n, d, 1e-12, xn.data_ptr(), inv.data_ptr(), _stream_ptr(f.device)),
+                       "gll_normalize_rows")
+        pred, st, _ = _forward_impl(xn, label_matrix, tau, epsilon)
+        ctx.gll_state = st
+        ctx.x_dtype = feat.dtype
+        ctx.save_for_backward(xn, inv)
+        ctx.set_materialize_grads(True)
+        return pred
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        xn, inv = ctx.saved_tensors
+        dxn = _backward_impl(ctx.gll_state, xn, grad_output)
+        dx = torch.empty_like(dxn)
+        n, d = xn.shape
+        with torch.cuda.device(xn.device):
+            _lib.check(lib.gll_normalize_rows_backward(xn.data_ptr(), inv.data_ptr(), dxn.data_ptr(), n, d, dx.data_ptr(),
+                                                       _stream_ptr(xn.device)), "gll_normalize_rows_backward")
+        if dx.dtype != ctx.x_dtype:
+            dx = dx.to(ctx.x_dtype)
+        return dx, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -6,7 +6,7 @@ The names resolve lazily so that ``python -m graphlearninglayer_b200.build`` can
 exists; the first access loads libgll_b200.so through ctypes and fails loudly if it is missing or stale.  There is no
 CPU or PyTorch fallback.
 """
-__all__ = ["LaplaceLearningSparseHard", "knn_sym_dist", "stable_conjgrad", "last_info", "GLL"]
+__all__ = ["LaplaceLearningSparseHard", "LaplaceLearningSparseHardNormalized", "knn_sym_dist", "stable_conjgrad", "last_info", "GLL"]
 
 
 def __getattr__(name):

@@ -88,6 +88,8 @@ def _load():
     sig("gll_cg_rows_init_p2p", i32, [vp, vp, i32, i32, i32, i32, vp, pp, u32, vp, sz, vp])
     sig("gll_cg_rows_spmv_p2p", i32, [vp, vp, vp, vp, i32, i32, i32, i32, pp, u32, vp, vp, sz, vp])
     sig("gll_cg_rows_update_p2p", i32, [vp, i32, i32, i32, i32, i32, i32, f32, vp, pp, u32, vp, vp, vp, sz, vp])
+    sig("gll_normalize_rows", i32, [vp, i32, i32, f32, vp, vp, vp])
+    sig("gll_normalize_rows_backward", i32, [vp, vp, vp, i32, i32, vp, vp])
     sig("gll_csr_residual_f64", i32, [vp, vp, vp, vp, vp, i32, i32, vp, vp])
     sig("gll_ce_loss_workspace_bytes", sz, [i32])
     sig("gll_ce_loss", i32, [vp, i32, vp, i32, i32, vp, vp, vp, vp, sz, vp])
@@ -111,7 +113,8 @@ EXPORTS = ["gll_last_error", "gll_version", "gll_device_sm_count", "gll_kernel_c
            "gll_backward_edges_rows", "gll_pack_columns", "gll_unpack_columns", "gll_unpack_pred", "gll_pack_grad",
            "gll_cg_rows_workspace_bytes", "gll_cg_rows_init", "gll_cg_rows_spmv", "gll_cg_rows_update", "gll_ce_loss", "gll_ce_loss_workspace_bytes",
            "gll_cg_rows_peer_mail_bytes", "gll_cg_rows_peer_flag_bytes", "gll_cg_rows_init_p2p", "gll_cg_rows_spmv_p2p",
-           "gll_cg_rows_update_p2p", "gll_csr_residual_f64"]
+           "gll_cg_rows_update_p2p", "gll_csr_residual_f64", "gll_normalize_rows",
+           "gll_normalize_rows_backward"]
 
 
 def check(rc: int, what: str) -> None:

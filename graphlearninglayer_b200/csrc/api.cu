@@ -130,6 +130,42 @@ __global__ void __launch_bounds__(32) ce_loss_finish_kernel(const double* __rest
   if (threadIdx.x == 0) *loss = (T)(-v / (double)m);
 }
 
+// F.normalize(feat, dim=1) (networks/BuildNet.py:101: every caller feeds the layer L2-normalised rows) and its backward,
+// one warp per row each:  xn = x / max(|x|, eps);  dx = (dxn - xn <xn, dxn>) / |x|   (dx = dxn / eps where |x| <= eps).
+__global__ void __launch_bounds__(256)
+normalize_rows_kernel(const float* __restrict__ X, int n, int d, float eps, float* __restrict__ Xn, float* __restrict__ inv_norm) {
+  const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* x = X + (size_t)row * d;
+  double s = 0.0;
+  for (int c = lane; c < d; c += 32) {
+    const double v = (double)__ldg(x + c);
+    s += v * v;
+  }
+  s = warp_sum(s);
+  const float nrm = (float)sqrt(s);
+  const float inv = 1.f / fmaxf(nrm, eps);
+  for (int c = lane; c < d; c += 32) Xn[(size_t)row * d + c] = __ldg(x + c) * inv;
+  if (lane == 0) inv_norm[row] = (nrm > eps) ? inv : -inv;  // sign bit marks the clamped rows (no projection in the backward)
+}
+
+__global__ void __launch_bounds__(256)
+normalize_rows_backward_kernel(const float* __restrict__ Xn, const float* __restrict__ inv_norm, const float* __restrict__ dXn, int n,
+                               int d, float* __restrict__ dX) {
+  const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* xn = Xn + (size_t)row * d;
+  const float* g = dXn + (size_t)row * d;
+  const float iv = inv_norm[row];
+  double dot = 0.0;
+  if (iv > 0.f) {
+    for (int c = lane; c < d; c += 32) dot += (double)__ldg(xn + c) * (double)__ldg(g + c);
+    dot = warp_sum(dot);
+  }
+  const float dt = (float)dot, inv = fabsf(iv);
+  for (int c = lane; c < d; c += 32) dX[(size_t)row * d + c] = (__ldg(g + c) - __ldg(xn + c) * dt) * inv;
+}
+
 // r = b - A x in fp64 (CSR with the diagonal included, int32 indices, m x l dense row-major): the refinement residual of
 // the stable_conjgrad wrapper (GLL.py:247-276 asks for ||b - A x|| <= 1e-10, below what the fp32 solver alone reaches).
 // One thread per (row, class column): lanes run along the contiguous class index.
@@ -375,6 +411,24 @@ int gll_cg_rows_update(const float* diag, int m, int l, int row_lo, int row_hi, 
 }
 
 size_t gll_ce_loss_workspace_bytes(int m) { return (m <= 4096) ? 0 : sizeof(double) * 1024; }
+
+int gll_normalize_rows(const float* X, int n, int d, float eps, float* Xn, float* inv_norm, void* stream) {
+  GLL_REQUIRE(X && Xn && inv_norm && n >= 1 && d >= 1 && eps > 0.f, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  GLL_PROF(KID_CONVERT, st);
+  normalize_rows_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(X, n, d, eps, Xn, inv_norm);
+  GLL_LAUNCH_CHECK();
+  return GLL_OK;
+}
+
+int gll_normalize_rows_backward(const float* Xn, const float* inv_norm, const float* dXn, int n, int d, float* dX, void* stream) {
+  GLL_REQUIRE(Xn && inv_norm && dXn && dX && n >= 1 && d >= 1, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  GLL_PROF(KID_CONVERT, st);
+  normalize_rows_backward_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(Xn, inv_norm, dXn, n, d, dX);
+  GLL_LAUNCH_CHECK();
+  return GLL_OK;
+}
 
 int gll_csr_residual_f64(const int* ptr, const int* col, const double* val, const double* x, const double* b, int m, int l,
                          double* r, void* stream) {

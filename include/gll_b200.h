@@ -217,6 +217,12 @@ int gll_cg_rows_update_p2p(const float* diag, int m, int l, int row_lo, int row_
 int gll_unpack_pred(const float* u, int m, int l, void* pred, int pred_is_f64, void* stream);
 int gll_pack_grad(const void* grad_out, int grad_is_f64, int m, int l, float* rhs, void* stream);
 
+/* The step in front of the layer in every caller: F.normalize(feat, dim=1) (networks/BuildNet.py:101), and its backward.
+ * Xn = X / max(|X_row|, eps) (eps = 1e-12 in PyTorch); inv_norm[n] is kept for the backward (sign bit set for rows that
+ * hit the clamp); dX = (dXn - Xn <Xn, dXn>) * inv_norm.  X, Xn, dXn, dX: n x d fp32 row-major. */
+int gll_normalize_rows(const float* X, int n, int d, float eps, float* Xn, float* inv_norm, void* stream);
+int gll_normalize_rows_backward(const float* Xn, const float* inv_norm, const float* dXn, int n, int d, float* dX, void* stream);
+
 /* r = b - A x in fp64: A in CSR (diagonal included, int32 indices, fp64 values, m x m), x, b, r dense m x l row-major fp64.
  * The iterative-refinement residual of the stable_conjgrad wrapper (GLL.py:247-276, tol = 1e-10). */
 int gll_csr_residual_f64(const int* ptr, const int* col, const double* val, const double* x, const double* b, int m, int l,

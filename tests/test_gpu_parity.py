@@ -739,3 +739,22 @@ def test_knn_large_graph_mode_against_brute_force(gll):
     assert same.float().mean().item() > 0.99
     assert torch.equal(torch.sort(got_i, dim=1).values[same], torch.sort(ref_i, dim=1).values[same])
     assert torch.allclose(dist[rows][:, 1:].double(), ref_d[:, 1:], rtol=1e-6, atol=0.0)
+
+
+def test_normalized_variant_matches_torch_normalize_plus_layer(gll):
+    """LaplaceLearningSparseHardNormalized(feat) == LaplaceLearningSparseHard(F.normalize(feat, dim=1)) with PyTorch's own
+    autograd through the normalisation (networks/BuildNet.py:101), value and gradient with respect to the raw features."""
+    pkg, _ = gll
+    X, Y, _, yq = O.synth_inputs(51, 400, 600, 64, 10, 2.0)
+    g = torch.Generator().manual_seed(2)
+    raw = (torch.as_tensor(X) * (0.5 + 3.0 * torch.rand(X.shape[0], 1, generator=g))).cuda()   # rows of different lengths
+    Yt = torch.as_tensor(Y).cuda()
+    tgt = torch.nn.functional.one_hot(torch.as_tensor(yq).cuda(), 10).double()
+    a = raw.clone().requires_grad_(True)
+    pa = pkg.LaplaceLearningSparseHard.apply(torch.nn.functional.normalize(a, dim=1), Yt, 0.0, "auto")
+    (-torch.sum(tgt * torch.log(pa + 1e-8)) / 600).backward()
+    b = raw.clone().requires_grad_(True)
+    pb = pkg.LaplaceLearningSparseHardNormalized.apply(b, Yt, 0.0, "auto")
+    (-torch.sum(tgt * torch.log(pb + 1e-8)) / 600).backward()
+    assert O.max_rel(pb.detach().cpu().numpy(), pa.detach().cpu().numpy()) < 2e-6
+    assert O.max_rel(b.grad.cpu().numpy(), a.grad.cpu().numpy()) < 1e-5
