@@ -151,7 +151,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": len(warm), "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic gaussian clusters (oracle.synth_inputs), L2-normalised",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic gaussian clusters (graphlearninglayer_b200.synth), L2-normalised",
         "config": {"workload": args.workload + ": " + WORKLOAD_DESC[args.workload],
                    "what": "oracle port of /root/reference GLL.py (exact kNN instead of annoy, scipy sparse, SuperLU/CG), "
                            "one process on the host cores; the Python reference itself cannot travel to the GPU box"},
@@ -194,7 +194,7 @@ def run_b200(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
     import graphlearninglayer_b200 as pkg
     from graphlearninglayer_b200 import _lib, ranks
-    from oracle.gll_oracle import synth_inputs  # input generator only (shared with the tests); not on the timed path
+    from graphlearninglayer_b200.synth import synth_inputs  # numpy input generator (the oracle is not imported by this arm)
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -416,7 +416,7 @@ def run_b200(args, rank, world, local_rank):
             "metric": METRIC, "value": jobs * 1e3 / per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per_step, "higher_is_better": True,
             "scaling": "strong" if sharded else "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic gaussian clusters (oracle.synth_inputs), L2-normalised, one graph per rank",
+            "dtype": "f32", "data": "synthetic gaussian clusters (graphlearninglayer_b200.synth), L2-normalised, one graph per rank",
             "config": {"workload": args.workload + ": " + WORKLOAD_DESC[args.workload], "l2": "flushed between timed steps "
                        "(256 MiB memset outside the event pairs)", "parallelism": (f"one graph over {world} rank(s): rows (kNN, backward) + "
                                        + ("class columns (CG, no per-iteration collective)" if args.cg_partition == "columns" else

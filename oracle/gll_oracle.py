@@ -34,19 +34,7 @@ K_DEFAULT = 25  # hard-coded at GLL.py:27
 # --------------------------------------------------------------------------------------
 # synthetic inputs: Gaussian clusters, L2-normalised, base rows first
 # --------------------------------------------------------------------------------------
-def synth_inputs(seed: int, k_lab: int, m: int, d: int, l: int, sigma: float):
-    """Returns X (n,d) float32, Y (k_lab,l) float32 one-hot, y_base (k_lab,), y_query (m,)."""
-    rng = np.random.default_rng(seed)
-    centres = rng.standard_normal((l, d))
-    y_base = np.arange(k_lab) % l
-    y_query = rng.integers(0, l, size=m)
-    y = np.concatenate([y_base, y_query])
-    X = centres[y] + sigma * rng.standard_normal((k_lab + m, d))
-    X /= np.linalg.norm(X, axis=1, keepdims=True)
-    X = X.astype(np.float32)
-    Y = np.zeros((k_lab, l), dtype=np.float32)
-    Y[np.arange(k_lab), y_base] = 1.0
-    return X, Y, y_base, y_query
+from graphlearninglayer_b200.synth import synth_inputs  # noqa: E402,F401  (numpy-only generator shared with bench.py)
 
 
 def ce_loss_and_grad(pred: np.ndarray, y_query: np.ndarray):
