@@ -268,9 +268,14 @@ def test_graph_drops_zero_distance_edges(gll):
 # ----------------------------------------------------------------------------------------------------------------
 # K4: CG
 # ----------------------------------------------------------------------------------------------------------------
+# "": the dispatch by size (here the multi-CTA on-chip kernel); "streaming": the global-memory kernel that only ~1M-row systems
+# reach on their own, forced so that it is covered at a size the CPU checker can solve
+@pytest.mark.parametrize("path", ["", "streaming"])
 @pytest.mark.parametrize("l", [1, 3, 10, 37, 100])
-def test_cg_vs_direct_solve(gll, l):
+def test_cg_vs_direct_solve(gll, monkeypatch, l, path):
     _, _lib = gll
+    if path:
+        monkeypatch.setenv("GLL_B200_CG_PATH", path)
     X, Y, *_ = O.synth_inputs(3, 160, 1500, 24, l, 1.5)
     f = O.forward(X, Y, 0.02, 1.0, solver="lu")
     x, iters, resid, status = run_cg(_lib, f.Luu, f.B, tol=1e-7)
@@ -280,9 +285,12 @@ def test_cg_vs_direct_solve(gll, l):
     assert true_res < 5e-5  # fp32 storage of A and x bounds the true residual
 
 
-def test_cg_zero_rhs_column_and_maxiter(gll):
+@pytest.mark.parametrize("path", ["", "streaming", "small"])
+def test_cg_zero_rhs_column_and_maxiter(gll, monkeypatch, path):
     _, _lib = gll
-    X, Y, *_ = O.synth_inputs(5, 100, 900, 16, 4, 1.5)
+    if path == "streaming":
+        monkeypatch.setenv("GLL_B200_CG_PATH", path)
+    X, Y, *_ = O.synth_inputs(5, 100, 400 if path == "small" else 900, 16, 4, 1.5)  # <= 512 rows: the one-CTA kernel
     f = O.forward(X, Y, 0.05, 1.0, solver="lu")
     B = f.B.copy()
     B[:, 2] = 0.0  # a frozen column from the start (the per-column mask of GLL.py:262-263 must not divide 0/0)
