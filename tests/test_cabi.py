@@ -76,3 +76,36 @@ def test_dropin_module_exports_reference_names(libmod):
     assert sig.parameters["tau"].default == 0 and sig.parameters["epsilon"].default == "auto"
     assert list(inspect.signature(mod.stable_conjgrad).parameters) == ["A", "b", "x0", "max_iter", "tol"]  # GLL.py:247
     assert list(inspect.signature(mod.knn_sym_dist).parameters) == ["data", "k", "epsilon"]  # GLL.py:180
+
+
+def test_side_modules_refuse_cpu_tensors_and_mirror_reference_signatures(libmod):
+    """No CPU path anywhere: the fused loss, the normalised variant and the host pipeline all raise on CPU inputs; the loss
+    keeps the reference signature custom_ce_loss(softmax_logits, targets) (losses.py:128)."""
+    import inspect
+
+    import torch
+
+    import graphlearninglayer_b200 as pkg
+    from graphlearninglayer_b200 import hostpipe, losses
+
+    assert list(inspect.signature(losses.custom_ce_loss).parameters) == ["softmax_logits", "targets"]
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        losses.custom_ce_loss(torch.full((4, 3), 1 / 3), torch.zeros(4, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        pkg.LaplaceLearningSparseHardNormalized.apply(torch.randn(64, 8), torch.eye(4)[torch.arange(16) % 4])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        hostpipe.HostPipeline(64, 8, 16, 4, "cpu", loss_fn=lambda p, s: p.sum())
+    sig = inspect.signature(pkg.LaplaceLearningSparseHardNormalized.forward)
+    assert list(sig.parameters) == ["ctx", "feat", "label_matrix", "tau", "epsilon"]
+
+
+def test_peer_table_matches_the_header(libmod):
+    """ctypes mirror of struct gll_peers: 3 x 8 pointers + world + rank, and the host-side size queries of the peer-memory CG."""
+    P = libmod.Peers
+    assert ctypes.sizeof(P) == 3 * 8 * ctypes.sizeof(ctypes.c_void_p) + 2 * ctypes.sizeof(ctypes.c_int)
+    assert [f[0] for f in P._fields_] == ["u", "mail", "flags", "world", "rank"]
+    lib = libmod.lib
+    assert lib.gll_cg_rows_peer_flag_bytes() == 2 * 8 * 4           # [2 flag kinds][8 ranks] unsigned
+    assert lib.gll_cg_rows_peer_mail_bytes() == 2 * 8 * 3 * 128 * 8  # [2 parities][8 ranks][3 dots x 128 columns] doubles
+    assert lib.gll_ce_loss_workspace_bytes(512) == 0 and lib.gll_ce_loss_workspace_bytes(100000) > 0
+    assert lib.gll_cg_rows_workspace_bytes(1000, 10) > 4 * 1000 * 12 * 4
