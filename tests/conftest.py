@@ -18,7 +18,9 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Layer fixtures (oracle/make_golden.py); eval_* fixtures (oracle/make_golden_eval.py) have their own loaders."""
+    names = (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return sorted(n for n in names if not n.startswith("eval_"))
 
 
 def load_golden(name):

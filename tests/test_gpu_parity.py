@@ -766,3 +766,29 @@ def test_normalized_variant_matches_torch_normalize_plus_layer(gll):
     (-torch.sum(tgt * torch.log(pb + 1e-8)) / 600).backward()
     assert O.max_rel(pb.detach().cpu().numpy(), pa.detach().cpu().numpy()) < 2e-6
     assert O.max_rel(b.grad.cpu().numpy(), a.grad.cpu().numpy()) < 1e-5
+
+
+def test_eval_path_matches_reference_fixture(gll):
+    """utils.laplace (utils.py:570-593) as the reference runs it -- UNMODIFIED knn_sym_dist (k = 50) and stable_conjgrad of
+    GLL.py, fixture tests/golden/eval_k50.npz -- against the same steps on our drop-in wrappers."""
+    import hashlib
+    import os
+
+    import scipy.sparse as sparse
+
+    pkg, _ = gll
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eval_k50.npz"))
+    seed, k_lab, m, d, l, knn = (int(v) for v in g["params"])
+    X, Y, _, yq = O.synth_inputs(seed, k_lab, m, d, l, float(g["sigma"]))
+    assert hashlib.sha256(X.tobytes()).hexdigest() == str(g["x_sha256"])
+    W_ref = sparse.csr_matrix((g["w_data"], g["w_indices"], g["w_indptr"]), shape=(k_lab + m, k_lab + m))
+    W = sparse.csr_matrix(pkg.knn_sym_dist(X, knn, "auto")[0])
+    W.sort_indices()
+    assert np.array_equal(W.indptr, W_ref.indptr) and np.array_equal(W.indices, W_ref.indices)   # same graph
+    assert np.max(np.abs(W.data - W_ref.data)) < 2e-6                                            # fp32 weights
+    L = (sparse.diags(np.asarray(W.sum(axis=0)).ravel()) - W).tocsr()
+    Luu = (L[k_lab:, k_lab:] + float(g["tau"]) * sparse.identity(m)).tocsr()
+    M = sparse.diags(1.0 / np.sqrt(Luu.diagonal() + 1e-10))
+    Pred = M @ pkg.stable_conjgrad(M @ Luu @ M, -(M @ (L[k_lab:, :k_lab] @ Y.astype(np.float64))))
+    assert O.max_rel(Pred, g["pred"]) < 1e-5
+    assert np.array_equal(Pred.argmax(axis=1), g["pred"].argmax(axis=1))

@@ -93,3 +93,32 @@ def test_knn_tie_helper():
     assert O.knn_sets_match(np.array([[0, 1, 2, 3]]), ref_ind, ref_dist) == (1, 0, 0)
     assert O.knn_sets_match(np.array([[0, 1, 2, 9]]), ref_ind, ref_dist) == (0, 1, 0)
     assert O.knn_sets_match(np.array([[0, 9, 2, 3]]), ref_ind, ref_dist) == (0, 0, 1)
+
+
+def _load_eval_fixture():
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eval_k50.npz"))
+    seed, k_lab, m, d, l, knn = (int(v) for v in g["params"])
+    X, Y, _, yq = O.synth_inputs(seed, k_lab, m, d, l, float(g["sigma"]))
+    import hashlib
+
+    assert hashlib.sha256(X.tobytes()).hexdigest() == str(g["x_sha256"])
+    W = sp.csr_matrix((g["w_data"], g["w_indices"], g["w_indptr"]), shape=(k_lab + m, k_lab + m))
+    return g, X, Y, yq, k_lab, knn, W
+
+
+def test_oracle_matches_reference_eval_path_fixture():
+    """The reference's evaluation routine (utils.py:570-593) on the UNMODIFIED knn_sym_dist (k = 50) and stable_conjgrad of
+    GLL.py (oracle/make_golden_eval.py): the restated graph and a textbook CG on the same Jacobi-scaled system agree."""
+    g, X, Y, yq, k_lab, knn, W_ref = _load_eval_fixture()
+    gr = O.build_graph(X, knn, "auto")
+    W = sp.csr_matrix(gr.W)
+    W.sort_indices()
+    assert np.array_equal(W.indptr, W_ref.indptr) and np.array_equal(W.indices, W_ref.indices)
+    assert np.max(np.abs(W.data - W_ref.data)) < 1e-12
+    L = (sp.diags(np.asarray(W.sum(axis=0)).ravel()) - W).tocsr()
+    Luu = (L[k_lab:, k_lab:] + float(g["tau"]) * sp.identity(X.shape[0] - k_lab)).tocsr()
+    M = sp.diags(1.0 / np.sqrt(Luu.diagonal() + 1e-10))
+    y = O.textbook_cg(sp.csr_matrix(M @ Luu @ M), -(M @ (L[k_lab:, :k_lab] @ Y.astype(np.float64))), tol=1e-12)[0]
+    assert O.max_rel(M @ y, g["pred"]) < 1e-8   # the reference stops at a 1e-10 residual
