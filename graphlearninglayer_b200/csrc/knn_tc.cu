@@ -409,38 +409,47 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
           if (hits) {
             const int c = __ffs(hits) - 1;
             hits &= hits - 1;
-            float dsel = v[0];
+            // The whole insertion is latency-bound (one warp's dependent chain), so every selection below is a balanced
+            // tree, not a scan: v[c] by the bits of c (depth 4 instead of 15) ...
+            float s8[8], s4[4];
 #pragma unroll
-            for (int t = 1; t < TC_CHUNK; ++t) dsel = (t == c) ? v[t] : dsel;
+            for (int t = 0; t < 8; ++t) s8[t] = (c & 1) ? v[2 * t + 1] : v[2 * t];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) s4[t] = (c & 2) ? s8[2 * t + 1] : s8[2 * t];
+            const float s2a = (c & 4) ? s4[1] : s4[0], s2b = (c & 4) ? s4[3] : s4[2];
+            const float dsel = (c & 8) ? s2b : s2a;
             // second round: the key is rebuilt exactly as the first round flushed it (dd + |x_i|^2, index), so the
             // lexicographic test excludes precisely the first round's set
             const bool fresh = (P.excl == nullptr) || (make_key(dsel + sqi_row, j0 + c) > excl_row);
             if (dsel < thr && fresh) {  // thr may have tightened since the scan
               // the row's 32 slots are 4 groups of 8 with the group maxima (value, slot) cached in registers: replace
-              // the overall maximum, rescan only its group (8 shared-memory loads instead of 32)
-              int g = 0;
-              float gmax = gm[0];
-#pragma unroll
-              for (int t = 1; t < 4; ++t)
-                if (gm[t] > gmax) {
-                  gmax = gm[t];
-                  g = t;
-                }
-              int pos = gp[0];
-#pragma unroll
-              for (int t = 1; t < 4; ++t) pos = (t == g) ? gp[t] : pos;
+              // the overall maximum, rescan only its group (8 shared-memory loads instead of 32).  First maximum wins ties.
+              const bool h01 = gm[1] > gm[0], h23 = gm[3] > gm[2];
+              const float m01 = h01 ? gm[1] : gm[0], m23 = h23 ? gm[3] : gm[2];
+              const int p01 = h01 ? gp[1] : gp[0], p23 = h23 ? gp[3] : gp[2];
+              const bool hi = m23 > m01;
+              const int g = hi ? (h23 ? 3 : 2) : (h01 ? 1 : 0);
+              const int pos = hi ? p23 : p01;
               Ld[pos * 32] = dsel;
               Li[pos * 32] = j0 + c;
-              float mx = -INFINITY;
-              int mp = 0;
+              float tv[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float t = Ld[(g * 8 + e) * 32];
-                if (t > mx) {
-                  mx = t;
-                  mp = g * 8 + e;
-                }
+              for (int e = 0; e < 8; ++e) tv[e] = Ld[(g * 8 + e) * 32];
+              // ... and the group's new maximum by a three-level tournament (lower slot wins ties, as a scan would)
+              float a4[4];
+              int i4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const bool h = tv[2 * e + 1] > tv[2 * e];
+                a4[e] = h ? tv[2 * e + 1] : tv[2 * e];
+                i4[e] = h ? 2 * e + 1 : 2 * e;
               }
+              const bool ha = a4[1] > a4[0], hb = a4[3] > a4[2];
+              const float a2a = ha ? a4[1] : a4[0], a2b = hb ? a4[3] : a4[2];
+              const int i2a = ha ? i4[1] : i4[0], i2b = hb ? i4[3] : i4[2];
+              const bool hc = a2b > a2a;
+              const float mx = hc ? a2b : a2a;
+              const int mp = g * 8 + (hc ? i2b : i2a);
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 gm[t] = (t == g) ? mx : gm[t];
