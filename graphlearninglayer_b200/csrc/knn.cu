@@ -17,6 +17,7 @@
 #include <stdlib.h>
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "knn_common.cuh"
@@ -65,6 +66,64 @@ sqnorm_split_kernel(const float* __restrict__ X, int n, int d, int d_pad, float*
     sq[row] = f;
     if (thr_g != nullptr) thr_g[row] = 0xFF800000u;  // float_to_ordered(+inf): the row's shared threshold (knn_tc.cu)
     if (f == f) atomicMax(sqmax_bits, __float_as_uint(f));  // non-negative floats order like their bits
+  }
+}
+
+// f16x2 operands (knn_tc.cu), fused with the norms so that X is read from HBM once: row i is scaled by 2^-E_i with
+// 2^(E_i - 1) <= max_k |x_ik| < 2^E_i (exact; no fp16 overflow, and fp16's subnormal granularity 2^-24 is relative to the
+// row's own largest element), then hi = fp16(z), lo = fp16(z - hi), row stride d_pad, zero padded.  rscale[i] = 2^E_i undoes
+// the scaling in the Gram epilogue.  Also the largest B-side residual rho = max_j |x_j - hi_j 2^E_j|_2 (exact in fp64,
+// rounded up): the Gram kernel computes (hi + lo)_i . hi_j, so its error is |x_i| rho + O(2^-22).
+__global__ void __launch_bounds__(256)
+sqnorm_split_f16_kernel(const float* __restrict__ X, int n, int d, int d_pad, float* __restrict__ sq, unsigned* __restrict__ small,
+                        __half* __restrict__ H, __half* __restrict__ L, float* __restrict__ rscale, unsigned* __restrict__ thr_g) {
+  const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* x = X + (size_t)row * d;
+  double s = 0.0;
+  float mx = 0.f;
+  for (int c = 2 * lane; c < d; c += 64) {
+    const float x0 = __ldg(x + c);
+    const float x1 = (c + 1 < d) ? __ldg(x + c + 1) : 0.f;
+    s += (double)x0 * (double)x0;
+    s += (double)x1 * (double)x1;
+    mx = fmaxf(mx, fmaxf(fabsf(x0), fabsf(x1)));  // NaN elements are ignored here; they poison sq[] below
+  }
+  s = warp_sum(s);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+  int E = 0;
+  {
+    const unsigned b = __float_as_uint(mx);
+    const int ex = (int)((b >> 23) & 0xFFu);
+    if (b != 0u && ex != 0xFF) E = min(60, max(-60, ex - 126));  // mx in [2^(ex-127), 2^(ex-126))
+  }
+  double r2 = 0.0;
+  for (int c = 2 * lane; c < d_pad; c += 64) {  // second sweep over the row: L1 hits
+    const float x0 = (c < d) ? __ldg(x + c) : 0.f;
+    const float x1 = (c + 1 < d) ? __ldg(x + c + 1) : 0.f;
+    const float z0 = ldexpf(x0, -E), z1 = ldexpf(x1, -E);
+    const __half h0 = __float2half_rn(z0), h1 = __float2half_rn(z1);
+    const float f0 = __half2float(h0), f1 = __half2float(h1);
+    __half2 hv, lv;
+    hv.x = h0;
+    hv.y = h1;
+    lv.x = __float2half_rn(z0 - f0);
+    lv.y = __float2half_rn(z1 - f1);
+    *reinterpret_cast<__half2*>(H + (size_t)row * d_pad + c) = hv;
+    *reinterpret_cast<__half2*>(L + (size_t)row * d_pad + c) = lv;
+    const double e0 = (double)x0 - ldexp((double)f0, E), e1 = (double)x1 - ldexp((double)f1, E);
+    r2 += e0 * e0 + e1 * e1;
+  }
+  r2 = warp_sum(r2);
+  if (lane == 0) {
+    const float f = (float)s;
+    sq[row] = f;
+    rscale[row] = ldexpf(1.f, E);
+    if (thr_g != nullptr) thr_g[row] = 0xFF800000u;  // float_to_ordered(+inf): the row's shared threshold (knn_tc.cu)
+    if (f == f) atomicMax(small, __float_as_uint(f));  // non-negative floats order like their bits
+    const float rho = __double2float_ru(sqrt(r2) * 1.000001);
+    if (rho == rho) atomicMax(small + 2, __float_as_uint(rho));
   }
 }
 
@@ -281,6 +340,13 @@ __device__ __forceinline__ double exact_d2_reg(const double (&xr)[16], const flo
   return warp_sum(part);
 }
 
+// |d~^2_ij - d^2_ij| <= err_coef (|x_i|^2 + max|x|^2) + 2 |x_i| rho.  small[0] = bits of max_j |x_j|^2, small[2] = bits of
+// rho, the largest one-sided operand residual of the f16x2 Gram path (0 on the other paths).
+__device__ __forceinline__ double knn_err_bound(float err_coef, float sqi, const unsigned* __restrict__ small) {
+  const double sqm = (double)__uint_as_float(small[0]), rho = (double)__uint_as_float(small[2]);
+  return (double)err_coef * ((double)sqi + sqm) + 2.0 * sqrt((double)sqi) * rho * 1.000001;
+}
+
 template <bool VEC4>
 __global__ void __launch_bounds__(RERANK_WARPS * 32)
 knn_rerank_kernel(const float* __restrict__ X, const float* __restrict__ sq, const unsigned* __restrict__ sqmax_bits,
@@ -329,7 +395,7 @@ knn_rerank_kernel(const float* __restrict__ X, const float* __restrict__ sq, con
 
   // Candidates whose approximate distance exceeds the (k-1)-th approximate distance by more than twice the error bound
   // cannot be among the k-1 nearest (k-1 others are provably closer): their exact distance is not needed.
-  const double errb = (double)err_coef * ((double)sq[i] + (double)__uint_as_float(*sqmax_bits));
+  const double errb = knn_err_bound(err_coef, sq[i], sqmax_bits);
   const u64 kth = __shfl_sync(FULL, mine, k - 2);
   const float cutoff = (kth == KEY_INF) ? INFINITY : (float)((double)key_dist(kth) + 2.0 * errb + 1e-30) * (1.f + 1e-6f);
   double myd2 = INFINITY;
@@ -534,8 +600,7 @@ knn_rerank64_kernel(const float* __restrict__ X, const float* __restrict__ sq, c
   bool ok = false;
   if (wa | wb) {
     const double dk = wa ? __shfl_sync(FULL, da, __ffs(wa) - 1) : __shfl_sync(FULL, db, __ffs(wb) - 1);
-    const float sqm = __uint_as_float(*sqmax_bits);
-    const double errb = (double)err_coef * ((double)sq[i] + (double)sqm);
+    const double errb = knn_err_bound(err_coef, sq[i], sqmax_bits);
     ok = ((double)lower - errb > dk) || (lower == INFINITY);
   }
   if (!ok && lane == 0) {
@@ -647,6 +712,7 @@ size_t knn_ws_bytes(int n, int d, int k, int row_begin, int row_end) {
   b += align_up(sizeof(int) * rows, 256);                                                          // flag_rows
   b += knn_tc_ws_upper(n, d);                                           // bf16 hi / lo copies for the tensor-core path
   b += align_up(sizeof(unsigned) * (size_t)n, 256);                     // per-row shared thresholds
+  b += align_up(sizeof(float) * (size_t)n, 256);                        // per-row operand scale (f16x2 split)
   if (k > KC + 1) b += 2 * align_up(sizeof(u64) * rows * KC, 256) + align_up(sizeof(u64) * (size_t)n, 256);  // merged lists, excl
   return b + 1024;
 }
@@ -674,6 +740,7 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
   int* flag_rows = cv.take<int>(rows);
   char* tc_ws = cv.take<char>(knn_tc_ws_upper(n, d));
   unsigned* thr_g = cv.take<unsigned>(n);
+  float* rscale = cv.take<float>(n);  // per-row power-of-two scale of the f16x2 operand split
   {
     const char* sh = getenv("GLL_B200_KNN_SHARE");  // "0": every candidate set keeps its own threshold (experiments)
     if (sh && sh[0] == '0') thr_g = nullptr;
@@ -690,7 +757,12 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
   GLL_CUDA_CHECK(cudaMemsetAsync(small, 0, 256, st));
   {
     GLL_PROF(KID_SQNORM, st);
-    sqnorm_split_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(X, n, d, plan.ok ? plan.d_pad : d, sq, sqmax_bits, H, L, thr_g);
+    if (plan.ok && plan.f16x2) {
+      sqnorm_split_f16_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(X, n, d, plan.d_pad, sq, small, reinterpret_cast<__half*>(H),
+                                                                                reinterpret_cast<__half*>(L), rscale, thr_g);
+    } else {
+      sqnorm_split_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(X, n, d, plan.ok ? plan.d_pad : d, sq, sqmax_bits, H, L, thr_g);
+    }
   }
   GLL_LAUNCH_CHECK();
 
@@ -708,25 +780,25 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
     lay.units = plan.units;
     lay.row_begin = row_begin;
     const int mblocks = ceil_div(rows, RERANK_WARPS);
-    int rc = knn_tc_candidates(X, sq, n, d, row_end, plan, tc_ws, cand, nullptr, thr_g, st);
+    int rc = knn_tc_candidates(X, sq, plan.f16x2 ? rscale : nullptr, n, d, row_end, plan, tc_ws, cand, nullptr, thr_g, st);
     if (rc) return rc;
     {
       GLL_PROF(KID_RERANK, st);
       knn_merge_kernel<<<mblocks, RERANK_WARPS * 32, 0, st>>>(row_end, lay, cand, merged1, excl);
     }
     GLL_LAUNCH_CHECK();
-    rc = knn_tc_candidates(X, sq, n, d, row_end, plan, tc_ws, cand, excl, nullptr, st);  // second round: own thresholds
+    rc = knn_tc_candidates(X, sq, plan.f16x2 ? rscale : nullptr, n, d, row_end, plan, tc_ws, cand, excl, nullptr, st);  // second round: own thresholds
     if (rc) return rc;
     {
       GLL_PROF(KID_RERANK, st);
       knn_merge_kernel<<<mblocks, RERANK_WARPS * 32, 0, st>>>(row_end, lay, cand, merged2, nullptr);
     }
     GLL_LAUNCH_CHECK();
-    return knn_finish64(X, sq, sqmax_bits, n, d, k, row_begin, row_end, merged1, merged2, knn_tc_err_coef(d), knn_idx, knn_dist,
+    return knn_finish64(X, sq, sqmax_bits, n, d, k, row_begin, row_end, merged1, merged2, knn_tc_err_coef(d, plan.f16x2), knn_idx, knn_dist,
                         flag_count, flag_rows, info, st);
   }
   if (plan.ok) {  // tcgen05 / TMA Gram GEMM with the fused top-k epilogue
-    int rc = knn_tc_candidates(X, sq, n, d, row_end, plan, tc_ws, cand, nullptr, thr_g, st);
+    int rc = knn_tc_candidates(X, sq, plan.f16x2 ? rscale : nullptr, n, d, row_end, plan, tc_ws, cand, nullptr, thr_g, st);
     if (rc) return rc;
     lay.stride = plan.max_splits;
     lay.tc = plan.aligned ? 2 : 1;
@@ -734,7 +806,7 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
     lay.col_tiles = plan.col_tiles;
     lay.grid = plan.grid;
     lay.units = plan.units;
-    err_coef = knn_tc_err_coef(d);
+    err_coef = knn_tc_err_coef(d, plan.f16x2);
   } else {  // fp32 SIMT Gram (tiny graphs, or forced by GLL_B200_KNN_PATH=simt)
     int cps;
     const int splits = simt_splits(n, rows, &cps);

@@ -70,14 +70,16 @@ __device__ __forceinline__ void list_merge_set(u64& mine, u64 c, int lane) {
 // Tensor-core candidate generation (knn_tc.cu).  plan.ok == 0: shape or configuration not handled, use the SIMT path.
 struct TcPlan {
   int ok, d_pad, kblocks, row_tiles, col_tiles, grid, max_splits, rt0, aligned, rstep;  // row_tiles counts row GROUPS of rstep tiles
+  int f16x2;        // 1: operands are the fp16 split of the rows of X, each scaled by a power of two, and the Gram entry is (hi + lo).hi (two MMA passes)
   long long units;
-  size_t ws_bytes;  // bf16 hi / lo copies of X
+  size_t ws_bytes;  // 16-bit hi / lo copies of X
 };
+
 TcPlan knn_tc_plan(int n, int d, int row_begin, int row_end);
 size_t knn_tc_ws_upper(int n, int d);
-int knn_tc_candidates(const float* X, const float* sq, int n, int d, int row_end, const TcPlan& plan, void* tc_ws, u64* cand,
-                      const u64* excl, unsigned* thr_g, cudaStream_t st);
-float knn_tc_err_coef(int d);
+int knn_tc_candidates(const float* X, const float* sq, const float* rscale, int n, int d, int row_end, const TcPlan& plan,
+                      void* tc_ws, u64* cand, const u64* excl, unsigned* thr_g, cudaStream_t st);
+float knn_tc_err_coef(int d, int f16x2);
 
 // How the candidate lists of a row are laid out in cand[n][stride][KC]: uniform (SIMT: every row has `stride` lists)
 // or the tensor-core work split (row tile rt was touched by CTAs b0(rt)..b1(rt); slot = b - b0).

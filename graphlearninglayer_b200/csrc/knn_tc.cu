@@ -39,25 +39,29 @@ namespace {
 // Stage = one K block of {A_hi, A_lo, B_hi, B_lo}: 48 KB at a K block of 32 (64-byte swizzle).  Three stages already run
 // the MMA pipe at 98 % of the cuBLAS peak when the epilogue does nothing (GLL_B200_KNN_DEBUG=2: 0.22 ms at 10k nodes), and
 // leave room for the candidate sets of EIGHT epilogue warps.
-constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 32, TC_STAGES = 3;
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 32, TC_STAGES = 3, TC_MAX_STAGES = 4;
 constexpr int TC_EPI_WARPS = 8;                        // two per TMEM lane quarter: each takes one half of the 256 columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 8 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;          // 16 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // 48 KB
-constexpr int TC_CHUNK = 16;                           // columns per tcgen05.ld
+constexpr int TC_CHUNK = 32;                           // columns per tcgen05.ld
 constexpr int TC_TMEM_COLS = 512, TC_ACC_STRIDE = 256;
 
 constexpr size_t TC_OFF_LD = (size_t)TC_STAGES * TC_STAGE_BYTES;             // float [8 warps][KC entries][32 rows]
 constexpr size_t TC_OFF_LI = TC_OFF_LD + TC_EPI_WARPS * KC * 32 * 4;         // int   [8 warps][KC entries][32 rows]
 constexpr size_t TC_OFF_SQJ = TC_OFF_LI + TC_EPI_WARPS * KC * 32 * 4;        // float [TC_BN]  |x_j|^2 of the unit's columns
-constexpr size_t TC_OFF_BAR = TC_OFF_SQJ + TC_BN * 4;                        // mbarriers + tmem pointer
+constexpr size_t TC_OFF_BAR = TC_OFF_SQJ + 2 * TC_BN * 4;                    // (then float [TC_BN] -2 rscale_j) mbarriers + tmem pointer
 constexpr size_t TC_SMEM_BYTES = TC_OFF_BAR + 128 + 1024;                    // + slack for manual 1024 B alignment
 static_assert(TC_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(TC_MAX_STAGES * (TC_STAGE_BYTES - TC_B_BYTES) <= TC_STAGES * TC_STAGE_BYTES, "f16x2 stages fit in the same space");
+static_assert(8 * (2 * TC_MAX_STAGES + 4) <= 96, "mbarriers end where the TMEM pointer slot begins");
 static_assert(2 * TC_BN <= TC_TMEM_COLS && TC_ACC_STRIDE >= TC_BN, "two accumulators must fit in TMEM");
 
 // M = 128, N = 256, A/B bf16 K-major, D fp32 (layout: cute::UMMA::InstrDescriptor)
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+// the same shape with fp16 operands (A / B format fields 0): the f16x2 split
+constexpr uint32_t TC_IDESC_F16 = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -143,23 +147,30 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
   constexpr uint64_t sbo = (uint64_t)(8 * TC_BK * 2) >> 4, layout = (TC_BK == 64) ? 2 : 4;
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | (sbo << 32) | ((uint64_t)1 << 46) | (layout << 61);
 }
-// Asynchronous TMEM -> register load of 16 consecutive columns of this thread's row; the registers are valid only after
-// tc_ld_wait(), which names them as in/out operands so that no use can be scheduled ahead of the wait.
-__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[TC_CHUNK]) {
+// Asynchronous TMEM -> register load of 32 consecutive columns of this thread's row; the registers are valid only after
+// tc_ld_wait(), which names them as in/out operands so that no use can be scheduled ahead of the wait.  (16-column loads
+// left the epilogue latency-bound once the f16x2 split had shortened the MMA time per unit: one wait + one vote per chunk.)
+#define TC_R8(o, b) o(r[b + 0]), o(r[b + 1]), o(r[b + 2]), o(r[b + 3]), o(r[b + 4]), o(r[b + 5]), o(r[b + 6]), o(r[b + 7])
+#define TC_OUT(x) "=r"(x)
+#define TC_INOUT(x) "+r"(x)
+__device__ __forceinline__ void tc_ld_issue(uint32_t taddr, uint32_t (&r)[TC_CHUNK]) {
+  static_assert(TC_CHUNK == 32, "the asm below names 32 registers");
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : TC_R8(TC_OUT, 0), TC_R8(TC_OUT, 8), TC_R8(TC_OUT, 16), TC_R8(TC_OUT, 24)
       : "r"(taddr)
       : "memory");
 }
 __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[TC_CHUNK]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               : TC_R8(TC_INOUT, 0), TC_R8(TC_INOUT, 8), TC_R8(TC_INOUT, 16), TC_R8(TC_INOUT, 24)
                :
                : "memory");
 }
+#undef TC_R8
+#undef TC_OUT
+#undef TC_INOUT
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory"); }  // the epilogue warps
 
 struct TcParams {
@@ -173,6 +184,8 @@ struct TcParams {
   unsigned* thr_g;    // [n] per-row threshold shared by every candidate set of the row (ordered-uint of the float), or NULL
   int debug;          // GLL_B200_KNN_DEBUG (timing experiments only, results are wrong): 1 no insertions, 2 no TMEM drain
   const u64* excl;    // optional [n]: per row, only keys > excl[row] are candidates (second round of a k > 33 search)
+  int f16x2;          // operands are fp16(x_i 2^-E_i): Gram = (hi + lo).hi in two MMA passes, B_lo is never loaded
+  const float* rscale;  // [n] 2^E_i (f16x2) or NULL: the accumulator holds x_i.x_j / (rscale_i rscale_j)
 };
 
 // CTA that owns unit u when `units` units are dealt contiguously to G CTAs (CTA b owns [b*units/G, (b+1)*units/G))
@@ -206,9 +219,12 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     u_end = (long long)(b + 1) * P.units / G;
   }
 
-  const uint32_t bar_full = base + (uint32_t)TC_OFF_BAR;        // [TC_STAGES]
-  const uint32_t bar_empty = bar_full + 8 * TC_STAGES;          // [TC_STAGES]
-  const uint32_t bar_tfull = bar_empty + 8 * TC_STAGES;         // [2]
+  // f16x2 stages hold {A_hi, A_lo, B_hi} = 32 KB, so FOUR of them fit where three 48 KB stages of the bf16x3 split do
+  const int nstages = P.f16x2 ? TC_MAX_STAGES : TC_STAGES;
+  const uint32_t stage_bytes = P.f16x2 ? (uint32_t)(TC_STAGE_BYTES - TC_B_BYTES) : (uint32_t)TC_STAGE_BYTES;
+  const uint32_t bar_full = base + (uint32_t)TC_OFF_BAR;        // [TC_MAX_STAGES]
+  const uint32_t bar_empty = bar_full + 8 * TC_MAX_STAGES;      // [TC_MAX_STAGES]
+  const uint32_t bar_tfull = bar_empty + 8 * TC_MAX_STAGES;     // [2]
   const uint32_t bar_tempty = bar_tfull + 16;                   // [2]
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + TC_OFF_BAR + 96);
 
@@ -217,7 +233,7 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     tma_prefetch_desc(&mapAL);
     tma_prefetch_desc(&mapBH);
     tma_prefetch_desc(&mapBL);
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < TC_MAX_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, PAIR ? 2 : 1);  // PAIR: both CTAs' MMAs must have consumed the stage
     }
@@ -251,19 +267,20 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
         for (int kk = 0; kk < KB; ++kk) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
           const uint32_t full = bar_full + 8 * stage;
-          const uint32_t s0 = base + (uint32_t)stage * TC_STAGE_BYTES;
-          mbar_arrive_expect_tx(full, TC_STAGE_BYTES);
+          const uint32_t s0 = base + (uint32_t)stage * stage_bytes;
+          mbar_arrive_expect_tx(full, stage_bytes);
           tma_load_2d(s0, &mapAH, full, kk * TC_BK, rt * TC_BM);
           tma_load_2d(s0 + TC_A_BYTES, &mapAL, full, kk * TC_BK, rt * TC_BM);
           if (PAIR) {  // my half of the B tiles (128 of the 256 rows), delivered to both CTAs (128-row boxes: the A maps)
             const uint32_t half = (uint32_t)crank * (TC_B_BYTES / 2);
             tma_load_2d_mc(s0 + 2 * TC_A_BYTES + half, &mapAH, full, kk * TC_BK, ct * TC_BN + crank * (TC_BN / 2), 3);
-            tma_load_2d_mc(s0 + 2 * TC_A_BYTES + TC_B_BYTES + half, &mapAL, full, kk * TC_BK, ct * TC_BN + crank * (TC_BN / 2), 3);
+            if (!P.f16x2)
+              tma_load_2d_mc(s0 + 2 * TC_A_BYTES + TC_B_BYTES + half, &mapAL, full, kk * TC_BK, ct * TC_BN + crank * (TC_BN / 2), 3);
           } else {
             tma_load_2d(s0 + 2 * TC_A_BYTES, &mapBH, full, kk * TC_BK, ct * TC_BN);
-            tma_load_2d(s0 + 2 * TC_A_BYTES + TC_B_BYTES, &mapBL, full, kk * TC_BK, ct * TC_BN);
+            if (!P.f16x2) tma_load_2d(s0 + 2 * TC_A_BYTES + TC_B_BYTES, &mapBL, full, kk * TC_BK, ct * TC_BN);
           }
-          if (++stage == TC_STAGES) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -274,6 +291,8 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     // ================================================= MMA issuer ===================================================
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
+    const int nprod = P.f16x2 ? 2 : 3;
+    const uint32_t idesc = P.f16x2 ? TC_IDESC_F16 : TC_IDESC;
     for (long long u = u_begin; u < u_end; ++u) {
       mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);  // the epilogue has drained this accumulator
       tc_fence_after();
@@ -282,15 +301,16 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
         mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t s0 = base + (uint32_t)stage * TC_STAGE_BYTES;
+          const uint32_t s0 = base + (uint32_t)stage * stage_bytes;
           const uint64_t dAH = tc_smem_desc(s0), dAL = tc_smem_desc(s0 + TC_A_BYTES);
           const uint64_t dBH = tc_smem_desc(s0 + 2 * TC_A_BYTES), dBL = tc_smem_desc(s0 + 2 * TC_A_BYTES + TC_B_BYTES);
 #pragma unroll
           for (int g = 0; g < 3; ++g) {
+            if (g >= nprod) break;  // f16x2: hi.hi and lo.hi only
             const uint64_t da = (g == 1) ? dAL : dAH, db = (g == 2) ? dBL : dBH;  // hi.hi, lo.hi, hi.lo
 #pragma unroll
             for (int k4 = 0; k4 < TC_BK / 16; ++k4)  // +32 B (two 16 B units) per K=16 step inside the swizzle atom
-              tc_mma_bf16(d_tmem, da + (uint64_t)(2 * k4), db + (uint64_t)(2 * k4), TC_IDESC, (uint32_t)((kk | g | k4) != 0));
+              tc_mma_bf16(d_tmem, da + (uint64_t)(2 * k4), db + (uint64_t)(2 * k4), idesc, (uint32_t)((kk | g | k4) != 0));
           }
           if (PAIR)
             tc_commit_mc(bar_empty + 8 * stage, 3);  // frees the stage in BOTH CTAs (the peer multicasts into mine)
@@ -299,7 +319,7 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
           if (kk == KB - 1) tc_commit(bar_tfull + 8 * acc);  // accumulator complete
         }
         __syncwarp();
-        if (++stage == TC_STAGES) {
+        if (++stage == nstages) {
           stage = 0;
           phase ^= 1u;
         }
@@ -331,6 +351,9 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     float sqi_row = 0.f;
     float* sqj_s = reinterpret_cast<float*>(smem + TC_OFF_SQJ);
     const int et = (warp - 2) * 32 + lane;  // 0..255 over the epilogue warps
+    // d~^2 - |x_i|^2 = |x_j|^2 + (acc ri) cj with cj = -2 rscale_j, ri = rscale_i (powers of two: exact; 1 without scaling)
+    float* cj_s = sqj_s + TC_BN;
+    float ri = 1.f;
 
     auto flush = [&](int rt) {
       __syncwarp();
@@ -361,6 +384,7 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
           gp[t] = 8 * t;
         }
         gi = rt * TC_BM + quarter * 32 + lane;
+        ri = (P.rscale != nullptr && gi < P.n) ? __ldg(P.rscale + gi) : 1.f;
         if (P.excl != nullptr) {
           excl_row = (gi < P.n) ? __ldg(P.excl + gi) : 0ull;
           sqi_row = (gi < P.n) ? __ldg(P.sq + gi) : 0.f;
@@ -370,6 +394,7 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
       // stage |x_j|^2 of the unit's 256 columns for all four epilogue warps (+inf masks columns beyond n)
       epi_bar_sync();  // everybody is done with the previous unit's values
       sqj_s[et] = (c_begin + et < P.n) ? __ldg(P.sq + c_begin + et) : INFINITY;
+      cj_s[et] = (P.rscale != nullptr && c_begin + et < P.n) ? -2.f * __ldg(P.rscale + c_begin + et) : -2.f;
       epi_bar_sync();
       // once per unit (sharing every 32 columns instead measured the same): take what the row's other sets have published
       if (P.thr_g != nullptr && gi < P.n) {  // ordered + 1 = the next float up: ties with another set's bound stay admissible
@@ -391,12 +416,13 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
 #pragma unroll
         for (int c4 = 0; c4 < TC_CHUNK / 4; ++c4) {
           const float4 s4 = *reinterpret_cast<const float4*>(sqj_s + q * TC_CHUNK + 4 * c4);  // warp-wide broadcast
-          v[4 * c4 + 0] = fmaf(-2.f, __uint_as_float(raw[4 * c4 + 0]), s4.x);
-          v[4 * c4 + 1] = fmaf(-2.f, __uint_as_float(raw[4 * c4 + 1]), s4.y);
-          v[4 * c4 + 2] = fmaf(-2.f, __uint_as_float(raw[4 * c4 + 2]), s4.z);
-          v[4 * c4 + 3] = fmaf(-2.f, __uint_as_float(raw[4 * c4 + 3]), s4.w);
+          const float4 c4v = *reinterpret_cast<const float4*>(cj_s + q * TC_CHUNK + 4 * c4);
+          v[4 * c4 + 0] = fmaf(ri * __uint_as_float(raw[4 * c4 + 0]), c4v.x, s4.x);
+          v[4 * c4 + 1] = fmaf(ri * __uint_as_float(raw[4 * c4 + 1]), c4v.y, s4.y);
+          v[4 * c4 + 2] = fmaf(ri * __uint_as_float(raw[4 * c4 + 2]), c4v.z, s4.z);
+          v[4 * c4 + 3] = fmaf(ri * __uint_as_float(raw[4 * c4 + 3]), c4v.w, s4.w);
         }
-        if (diag && j0 < wrow0 + 32 && j0 + TC_CHUNK > wrow0) {  // warp-uniform, true for at most 3 chunks of one unit
+        if (diag && j0 < wrow0 + 32 && j0 + TC_CHUNK > wrow0) {  // warp-uniform, true for at most 2 chunks of one unit
 #pragma unroll
           for (int c = 0; c < TC_CHUNK; ++c)
             if (j0 + c == gi) v[c] = INFINITY;  // self is slot 0 by construction (knn_finish)
@@ -410,14 +436,16 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
             const int c = __ffs(hits) - 1;
             hits &= hits - 1;
             // The whole insertion is latency-bound (one warp's dependent chain), so every selection below is a balanced
-            // tree, not a scan: v[c] by the bits of c (depth 4 instead of 15) ...
-            float s8[8], s4[4];
+            // tree, not a scan: v[c] by the bits of c (depth 5 instead of 31) ...
+            float s16[16], s8[8], s4[4];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) s8[t] = (c & 1) ? v[2 * t + 1] : v[2 * t];
+            for (int t = 0; t < 16; ++t) s16[t] = (c & 1) ? v[2 * t + 1] : v[2 * t];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) s4[t] = (c & 2) ? s8[2 * t + 1] : s8[2 * t];
-            const float s2a = (c & 4) ? s4[1] : s4[0], s2b = (c & 4) ? s4[3] : s4[2];
-            const float dsel = (c & 8) ? s2b : s2a;
+            for (int t = 0; t < 8; ++t) s8[t] = (c & 2) ? s16[2 * t + 1] : s16[2 * t];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) s4[t] = (c & 4) ? s8[2 * t + 1] : s8[2 * t];
+            const float s2a = (c & 8) ? s4[1] : s4[0], s2b = (c & 8) ? s4[3] : s4[2];
+            const float dsel = (c & 16) ? s2b : s2a;
             // second round: the key is rebuilt exactly as the first round flushed it (dd + |x_i|^2, index), so the
             // lexicographic test excludes precisely the first round's set
             const bool fresh = (P.excl == nullptr) || (make_key(dsel + sqi_row, j0 + c) > excl_row);
@@ -461,7 +489,7 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
           }
         }
       };
-      // two register sets: the TMEM load of the next 16 columns is in flight while the current ones are processed
+      // two register sets: the TMEM load of the next 32 columns is in flight while the current ones are processed
       constexpr int QH = TC_BN / TC_CHUNK / 2;  // chunks per warp (its half of the columns)
       const int q0 = half * QH;
       if (P.debug >= 2) {  // timing experiment: hand the accumulator back untouched
@@ -469,15 +497,15 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       } else
-        tc_ld16_issue(taddr + q0 * TC_CHUNK, rawA);
+        tc_ld_issue(taddr + q0 * TC_CHUNK, rawA);
 #pragma unroll 1
       for (int q = q0; q < ((P.debug >= 2) ? 0 : q0 + QH); q += 2) {
         tc_ld_wait(rawA);
-        tc_ld16_issue(taddr + (q + 1) * TC_CHUNK, rawB);
+        tc_ld_issue(taddr + (q + 1) * TC_CHUNK, rawB);
         process(rawA, q);
         tc_ld_wait(rawB);
         if (q + 2 < q0 + QH) {
-          tc_ld16_issue(taddr + (q + 2) * TC_CHUNK, rawA);
+          tc_ld_issue(taddr + (q + 2) * TC_CHUNK, rawA);
         } else {  // this warp's half of the accumulator is in registers or consumed: hand it back to the MMA warp early
           tc_fence_before();
           __syncwarp();
@@ -521,7 +549,7 @@ PFN_cuTensorMapEncodeTiled get_encode_fn() {
   return fn;
 }
 
-int make_map(CUtensorMap* m, const void* base, int n, int d_pad, int box_rows) {
+int make_map(CUtensorMap* m, const void* base, int n, int d_pad, int box_rows, int f16) {
   PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -531,7 +559,7 @@ int make_map(CUtensorMap* m, const void* base, int n, int d_pad, int box_rows) {
   const cuuint64_t gstride[1] = {(cuuint64_t)d_pad * 2};
   const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, (TC_BK == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -579,6 +607,11 @@ TcPlan knn_tc_plan(int n, int d, int row_begin, int row_end) {
   }
   p.ws_bytes = 2 * align_up((size_t)n * p.d_pad * 2, 256);
   p.ok = (p.max_splits <= KNN_MAX_SPLITS) ? 1 : 0;
+  // Operand split.  "f16x2": fp16 hi/lo of the scaled features, Gram = (hi + lo).hi -- two MMA passes; the one-sided
+  // residual (~2^-12 |x_j|, measured per call) enters the completeness proof.  "bf16x3": hi.hi + lo.hi + hi.lo, three
+  // passes, residual 2^-18.  Both only SELECT candidates; the emitted lists are exact either way.
+  const char* sp = getenv("GLL_B200_KNN_SPLIT");
+  p.f16x2 = (sp && strcmp(sp, "bf16x3") == 0) ? 0 : 1;  // default f16x2 (a third fewer MMAs; same lists, same proof)
   return p;
 }
 
@@ -586,23 +619,27 @@ size_t knn_tc_ws_upper(int n, int d) { return 2 * align_up((size_t)n * (size_t)(
 
 // |d~^2 - d^2| <= coef * (|xi|^2 + |xj|^2): split residual 3*2^-18, fp32 accumulation over 3*d/16 MMA steps of unknown
 // internal rounding (budgeted at 2^-21 per step and per 16-term tree), final fp32 expression 4u; then a 4x margin.
-float knn_tc_err_coef(int d) {
-  const double steps = 3.0 * ceil_div(d, 16) + 8.0;
-  const double e = 3.0 / 262144.0 + steps * 4.76837158203125e-7 + 4.0 * 5.9604644775390625e-8;
+// f16x2: the A side is x_i = (hi + lo) 2^E_i + r_i with |r_i| <= 2^-22 |x_i| + 2^-25 sqrt(d) 2^E_i, 2^E_i <= 2 |x_i| (fp16 normal
+// rounding twice, subnormal granularity 2^-24 below 2^-14): 2 |r_i| |x_j| <= (2^-22 + 2^-24 sqrt(d)) (|xi|^2 + |xj|^2);
+// two MMA passes; the B-side residual is NOT in this coefficient -- it is measured (rho) and added by knn_err_bound().
+float knn_tc_err_coef(int d, int f16x2) {
+  const double steps = (f16x2 ? 2.0 : 3.0) * ceil_div(d, 16) + 8.0;
+  const double split = f16x2 ? (1.0 + 0.5 * sqrt((double)d)) / 4194304.0 * 1.01 : 3.0 / 262144.0;
+  const double e = split + steps * 4.76837158203125e-7 + 4.0 * 5.9604644775390625e-8;
   return (float)(4.0 * e);
 }
 
-int knn_tc_candidates(const float* X, const float* sq, int n, int d, int row_end, const TcPlan& plan, void* tc_ws, u64* cand,
-                      const u64* excl, unsigned* thr_g, cudaStream_t st) {
+int knn_tc_candidates(const float* X, const float* sq, const float* rscale, int n, int d, int row_end, const TcPlan& plan,
+                      void* tc_ws, u64* cand, const u64* excl, unsigned* thr_g, cudaStream_t st) {
   __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(tc_ws);
   __nv_bfloat16* L = reinterpret_cast<__nv_bfloat16*>((char*)tc_ws + align_up((size_t)n * plan.d_pad * 2, 256));
   // H and L (bf16 hi / lo split of X, row stride d_pad) were written by sqnorm_split_kernel (knn.cu)
   CUtensorMap mAH, mAL, mBH, mBL;
   int rc;
-  if ((rc = make_map(&mAH, H, n, plan.d_pad, TC_BM))) return rc;
-  if ((rc = make_map(&mAL, L, n, plan.d_pad, TC_BM))) return rc;
-  if ((rc = make_map(&mBH, H, n, plan.d_pad, TC_BN))) return rc;
-  if ((rc = make_map(&mBL, L, n, plan.d_pad, TC_BN))) return rc;
+  if ((rc = make_map(&mAH, H, n, plan.d_pad, TC_BM, plan.f16x2))) return rc;
+  if ((rc = make_map(&mAL, L, n, plan.d_pad, TC_BM, plan.f16x2))) return rc;
+  if ((rc = make_map(&mBH, H, n, plan.d_pad, TC_BN, plan.f16x2))) return rc;
+  if ((rc = make_map(&mBL, L, n, plan.d_pad, TC_BN, plan.f16x2))) return rc;
   TcParams P;
   P.n = n;
   P.kblocks = plan.kblocks;
@@ -617,6 +654,8 @@ int knn_tc_candidates(const float* X, const float* sq, int n, int d, int row_end
   P.cand = cand;
   P.excl = excl;
   P.thr_g = thr_g;
+  P.f16x2 = plan.f16x2;
+  P.rscale = rscale;
   {
     const char* dbg = getenv("GLL_B200_KNN_DEBUG");
     P.debug = dbg ? atoi(dbg) : 0;

@@ -128,11 +128,18 @@ KNN_SHAPES = [(0, 300, 500, 64, 10, 2.0), (3, 37, 91, 19, 3, 1.0), (1, 1000, 100
               (4, 2048, 1024, 512, 10, 4.5), (6, 10, 20, 7, 2, 0.5), (8, 500, 700, 130, 5, 2.0)]
 
 
-@pytest.mark.parametrize("path", ["simt", "tc"])  # fp32 SIMT Gram / tcgen05 bf16x3 Gram: both must give the exact lists
+def _set_knn_path(monkeypatch, path):
+    """simt: fp32 SIMT Gram; tc: tcgen05 Gram with the bf16 hi/lo split (three MMA passes); tc-f16x2: tcgen05 Gram with the
+    scaled fp16 split, (hi + lo).hi (two passes)."""
+    monkeypatch.setenv("GLL_B200_KNN_PATH", "tc" if path.startswith("tc") else path)
+    monkeypatch.setenv("GLL_B200_KNN_SPLIT", "f16x2" if path == "tc-f16x2" else "bf16x3")
+
+
+@pytest.mark.parametrize("path", ["simt", "tc", "tc-f16x2"])  # every Gram path must give the exact lists
 @pytest.mark.parametrize("seed,k_lab,m,d,l,sigma", KNN_SHAPES)
 def test_knn_bit_exact_vs_oracle(gll, monkeypatch, path, seed, k_lab, m, d, l, sigma):
     _, _lib = gll
-    monkeypatch.setenv("GLL_B200_KNN_PATH", path)
+    _set_knn_path(monkeypatch, path)
     X, *_ = O.synth_inputs(seed, k_lab, m, d, l, sigma)
     ref_ind, ref_dist = O.exact_knn(X, 25)
     idx, dist, info = run_knn(_lib, X)
@@ -146,10 +153,10 @@ def test_knn_bit_exact_vs_oracle(gll, monkeypatch, path, seed, k_lab, m, d, l, s
     assert np.array_equal(d_gpu[same], ref_dist[same].astype(np.float32))  # fp64 direct differences rounded to fp32
 
 
-@pytest.mark.parametrize("path", ["simt", "tc"])
+@pytest.mark.parametrize("path", ["simt", "tc", "tc-f16x2"])
 def test_knn_duplicates_and_tiny_n(gll, monkeypatch, path):
     _, _lib = gll
-    monkeypatch.setenv("GLL_B200_KNN_PATH", path)
+    _set_knn_path(monkeypatch, path)
     rng = np.random.default_rng(0)
     X = rng.standard_normal((60, 16)).astype(np.float32)
     X[10:40] = X[10]  # 30 identical points: zero distances, ties broken by index
@@ -162,6 +169,37 @@ def test_knn_duplicates_and_tiny_n(gll, monkeypatch, path):
     X2 = rng.standard_normal((25, 8)).astype(np.float32)
     idx2, _, _ = run_knn(_lib, X2)
     assert np.array_equal(np.sort(idx2.cpu().numpy(), axis=1), np.tile(np.arange(25), (25, 1)))
+
+
+@pytest.mark.parametrize("scale", [1.0, 3.0e4, 2.0e-6, "ragged"])
+def test_knn_f16x2_split_any_feature_scale(gll, monkeypatch, scale):
+    """The fp16 split scales X by a power of two derived from max |x_i|^2, so features far outside fp16's range (or rows of very
+    different norms) must give the same exact lists as the SIMT path, with (almost) no rows sent to the brute-force fallback."""
+    _, _lib = gll
+    X, *_ = O.synth_inputs(5, 1500, 1100, 192, 10, 3.0)
+    if scale == "ragged":
+        X = X * np.logspace(-3, 3, X.shape[0], dtype=np.float32)[np.random.default_rng(0).permutation(X.shape[0]), None]
+    else:
+        X = (X * np.float32(scale)).astype(np.float32)
+    _set_knn_path(monkeypatch, "simt")
+    i_s, d_s, _ = run_knn(_lib, X)
+    _set_knn_path(monkeypatch, "tc-f16x2")
+    i_h, d_h, info = run_knn(_lib, X)
+    assert torch.equal(i_s, i_h) and torch.equal(d_s, d_h)
+    if scale != "ragged":  # rows 1e6 apart in norm: small rows are legitimately unprovable against the largest row's error
+        assert int(info[_lib.INFO_KNN_FALLBACK_ROWS].item()) < 0.02 * X.shape[0]
+
+
+def test_knn_f16x2_full_size_matches_bf16x3(gll, monkeypatch):
+    """C2 size: the two operand splits select the same exact lists, neither needs the fallback."""
+    _, _lib = gll
+    X, *_ = O.synth_inputs(1, 10000, 512, 512, 10, 4.5)
+    _set_knn_path(monkeypatch, "tc")
+    i0, d0, info0 = run_knn(_lib, X)
+    _set_knn_path(monkeypatch, "tc-f16x2")
+    i1, d1, info1 = run_knn(_lib, X)
+    assert torch.equal(i0, i1) and torch.equal(d0, d1)
+    assert int(info0[_lib.INFO_KNN_FALLBACK_ROWS].item()) == 0 and int(info1[_lib.INFO_KNN_FALLBACK_ROWS].item()) == 0
 
 
 def test_knn_paths_agree_and_tc_is_used(gll, monkeypatch):

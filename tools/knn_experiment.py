@@ -25,12 +25,20 @@ lib.gll_profile_enable(1); _lib.profile_collect()
 for _ in range(10): run()
 torch.cuda.synchronize()
 p = _lib.profile_collect()
-print({k: round(v[0] / v[1], 4) for k, v in p.items()})
+print({k: round(v[0] / v[1], 4) for k, v in p.items()}, "fallback_rows", int(info[_lib.INFO_KNN_FALLBACK_ROWS].item()))
 '''
 
 n, d = (sys.argv[1:3] + ["10512", "512"])[:2] if len(sys.argv) >= 3 else ("10512", "512")
-for env in ({}, {"GLL_B200_KNN_DEBUG": "1"}, {"GLL_B200_KNN_DEBUG": "2"}, {"GLL_B200_KNN_PAIR": "1"},
-            {"GLL_B200_KNN_PAIR": "1", "GLL_B200_KNN_DEBUG": "2"}):
+F16 = {"GLL_B200_KNN_SPLIT": "f16x2"}
+ENVS = ({}, {"GLL_B200_KNN_DEBUG": "1"}, {"GLL_B200_KNN_DEBUG": "2"}, {"GLL_B200_KNN_PAIR": "1"},
+        {"GLL_B200_KNN_PAIR": "1", "GLL_B200_KNN_DEBUG": "2"}, F16, dict(F16, GLL_B200_KNN_DEBUG="1"),
+        dict(F16, GLL_B200_KNN_DEBUG="2"))
+if os.environ.get("KNN_EXPERIMENT_ENVS") == "split":  # only the two operand splits
+    ENVS = ({"GLL_B200_KNN_SPLIT": "bf16x3"}, F16, dict(F16, GLL_B200_KNN_DEBUG="1"), dict(F16, GLL_B200_KNN_DEBUG="2"),
+            dict(F16, GLL_B200_KNN_PAIR="1"), dict(F16, GLL_B200_KNN_PAIR="1", GLL_B200_KNN_DEBUG="2"))
+if os.environ.get("KNN_EXPERIMENT_ENVS") == "default":  # the default configuration, and without the set insertions
+    ENVS = ({}, {"GLL_B200_KNN_DEBUG": "1"})
+for env in ENVS:
     e = dict(os.environ, **env)
     out = subprocess.run([sys.executable, "-c", CODE, n, d], env=e, capture_output=True, text=True)
     print(env, out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-400:], flush=True)

@@ -24,9 +24,17 @@ for _ in range(3): run()
 torch.cuda.synchronize()
 p = _lib.profile_collect()
 ms = p["knn_gram_topk_tcgen05"][0] / p["knn_gram_topk_tcgen05"][1]
-print({k: round(v[0] / v[1], 3) for k, v in p.items()}, "issued PFLOP/s", round(3 * 2.0 * rows * n * d / ms / 1e12, 3))
+import os
+npass = 3 if os.environ.get("GLL_B200_KNN_SPLIT") == "bf16x3" else 2
+print({k: round(v[0] / v[1], 3) for k, v in p.items()}, "issued PFLOP/s", round(npass * 2.0 * rows * n * d / ms / 1e12, 3),
+      "fallback_rows", int(info[_lib.INFO_KNN_FALLBACK_ROWS].item()))
 '''
-for env in ({}, {"GLL_B200_KNN_SHARE": "0"}, {"GLL_B200_KNN_DEBUG": "1"}, {"GLL_B200_KNN_DEBUG": "2"}):
+ENVS = ({}, {"GLL_B200_KNN_SHARE": "0"}, {"GLL_B200_KNN_DEBUG": "1"}, {"GLL_B200_KNN_DEBUG": "2"})
+if os.environ.get("KNN_EXPERIMENT_ENVS") == "split":  # the two operand splits, and the MMA/TMA pipeline alone
+    ENVS = ({"GLL_B200_KNN_SPLIT": "bf16x3"}, {"GLL_B200_KNN_SPLIT": "f16x2"}, {"GLL_B200_KNN_SPLIT": "f16x2", "GLL_B200_KNN_DEBUG": "2"})
+if os.environ.get("KNN_EXPERIMENT_ENVS") == "default":  # the default configuration, and without the set insertions
+    ENVS = ({}, {"GLL_B200_KNN_DEBUG": "1"})
+for env in ENVS:
     e = dict(os.environ, **env)
     out = subprocess.run([sys.executable, "-c", CODE], env=e, capture_output=True, text=True)
     print(env, out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-600:], flush=True)
