@@ -407,6 +407,11 @@ def run_b200(args, rank, world, local_rank):
         roofline = {"kernel": top, "bound": bound, "achieved": ach, "peak": peak, "unit": u,
                     "frac": (ach / peak if ach else None), "traffic": traffic, "peak_source": peaks["source"],
                     "algorithmic_work_per_launch": work, "work_unit": unit, "launch_ms": t_s * 1e3}
+        if bound == "tensor" and top == "knn_gram_topk_tcgen05":
+            # the Gram entry is accumulated from split operands: (hi + lo).hi in fp16 = 2 MMA passes (default), or
+            # hi.hi + lo.hi + hi.lo in bf16 = 3 passes (GLL_B200_KNN_SPLIT=bf16x3); `achieved` counts 2 n^2 d once
+            passes = 3 if os.environ.get("GLL_B200_KNN_SPLIT") == "bf16x3" else 2
+            roofline.update({"mma_passes": passes, "issued": ach * passes, "issued_frac": ach * passes / peak})
         cpu = None
         if world == 1 and not args.no_cpu_baseline and not sharded:
             times = cpu_calls(args.workload, 1000, 4, 25.0)

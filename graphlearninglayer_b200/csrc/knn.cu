@@ -99,10 +99,12 @@ sqnorm_split_f16_kernel(const float* __restrict__ X, int n, int d, int d_pad, fl
     if (b != 0u && ex != 0xFF) E = min(60, max(-60, ex - 126));  // mx in [2^(ex-127), 2^(ex-126))
   }
   double r2 = 0.0;
+  const float down = ldexpf(1.f, -E);  // |E| <= 60: both factors are normal numbers, the products below are exact
+  const double up = ldexp(1.0, E);
   for (int c = 2 * lane; c < d_pad; c += 64) {  // second sweep over the row: L1 hits
     const float x0 = (c < d) ? __ldg(x + c) : 0.f;
     const float x1 = (c + 1 < d) ? __ldg(x + c + 1) : 0.f;
-    const float z0 = ldexpf(x0, -E), z1 = ldexpf(x1, -E);
+    const float z0 = x0 * down, z1 = x1 * down;
     const __half h0 = __float2half_rn(z0), h1 = __float2half_rn(z1);
     const float f0 = __half2float(h0), f1 = __half2float(h1);
     __half2 hv, lv;
@@ -112,7 +114,7 @@ sqnorm_split_f16_kernel(const float* __restrict__ X, int n, int d, int d_pad, fl
     lv.y = __float2half_rn(z1 - f1);
     *reinterpret_cast<__half2*>(H + (size_t)row * d_pad + c) = hv;
     *reinterpret_cast<__half2*>(L + (size_t)row * d_pad + c) = lv;
-    const double e0 = (double)x0 - ldexp((double)f0, E), e1 = (double)x1 - ldexp((double)f1, E);
+    const double e0 = (double)x0 - (double)f0 * up, e1 = (double)x1 - (double)f1 * up;
     r2 += e0 * e0 + e1 * e1;
   }
   r2 = warp_sum(r2);

@@ -10,6 +10,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 python bench.py $ARGS > gpurun_out/${TAG}_plain_c2b.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"knn_gram|knn_rerank|cg_small|cg_resident|row_gather" -s 15 -c 5 \
     -o gpurun_out/${TAG}_c2_top python bench.py $ARGS > gpurun_out/${TAG}_ncu_full_c2.log 2>&1
+if [ -n "$SKIP_C4" ]; then ls -la gpurun_out/${TAG}_*; exit 0; fi  # the CG kernels did not change: keep the previous capture
 ARGS4="--steps 2 --warmup 3 --no-cpu-baseline --workload c4"
 python bench.py $ARGS4 > gpurun_out/${TAG}_plain_c4.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"cg_resident" -s 6 -c 2 \
