@@ -34,6 +34,13 @@ constexpr size_t gemm_smem_bytes() {
          sizeof(float) * BM + sizeof(int) * BM;
 }
 
+// Running maximum in one global word.  Every row contributes, and same-address atomics serialise in L2 (four per row cost
+// more than the rest of the split kernel), so the atomic is only issued when the value read from L2 is still smaller: a
+// stale read merely issues a redundant atomic, the maximum itself stays exact.
+__device__ __forceinline__ void max_into(unsigned* addr, unsigned v) {
+  if (__ldcg(addr) < v) atomicMax(addr, v);
+}
+
 // |x_i|^2 (fp64 accumulate -> fp32) and the global maximum; when H/L are given also the bf16 split x = hi + lo that
 // feeds the tensor-core Gram kernel (row stride d_pad, zero padded), so X is read once.
 __global__ void __launch_bounds__(256)
@@ -65,13 +72,13 @@ sqnorm_split_kernel(const float* __restrict__ X, int n, int d, int d_pad, float*
     float f = (float)s;
     sq[row] = f;
     if (thr_g != nullptr) thr_g[row] = 0xFF800000u;  // float_to_ordered(+inf): the row's shared threshold (knn_tc.cu)
-    if (f == f) atomicMax(sqmax_bits, __float_as_uint(f));  // non-negative floats order like their bits
+    if (f == f) max_into(sqmax_bits, __float_as_uint(f));  // non-negative floats order like their bits
   }
 }
 
-// f16x2 operands (knn_tc.cu), fused with the norms so that X is read from HBM once: row i is scaled by 2^-E_i with
-// 2^(E_i - 1) <= max_k |x_ik| < 2^E_i (exact; no fp16 overflow, and fp16's subnormal granularity 2^-24 is relative to the
-// row's own largest element), then hi = fp16(z), lo = fp16(z - hi), row stride d_pad, zero padded.  rscale[i] = 2^E_i undoes
+// f16x2 operands (knn_tc.cu), fused with the norms so that X is read from HBM once: row i is scaled by 2^-E_i to a norm
+// in [0.58, 1.16) (exact; no fp16 overflow, and fp16's subnormal granularity 2^-24 is relative to the row's own norm),
+// then hi = fp16(z), lo = fp16(z - hi), row stride d_pad, zero padded.  rscale[i] = 2^E_i undoes
 // the scaling in the Gram epilogue.  Also the largest B-side residual rho = max_j |x_j - hi_j 2^E_j|_2 (exact in fp64,
 // rounded up): the Gram kernel computes (hi + lo)_i . hi_j, so its error is |x_i| rho + O(2^-22).
 __global__ void __launch_bounds__(256)
@@ -81,22 +88,20 @@ sqnorm_split_f16_kernel(const float* __restrict__ X, int n, int d, int d_pad, fl
   if (row >= n) return;
   const float* x = X + (size_t)row * d;
   double s = 0.0;
-  float mx = 0.f;
   for (int c = 2 * lane; c < d; c += 64) {
     const float x0 = __ldg(x + c);
     const float x1 = (c + 1 < d) ? __ldg(x + c + 1) : 0.f;
     s += (double)x0 * (double)x0;
     s += (double)x1 * (double)x1;
-    mx = fmaxf(mx, fmaxf(fabsf(x0), fabsf(x1)));  // NaN elements are ignored here; they poison sq[] below
   }
   s = warp_sum(s);
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+  // E_i from the row NORM, with the bucket boundaries at |x|^2 = 2^k / 1.5 so that rows normalised to 1 (every caller of the
+  // layer) all get E = 0 whatever their rounding: 2^(2E - 1) <= 1.5 |x_i|^2 < 2^(2E + 1), hence |z_ik| <= |z_i| < 1.16.
   int E = 0;
   {
-    const unsigned b = __float_as_uint(mx);
+    const unsigned b = __float_as_uint((float)(1.5 * s));
     const int ex = (int)((b >> 23) & 0xFFu);
-    if (b != 0u && ex != 0xFF) E = min(60, max(-60, ex - 126));  // mx in [2^(ex-127), 2^(ex-126))
+    if (b != 0u && ex != 0xFF) E = min(60, max(-60, (ex - 127 + 1) >> 1));  // arithmetic shift = floor
   }
   double r2 = 0.0;
   const float down = ldexpf(1.f, -E);  // |E| <= 60: both factors are normal numbers, the products below are exact
@@ -123,9 +128,11 @@ sqnorm_split_f16_kernel(const float* __restrict__ X, int n, int d, int d_pad, fl
     sq[row] = f;
     rscale[row] = ldexpf(1.f, E);
     if (thr_g != nullptr) thr_g[row] = 0xFF800000u;  // float_to_ordered(+inf): the row's shared threshold (knn_tc.cu)
-    if (f == f) atomicMax(small, __float_as_uint(f));  // non-negative floats order like their bits
+    if (f == f) max_into(small, __float_as_uint(f));  // non-negative floats order like their bits
     const float rho = __double2float_ru(sqrt(r2) * 1.000001);
-    if (rho == rho) atomicMax(small + 2, __float_as_uint(rho));
+    if (rho == rho) max_into(small + 2, __float_as_uint(rho));
+    max_into(small + 3, (unsigned)(E + 128));        // range of the row scales: when all rows share one scale (normalised
+    max_into(small + 4, 255u - (unsigned)(E + 128));  // features) the Gram epilogue skips the per-row / per-column factors
   }
 }
 
@@ -782,14 +789,14 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
     lay.units = plan.units;
     lay.row_begin = row_begin;
     const int mblocks = ceil_div(rows, RERANK_WARPS);
-    int rc = knn_tc_candidates(X, sq, plan.f16x2 ? rscale : nullptr, n, d, row_end, plan, tc_ws, cand, nullptr, thr_g, st);
+    int rc = knn_tc_candidates(X, sq, plan.f16x2 ? rscale : nullptr, small, n, d, row_end, plan, tc_ws, cand, nullptr, thr_g, st);
     if (rc) return rc;
     {
       GLL_PROF(KID_RERANK, st);
       knn_merge_kernel<<<mblocks, RERANK_WARPS * 32, 0, st>>>(row_end, lay, cand, merged1, excl);
     }
     GLL_LAUNCH_CHECK();
-    rc = knn_tc_candidates(X, sq, plan.f16x2 ? rscale : nullptr, n, d, row_end, plan, tc_ws, cand, excl, nullptr, st);  // second round: own thresholds
+    rc = knn_tc_candidates(X, sq, plan.f16x2 ? rscale : nullptr, small, n, d, row_end, plan, tc_ws, cand, excl, nullptr, st);  // second round: own thresholds
     if (rc) return rc;
     {
       GLL_PROF(KID_RERANK, st);
@@ -800,7 +807,7 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
                         flag_count, flag_rows, info, st);
   }
   if (plan.ok) {  // tcgen05 / TMA Gram GEMM with the fused top-k epilogue
-    int rc = knn_tc_candidates(X, sq, plan.f16x2 ? rscale : nullptr, n, d, row_end, plan, tc_ws, cand, nullptr, thr_g, st);
+    int rc = knn_tc_candidates(X, sq, plan.f16x2 ? rscale : nullptr, small, n, d, row_end, plan, tc_ws, cand, nullptr, thr_g, st);
     if (rc) return rc;
     lay.stride = plan.max_splits;
     lay.tc = plan.aligned ? 2 : 1;

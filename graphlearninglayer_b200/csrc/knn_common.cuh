@@ -77,7 +77,7 @@ struct TcPlan {
 
 TcPlan knn_tc_plan(int n, int d, int row_begin, int row_end);
 size_t knn_tc_ws_upper(int n, int d);
-int knn_tc_candidates(const float* X, const float* sq, const float* rscale, int n, int d, int row_end, const TcPlan& plan,
+int knn_tc_candidates(const float* X, const float* sq, const float* rscale, const unsigned* small, int n, int d, int row_end, const TcPlan& plan,
                       void* tc_ws, u64* cand, const u64* excl, unsigned* thr_g, cudaStream_t st);
 float knn_tc_err_coef(int d, int f16x2);
 

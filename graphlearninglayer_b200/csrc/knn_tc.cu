@@ -186,6 +186,7 @@ struct TcParams {
   const u64* excl;    // optional [n]: per row, only keys > excl[row] are candidates (second round of a k > 33 search)
   int f16x2;          // operands are fp16(x_i 2^-E_i): Gram = (hi + lo).hi in two MMA passes, B_lo is never loaded
   const float* rscale;  // [n] 2^E_i (f16x2) or NULL: the accumulator holds x_i.x_j / (rscale_i rscale_j)
+  const unsigned* small;  // small[3], small[4]: range of E_i over the rows (written by sqnorm_split_f16_kernel)
 };
 
 // CTA that owns unit u when `units` units are dealt contiguously to G CTAs (CTA b owns [b*units/G, (b+1)*units/G))
@@ -354,6 +355,14 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     // d~^2 - |x_i|^2 = |x_j|^2 + (acc ri) cj with cj = -2 rscale_j, ri = rscale_i (powers of two: exact; 1 without scaling)
     float* cj_s = sqj_s + TC_BN;
     float ri = 1.f;
+    // all rows share one scale (the usual case: normalised features; always without scaling): v = |x_j|^2 + cu acc
+    bool uniform = true;
+    float cu = -2.f;
+    if (P.rscale != nullptr) {
+      const unsigned emax = __ldg(P.small + 3), eminc = __ldg(P.small + 4);  // biased max E, 255 - biased min E (knn.cu)
+      uniform = (emax == 255u - eminc);
+      cu = -ldexpf(2.f, 2 * ((int)emax - 128));
+    }
 
     auto flush = [&](int rt) {
       __syncwarp();
@@ -413,23 +422,42 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
         const int j0 = c_begin + q * TC_CHUNK;
         float v[TC_CHUNK];
         uint32_t hits = 0;
+        if (uniform) {  // every row has the same scale: one FMA per element (same value, the factors are powers of two)
 #pragma unroll
-        for (int c4 = 0; c4 < TC_CHUNK / 4; ++c4) {
-          const float4 s4 = *reinterpret_cast<const float4*>(sqj_s + q * TC_CHUNK + 4 * c4);  // warp-wide broadcast
-          const float4 c4v = *reinterpret_cast<const float4*>(cj_s + q * TC_CHUNK + 4 * c4);
-          v[4 * c4 + 0] = fmaf(ri * __uint_as_float(raw[4 * c4 + 0]), c4v.x, s4.x);
-          v[4 * c4 + 1] = fmaf(ri * __uint_as_float(raw[4 * c4 + 1]), c4v.y, s4.y);
-          v[4 * c4 + 2] = fmaf(ri * __uint_as_float(raw[4 * c4 + 2]), c4v.z, s4.z);
-          v[4 * c4 + 3] = fmaf(ri * __uint_as_float(raw[4 * c4 + 3]), c4v.w, s4.w);
+          for (int c4 = 0; c4 < TC_CHUNK / 4; ++c4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(sqj_s + q * TC_CHUNK + 4 * c4);  // warp-wide broadcast
+            v[4 * c4 + 0] = fmaf(__uint_as_float(raw[4 * c4 + 0]), cu, s4.x);
+            v[4 * c4 + 1] = fmaf(__uint_as_float(raw[4 * c4 + 1]), cu, s4.y);
+            v[4 * c4 + 2] = fmaf(__uint_as_float(raw[4 * c4 + 2]), cu, s4.z);
+            v[4 * c4 + 3] = fmaf(__uint_as_float(raw[4 * c4 + 3]), cu, s4.w);
+          }
+        } else {
+#pragma unroll
+          for (int c4 = 0; c4 < TC_CHUNK / 4; ++c4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(sqj_s + q * TC_CHUNK + 4 * c4);  // warp-wide broadcast
+            const float4 c4v = *reinterpret_cast<const float4*>(cj_s + q * TC_CHUNK + 4 * c4);
+            v[4 * c4 + 0] = fmaf(ri * __uint_as_float(raw[4 * c4 + 0]), c4v.x, s4.x);
+            v[4 * c4 + 1] = fmaf(ri * __uint_as_float(raw[4 * c4 + 1]), c4v.y, s4.y);
+            v[4 * c4 + 2] = fmaf(ri * __uint_as_float(raw[4 * c4 + 2]), c4v.z, s4.z);
+            v[4 * c4 + 3] = fmaf(ri * __uint_as_float(raw[4 * c4 + 3]), c4v.w, s4.w);
+          }
         }
         if (diag && j0 < wrow0 + 32 && j0 + TC_CHUNK > wrow0) {  // warp-uniform, true for at most 2 chunks of one unit
 #pragma unroll
           for (int c = 0; c < TC_CHUNK; ++c)
             if (j0 + c == gi) v[c] = INFINITY;  // self is slot 0 by construction (knn_finish)
         }
+        // Steady state: no column of the chunk beats any row's threshold.  One min per element and one vote decide that; the
+        // per-column hit mask (three instructions per element) is only built for chunks that do have a survivor.  On the
+        // 1M-node graph the kernel runs under the power cap, where every SIMT instruction saved is tensor-pipe clock.
+        float vm[8];
 #pragma unroll
-        for (int c = 0; c < TC_CHUNK; ++c) hits |= (v[c] < thr) ? (1u << c) : 0u;
-        if (P.debug >= 1) hits = 0;
+        for (int t = 0; t < 8; ++t) vm[t] = fminf(fminf(v[4 * t], v[4 * t + 1]), fminf(v[4 * t + 2], v[4 * t + 3]));
+        const float vmin = fminf(fminf(fminf(vm[0], vm[1]), fminf(vm[2], vm[3])), fminf(fminf(vm[4], vm[5]), fminf(vm[6], vm[7])));
+        if (__any_sync(FULL, vmin < thr) && P.debug < 1) {
+#pragma unroll
+          for (int c = 0; c < TC_CHUNK; ++c) hits |= (v[c] < thr) ? (1u << c) : 0u;
+        }
         // ---- every row (thread) inserts its own survivors; rows proceed concurrently ----
         while (__any_sync(FULL, hits != 0)) {
           if (hits) {
@@ -619,7 +647,7 @@ size_t knn_tc_ws_upper(int n, int d) { return 2 * align_up((size_t)n * (size_t)(
 
 // |d~^2 - d^2| <= coef * (|xi|^2 + |xj|^2): split residual 3*2^-18, fp32 accumulation over 3*d/16 MMA steps of unknown
 // internal rounding (budgeted at 2^-21 per step and per 16-term tree), final fp32 expression 4u; then a 4x margin.
-// f16x2: the A side is x_i = (hi + lo) 2^E_i + r_i with |r_i| <= 2^-22 |x_i| + 2^-25 sqrt(d) 2^E_i, 2^E_i <= 2 |x_i| (fp16 normal
+// f16x2: the A side is x_i = (hi + lo) 2^E_i + r_i with |r_i| <= 2^-22 |x_i| + 2^-25 sqrt(d) 2^E_i, 2^E_i <= 1.74 |x_i| (fp16 normal
 // rounding twice, subnormal granularity 2^-24 below 2^-14): 2 |r_i| |x_j| <= (2^-22 + 2^-24 sqrt(d)) (|xi|^2 + |xj|^2);
 // two MMA passes; the B-side residual is NOT in this coefficient -- it is measured (rho) and added by knn_err_bound().
 float knn_tc_err_coef(int d, int f16x2) {
@@ -629,7 +657,7 @@ float knn_tc_err_coef(int d, int f16x2) {
   return (float)(4.0 * e);
 }
 
-int knn_tc_candidates(const float* X, const float* sq, const float* rscale, int n, int d, int row_end, const TcPlan& plan,
+int knn_tc_candidates(const float* X, const float* sq, const float* rscale, const unsigned* small, int n, int d, int row_end, const TcPlan& plan,
                       void* tc_ws, u64* cand, const u64* excl, unsigned* thr_g, cudaStream_t st) {
   __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(tc_ws);
   __nv_bfloat16* L = reinterpret_cast<__nv_bfloat16*>((char*)tc_ws + align_up((size_t)n * plan.d_pad * 2, 256));
@@ -656,6 +684,7 @@ int knn_tc_candidates(const float* X, const float* sq, const float* rscale, int 
   P.thr_g = thr_g;
   P.f16x2 = plan.f16x2;
   P.rscale = rscale;
+  P.small = small;
   {
     const char* dbg = getenv("GLL_B200_KNN_DEBUG");
     P.debug = dbg ? atoi(dbg) : 0;
