@@ -1,0 +1,80 @@
+"""numpy model of the operand split behind the tensor-core kNN candidate search -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+The product kernel (graphlearninglayer_b200/csrc/knn.cu: sqnorm_split_f16_kernel; knn_tc.cu: knn_gram_topk_tc_kernel,
+knn_tc_err_coef; knn.cu: knn_err_bound) replaces the distances behind ``gl.weightmatrix.knnsearch`` (GLL.py:181-189) by
+approximate ones that only SELECT candidates; exactness of the emitted lists rests on a proven bound
+``|d~^2_ij - d^2_ij| <= coef (|x_i|^2 + max|x|^2) + 2 |x_i| rho``.  This file restates the split and the bound in numpy so
+that tests/test_split_bound.py can check the bound itself on the CPU, for feature scales and shapes the GPU tests cannot
+sweep.  The fp32 accumulation order inside the tensor core is not modelled (it has its own budget inside ``coef``); the
+Gram entries here are the exact fp64 products of the split operands, and, as a second variant, numpy's fp32 matmul.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+def scale_exponent(sq64: np.ndarray) -> np.ndarray:
+    """E_i of sqnorm_split_f16_kernel: from the bits of float(1.5 |x_i|^2); 0 for zero / non-finite rows; clamped to +-60."""
+    t = (1.5 * sq64).astype(np.float32)
+    bits = t.view(np.uint32)
+    ex = ((bits >> 23) & 0xFF).astype(np.int64)
+    E = np.floor_divide(ex - 127 + 1, 2)
+    E = np.clip(E, -60, 60)
+    E[(bits == 0) | (ex == 0xFF)] = 0
+    return E
+
+
+def split_f16x2(X: np.ndarray):
+    """Returns hi, lo (float16, scaled rows), E (int), sq (float32 |x_i|^2) and rho (float32, rounded up)."""
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    s = (X.astype(np.float64) ** 2).sum(axis=1)
+    sq = s.astype(np.float32)
+    E = scale_exponent(s)
+    down = np.ldexp(np.float32(1.0), -E).astype(np.float32)[:, None]
+    z = X * down  # exact: powers of two
+    hi = z.astype(np.float16)
+    lo = (z - hi.astype(np.float32)).astype(np.float16)
+    resid = X.astype(np.float64) - np.ldexp(hi.astype(np.float64), E[:, None])
+    rho64 = math.sqrt(float((resid ** 2).sum(axis=1).max())) * 1.000001
+    rho = np.float32(rho64)
+    if float(rho) < rho64:
+        rho = np.nextafter(rho, np.float32(np.inf))
+    return hi, lo, E, sq, rho
+
+
+def approx_d2_f16x2(hi, lo, E, sq, fp32_accumulate: bool = False) -> np.ndarray:
+    """d~^2_ij = |x_i|^2 + (|x_j|^2 + (acc 2^E_i)(-2 2^E_j)) with acc = (hi_i + lo_i) . hi_j, as the epilogue forms it."""
+    if fp32_accumulate:
+        a = hi.astype(np.float32) @ hi.astype(np.float32).T + lo.astype(np.float32) @ hi.astype(np.float32).T
+        acc = a.astype(np.float32)
+    else:
+        a = (hi.astype(np.float64) + lo.astype(np.float64)) @ hi.astype(np.float64).T
+        acc = a.astype(np.float32)  # the accumulator is fp32
+    ri = np.ldexp(np.float32(1.0), E).astype(np.float32)
+    cj = (np.float32(-2.0) * ri).astype(np.float32)
+    t = (acc * ri[:, None]).astype(np.float32)
+    key = (t.astype(np.float64) * cj[None, :].astype(np.float64) + sq[None, :].astype(np.float64)).astype(np.float32)  # one fma
+    return (key + sq[:, None]).astype(np.float32)
+
+
+def err_coef(d: int, f16x2: bool = True) -> float:
+    """knn_tc_err_coef (knn_tc.cu)."""
+    steps = (2.0 if f16x2 else 3.0) * math.ceil(d / 16) + 8.0
+    split = (1.0 + 0.5 * math.sqrt(d)) / 4194304.0 * 1.01 if f16x2 else 3.0 / 262144.0
+    e = split + steps * 4.76837158203125e-7 + 4.0 * 5.9604644775390625e-8
+    return float(np.float32(4.0 * e))
+
+
+def err_bound(d: int, sq: np.ndarray, rho) -> np.ndarray:
+    """knn_err_bound (knn.cu), per row i."""
+    sq64 = sq.astype(np.float64)
+    return err_coef(d) * (sq64 + float(sq.max())) + 2.0 * np.sqrt(sq64) * float(rho) * 1.000001
+
+
+def exact_d2(X: np.ndarray) -> np.ndarray:
+    Xd = X.astype(np.float64)
+    g = Xd @ Xd.T
+    s = (Xd ** 2).sum(axis=1)
+    return s[:, None] + s[None, :] - 2.0 * g  # fp64 Gram form: its own error (1e-16 relative to the norms) is far below the bounds tested

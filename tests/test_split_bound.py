@@ -1,0 +1,66 @@
+"""CPU tests of the error bound behind the tensor-core kNN search's completeness proof (oracle/split_model.py restates the
+fp16 operand split of csrc/knn.cu and the bound of knn_tc_err_coef / knn_err_bound): the approximate squared distances
+may only be off by the bound, for any feature scale -- otherwise the exact re-rank could miss a neighbour silently."""
+import numpy as np
+import pytest
+
+from oracle import gll_oracle as O
+from oracle import split_model as S
+
+
+def _datasets():
+    rng = np.random.default_rng(0)
+    X, *_ = O.synth_inputs(3, 300, 340, 512, 10, 4.5)           # the C2 distribution (unit rows)
+    yield "unit_rows_d512", X
+    X2, *_ = O.synth_inputs(4, 200, 300, 200, 10, 3.0)          # d not a multiple of 16
+    yield "unit_rows_d200", X2
+    yield "scaled_3e4", (X2 * np.float32(3.0e4)).astype(np.float32)
+    yield "scaled_2e-6", (X2 * np.float32(2.0e-6)).astype(np.float32)
+    yield "ragged_norms", (X2 * np.logspace(-3, 3, X2.shape[0], dtype=np.float32)[rng.permutation(X2.shape[0]), None]).astype(np.float32)
+    relu = np.maximum(rng.standard_normal((400, 256)), 0).astype(np.float32) ** 3   # sparse, heavy-tailed (post-ReLU-like)
+    yield "relu_cubed", relu
+    spike = (1e-6 * rng.standard_normal((300, 128))).astype(np.float32)             # one dominant element: the rest goes subnormal in fp16
+    spike[np.arange(300), rng.integers(0, 128, 300)] = 1.0
+    yield "spike_plus_dust", spike
+    dup = rng.standard_normal((200, 64)).astype(np.float32)
+    dup[50:120] = dup[50]                                                            # duplicates: exact distance 0
+    dup[7] = 0.0                                                                     # a zero row
+    yield "duplicates_and_zero_row", dup
+
+
+@pytest.mark.parametrize("name,X", list(_datasets()), ids=[n for n, _ in _datasets()])
+@pytest.mark.parametrize("fp32_acc", [False, True])
+def test_f16x2_distance_error_within_proven_bound(name, X, fp32_acc):
+    hi, lo, E, sq, rho = S.split_f16x2(X)
+    d = X.shape[1]
+    approx = S.approx_d2_f16x2(hi, lo, E, sq, fp32_accumulate=fp32_acc).astype(np.float64)
+    exact = S.exact_d2(X)
+    err = np.abs(approx - exact)
+    bound = S.err_bound(d, sq, rho)[:, None]
+    worst = float((err / np.maximum(bound, 1e-300)).max())
+    assert worst <= 1.0, (name, worst)
+    # ... and the bound is not vacuous: for unit rows it stays below the 24th -> 32nd neighbour gap of the benchmark graphs (3e-3)
+    if name.startswith("unit_rows"):
+        assert float(bound.max()) < 1.0e-3
+
+
+def test_rows_normalised_to_one_share_one_scale():
+    """Every caller normalises the features (networks/BuildNet.py:101): all rows must land in the E = 0 bucket whatever their
+    rounding, because the Gram epilogue then takes its single-FMA path."""
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((5000, 96)).astype(np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True).astype(np.float32)
+    E = S.scale_exponent((X.astype(np.float64) ** 2).sum(axis=1))
+    assert (E == 0).all()
+    # bucket edges: 2^(2E-1) <= 1.5 |x|^2 < 2^(2E+1)
+    s = np.array([0.0, 1e-30, 1 / 3 - 1e-6, 1 / 3 + 1e-6, 4 / 3 - 1e-6, 4 / 3 + 1e-6, 16 / 3 + 1e-5, 1e30, np.inf])
+    assert S.scale_exponent(s).tolist() == [0, -50, -1, 0, 0, 1, 2, 50, 0]
+
+
+def test_scaled_rows_fit_fp16_without_overflow():
+    rng = np.random.default_rng(2)
+    X = (rng.standard_normal((100, 40)) * 10.0 ** rng.uniform(-15, 15, (100, 1))).astype(np.float32)
+    hi, lo, E, sq, rho = S.split_f16x2(X)
+    assert np.isfinite(hi.astype(np.float32)).all() and np.isfinite(lo.astype(np.float32)).all()
+    z = np.abs(hi.astype(np.float64))
+    assert z.max() < 1.16 and np.linalg.norm(hi.astype(np.float64), axis=1).min() > 0.57
