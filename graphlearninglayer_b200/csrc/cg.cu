@@ -22,6 +22,8 @@
 namespace gll {
 namespace {
 
+constexpr const char* CG_ORDER_DEFAULT = "0";  // row schedule of the streaming kernel (cg_order.cu): opt-in until measured
+
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -171,7 +173,13 @@ __global__ void __launch_bounds__(CG_THREADS, 1) cg_persistent_kernel(CgParams P
 
     // ---- phase 1: Ap = A p, partial <p, Ap> ----
     float4 dot[1] = {make_float4(0.f, 0.f, 0.f, 0.f)};
-    for (int i = row_begin + warp; i < row_end; i += CG_WARPS) {
+    // natural order: this CTA's row block; scheduled (P.order): consecutive positions of the schedule are dealt to the warps
+    // of the WHOLE grid, so that all rows in flight belong to one or two clusters and their gathers hit L2 (cg_order.cu)
+    const int k_begin = P.order ? (int)(blockIdx.x * CG_WARPS + warp) : row_begin + warp;
+    const int k_end = P.order ? P.m : row_end;
+    const int k_step = P.order ? (int)(gridDim.x * CG_WARPS) : CG_WARPS;
+    for (int k = k_begin; k < k_end; k += k_step) {
+      const int i = P.order ? __ldg(P.order + k) : k;
       const int e0 = __ldg(P.ptr + i), e1 = __ldg(P.ptr + i + 1);
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
       if (active) {
@@ -293,7 +301,16 @@ size_t cg_ws_bytes(int m, int l) {
   const int lp = padded_classes(l);
   size_t v = align_up(sizeof(float) * (size_t)m * lp, 256);
   return 3 * v + align_up(sizeof(double) * 2 * (2 * CG_MAX_LP) * (size_t)device_info().sms, 256) + 256 + 1024 +
-         cg_resident_ws_bytes(m, lp);
+         cg_resident_ws_bytes(m, lp) + align_up(sizeof(int) * (size_t)m, 256) + cg_order_ws_bytes(m);
+}
+
+// GLL_B200_CG_ORDER: "0" never, "1" when the iterate exceeds what L2 keeps resident, "force" always (tests).
+static int cg_order_mode(int m, int lp) {
+  const char* e = getenv("GLL_B200_CG_ORDER");
+  if (e == nullptr || e[0] == 0) e = CG_ORDER_DEFAULT;
+  if (strcmp(e, "force") == 0) return 1;
+  if (e[0] == '0') return 0;
+  return ((size_t)m * lp * sizeof(float) > ((size_t)96 << 20)) ? 1 : 0;
 }
 
 int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, const float* rhs, int m, int l,
@@ -329,6 +346,7 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
   P.resid_out = resid_out;
   P.status_out = status_out;
   P.rows_per_block = 0;
+  P.order = nullptr;
   {  // systems that fit on chip (every config except the sharded 1M-node graph) take the shared-memory-resident kernel
     const char* force = getenv("GLL_B200_CG_PATH");  // "streaming" / "resident": testing knobs
     if (force == nullptr || force[0] == 0) {  // minibatch-sized systems: the one-CTA, register-resident kernel
@@ -356,6 +374,14 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
     attr_set = true;
   }
   GLL_CUDA_CHECK(cudaMemsetAsync(P.barrier, 0, 256, st));
+  if (cg_order_mode(m, lp)) {
+    int* order = cv.take<int>(m);
+    const size_t ob = cg_order_ws_bytes(m);
+    void* ows = cv.take<char>(ob);
+    const int rc = cg_row_order(uu_ptr, uu_col, rhs, m, lp, order, ows, ob, st);
+    if (rc < 0) return rc;
+    P.order = order;
+  }
   void* args[] = {&P};
   GLL_PROF(KID_CG, st);
   GLL_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)cg_persistent_kernel, dim3(grid), dim3(CG_THREADS), args, smem, st));

@@ -340,6 +340,32 @@ def test_cg_zero_rhs_column_and_maxiter(gll, monkeypatch, path):
     assert it2 == 3 and status2 & 1  # GLL_STATUS_CG_NOT_CONVERGED <-> 'max iter reached' (GLL.py:273-274)
 
 
+@pytest.mark.parametrize("l", [3, 10, 100])
+def test_cg_streaming_row_schedule(gll, monkeypatch, l):
+    """The streaming kernel with its SpMV rows scheduled by right-hand-side class (csrc/cg_order.cu; what a 1M-node system
+    gets): every row is still computed from the same operands, so the solve matches the natural order to rounding of the
+    dot products, takes the same number of iterations, and matches the direct solve."""
+    _, _lib = gll
+    monkeypatch.setenv("GLL_B200_CG_PATH", "streaming")
+    X, Y, *_ = O.synth_inputs(3, 160, 1500, 24, l, 1.5)
+    f = O.forward(X, Y, 0.02, 1.0, solver="lu")
+    monkeypatch.setenv("GLL_B200_CG_ORDER", "0")
+    x0, it0, _, st0 = run_cg(_lib, f.Luu, f.B, tol=1e-7)
+    names = _lib.kernel_names()
+    before = _lib.launch_count(names.index("cg_row_order"))
+    monkeypatch.setenv("GLL_B200_CG_ORDER", "force")
+    x1, it1, resid1, st1 = run_cg(_lib, f.Luu, f.B, tol=1e-7)
+    assert _lib.launch_count(names.index("cg_row_order")) == before + 1
+    assert st0 == 0 and st1 == 0 and abs(it1 - it0) <= 1 and resid1 <= 1e-7
+    assert O.max_rel(x1, x0) < 1e-6
+    assert O.max_rel(x1, f.pred) < TOL
+    # a right-hand side with empty rows and a single live column (the adjoint's shape, GLL.py:93)
+    B = np.zeros_like(f.B)
+    B[::3, 0] = -1.0
+    x2, _, _, st2 = run_cg(_lib, f.Luu, B, tol=1e-7)
+    assert st2 == 0 and O.max_rel(x2, O.solve(f.Luu, B, "lu")) < TOL
+
+
 def test_cg_relative_tolerance(gll):
     _, _lib = gll
     X, Y, *_ = O.synth_inputs(5, 100, 900, 16, 4, 1.5)
