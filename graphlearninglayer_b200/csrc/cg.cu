@@ -108,7 +108,6 @@ __device__ __forceinline__ void grid_reduce(float4 (&acc)[NV], const CgParams& P
   __syncthreads();
 }
 
-template <bool WIDE>
 __global__ void __launch_bounds__(CG_THREADS, 1) cg_persistent_kernel(CgParams P) {
   extern __shared__ __align__(16) double sm[];
   const int lp = P.lp, Q = lp >> 2, S = 32 / Q;
@@ -183,35 +182,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) cg_persistent_kernel(CgParams P
       const int i = P.order ? __ldg(P.order + k) : k;
       const int e0 = __ldg(P.ptr + i), e1 = __ldg(P.ptr + i + 1);
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (WIDE && S == 1) {
-        // One neighbour slot per warp (more than 64 class columns).  The four-per-trip loop below pays TWO dependent memory
-        // latencies per trip (column index, then the gathered row): ~16 per row, and with one CTA of 32 warps per SM that
-        // chain -- not HBM -- bounded the 1M-node solve (3 ms per iteration).  Here the lanes fetch the metadata of 32
-        // edges with one coalesced load and broadcast it by shuffles, and six 128-bit gathers are in flight per lane.
-        constexpr int TW = 6;  // gathers in flight per lane (8 spill at the 64 registers a 1024-thread CTA leaves)
-        for (int base = e0; base < e1; base += 32) {
-          const int cnt = min(32, e1 - base);
-          const int cj = (lane < cnt) ? __ldg(P.col + base + lane) : 0;
-          const float wj = (lane < cnt) ? __ldg(P.val + base + lane) : 0.f;
-          for (int t0 = 0; t0 < cnt; t0 += TW) {
-            float wv[TW];
-            float4 pj[TW];
-#pragma unroll
-            for (int t = 0; t < TW; ++t) {
-              const int j = __shfl_sync(FULL, cj, (t0 + t) & 31);
-              wv[t] = (t0 + t < cnt) ? __shfl_sync(FULL, wj, (t0 + t) & 31) : 0.f;  // lanes beyond cnt hold (0, 0.f): row 0, weight 0
-              pj[t] = active ? ldcg4(P.p + (size_t)j * lp + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int t = 0; t < TW; ++t) {
-              a.x = fmaf(wv[t], pj[t].x, a.x);
-              a.y = fmaf(wv[t], pj[t].y, a.y);
-              a.z = fmaf(wv[t], pj[t].z, a.z);
-              a.w = fmaf(wv[t], pj[t].w, a.w);
-            }
-          }
-        }
-      } else if (active) {
+      if (active) {
         // four neighbours per trip: the four 128-bit gathers are independent, so a row of ~26 neighbours costs ~7 memory
         // round trips instead of 26 (with many class columns a warp has a single neighbour slot, S = 1)
         for (int e = e0 + s; e < e1; e += 4 * S) {
@@ -376,10 +347,6 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
   P.status_out = status_out;
   P.rows_per_block = 0;
   P.order = nullptr;
-  {
-    const char* w = getenv("GLL_B200_CG_SPMV");  // "wide": experimental SpMV phase of the streaming kernel (unvalidated, opt-in)
-    P.wide = (w && strcmp(w, "wide") == 0) ? 1 : 0;
-  }
   {  // systems that fit on chip (every config except the sharded 1M-node graph) take the shared-memory-resident kernel
     const char* force = getenv("GLL_B200_CG_PATH");  // "streaming" / "resident": testing knobs
     if (force == nullptr || force[0] == 0) {  // minibatch-sized systems: the one-CTA, register-resident kernel
@@ -402,9 +369,7 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
   const size_t smem = cg_smem_bytes(lp);
   static bool attr_set = false;
   if (!attr_set) {
-    GLL_CUDA_CHECK(cudaFuncSetAttribute(cg_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)cg_smem_bytes(CG_MAX_LP)));
-    GLL_CUDA_CHECK(cudaFuncSetAttribute(cg_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    GLL_CUDA_CHECK(cudaFuncSetAttribute(cg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)cg_smem_bytes(CG_MAX_LP)));
     attr_set = true;
   }
@@ -419,8 +384,7 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
   }
   void* args[] = {&P};
   GLL_PROF(KID_CG, st);
-  const void* fn = P.wide ? (const void*)cg_persistent_kernel<true> : (const void*)cg_persistent_kernel<false>;
-  GLL_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(CG_THREADS), args, smem, st));
+  GLL_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)cg_persistent_kernel, dim3(grid), dim3(CG_THREADS), args, smem, st));
   return GLL_OK;
 }
 

@@ -19,7 +19,6 @@ struct CgParams {
   float* r;
   float* p;
   float* ap;
-  int wide;           // streaming kernel, lp > 64: edge metadata by one coalesced load per 32 edges, 8 gathers in flight
   const int* order;   // streaming kernel: row schedule of the SpMV phase (cg_order.cu), or NULL = natural order
   double* partial;    // [2 buffers][2*lp columns][grid]
   unsigned* barrier;  // zeroed before launch
