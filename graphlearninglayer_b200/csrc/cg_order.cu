@@ -1,17 +1,20 @@
 // Row schedule for the streaming CG kernel (cg.cu) on systems whose iterate does not fit in L2 (the 1M-node graph: 393 MB).
+// Opt-in (GLL_B200_CG_ORDER=1; "force" for tests).
 //
-// The SpMV of an iteration gathers ~30 neighbour rows of 4*lp bytes per row.  With the nodes in arbitrary order those
-// gathers miss L2 (12 GB of DRAM traffic per iteration against 4.6 GB of algorithmic bytes: the kernel ran at the HBM
-// limit of its WASTED traffic).  Nothing has to be relabelled to fix that -- L2 caches scattered 400-byte rows as well as
-// contiguous ones; what matters is WHICH rows the 148 CTAs work on at the same time.  So the rows are only SCHEDULED by
-// cluster: key(i) = the class column that dominates the right-hand side of row i (forward: the labeled neighbours'
-// classes, GLL.py:53; adjoint: the label of the batch row, GLL.py:93), rows with an all-zero right-hand side adopt the key
-// of their first neighbour that has one; a stable 8-bit radix sort of (key, row) gives `order`, and the SpMV phase deals
-// consecutive positions of `order` to the warps of the whole grid.  kNN neighbours are overwhelmingly of the same class,
-// so the rows in flight at any moment gather from one or two clusters' worth of the iterate (a few MB).
-// The schedule only changes which warp computes which row: every row's result is bit-identical, the dot products are
-// summed in a different (still deterministic) order.
+// The SpMV of an iteration gathers ~30 neighbour rows of 4*lp bytes per row; with the nodes in arbitrary order those
+// gathers miss L2.  Nothing has to be relabelled to change that -- L2 caches scattered 400-byte rows as well as contiguous
+// ones; what matters is WHICH rows the 148 CTAs work on at the same time.  So the rows are only SCHEDULED by cluster:
+// key(i) = the class column that dominates the right-hand side of row i (forward: the labeled neighbours' classes,
+// GLL.py:53; adjoint: the label of the batch row, GLL.py:93), rows with an all-zero right-hand side adopt the key of their
+// first neighbour that has one; a stable 8-bit radix sort of (key, row) gives `order`, and the SpMV phase deals consecutive
+// positions of `order` to the warps of the whole grid.  The schedule only changes which warp computes which row: every
+// row's result is bit-identical, the dot products are summed in a different (still deterministic) order.
+// Measured at n = 2^20, l = 100 (profiles/r01f_cg_streaming_experiments.md): the adjoint solve gains 8 %, the forward solve
+// nothing -- the iteration is bound by the VOLUME crossing L2 -> SM (30 gathered rows per row), not by where it comes from.
+// Kept because the multi-GPU row partition needs such an ordering to exchange halos instead of the whole iterate.
 #include <cub/device/device_radix_sort.cuh>
+
+#include <mutex>
 
 #include "cg_common.cuh"
 
@@ -67,10 +70,23 @@ cg_row_key_fill_kernel(const int* __restrict__ ptr, const int* __restrict__ col,
   iota[i] = i;
 }
 
+// CUB's size query costs tens of microseconds of host time (device attribute and occupancy look-ups) and the workspace
+// size is asked for several times per layer call: remember the last few sizes.
 size_t sort_temp_bytes(int m) {
+  static std::mutex mu;
+  static int cached_m[8];
+  static size_t cached_bytes[8];
+  static int used = 0, next = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  for (int t = 0; t < used; ++t)
+    if (cached_m[t] == m) return cached_bytes[t];
   size_t bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned char*)nullptr, (unsigned char*)nullptr, (const int*)nullptr,
                                   (int*)nullptr, m, 0, 8, (cudaStream_t)0);
+  cached_m[next] = m;
+  cached_bytes[next] = bytes;
+  next = (next + 1) % 8;
+  if (used < 8) ++used;
   return bytes;
 }
 
