@@ -1,7 +1,8 @@
 // K1 -- exact k-nearest-neighbour search (replaces gl.weightmatrix.knnsearch(..., 'annoy'), GLL.py:181-189).
 //
 // Pipeline (all on one stream, no host sync):
-//   sqnorm      : ||x_i||^2 (fp64 accumulate -> fp32) and the global max
+//   sqnorm      : ||x_i||^2 (fp64 accumulate -> fp32) and the global max; for the tensor-core path also the 16-bit operand
+//                 split of X (fp16 hi/lo of the power-of-two scaled rows and the measured residual rho, or bf16 hi/lo)
 //   gemm_topk   : tiled Gram GEMM  d~^2_ij = |x_i|^2 + |x_j|^2 - 2 x_i.x_j  with a FUSED per-row top-KC epilogue:
 //                 a tile's distances are filtered against the row's running threshold and only the survivors
 //                 touch shared memory; the n x n matrix never reaches HBM.  Column range split across CTAs.
@@ -11,8 +12,9 @@
 //                 is >= L_i - err; rows where that does not exceed the k-th exact distance are queued for
 //   fallback    : brute-force fp64 search for the queued rows only.
 //
-// This file holds the fp32 SIMT Gram path (any d, any alignment).  The tcgen05/TMA Gram path for d % 64 == 0
-// lives in knn_tc.cu and reuses the rerank / fallback kernels through knn_finish().
+// This file holds the fp32 SIMT Gram path (tiny graphs; any d, any alignment), the operand-split kernels, re-rank and
+// fallback.  The tcgen05/TMA Gram path (n >= 256, any d: rows are zero-padded to a multiple of 32) lives in knn_tc.cu and
+// reuses the rerank / fallback kernels through knn_finish().
 #include <math.h>
 #include <stdlib.h>
 
@@ -719,7 +721,7 @@ size_t knn_ws_bytes(int n, int d, int k, int row_begin, int row_end) {
   b += 256;                                                                                        // sqmax + flag_count
   b += align_up(sizeof(u64) * rows * (size_t)cand_stride(n, d, row_begin, row_end) * KC, 256);     // cand
   b += align_up(sizeof(int) * rows, 256);                                                          // flag_rows
-  b += knn_tc_ws_upper(n, d);                                           // bf16 hi / lo copies for the tensor-core path
+  b += knn_tc_ws_upper(n, d);                                           // 16-bit hi / lo copies for the tensor-core path
   b += align_up(sizeof(unsigned) * (size_t)n, 256);                     // per-row shared thresholds
   b += align_up(sizeof(float) * (size_t)n, 256);                        // per-row operand scale (f16x2 split)
   if (k > KC + 1) b += 2 * align_up(sizeof(u64) * rows * KC, 256) + align_up(sizeof(u64) * (size_t)n, 256);  // merged lists, excl

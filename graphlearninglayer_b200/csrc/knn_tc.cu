@@ -1,21 +1,25 @@
 // K1 on the tensor cores: candidate generation for the exact kNN search as a tcgen05 / TMA Gram GEMM with a fused
 // per-row top-KC epilogue (replaces the annoy search behind gl.weightmatrix.knnsearch, GLL.py:181-189).
 //
-// Arithmetic.  bf16 alone (8 mantissa bits) cannot order neighbours whose squared distances differ by ~1e-3, so every
-// feature is split x = hi + lo (+ e, |e| <= 2^-18 |x|) into two bf16 numbers and the Gram entry is accumulated in fp32
-// TMEM as  hi.hi + lo.hi + hi.lo  (the dropped lo.lo term is O(2^-18)): three bf16 MMA passes that share operand
-// tiles.  The result is only used to pick KC = 32 candidates per row; knn_finish() (knn.cu) recomputes the survivors
-// exactly, proves that no true neighbour was missed (error budget knn_tc_err_coef) and redoes unprovable rows by brute
-// force, so the emitted neighbour lists do not depend on tensor-core rounding.
+// Arithmetic.  One 16-bit pass cannot order neighbours whose squared distances differ by ~1e-3, so the operands are split.
+// Default "f16x2": every row is scaled by an exact power of two to a norm in [0.58, 1.16) and split z = hi + lo into two
+// fp16 numbers (sqnorm_split_f16_kernel, knn.cu); the Gram entry is accumulated in fp32 TMEM as (hi_i + lo_i).hi_j -- TWO
+// MMA passes that share the B tile, whose lo half is never loaded.  The A side is exact to 2^-22; the one-sided B residual
+// rho = max_j |x_j - hi_j 2^E_j| is measured by the split kernel and enters the error bound (knn_err_bound, knn.cu).
+// Option GLL_B200_KNN_SPLIT=bf16x3: x = hi + lo in bf16, hi.hi + lo.hi + hi.lo, three passes (split residual 3 * 2^-18).
+// Either way the result is only used to pick KC = 32 candidates per row; knn_finish() (knn.cu) recomputes the survivors
+// exactly, proves that no true neighbour was missed (error budget knn_tc_err_coef + rho) and redoes unprovable rows by
+// brute force, so the emitted neighbour lists do not depend on tensor-core rounding.
 //
 // Kernel (one persistent CTA per SM, 10 warps, warp-specialised):
-//   warp 0   TMA producer: per 32-wide K block one stage = {A_hi, A_lo (128 rows), B_hi, B_lo (256 rows)} = 48 KB,
-//            64-byte swizzle, 3 stages
-//   warp 1   MMA issuer: one elected lane issues 6 tcgen05.mma (3 operand pairs x 2 K=16 steps) per stage into one of
-//            two 128 x 256 fp32 accumulators in TMEM (all 512 columns; double buffered against the epilogue)
+//   warp 0   TMA producer: per 32-wide K block one stage = {A_hi, A_lo (128 rows), B_hi (256 rows)} = 32 KB, four stages
+//            (bf16x3: + B_lo = 48 KB, three stages), 64-byte swizzle
+//   warp 1   MMA issuer: one elected lane issues 4 (bf16x3: 6) tcgen05.mma per stage (operand pairs x 2 K=16 steps) into one
+//            of two 128 x 256 fp32 accumulators in TMEM (all 512 columns; double buffered against the epilogue)
 //   warps 2-9 epilogue, two per SM sub-partition: warps w and w+4 read the same TMEM lane quarter (the same 32 rows) and
-//            take one half of the unit's 256 columns each.  tcgen05.ld gives each thread ONE row, 16 columns at a time;
-//            d~^2 = |xi|^2 + |xj|^2 - 2 acc is compared with the row's threshold (a register).  A thread owns its row's
+//            take one half of the unit's 256 columns each.  tcgen05.ld gives each thread ONE row, 32 columns at a time;
+//            d~^2 = |xi|^2 + |xj|^2 - 2 acc (times the rows' scales) is compared with the row's threshold (a register): one
+//            min per element and one vote decide whether the chunk holds any survivor at all.  A thread owns its row's
 //            candidate set for its column half: an unsorted 32-slot array in shared memory (slot-major, so the 32 threads
 //            of a warp never bank-conflict), 4 groups of 8 slots whose maxima are cached in registers; a survivor replaces
 //            the overall maximum and only that group is rescanned.  All rows of a warp insert concurrently.  The insertion
@@ -36,9 +40,9 @@
 namespace gll {
 namespace {
 
-// Stage = one K block of {A_hi, A_lo, B_hi, B_lo}: 48 KB at a K block of 32 (64-byte swizzle).  Three stages already run
-// the MMA pipe at 98 % of the cuBLAS peak when the epilogue does nothing (GLL_B200_KNN_DEBUG=2: 0.22 ms at 10k nodes), and
-// leave room for the candidate sets of EIGHT epilogue warps.
+// Stage = one K block of {A_hi, A_lo, B_hi, B_lo}: 48 KB at a K block of 32 (64-byte swizzle); the f16x2 split leaves B_lo
+// out and fits four 32 KB stages into the same space.  Three 48 KB stages already ran the MMA pipe at 98 % of the cuBLAS
+// peak when the epilogue does nothing (GLL_B200_KNN_DEBUG=2), and leave room for the candidate sets of EIGHT epilogue warps.
 constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 32, TC_STAGES = 3, TC_MAX_STAGES = 4;
 constexpr int TC_EPI_WARPS = 8;                        // two per TMEM lane quarter: each takes one half of the 256 columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
