@@ -81,8 +81,12 @@ size_t sort_temp_bytes(int m) {
   for (int t = 0; t < used; ++t)
     if (cached_m[t] == m) return cached_bytes[t];
   size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned char*)nullptr, (unsigned char*)nullptr, (const int*)nullptr,
-                                  (int*)nullptr, m, 0, 8, (cudaStream_t)0);
+  const cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned char*)nullptr, (unsigned char*)nullptr,
+                                                        (const int*)nullptr, (int*)nullptr, m, 0, 8, (cudaStream_t)0);
+  if (e != cudaSuccess || bytes == 0) {  // no device (CPU-only container) or a transient error: an upper bound, not cached
+    (void)cudaGetLastError();
+    return (size_t)m * 8 + ((size_t)1 << 20);
+  }
   cached_m[next] = m;
   cached_bytes[next] = bytes;
   next = (next + 1) % 8;
