@@ -78,3 +78,33 @@ def exact_d2(X: np.ndarray) -> np.ndarray:
     g = Xd @ Xd.T
     s = (Xd ** 2).sum(axis=1)
     return s[:, None] + s[None, :] - 2.0 * g  # fp64 Gram form: its own error (1e-16 relative to the norms) is far below the bounds tested
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the optional three-pass split (GLL_B200_KNN_SPLIT=bf16x3; sqnorm_split_kernel in knn.cu)
+# ---------------------------------------------------------------------------------------------------------------------------
+def to_bf16(x32: np.ndarray) -> np.ndarray:
+    """Round-to-nearest-even float32 -> bfloat16, returned as float32 (what __float2bfloat16_rn produces)."""
+    u = np.ascontiguousarray(x32, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return r.astype(np.uint32).view(np.float32)
+
+
+def approx_d2_bf16x3(X: np.ndarray, fp32_accumulate: bool = False) -> np.ndarray:
+    """d~^2_ij = |x_i|^2 + (|x_j|^2 - 2 acc), acc = hi_i.hi_j + lo_i.hi_j + hi_i.lo_j."""
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    sq = (X.astype(np.float64) ** 2).sum(axis=1).astype(np.float32)
+    hi = to_bf16(X)
+    lo = to_bf16(X - hi)
+    if fp32_accumulate:
+        acc = (hi @ hi.T + lo @ hi.T + hi @ lo.T).astype(np.float32)
+    else:
+        h, l = hi.astype(np.float64), lo.astype(np.float64)
+        acc = (h @ h.T + l @ h.T + h @ l.T).astype(np.float32)
+    key = (acc.astype(np.float64) * -2.0 + sq[None, :].astype(np.float64)).astype(np.float32)
+    return (key + sq[:, None]).astype(np.float32), sq
+
+
+def err_bound_bf16x3(d: int, sq: np.ndarray) -> np.ndarray:
+    sq64 = sq.astype(np.float64)
+    return err_coef(d, f16x2=False) * (sq64 + float(sq.max()))

@@ -64,3 +64,14 @@ def test_scaled_rows_fit_fp16_without_overflow():
     assert np.isfinite(hi.astype(np.float32)).all() and np.isfinite(lo.astype(np.float32)).all()
     z = np.abs(hi.astype(np.float64))
     assert z.max() < 1.16 and np.linalg.norm(hi.astype(np.float64), axis=1).min() > 0.57
+
+
+@pytest.mark.parametrize("name,X", list(_datasets()), ids=[n for n, _ in _datasets()])
+@pytest.mark.parametrize("fp32_acc", [False, True])
+def test_bf16x3_distance_error_within_proven_bound(name, X, fp32_acc):
+    """The optional three-pass bf16 split (GLL_B200_KNN_SPLIT=bf16x3): same check against knn_tc_err_coef(d, 0)."""
+    approx, sq = S.approx_d2_bf16x3(X, fp32_accumulate=fp32_acc)
+    err = np.abs(approx.astype(np.float64) - S.exact_d2(X))
+    bound = S.err_bound_bf16x3(X.shape[1], sq)[:, None]
+    worst = float((err / np.maximum(bound, 1e-300)).max())
+    assert worst <= 1.0, (name, worst)
