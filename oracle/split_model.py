@@ -108,3 +108,31 @@ def approx_d2_bf16x3(X: np.ndarray, fp32_accumulate: bool = False) -> np.ndarray
 def err_bound_bf16x3(d: int, sq: np.ndarray) -> np.ndarray:
     sq64 = sq.astype(np.float64)
     return err_coef(d, f16x2=False) * (sq64 + float(sq.max()))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the selection pipeline on top of the approximate distances (knn_rerank_kernel / knn_fallback_kernel in knn.cu)
+# ---------------------------------------------------------------------------------------------------------------------------
+def select_rerank_prove(X: np.ndarray, approx: np.ndarray, bound: np.ndarray, k: int = 25, kc: int = 32):
+    """Restates what the GPU does with the approximate distances: per row the kc candidates with the smallest (approximate
+    distance, index) key (self excluded), exact fp64 re-rank of those candidates by (distance, index), and the completeness
+    proof ``approx(kc-th candidate) - bound > exact (k-1)-th distance``.  Returns (ind (n,k) with self in slot 0,
+    proven (n,) bool).  Rows that are not proven go to the brute-force fallback on the GPU, so only proven rows have to
+    be right here."""
+    Xd = np.ascontiguousarray(X, dtype=np.float32).astype(np.float64)
+    n = Xd.shape[0]
+    a = approx.astype(np.float32).copy()
+    a[np.arange(n), np.arange(n)] = np.inf
+    ind = np.empty((n, k), dtype=np.int64)
+    proven = np.zeros(n, dtype=bool)
+    for i in range(n):
+        order = np.lexsort((np.arange(n), a[i]))[:kc]
+        order = order[np.isfinite(a[i][order])]
+        lower = np.float32(np.inf) if len(order) < kc else a[i][order[-1]]
+        d2 = ((Xd[i][None, :] - Xd[order]) ** 2).sum(axis=1)
+        rr = np.lexsort((order, d2))[: k - 1]
+        ind[i, 0] = i
+        ind[i, 1:1 + len(rr)] = order[rr]
+        dk = d2[rr[-1]]
+        proven[i] = bool(np.isinf(lower) or (float(lower) - float(bound[i]) > dk))
+    return ind, proven

@@ -75,3 +75,34 @@ def test_bf16x3_distance_error_within_proven_bound(name, X, fp32_acc):
     bound = S.err_bound_bf16x3(X.shape[1], sq)[:, None]
     worst = float((err / np.maximum(bound, 1e-300)).max())
     assert worst <= 1.0, (name, worst)
+
+
+def _hard_datasets():
+    rng = np.random.default_rng(5)
+    X, *_ = O.synth_inputs(9, 300, 500, 128, 10, 3.0)
+    yield "clusters_d128", X
+    tight = (1.0 + 2e-3 * rng.standard_normal((600, 48))).astype(np.float32)   # one tight blob: neighbour gaps far below the bound
+    yield "tight_blob", tight
+    grid = np.stack(np.meshgrid(np.arange(25.0), np.arange(24.0)), -1).reshape(-1, 2).astype(np.float32)  # lattice: many exact ties
+    yield "lattice_ties", np.hstack([grid, np.zeros((grid.shape[0], 6), np.float32)])
+    dup = rng.standard_normal((300, 32)).astype(np.float32)
+    dup[100:160] = dup[100]
+    yield "duplicates", dup
+
+
+@pytest.mark.parametrize("name,X", list(_hard_datasets()), ids=[n for n, _ in _hard_datasets()])
+def test_proven_rows_equal_exact_knn(name, X):
+    """Selection by approximate distance + exact re-rank + completeness proof (the GPU pipeline, restated): every row the
+    proof accepts must carry exactly the oracle's neighbour list; rows it rejects are the fallback's business.  On well
+    separated data almost every row is proven; on the degenerate sets the proof must refuse rather than be wrong."""
+    hi, lo, E, sq, rho = S.split_f16x2(X)
+    approx = S.approx_d2_f16x2(hi, lo, E, sq, fp32_accumulate=True)
+    bound = S.err_bound(X.shape[1], sq, rho)
+    ind, proven = S.select_rerank_prove(X, approx, bound)
+    ref_ind, ref_dist = O.exact_knn(X, 25)
+    exact, tie, bad = O.knn_sets_match(ind[proven], ref_ind[proven], ref_dist[proven])
+    assert bad == 0, (name, exact, tie, bad)
+    if name == "clusters_d128":
+        assert proven.mean() > 0.98
+    if name == "tight_blob":
+        assert proven.mean() < 0.5   # gaps of ~1e-6 against a bound of ~1e-4: the proof has to give up, and does
