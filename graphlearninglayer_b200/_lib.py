@@ -75,6 +75,7 @@ def _load():
                                   vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp])
     sig("gll_cg_solve", i32, [vp, vp, vp, vp, vp, i32, i32, f32, i32, vp, vp, vp, vp, vp, sz, vp])
     sig("gll_backward_edges", i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
+    sig("gll_debug_gram_tile", i32, [vp, i32, i32, i32, i32, vp, vp, vp, sz, vp])
     sig("gll_knn_rows_workspace_bytes", sz, [i32, i32, i32, i32, i32])
     sig("gll_knn_rows", i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp])
     sig("gll_backward_edges_rows", i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp])
@@ -114,7 +115,7 @@ EXPORTS = ["gll_last_error", "gll_version", "gll_device_sm_count", "gll_kernel_c
            "gll_cg_rows_workspace_bytes", "gll_cg_rows_init", "gll_cg_rows_spmv", "gll_cg_rows_update", "gll_ce_loss", "gll_ce_loss_workspace_bytes",
            "gll_cg_rows_peer_mail_bytes", "gll_cg_rows_peer_flag_bytes", "gll_cg_rows_init_p2p", "gll_cg_rows_spmv_p2p",
            "gll_cg_rows_update_p2p", "gll_csr_residual_f64", "gll_normalize_rows",
-           "gll_normalize_rows_backward"]
+           "gll_normalize_rows_backward", "gll_debug_gram_tile"]
 
 
 def check(rc: int, what: str) -> None:

@@ -350,6 +350,11 @@ int gll_knn(const float* X, int n, int d, int k, int* knn_idx, float* knn_dist, 
   return knn_run(X, n, d, k, 0, n, knn_idx, knn_dist, info, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int gll_debug_gram_tile(const float* X, int n, int d, int row_tile, int col_tile, float* acc_out, float* rscale_out, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  return knn_debug_gram_tile(X, n, d, row_tile, col_tile, acc_out, rscale_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 int gll_knn_rows(const float* X, int n, int d, int k, int row_begin, int row_end, int* knn_idx, float* knn_dist, int* info,
                  void* workspace, size_t workspace_bytes, void* stream) {
   return knn_run(X, n, d, k, row_begin, row_end, knn_idx, knn_dist, info, workspace, workspace_bytes, (cudaStream_t)stream);

@@ -108,6 +108,8 @@ struct ProfScope {
 int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int* knn_idx, float* knn_dist, int* info,
             void* ws, size_t ws_bytes, cudaStream_t st);
 size_t knn_ws_bytes(int n, int d, int k, int row_begin, int row_end);
+int knn_debug_gram_tile(const float* X, int n, int d, int row_tile, int col_tile, float* acc_out, float* rscale_out, void* ws,
+                        size_t ws_bytes, cudaStream_t st);
 
 int graph_run(const int* knn_idx, const float* knn_dist, int n, int k, int* row_ptr, int* col, float* dist,
               int* info, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -78,8 +78,10 @@ sqnorm_split_kernel(const float* __restrict__ X, int n, int d, int d_pad, float*
   }
 }
 
+constexpr int F16_TARGET_LOG2 = 8;  // rows are scaled to a norm in [0.58, 1.16) * 2^8
+
 // f16x2 operands (knn_tc.cu), fused with the norms so that X is read from HBM once: row i is scaled by 2^-E_i to a norm
-// in [0.58, 1.16) (exact; no fp16 overflow, and fp16's subnormal granularity 2^-24 is relative to the row's own norm),
+// in [148, 296) (exact; no fp16 overflow, and fp16's subnormal range lies 2^-22 below the row's own norm),
 // then hi = fp16(z), lo = fp16(z - hi), row stride d_pad, zero padded.  rscale[i] = 2^E_i undoes
 // the scaling in the Gram epilogue.  Also the largest B-side residual rho = max_j |x_j - hi_j 2^E_j|_2 (exact in fp64,
 // rounded up): the Gram kernel computes (hi + lo)_i . hi_j, so its error is |x_i| rho + O(2^-22).
@@ -98,12 +100,15 @@ sqnorm_split_f16_kernel(const float* __restrict__ X, int n, int d, int d_pad, fl
   }
   s = warp_sum(s);
   // E_i from the row NORM, with the bucket boundaries at |x|^2 = 2^k / 1.5 so that rows normalised to 1 (every caller of the
-  // layer) all get E = 0 whatever their rounding: 2^(2E - 1) <= 1.5 |x_i|^2 < 2^(2E + 1), hence |z_ik| <= |z_i| < 1.16.
-  int E = 0;
+  // layer) all get the same E whatever their rounding: 2^(2F - 1) <= 1.5 |x_i|^2 < 2^(2F + 1), E = F - 8, hence
+  // 148 <= |z_i| < 296.  The target norm 2^8 (not 1) keeps `lo` = z - hi a NORMAL fp16 number for every element above
+  // 2^-11 |x_i|: the split then does not lean on how the tensor core treats fp16 subnormals (with a target of 1, 99.99 % of
+  // the lo values of a 512-dimensional unit row were subnormal); |z_ik| < 296 is far from fp16's 65504.
+  int E = -F16_TARGET_LOG2;
   {
     const unsigned b = __float_as_uint((float)(1.5 * s));
     const int ex = (int)((b >> 23) & 0xFFu);
-    if (b != 0u && ex != 0xFF) E = min(60, max(-60, (ex - 127 + 1) >> 1));  // arithmetic shift = floor
+    if (b != 0u && ex != 0xFF) E = min(60, max(-60, ((ex - 127 + 1) >> 1) - F16_TARGET_LOG2));  // arithmetic shift = floor
   }
   double r2 = 0.0;
   const float down = ldexpf(1.f, -E);  // |E| <= 60: both factors are normal numbers, the products below are exact
@@ -726,6 +731,46 @@ size_t knn_ws_bytes(int n, int d, int k, int row_begin, int row_end) {
   b += align_up(sizeof(float) * (size_t)n, 256);                        // per-row operand scale (f16x2 split)
   if (k > KC + 1) b += 2 * align_up(sizeof(u64) * rows * KC, 256) + align_up(sizeof(u64) * (size_t)n, 256);  // merged lists, excl
   return b + 1024;
+}
+
+namespace {
+__global__ void fill_ones_kernel(float* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 1.f;
+}
+}  // namespace
+
+// Verification entry (gll_debug_gram_tile): operand split of the whole matrix as knn_run does it, then the raw tensor-core
+// accumulator of unit (row_tile, col_tile) and the rows' operand scale (2^E_i; 1 for the bf16 split).
+int knn_debug_gram_tile(const float* X, int n, int d, int row_tile, int col_tile, float* acc_out, float* rscale_out, void* ws,
+                        size_t ws_bytes, cudaStream_t st) {
+  GLL_REQUIRE(X && acc_out && rscale_out && ws, "null pointer");
+  GLL_REQUIRE(n >= 256 && d >= 1, "the tensor-core path needs n >= 256");
+  if (ws_bytes < knn_ws_bytes(n, d, 25, 0, n)) {
+    set_error("workspace too small: %zu < %zu", ws_bytes, knn_ws_bytes(n, d, 25, 0, n));
+    return GLL_ERR_WORKSPACE;
+  }
+  const TcPlan plan = knn_tc_plan(n, d, 0, n);
+  GLL_REQUIRE(plan.ok, "tensor-core plan not available for this shape");
+  GLL_REQUIRE(row_tile >= 0 && row_tile * 128 < n && col_tile >= 0 && col_tile * 256 < n, "tile out of range");
+  Carver cv(ws, ws_bytes);
+  float* sq = cv.take<float>(n);
+  unsigned* small = cv.take<unsigned>(64);
+  char* tc_ws = cv.take<char>(knn_tc_ws_upper(n, d));
+  float* rscale = cv.take<float>(n);
+  __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(tc_ws);
+  __nv_bfloat16* L = reinterpret_cast<__nv_bfloat16*>(tc_ws + align_up((size_t)n * plan.d_pad * 2, 256));
+  GLL_CUDA_CHECK(cudaMemsetAsync(small, 0, 256, st));
+  if (plan.f16x2) {
+    sqnorm_split_f16_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(X, n, d, plan.d_pad, sq, small, reinterpret_cast<__half*>(H),
+                                                                              reinterpret_cast<__half*>(L), rscale, nullptr);
+  } else {
+    sqnorm_split_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(X, n, d, plan.d_pad, sq, small, H, L, nullptr);
+    fill_ones_kernel<<<ceil_div(n, 256), 256, 0, st>>>(rscale, n);
+  }
+  GLL_LAUNCH_CHECK();
+  GLL_CUDA_CHECK(cudaMemcpyAsync(rscale_out, rscale, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+  return knn_tc_debug_tile(plan, n, tc_ws, row_tile, col_tile, acc_out, st);
 }
 
 int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int* knn_idx, float* knn_dist, int* info,

@@ -80,6 +80,8 @@ size_t knn_tc_ws_upper(int n, int d);
 int knn_tc_candidates(const float* X, const float* sq, const float* rscale, const unsigned* small, int n, int d, int row_end, const TcPlan& plan,
                       void* tc_ws, u64* cand, const u64* excl, unsigned* thr_g, cudaStream_t st);
 float knn_tc_err_coef(int d, int f16x2);
+// verification: raw accumulator of one (row tile, column tile) unit, acc_out[128][256] (knn_gram_tile_debug_kernel)
+int knn_tc_debug_tile(const TcPlan& plan, int n, void* tc_ws, int rt, int ct, float* acc_out, cudaStream_t st);
 
 // How the candidate lists of a row are laid out in cand[n][stride][KC]: uniform (SIMT: every row has `stride` lists)
 // or the tensor-core work split (row tile rt was touched by CTAs b0(rt)..b1(rt); slot = b - b0).

@@ -2,9 +2,10 @@
 // per-row top-KC epilogue (replaces the annoy search behind gl.weightmatrix.knnsearch, GLL.py:181-189).
 //
 // Arithmetic.  One 16-bit pass cannot order neighbours whose squared distances differ by ~1e-3, so the operands are split.
-// Default "f16x2": every row is scaled by an exact power of two to a norm in [0.58, 1.16) and split z = hi + lo into two
+// Default "f16x2": every row is scaled by an exact power of two to a norm in [148, 296) and split z = hi + lo into two
 // fp16 numbers (sqnorm_split_f16_kernel, knn.cu); the Gram entry is accumulated in fp32 TMEM as (hi_i + lo_i).hi_j -- TWO
-// MMA passes that share the B tile, whose lo half is never loaded.  The A side is exact to 2^-22; the one-sided B residual
+// MMA passes that share the B tile, whose lo half is never loaded.  The A side is exact to ~2^-21 (even if fp16 subnormals
+// were flushed: at that norm lo is a normal number for every element that matters); the one-sided B residual
 // rho = max_j |x_j - hi_j 2^E_j| is measured by the split kernel and enters the error bound (knn_err_bound, knn.cu).
 // Option GLL_B200_KNN_SPLIT=bf16x3: x = hi + lo in bf16, hi.hi + lo.hi + hi.lo, three passes (split residual 3 * 2^-18).
 // Either way the result is only used to pick KC = 32 candidates per row; knn_finish() (knn.cu) recomputes the survivors
@@ -566,6 +567,81 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
   }
 }
 
+// ---------------------------------------------------------------------------------------------- verification kernel
+// ONE (row tile, column tile) unit with the production operand maps, descriptors and MMA sequence, but no pipeline and no
+// epilogue: the raw fp32 accumulator goes to global memory so that a test can compare what the tensor core accumulated
+// with the numpy model of the split (oracle/split_model.py) -- in particular that fp16 subnormal operands take part.
+constexpr size_t TCD_OFF_BAR = TC_STAGE_BYTES;
+constexpr size_t TCD_SMEM_BYTES = TCD_OFF_BAR + 64 + 1024;
+
+__global__ void __launch_bounds__(128, 1)
+knn_gram_tile_debug_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_constant__ CUtensorMap mapAL,
+                           const __grid_constant__ CUtensorMap mapBH, const __grid_constant__ CUtensorMap mapBL, int kblocks, int rt,
+                           int ct, int f16x2, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = base + (uint32_t)TCD_OFF_BAR, bar_mma = bar_full + 8, slot = bar_full + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + TCD_OFF_BAR + 16);
+  if (threadIdx.x == 0) {
+    mbar_init(bar_full, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"((uint32_t)TC_BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t stage_bytes = f16x2 ? (uint32_t)(TC_STAGE_BYTES - TC_B_BYTES) : (uint32_t)TC_STAGE_BYTES;
+  const int nprod = f16x2 ? 2 : 3;
+  const uint32_t idesc = f16x2 ? TC_IDESC_F16 : TC_IDESC;
+  uint32_t phase = 0;
+  for (int kk = 0; kk < kblocks; ++kk) {
+    if (threadIdx.x == 0) {
+      mbar_arrive_expect_tx(bar_full, stage_bytes);
+      tma_load_2d(base, &mapAH, bar_full, kk * TC_BK, rt * TC_BM);
+      tma_load_2d(base + TC_A_BYTES, &mapAL, bar_full, kk * TC_BK, rt * TC_BM);
+      tma_load_2d(base + 2 * TC_A_BYTES, &mapBH, bar_full, kk * TC_BK, ct * TC_BN);
+      if (!f16x2) tma_load_2d(base + 2 * TC_A_BYTES + TC_B_BYTES, &mapBL, bar_full, kk * TC_BK, ct * TC_BN);
+    }
+    mbar_wait(bar_full, phase);
+    tc_fence_after();
+    if (threadIdx.x == 0) {
+      const uint64_t dAH = tc_smem_desc(base), dAL = tc_smem_desc(base + TC_A_BYTES);
+      const uint64_t dBH = tc_smem_desc(base + 2 * TC_A_BYTES), dBL = tc_smem_desc(base + 2 * TC_A_BYTES + TC_B_BYTES);
+      for (int g = 0; g < nprod; ++g) {
+        const uint64_t da = (g == 1) ? dAL : dAH, db = (g == 2) ? dBL : dBH;
+        for (int k4 = 0; k4 < TC_BK / 16; ++k4)
+          tc_mma_bf16(tmem_base, da + (uint64_t)(2 * k4), db + (uint64_t)(2 * k4), idesc, (uint32_t)((kk | g | k4) != 0));
+      }
+      tc_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, phase);  // the MMAs have retired: the stage may be overwritten, and after the last block D is complete
+    tc_fence_after();
+    phase ^= 1u;
+  }
+  const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  uint32_t r[TC_CHUNK];
+  for (int q = 0; q < TC_BN / TC_CHUNK; ++q) {
+    tc_ld_issue(taddr + q * TC_CHUNK, r);
+    tc_ld_wait(r);
+#pragma unroll
+    for (int c = 0; c < TC_CHUNK; ++c) out[(size_t)(warp * 32 + lane) * TC_BN + q * TC_CHUNK + c] = __uint_as_float(r[c]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_BN) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 PFN_cuTensorMapEncodeTiled get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled fn = nullptr;
@@ -651,14 +727,30 @@ size_t knn_tc_ws_upper(int n, int d) { return 2 * align_up((size_t)n * (size_t)(
 
 // |d~^2 - d^2| <= coef * (|xi|^2 + |xj|^2): split residual 3*2^-18, fp32 accumulation over 3*d/16 MMA steps of unknown
 // internal rounding (budgeted at 2^-21 per step and per 16-term tree), final fp32 expression 4u; then a 4x margin.
-// f16x2: the A side is x_i = (hi + lo) 2^E_i + r_i with |r_i| <= 2^-22 |x_i| + 2^-25 sqrt(d) 2^E_i, 2^E_i <= 1.74 |x_i| (fp16 normal
-// rounding twice, subnormal granularity 2^-24 below 2^-14): 2 |r_i| |x_j| <= (2^-22 + 2^-24 sqrt(d)) (|xi|^2 + |xj|^2);
+// f16x2: rows are scaled to a norm of at least 148, so the A side is x_i = (hi + lo) 2^E_i + r_i with
+// |r_ik| <= 2^-22 |x_ik| wherever lo is a normal fp16 number and |r_ik| < 2^-14 2^E_i <= 2^-21.2 |x_i| elsewhere -- even if the
+// tensor core flushed fp16 subnormals to zero: |r_i| <= (2^-22 + 2^-21.2 sqrt(d)) |x_i|, 2 |r_i| |x_j| <= (1 + sqrt(d)) 2^-21 (|xi|^2 + |xj|^2) / 2, budgeted without the 1/2;
 // two MMA passes; the B-side residual is NOT in this coefficient -- it is measured (rho) and added by knn_err_bound().
 float knn_tc_err_coef(int d, int f16x2) {
   const double steps = (f16x2 ? 2.0 : 3.0) * ceil_div(d, 16) + 8.0;
-  const double split = f16x2 ? (1.0 + 0.5 * sqrt((double)d)) / 4194304.0 * 1.01 : 3.0 / 262144.0;
+  const double split = f16x2 ? (1.0 + sqrt((double)d)) / 2097152.0 * 1.01 : 3.0 / 262144.0;
   const double e = split + steps * 4.76837158203125e-7 + 4.0 * 5.9604644775390625e-8;
   return (float)(4.0 * e);
+}
+
+int knn_tc_debug_tile(const TcPlan& plan, int n, void* tc_ws, int rt, int ct, float* acc_out, cudaStream_t st) {
+  __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(tc_ws);
+  __nv_bfloat16* L = reinterpret_cast<__nv_bfloat16*>((char*)tc_ws + align_up((size_t)n * plan.d_pad * 2, 256));
+  CUtensorMap mAH, mAL, mBH, mBL;
+  int rc;
+  if ((rc = make_map(&mAH, H, n, plan.d_pad, TC_BM, plan.f16x2))) return rc;
+  if ((rc = make_map(&mAL, L, n, plan.d_pad, TC_BM, plan.f16x2))) return rc;
+  if ((rc = make_map(&mBH, H, n, plan.d_pad, TC_BN, plan.f16x2))) return rc;
+  if ((rc = make_map(&mBL, L, n, plan.d_pad, TC_BN, plan.f16x2))) return rc;
+  GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_gram_tile_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCD_SMEM_BYTES));
+  knn_gram_tile_debug_kernel<<<1, 128, TCD_SMEM_BYTES, st>>>(mAH, mAL, mBH, mBL, plan.kblocks, rt, ct, plan.f16x2, acc_out);
+  GLL_LAUNCH_CHECK();
+  return GLL_OK;
 }
 
 int knn_tc_candidates(const float* X, const float* sq, const float* rscale, const unsigned* small, int n, int d, int row_end, const TcPlan& plan,

@@ -154,6 +154,12 @@ int gll_backward_edges(const float* X, int n, int d, int l, int k_lab, int eps_a
  * ------------------------------------------------------------------------------------------- */
 /* gll_knn for rows [row_begin, row_end) against all n columns; writes rows [row_begin, row_end) of the full n x k
  * arrays.  row_begin should be a multiple of 128 (otherwise the SIMT Gram path is taken). */
+/* Verification only: the raw fp32 accumulator acc_out[128][256] that the tensor-core kNN kernel forms for rows
+ * [128 row_tile, +128) against columns [256 col_tile, +256) from the split operands (mode of GLL_B200_KNN_SPLIT), and the
+ * operands' per-row scale rscale_out[n] (the accumulator holds x_i.x_j / (rscale_i rscale_j); all ones for the bf16 split).
+ * tests compare it with the numpy model of the split (oracle/split_model.py).  workspace: gll_knn_workspace_bytes(n, d, 25). */
+int gll_debug_gram_tile(const float* X, int n, int d, int row_tile, int col_tile, float* acc_out, float* rscale_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
 size_t gll_knn_rows_workspace_bytes(int n, int d, int k, int row_begin, int row_end);
 int gll_knn_rows(const float* X, int n, int d, int k, int row_begin, int row_end, int* knn_idx, float* knn_dist, int* info,
                  void* workspace, size_t workspace_bytes, void* stream);

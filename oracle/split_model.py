@@ -15,14 +15,18 @@ import math
 import numpy as np
 
 
+F16_TARGET_LOG2 = 8  # rows are scaled to a norm in [0.58, 1.16) * 2^8 (knn.cu)
+
+
 def scale_exponent(sq64: np.ndarray) -> np.ndarray:
-    """E_i of sqnorm_split_f16_kernel: from the bits of float(1.5 |x_i|^2); 0 for zero / non-finite rows; clamped to +-60."""
+    """E_i of sqnorm_split_f16_kernel: from the bits of float(1.5 |x_i|^2), minus the target exponent; zero / non-finite rows take
+    the unit-norm bucket; clamped to +-60."""
     t = (1.5 * sq64).astype(np.float32)
     bits = t.view(np.uint32)
     ex = ((bits >> 23) & 0xFF).astype(np.int64)
-    E = np.floor_divide(ex - 127 + 1, 2)
+    E = np.floor_divide(ex - 127 + 1, 2) - F16_TARGET_LOG2
     E = np.clip(E, -60, 60)
-    E[(bits == 0) | (ex == 0xFF)] = 0
+    E[(bits == 0) | (ex == 0xFF)] = -F16_TARGET_LOG2
     return E
 
 
@@ -44,8 +48,17 @@ def split_f16x2(X: np.ndarray):
     return hi, lo, E, sq, rho
 
 
-def approx_d2_f16x2(hi, lo, E, sq, fp32_accumulate: bool = False) -> np.ndarray:
+def flush_fp16_subnormals(h: np.ndarray) -> np.ndarray:
+    """What a multiplier WITHOUT fp16 subnormal support would see (the bound must hold for it too)."""
+    out = h.copy()
+    out[np.abs(out.astype(np.float32)) < np.float32(2.0 ** -14)] = 0
+    return out
+
+
+def approx_d2_f16x2(hi, lo, E, sq, fp32_accumulate: bool = False, flush_subnormals: bool = False) -> np.ndarray:
     """d~^2_ij = |x_i|^2 + (|x_j|^2 + (acc 2^E_i)(-2 2^E_j)) with acc = (hi_i + lo_i) . hi_j, as the epilogue forms it."""
+    if flush_subnormals:
+        hi, lo = flush_fp16_subnormals(hi), flush_fp16_subnormals(lo)
     if fp32_accumulate:
         a = hi.astype(np.float32) @ hi.astype(np.float32).T + lo.astype(np.float32) @ hi.astype(np.float32).T
         acc = a.astype(np.float32)
@@ -62,7 +75,7 @@ def approx_d2_f16x2(hi, lo, E, sq, fp32_accumulate: bool = False) -> np.ndarray:
 def err_coef(d: int, f16x2: bool = True) -> float:
     """knn_tc_err_coef (knn_tc.cu)."""
     steps = (2.0 if f16x2 else 3.0) * math.ceil(d / 16) + 8.0
-    split = (1.0 + 0.5 * math.sqrt(d)) / 4194304.0 * 1.01 if f16x2 else 3.0 / 262144.0
+    split = (1.0 + math.sqrt(d)) / 2097152.0 * 1.01 if f16x2 else 3.0 / 262144.0
     e = split + steps * 4.76837158203125e-7 + 4.0 * 5.9604644775390625e-8
     return float(np.float32(4.0 * e))
 

@@ -202,6 +202,50 @@ def test_knn_f16x2_full_size_matches_bf16x3(gll, monkeypatch):
     assert int(info0[_lib.INFO_KNN_FALLBACK_ROWS].item()) == 0 and int(info1[_lib.INFO_KNN_FALLBACK_ROWS].item()) == 0
 
 
+@pytest.mark.skipif(os.environ.get("GLL_B200_EXPERIMENTAL") != "1",
+                    reason="verification kernel written after the round's GPU budget was spent; run with GLL_B200_EXPERIMENTAL=1")
+@pytest.mark.parametrize("split", ["f16x2", "bf16x3"])
+@pytest.mark.parametrize("d", [512, 200])
+def test_tensor_core_accumulator_matches_split_model(gll, monkeypatch, split, d):
+    """What the tensor core accumulates for one (row tile, column tile) unit against the numpy model of the operand split
+    (oracle/split_model.py), within the fp32-accumulation budget of knn_tc_err_coef.  In particular: fp16 SUBNORMAL `lo`
+    operands must take part (most of them are subnormal for unit rows), or the f16x2 bound would not hold on the device."""
+    from oracle import split_model as S
+
+    _, _lib = gll
+    _set_knn_path(monkeypatch, "tc-f16x2" if split == "f16x2" else "tc")
+    X, *_ = O.synth_inputs(13, 600, 680, d, 10, 4.5)
+    n = X.shape[0]
+    rt, ct = 3, 2
+    Xt = dev_t(X, torch.float32)
+    acc = torch.empty((128, 256), dtype=torch.float32, device="cuda")
+    rscale = torch.empty(n, dtype=torch.float32, device="cuda")
+    wsb = _lib.lib.gll_knn_workspace_bytes(n, d, 25)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.lib.gll_debug_gram_tile(Xt.data_ptr(), n, d, rt, ct, acc.data_ptr(), rscale.data_ptr(), ws.data_ptr(), wsb,
+                                            torch.cuda.current_stream().cuda_stream), "gll_debug_gram_tile")
+    torch.cuda.synchronize()
+    rows, cols = np.arange(rt * 128, rt * 128 + 128), np.arange(ct * 256, ct * 256 + 256)
+    if split == "f16x2":
+        hi, lo, E, sq, rho = S.split_f16x2(X)
+        assert np.array_equal(rscale.cpu().numpy(), np.ldexp(np.float32(1), E).astype(np.float32))
+        a, b = (hi.astype(np.float64) + lo.astype(np.float64))[rows], hi.astype(np.float64)[cols]
+        want = a @ b.T
+        passes = 2
+    else:
+        assert bool((rscale == 1).all())
+        hi = S.to_bf16(X)
+        lo = S.to_bf16(X - hi)
+        h, l = hi.astype(np.float64), lo.astype(np.float64)
+        want = h[rows] @ h[cols].T + l[rows] @ h[cols].T + h[rows] @ l[cols].T
+        a, b = h[rows], h[cols]
+    got = acc.cpu().numpy().astype(np.float64)
+    steps = passes * int(np.ceil(d / 16)) + 8 if split == "f16x2" else 3 * int(np.ceil(d / 16)) + 8
+    budget = steps * 2.0 ** -22 * ((a ** 2).sum(axis=1)[:, None] + (b ** 2).sum(axis=1)[None, :])  # un-margined share of the coefficient
+    err = np.abs(got - want)
+    assert float((err / budget).max()) <= 1.0, float((err / budget).max())
+
+
 def test_knn_paths_agree_and_tc_is_used(gll, monkeypatch):
     """Default dispatch takes the tensor-core kernel at this size; its lists are identical to the SIMT kernel's."""
     _, _lib = gll

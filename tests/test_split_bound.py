@@ -29,11 +29,13 @@ def _datasets():
 
 
 @pytest.mark.parametrize("name,X", list(_datasets()), ids=[n for n, _ in _datasets()])
-@pytest.mark.parametrize("fp32_acc", [False, True])
-def test_f16x2_distance_error_within_proven_bound(name, X, fp32_acc):
+@pytest.mark.parametrize("fp32_acc,flush", [(False, False), (True, False), (True, True)])
+def test_f16x2_distance_error_within_proven_bound(name, X, fp32_acc, flush):
+    """flush: the same with every fp16 subnormal operand replaced by zero -- the bound does not lean on how the tensor core
+    treats subnormals (rows are scaled to a norm of ~2^8, so only elements below 2^-11 of the row norm lose their `lo`)."""
     hi, lo, E, sq, rho = S.split_f16x2(X)
     d = X.shape[1]
-    approx = S.approx_d2_f16x2(hi, lo, E, sq, fp32_accumulate=fp32_acc).astype(np.float64)
+    approx = S.approx_d2_f16x2(hi, lo, E, sq, fp32_accumulate=fp32_acc, flush_subnormals=flush).astype(np.float64)
     exact = S.exact_d2(X)
     err = np.abs(approx - exact)
     bound = S.err_bound(d, sq, rho)[:, None]
@@ -51,10 +53,10 @@ def test_rows_normalised_to_one_share_one_scale():
     X = rng.standard_normal((5000, 96)).astype(np.float32)
     X /= np.linalg.norm(X, axis=1, keepdims=True).astype(np.float32)
     E = S.scale_exponent((X.astype(np.float64) ** 2).sum(axis=1))
-    assert (E == 0).all()
+    assert (E == -S.F16_TARGET_LOG2).all()
     # bucket edges: 2^(2E-1) <= 1.5 |x|^2 < 2^(2E+1)
     s = np.array([0.0, 1e-30, 1 / 3 - 1e-6, 1 / 3 + 1e-6, 4 / 3 - 1e-6, 4 / 3 + 1e-6, 16 / 3 + 1e-5, 1e30, np.inf])
-    assert S.scale_exponent(s).tolist() == [0, -50, -1, 0, 0, 1, 2, 50, 0]
+    assert (S.scale_exponent(s) + S.F16_TARGET_LOG2).tolist() == [0, -50, -1, 0, 0, 1, 2, 50, 0]
 
 
 def test_scaled_rows_fit_fp16_without_overflow():
@@ -63,7 +65,7 @@ def test_scaled_rows_fit_fp16_without_overflow():
     hi, lo, E, sq, rho = S.split_f16x2(X)
     assert np.isfinite(hi.astype(np.float32)).all() and np.isfinite(lo.astype(np.float32)).all()
     z = np.abs(hi.astype(np.float64))
-    assert z.max() < 1.16 and np.linalg.norm(hi.astype(np.float64), axis=1).min() > 0.57
+    assert z.max() < 1.16 * 256 and np.linalg.norm(hi.astype(np.float64), axis=1).min() > 0.57 * 256
 
 
 @pytest.mark.parametrize("name,X", list(_datasets()), ids=[n for n, _ in _datasets()])
