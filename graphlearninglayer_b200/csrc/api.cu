@@ -40,6 +40,24 @@ const DeviceInfo& device_info() {
   return cache[dev];
 }
 
+cudaError_t set_max_dynamic_smem_once(const void* func, int bytes) {
+  struct Key {
+    const void* f;
+    int dev, bytes;
+  };
+  static std::mutex mu;
+  static std::vector<Key> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  for (const Key& k : done)
+    if (k.f == func && k.dev == dev && k.bytes >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.push_back(Key{func, dev, bytes});
+  return e;
+}
+
 // ------------------------------------------------------------------------------------------------ profiling
 namespace {
 struct ProfRec {

@@ -367,12 +367,7 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
   rpb = ceil_div(rpb, S) * S;  // keep phase-2/3 spans aligned to whole lane groups
   P.rows_per_block = rpb;
   const size_t smem = cg_smem_bytes(lp);
-  static bool attr_set = false;
-  if (!attr_set) {
-    GLL_CUDA_CHECK(cudaFuncSetAttribute(cg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)cg_smem_bytes(CG_MAX_LP)));
-    attr_set = true;
-  }
+  GLL_CUDA_CHECK(set_max_dynamic_smem_once((const void*)cg_persistent_kernel, (int)cg_smem_bytes(CG_MAX_LP)));
   GLL_CUDA_CHECK(cudaMemsetAsync(P.barrier, 0, 256, st));
   if (cg_order_mode(m, lp)) {
     int* order = cv.take<int>(m);

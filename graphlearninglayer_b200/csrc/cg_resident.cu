@@ -1,22 +1,31 @@
 // K4, on-chip variant -- multi-right-hand-side Jacobi-preconditioned CG whose state never leaves the SM.
 // (replaces spsolve at GLL.py:53 / GLL.py:93; stopping rule and per-column freeze of stable_conjgrad, GLL.py:247-276)
 //
-// Every CTA owns a block of rows for the whole solve and keeps x, r, p, s = Ap, w = Au (u = r/diag), 1/diag and -- when
-// it fits -- its slice of the CSR in SHARED MEMORY across iterations.  The only global traffic per iteration is
+// Every CTA owns a block of rows for the whole solve and keeps x, r, p, s = Ap, w = Au (u = r/diag), 1/diag and its slice
+// of the matrix in SHARED MEMORY across iterations.  The only global traffic per iteration is
 //   * the preconditioned residual u, published by its owner and gathered by the CTAs whose rows reference it (L2), and
-//   * 3*lp dot-product partials per CTA.
+//   * 3*l dot-product partials per CTA (fp64).
 // Recurrences are Chronopoulos-Gear's single-reduction CG (one SpMV, one reduction of <r,u>, <w,u>, <r,r> per iteration):
 //     p = u + b p ;  s = w + b s ;  x += a p ;  r -= a s ;  u = r/diag ;  w = A u
 //     b = g'/g ,  a = g' / (d - b g'/a_old)      with g = <r,u>, d = <w,u>
-// so an iteration has two grid-wide exchanges instead of textbook CG's three:
-//   E1  "u is published": one release-store of an epoch flag per CTA, every CTA acquires all flags (u is double buffered)
-//   E2  dot products: each CTA stores {fp32 partial, epoch} as ONE 64-bit word per column, so the value arrives with
-//       its flag in a single L2 round trip and no fence is needed; the column's owner CTA sums the G words and
-//       publishes {sum, epoch}, which is all the other CTAs poll (fan-in G per column instead of G*G).
-// Sums over CTAs are taken in double in a fixed order and every CTA reads the same published value, so all CTAs take
-// identical branches and the result
-// is bit-reproducible (no floating-point atomics).  With a single CTA (small systems: the 512-row minibatch solves) the
-// exchanges degenerate to __syncthreads and nothing but the CSR and the answer touches global memory.
+// (the pipelined variant that hides the reduction behind the SpMV was tried in an fp32 model of this system and does not
+// reach the 1e-7 residual: its recurrences for u and w drift, profiles/r02_cg_trace.md).
+//
+// What an iteration costs on 148 SMs is latency, not bandwidth (a C4-size system, 14336 rows x 10 classes, is 97 rows
+// per CTA), so the kernel is organised around the measured costs (tools/xchg_bench.cu, profiles/r02a_xchg_bench.txt):
+//   * one L2 hop between two SMs is ~450 ns; a grid barrier through ONE atomic counter (red.release + ld.acquire spin by
+//     one thread per CTA) costs 1.2 us with 148 CTAs -- cheaper than any mailbox scheme (4-5 us), so both exchanges of an
+//     iteration are a counter barrier: (B) "u is published", (A) "dot-product partials are written".  After (A) every CTA
+//     reads all G x 3l partials with coalesced loads and adds them in the same fixed order, so all CTAs take identical
+//     branches and the result is bit-reproducible (no floating-point atomics).
+//   * the SpMV is bound by the L1TEX wavefront rate (one 128-byte line per gathered row of u: ~2 us for the 2.5 k gathers
+//     of a CTA), so it issues exactly one gather per edge and nothing else: rows are cut into SEGMENTS of 8 edges
+//     (built once per solve in shared memory), a thread owns one (segment, class quad) and has its 8 loads in flight at
+//     once -- no idle lanes for short rows, no tail for hub rows (degree 91 against a mean of 26) -- and u rows of 48
+//     bytes are stored with a 64-byte stride so that no gather straddles a line.  Segment sums are added per row in a
+//     second, shared-memory-only pass.
+//   * the three dot products take one warp per (product, class column) with ONE butterfly each.
+// With a single CTA (systems of a few hundred rows) the exchanges degenerate to __syncthreads and u stays in shared memory.
 #include <math.h>
 
 #include "cg_common.cuh"
@@ -26,48 +35,44 @@ namespace {
 
 constexpr int CR_THREADS = 1024;
 constexpr int CR_WARPS = CR_THREADS / 32;
-constexpr int CR_ROWS_ILP = 4;          // rows a warp gathers for at once (independent L2 loads in flight)
+// Edges per segment = independent gathers in flight per thread.  10 makes the C4-size system (97 rows x ~26 edges x 3
+// class quads per CTA) exactly one round of <= 1024 (segment, quad) tasks; with 8 it is 1092 tasks = a second, nearly
+// empty round that costs a full L2 round trip.
+constexpr int CR_SEG_DEFAULT = 10;
 constexpr size_t CR_SMEM_BUDGET = 200 * 1024;
+constexpr int CR_MAX_GRID = 160;  // the sum over CTAs keeps CR_MAX_GRID / 32 loads per lane in flight
 
 struct CrParams {
   CgParams cg;
-  float* ubuf;                // [2][m*lp] published u
-  unsigned* flags;            // [grid][grid] E1 mailboxes: flags[d][b] = epoch of CTA b's latest published u
-  unsigned long long* words;  // [3*lp][grid] E2 {partial, epoch}
-  unsigned long long* results;  // [grid][3*l] E2 mailboxes {sum over CTAs, epoch}, written by the column's owner CTA
-  int rows_cap;               // rows per CTA
-  int csr_cap;                // nnz a CTA can cache in shared memory
-  unsigned long long* trace;  // debug: [grid][16 passes][8 phases] %globaltimer stamps (NULL = off)
+  float* ubuf;        // [m][ustride] published u
+  double* part;       // [3*lp][grid] dot-product partials of every CTA (column-major)
+  unsigned* counter;  // grid barrier (zeroed before the launch)
+  int rows_cap;       // rows per CTA
+  int seg_cap;        // segments a CTA can hold in shared memory
+  int ustride;        // floats per row of ubuf
+  unsigned long long* trace;  // debug: [grid][16 passes][16 phases] clock64 stamps (NULL = off)
 };
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
-  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// lane = q*S + s with S a power of two: xor butterfly inside each group of S lanes (every lane of the group gets the sum)
-__device__ __forceinline__ float4 reduce_slots(float4 a, int S) {
-#pragma unroll 1
-  for (int o = S >> 1; o >= 1; o >>= 1) {
-    a.x += __shfl_xor_sync(FULL, a.x, o);
-    a.y += __shfl_xor_sync(FULL, a.y, o);
-    a.z += __shfl_xor_sync(FULL, a.z, o);
-    a.w += __shfl_xor_sync(FULL, a.w, o);
+// All CTAs are co-resident (cooperative launch).  The release of thread 0 is cumulative over the CTA's earlier stores
+// (ordered before it by bar.sync), the acquire + bar.sync order every thread's later loads after the peers' stores.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    red_release_add_u32(counter, 1u);
+    while (ld_acquire_u32(counter) < target) {
+    }
   }
-  return a;
+  __syncthreads();
 }
 
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
@@ -76,48 +81,71 @@ __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
   acc.z = fmaf(w, v.z, acc.z);
   acc.w = fmaf(w, v.w, acc.w);
 }
-__device__ __forceinline__ void dot4(float4& acc, const float4& a, const float4& b) {
-  acc.x = fmaf(a.x, b.x, acc.x);
-  acc.y = fmaf(a.y, b.y, acc.y);
-  acc.z = fmaf(a.z, b.z, acc.z);
-  acc.w = fmaf(a.w, b.w, acc.w);
-}
 __device__ __forceinline__ float4 scale4(const float4& a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
-__device__ __forceinline__ float4 warp_sum4(float4 a) {
-  a.x = warp_sum(a.x);
-  a.y = warp_sum(a.y);
-  a.z = warp_sum(a.z);
-  a.w = warp_sum(a.w);
-  return a;
-}
 
-__device__ __forceinline__ void cr_stamp(const CrParams& R, int pass, int phase, int who = 0) {
-  if (R.trace != nullptr && threadIdx.x == who && pass < 16) {
-    const unsigned long long t = (unsigned long long)clock64();  // SM cycle counter: cheap to read
-    R.trace[((size_t)blockIdx.x * 16 + pass) * 8 + phase] = t;
+// debug timeline (TRACE instantiation only).  BAR.SYNC is deferred-blocking (a clock read right behind it can run before the barrier releases), so
+// the stamp first touches shared memory, which waits for the barrier.
+__device__ __forceinline__ void cr_stamp(const CrParams& R, int pass, int phase) {
+  if (R.trace != nullptr && threadIdx.x == 0 && pass < 16) {
+    unsigned dummy;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(dummy) : "r"(0u) : "memory");
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(dummy) : "memory");
+    R.trace[((size_t)blockIdx.x * 16 + pass) * 16 + phase] = t;
   }
 }
 
-constexpr int CR_POLL = 5;  // 32 * CR_POLL >= max grid (148 SMs)
-
-struct Ctrl {  // written by warp 0, read by everybody after a __syncthreads
-  int stop;
-  int pad[3];
+struct Ctrl {
+  double tol2;  // squared absolute tolerance, fixed in pass 0
+  int pad[2];
 };
 
+// Rare path: a row block whose segments do not fit in shared memory walks the CSR in global memory, one thread per
+// (row, class quad).
 template <bool SINGLE>
+__device__ __forceinline__ void spmv_rows_from_global(const CgParams& P, int row0, int rows, const float* ub, int ust, const float* rs,
+                                                   float* ws, const float* dg, const float* dinv) {
+  const int lp = P.lp, Q = lp >> 2;
+#pragma unroll 1
+  for (int it = threadIdx.x; it < rows * Q; it += CR_THREADS) {
+    const int i = it / Q, q = it - i * Q;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int e1 = __ldg(P.ptr + row0 + i + 1);
+#pragma unroll 1
+    for (int e = __ldg(P.ptr + row0 + i); e < e1; ++e) {
+      const int j = __ldg(P.col + e);
+      const float4 uj = SINGLE ? *reinterpret_cast<const float4*>(ub + (size_t)j * ust + 4 * q) : ldcg4(ub + (size_t)j * ust + 4 * q);
+      fma4(a, __ldg(P.val + e), uj);
+    }
+    const size_t o = (size_t)i * lp + 4 * q;
+    const float4 u4 = scale4(*reinterpret_cast<const float4*>(rs + o), dinv[i]);
+    const float dgi = dg[i];
+    *reinterpret_cast<float4*>(ws + o) = make_float4(fmaf(dgi, u4.x, -a.x), fmaf(dgi, u4.y, -a.y), fmaf(dgi, u4.z, -a.z), fmaf(dgi, u4.w, -a.w));
+  }
+}
+
+// Rare path (once per solve, one thread): iteration count, residual and status word.
+__device__ __forceinline__ void write_stats(const CgParams& P, const double* red, int lp, int iter, int bad, double tol2) {
+  double mx_all = 0.0;
+#pragma unroll 1
+  for (int c = 0; c < lp; ++c) mx_all = fmax(mx_all, red[2 * lp + c]);
+  if (P.iters_out) *P.iters_out = iter;
+  if (P.resid_out) *P.resid_out = sqrtf((float)mx_all);
+  if (P.status_out) {
+    int st = 0;
+    if (bad) st |= GLL_STATUS_NONFINITE;
+    if (!bad && !(mx_all <= tol2)) st |= GLL_STATUS_CG_NOT_CONVERGED;
+    if (st) atomicOr(P.status_out, st);
+  }
+}
+
+template <bool SINGLE, int CR_SEG, bool TRACE>
 __global__ void __launch_bounds__(CR_THREADS, 1) cg_resident_kernel(CrParams R) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const CgParams& P = R.cg;
-  const int lp = P.lp, Q = lp >> 2;
-  int S = 1;  // neighbour slots per class quad: largest power of two with Q*S <= 32
-  while (2 * S * Q <= 32) S <<= 1;
+  const int lp = P.lp, Q = lp >> 2, E3 = 3 * lp;
   const int G = gridDim.x, b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int q_idx = lane / S, s_idx = lane - q_idx * S;
-  const bool lane_on = lane < S * Q;
-  const int q_ld = lane_on ? q_idx : 0;  // inactive lanes still issue (harmless) loads
-  const int NCH = max(1, CR_WARPS / Q);  // row chunks of the dot-product phase (one warp per (chunk, class quad))
 
   const int row0 = min(P.m, b * R.rows_cap);
   const int rows = min(P.m, row0 + R.rows_cap) - row0;
@@ -129,52 +157,77 @@ __global__ void __launch_bounds__(CR_THREADS, 1) cg_resident_kernel(CrParams R) 
   float* ps = rs + vec;
   float* ss = ps + vec;
   float* ws = ss + vec;
-  float* dg = ws + vec;               // diag          [rows_cap]
-  float* dinv = dg + R.rows_cap;      // 1/diag        [rows_cap]
-  int* lptr = reinterpret_cast<int*>(dinv + R.rows_cap);  // local CSR pointers [rows_cap + 1]
-  double* red = reinterpret_cast<double*>(sm_raw + align_up((size_t)((char*)(lptr + R.rows_cap + 1) - (char*)sm_raw), 16));  // [3*lp] g', d, rr
-  float* inv_g_old = reinterpret_cast<float*>(red + 3 * lp);  // [lp]  1/<r,u> of the previous pass
+  float* us = ws + vec;                           // SINGLE only: u = r/diag (otherwise u lives in global memory)
+  float* dg = us + (SINGLE ? vec : 0);            // diag          [rows_cap]
+  float* dinv = dg + R.rows_cap;                  // 1/diag        [rows_cap]
+  int* rseg = reinterpret_cast<int*>(dinv + R.rows_cap);  // first segment of every row [rows_cap + 1]
+  double* red = reinterpret_cast<double*>(sm_raw + align_up((size_t)((char*)(rseg + R.rows_cap + 1) - (char*)sm_raw), 16));  // [3*lp] g', d, rr
+  float* inv_g_old = reinterpret_cast<float*>(red + E3);       // [lp]  1/<r,u> of the previous pass
   float* inv_a_old = inv_g_old + lp;                           // [lp]  1/alpha of the previous pass
-  float* wpart = inv_a_old + lp;                               // [3][CR_WARPS][lp]  per-chunk partial dots
-  float* alpha = wpart + 3 * CR_WARPS * lp;              // [lp]
-  float* beta = alpha + lp;                              // [lp]
-  int* frozen = reinterpret_cast<int*>(beta + lp);       // [lp]
-  Ctrl* ctrl = reinterpret_cast<Ctrl*>(frozen + lp);     // 16 bytes
-  int* ccol = reinterpret_cast<int*>(ctrl) + 4;          // [csr_cap]
-  float* cval = reinterpret_cast<float*>(ccol + R.csr_cap);
+  float* alpha = inv_a_old + lp;                               // [lp]
+  float* beta = alpha + lp;                                    // [lp]
+  int* frozen = reinterpret_cast<int*>(beta + lp);             // [lp]
+  Ctrl* ctrl = reinterpret_cast<Ctrl*>(frozen + lp);           // 16 bytes
+  float* spart = reinterpret_cast<float*>(reinterpret_cast<int*>(ctrl) + 4);  // [seg_cap][lp] segment sums (16-byte aligned)
+  int* ecol = reinterpret_cast<int*>(spart + (size_t)R.seg_cap * lp);         // [seg_cap][CR_SEG] column (-1 = padding)
+  float* eval = reinterpret_cast<float*>(ecol + (size_t)R.seg_cap * CR_SEG);  // [seg_cap][CR_SEG]
 
-  const int nnz0 = (rows > 0) ? __ldg(P.ptr + row0) : 0;
-  const int nnz_mine = (rows > 0) ? __ldg(P.ptr + row0 + rows) - nnz0 : 0;
-  const bool cached = nnz_mine <= R.csr_cap;
-  const int* col = cached ? ccol : P.col + nnz0;
-  const float* val = cached ? cval : P.val + nnz0;
-
+  // ---- segments: row i owns ceil(deg_i / CR_SEG) of them, numbered consecutively ----
+  if (warp == 0) {
+    const int per = (rows + 31) >> 5;
+    const int lo = min(rows, lane * per), hi = min(rows, lo + per);
+    int sum = 0;
 #pragma unroll 1
-  for (int i = tid; i <= rows; i += CR_THREADS) lptr[i] = __ldg(P.ptr + row0 + i) - nnz0;
+    for (int i = lo; i < hi; ++i) sum += (__ldg(P.ptr + row0 + i + 1) - __ldg(P.ptr + row0 + i) + CR_SEG - 1) / CR_SEG;
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int run = incl - sum;
+#pragma unroll 1
+    for (int i = lo; i < hi; ++i) {
+      rseg[i] = run;
+      run += (__ldg(P.ptr + row0 + i + 1) - __ldg(P.ptr + row0 + i) + CR_SEG - 1) / CR_SEG;
+    }
+    if (lane == 31) rseg[rows] = incl;
+  }
 #pragma unroll 1
   for (int i = tid; i < rows; i += CR_THREADS) {
     const float d = __ldg(P.diag + row0 + i);
     dg[i] = d;
     dinv[i] = 1.f / d;
   }
-  if (cached)
-#pragma unroll 1
-    for (int e = tid; e < nnz_mine; e += CR_THREADS) {
-      ccol[e] = __ldg(P.col + nnz0 + e);
-      cval[e] = __ldg(P.val + nnz0 + e);
-    }
 #pragma unroll 1
   for (int c = tid; c < lp; c += CR_THREADS) {
     inv_g_old[c] = 1.f;
     inv_a_old[c] = 1.f;
     frozen[c] = 0;
   }
-  __syncthreads();
-  // x = 0, r = b, p = s = 0; publish u0 = r/diag
-  const int items = rows * Q;
 #pragma unroll 1
-  for (int it = tid; it < items; it += CR_THREADS) {
-    const int i = it / Q, q = it - i * Q;
+  for (int c = tid; c < E3; c += CR_THREADS) red[c] = 0.0;  // padded class columns stay zero
+  __syncthreads();
+  const int nseg = rseg[rows];
+  const bool fits = nseg <= R.seg_cap;  // otherwise (huge row blocks) the SpMV walks the CSR in global memory row by row
+  if (fits) {
+#pragma unroll 1
+    for (int i = warp; i < rows; i += CR_WARPS) {
+      const int e0 = __ldg(P.ptr + row0 + i), deg = __ldg(P.ptr + row0 + i + 1) - e0;
+      const int s0 = rseg[i] * CR_SEG, npad = (rseg[i + 1] - rseg[i]) * CR_SEG;
+#pragma unroll 1
+      for (int e = lane; e < npad; e += 32) {
+        ecol[s0 + e] = (e < deg) ? __ldg(P.col + e0 + e) : -1;
+        eval[s0 + e] = (e < deg) ? __ldg(P.val + e0 + e) : 0.f;
+      }
+    }
+  }
+  // Thread t works on class quad q = t mod Q of rows (or segments) t / Q, t / Q + istep, ...: the first Q * istep threads
+  // are active and nothing inside the iteration divides by Q.
+  const int istep = CR_THREADS / Q, q = tid % Q, i_first = (tid < istep * Q) ? tid / Q : (1 << 30);
+  // x = 0, r = b, p = s = 0; publish u0 = r/diag
+#pragma unroll 1
+  for (int i = i_first; i < rows; i += istep) {
     const size_t o = (size_t)i * lp + 4 * q;
     const float4 bq = __ldg(reinterpret_cast<const float4*>(P.rhs + (size_t)(row0 + i) * lp + 4 * q));
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -182,58 +235,66 @@ __global__ void __launch_bounds__(CR_THREADS, 1) cg_resident_kernel(CrParams R) 
     *reinterpret_cast<float4*>(rs + o) = bq;
     *reinterpret_cast<float4*>(ps + o) = z;
     *reinterpret_cast<float4*>(ss + o) = z;
-    if (!SINGLE) *reinterpret_cast<float4*>(R.ubuf + (size_t)(row0 + i) * lp + 4 * q) = scale4(bq, dinv[i]);
+    if (SINGLE)
+      *reinterpret_cast<float4*>(us + o) = scale4(bq, dinv[i]);
+    else
+      *reinterpret_cast<float4*>(R.ubuf + (size_t)(row0 + i) * R.ustride + 4 * q) = scale4(bq, dinv[i]);
   }
 
-  double tol2 = 0.0;  // squared absolute tolerance; meaningful in warp 0 only
   int iter = 0;
+  unsigned nbar = 0;
+  const float* ub = SINGLE ? us : R.ubuf;
+  const int ust = SINGLE ? lp : R.ustride;
+  const int jobs = 3 * P.l;  // (product, class column) pairs: <r,u>, <w,u>, <r,r>
 
+  // The loop body is kept SMALL on purpose (~1 k instructions): the SM's instruction cache holds ~32 KB, a body that
+  // does not fit is re-fetched from L2 every pass, and a phase executed by a single warp then pays the full fetch latency
+  // per 128-byte line (measured: a 120-instruction scalar section took 3.9 us, profiles/r02_cg_trace.md).  Hence: no
+  // single-warp phase, loops with warp-uniform trip counts (no divergent-shuffle slow paths), rare paths out of line.
   while (true) {
-    // ================= E1: u of this pass is visible everywhere =================
-    const unsigned epoch = (unsigned)iter + 1u;
-    __syncthreads();
-    cr_stamp(R, iter, 0);
-    if (!SINGLE) {
-      // Mailboxes: CTA b tells every CTA d "my u is published" by writing flags[d][b]; each CTA polls only its own row
-      // of the table, so no line is spun on by more than one SM (148 SMs spinning on shared lines delay the very
-      // stores they wait for by microseconds).
-      if (warp == 0) {
-        __threadfence();  // the CTA's u stores (ordered before this warp by the barrier) become visible first
-#pragma unroll
-        for (int k = 0; k < CR_POLL; ++k)
-          if (lane + 32 * k < G) st_relaxed_u32(R.flags + (size_t)(lane + 32 * k) * G + b, epoch);
-      }
-      if (warp == 1) {  // all sources polled concurrently with relaxed loads; ONE acquire fence at the end
-        const unsigned* mine = R.flags + (size_t)b * G;
-        bool done[CR_POLL];
-#pragma unroll
-        for (int k = 0; k < CR_POLL; ++k) done[k] = lane + 32 * k >= G;
-        bool all;
-        do {
-          all = true;
-#pragma unroll
-          for (int k = 0; k < CR_POLL; ++k)
-            if (!done[k]) {
-              done[k] = ld_relaxed_u32(mine + lane + 32 * k) >= epoch;
-              all &= done[k];
-            }
-        } while (!all);
-        __threadfence();
-      }
-      __syncthreads();
-    }
-    cr_stamp(R, iter, 1);
-    // ================= w = A u for my rows =================
+    // ================= (B) u of this pass is visible everywhere =================
+    if (TRACE) cr_stamp(R, iter, 0);
     if (SINGLE) {
-      // every referenced row is local: gather straight from shared memory, one thread per (row, class quad)
+      __syncthreads();
+    } else {
+      nbar += (unsigned)G;
+      grid_barrier(R.counter, nbar);
+    }
+    if (TRACE) cr_stamp(R, iter, 1);
+    // ================= w = A u for my rows =================
+    if (fits) {
 #pragma unroll 1
-      for (int it = tid; it < items; it += CR_THREADS) {
-        const int i = it / Q, q = it - i * Q;
+      for (int sg = i_first; sg < nseg; sg += istep) {
+        const int2* cp = reinterpret_cast<const int2*>(ecol + (size_t)sg * CR_SEG);   // CR_SEG is even: 8-byte aligned
+        const float2* vp = reinterpret_cast<const float2*>(eval + (size_t)sg * CR_SEG);
+        float4 u[CR_SEG];
+#pragma unroll
+        for (int e = 0; e < CR_SEG; e += 2) {
+          const int2 cj = cp[e >> 1];
+          u[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+          u[e + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cj.x >= 0) u[e] = SINGLE ? *reinterpret_cast<const float4*>(ub + (size_t)cj.x * ust + 4 * q) : ldcg4(ub + (size_t)cj.x * ust + 4 * q);
+          if (cj.y >= 0) u[e + 1] = SINGLE ? *reinterpret_cast<const float4*>(ub + (size_t)cj.y * ust + 4 * q) : ldcg4(ub + (size_t)cj.y * ust + 4 * q);
+        }
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < CR_SEG; e += 2) {  // the edge values are only read now, behind the gathers (registers)
+          const float2 vj = vp[e >> 1];
+          fma4(a, vj.x, u[e]);
+          fma4(a, vj.y, u[e + 1]);
+        }
+        *reinterpret_cast<float4*>(spart + (size_t)sg * lp + 4 * q) = a;
+      }
+      if (TRACE) cr_stamp(R, iter, 2);
+      __syncthreads();
+      if (TRACE) cr_stamp(R, iter, 3);
+#pragma unroll 1
+      for (int i = i_first; i < rows; i += istep) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-        for (int e = lptr[i]; e < lptr[i + 1]; ++e) {
-          const int j = col[e];
-          fma4(a, val[e] * dinv[j], *reinterpret_cast<const float4*>(rs + (size_t)j * lp + 4 * q));
+        for (int sg = rseg[i]; sg < rseg[i + 1]; ++sg) {
+          const float4 sp = *reinterpret_cast<const float4*>(spart + (size_t)sg * lp + 4 * q);
+          a.x += sp.x; a.y += sp.y; a.z += sp.z; a.w += sp.w;
         }
         const size_t o = (size_t)i * lp + 4 * q;
         const float4 u4 = scale4(*reinterpret_cast<const float4*>(rs + o), dinv[i]);
@@ -241,232 +302,107 @@ __global__ void __launch_bounds__(CR_THREADS, 1) cg_resident_kernel(CrParams R) 
         *reinterpret_cast<float4*>(ws + o) = make_float4(fmaf(dgi, u4.x, -a.x), fmaf(dgi, u4.y, -a.y), fmaf(dgi, u4.z, -a.z), fmaf(dgi, u4.w, -a.w));
       }
     } else {
-      // warp per row, lane = (neighbour slot, class quad); CR_ROWS_ILP rows x 2 slots per lane = 8 independent
-      // 128-bit L2 gathers in flight before the first use
-      const float* ub = R.ubuf + (size_t)(iter & 1) * P.m * lp;
-#pragma unroll 1
-      for (int ibase = warp; ibase < rows; ibase += CR_WARPS * CR_ROWS_ILP) {
-        float4 a[CR_ROWS_ILP];
-        int e[CR_ROWS_ILP], e_end[CR_ROWS_ILP];
-        bool more = false;
-#pragma unroll
-        for (int t = 0; t < CR_ROWS_ILP; ++t) {
-          const int i = ibase + t * CR_WARPS;
-          a[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-          const bool ok = lane_on && i < rows;
-          e[t] = ok ? lptr[i] + s_idx : 0;
-          e_end[t] = ok ? lptr[i + 1] : 0;
-          more |= e[t] < e_end[t];
-        }
-#pragma unroll 1
-        while (more) {
-          float4 u0[CR_ROWS_ILP], u1[CR_ROWS_ILP];
-          float w0[CR_ROWS_ILP], w1[CR_ROWS_ILP];
-#pragma unroll
-          for (int t = 0; t < CR_ROWS_ILP; ++t) {
-            const bool v0 = e[t] < e_end[t], v1 = e[t] + S < e_end[t];
-            w0[t] = v0 ? val[e[t]] : 0.f;
-            w1[t] = v1 ? val[e[t] + S] : 0.f;
-            const int j0 = v0 ? col[e[t]] : row0, j1 = v1 ? col[e[t] + S] : row0;  // row0: a harmless valid address
-            u0[t] = ldcg4(ub + (size_t)j0 * lp + 4 * q_ld);
-            u1[t] = ldcg4(ub + (size_t)j1 * lp + 4 * q_ld);
-          }
-          more = false;
-#pragma unroll
-          for (int t = 0; t < CR_ROWS_ILP; ++t) {
-            fma4(a[t], w0[t], u0[t]);
-            fma4(a[t], w1[t], u1[t]);
-            e[t] += 2 * S;
-            more |= e[t] < e_end[t];
-          }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < CR_ROWS_ILP; ++t) {
-          const int i = ibase + t * CR_WARPS;
-          const float4 at = reduce_slots(a[t], S);
-          if (i < rows && lane_on && s_idx == 0) {
-            const size_t o = (size_t)i * lp + 4 * q_idx;
-            const float4 u4 = scale4(*reinterpret_cast<const float4*>(rs + o), dinv[i]);
-            const float dgi = dg[i];
-            *reinterpret_cast<float4*>(ws + o) = make_float4(fmaf(dgi, u4.x, -at.x), fmaf(dgi, u4.y, -at.y), fmaf(dgi, u4.z, -at.z), fmaf(dgi, u4.w, -at.w));
-          }
-        }
-      }
+      spmv_rows_from_global<SINGLE>(P, row0, rows, ub, ust, rs, ws, dg, dinv);
     }
+    if (TRACE) cr_stamp(R, iter, 4);
     __syncthreads();
-    cr_stamp(R, iter, 2);
-    // ================= partial <r,u>, <w,u>, <r,r>: one warp per (row chunk, class quad), fixed summation order ======
+    if (TRACE) cr_stamp(R, iter, 5);
+    // ================= partial <r,u>, <w,u>, <r,r>: one warp per (product, class column), one butterfly each =========
 #pragma unroll 1
-    for (int job = warp; job < NCH * Q; job += CR_WARPS) {
-      const int ch = job / Q, q = job - ch * Q;
-      const int i_lo = (int)((long long)rows * ch / NCH), i_hi = (int)((long long)rows * (ch + 1) / NCH);
-      float4 d_ru = make_float4(0.f, 0.f, 0.f, 0.f), d_wu = d_ru, d_rr = d_ru;
+    for (int job = warp; job < jobs; job += CR_WARPS) {
+      const int v = (job >= 2 * P.l) ? 2 : (job >= P.l ? 1 : 0), cc = job - v * P.l;
+      const float* av = (v == 1) ? ws : rs;
+      double t = 0.0;
 #pragma unroll 1
-      for (int i = i_lo + lane; i < i_hi; i += 32) {
-        const size_t o = (size_t)i * lp + 4 * q;
-        const float4 r4 = *reinterpret_cast<const float4*>(rs + o), w4 = *reinterpret_cast<const float4*>(ws + o);
-        const float4 u4 = scale4(r4, dinv[i]);
-        dot4(d_ru, r4, u4);
-        dot4(d_wu, w4, u4);
-        dot4(d_rr, r4, r4);
+      for (int i0 = 0; i0 < rows; i0 += 32) {  // warp-uniform trip count
+        const int i = i0 + lane;
+        if (i < rows) {
+          const float r = rs[(size_t)i * lp + cc];
+          t += (double)av[(size_t)i * lp + cc] * (double)((v == 2) ? r : r * dinv[i]);
+        }
       }
-      d_ru = warp_sum4(d_ru);
-      d_wu = warp_sum4(d_wu);
-      d_rr = warp_sum4(d_rr);
+      t = warp_sum(t);  // xor butterfly: fixed order
       if (lane == 0) {
-        *reinterpret_cast<float4*>(wpart + ((size_t)0 * CR_WARPS + ch) * lp + 4 * q) = d_ru;
-        *reinterpret_cast<float4*>(wpart + ((size_t)1 * CR_WARPS + ch) * lp + 4 * q) = d_wu;
-        *reinterpret_cast<float4*>(wpart + ((size_t)2 * CR_WARPS + ch) * lp + 4 * q) = d_rr;
+        if (SINGLE)
+          red[v * lp + cc] = t;
+        else
+          R.part[(size_t)(v * lp + cc) * G + b] = t;  // column-major: the readers' loads are coalesced
       }
     }
-    __syncthreads();
-    cr_stamp(R, iter, 3);
-    // ================= E2: dot products over all CTAs =================
-    if (tid < lp) {  // thread cc sums the chunk partials of its class column for the three dot products
-      const int cc = tid;
+    if (TRACE) cr_stamp(R, iter, 6);
+    // ================= (A) dot products over all CTAs =================
+    if (SINGLE) {
+      __syncthreads();
+    } else {
+      nbar += (unsigned)G;
+      grid_barrier(R.counter, nbar);
+      if (TRACE) cr_stamp(R, iter, 7);
+      // every CTA adds the G partials of every column itself, in the same order: one warp per column, all loads of a lane
+      // in flight at once, one butterfly
 #pragma unroll 1
-      for (int v = 0; v < 3; ++v) {
-        double t = 0.0;
-#pragma unroll 1
-        for (int ch = 0; ch < NCH; ++ch) t += (double)wpart[((size_t)v * CR_WARPS + ch) * lp + cc];
-        if (SINGLE || cc >= P.l) {
-          red[v * lp + cc] = (cc < P.l) ? t : 0.0;
-        } else {
-          const unsigned long long word = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint((float)t);
-          st_relaxed_u64(R.words + (size_t)(v * lp + cc) * G + b, word);
-        }
-      }
-    }
-    if (!SINGLE) {
-      // Padded class columns are identically zero: only the 3*l real columns travel.  Column cr is summed by ONE owner
-      // CTA (cr mod G), which publishes {sum, epoch}; everybody else polls just those 3*l result words.  (All CTAs
-      // polling all G partials of every column is an L2 hot spot: G*G*3l reads of a few hundred lines per round.)
-      const int ncols = 3 * P.l;
-#pragma unroll 1
-      for (int k = warp; b + k * G < ncols; k += CR_WARPS) {
-        const int cr = b + k * G;
-        const int v_of = (cr >= 2 * P.l) ? 2 : (cr >= P.l ? 1 : 0);
-        const int c = v_of * lp + (cr - v_of * P.l);
-        const unsigned long long* wbase = R.words + (size_t)c * G;
-        unsigned long long word[CR_POLL];
-        bool done[CR_POLL];
-#pragma unroll
-        for (int kk = 0; kk < CR_POLL; ++kk) {
-          done[kk] = lane + 32 * kk >= G;
-          word[kk] = 0ull;
-        }
-        bool all;
-        do {  // all CTAs' words polled concurrently; the value arrives with its epoch tag
-          all = true;
-#pragma unroll
-          for (int kk = 0; kk < CR_POLL; ++kk)
-            if (!done[kk]) {
-              word[kk] = ld_relaxed_u64(wbase + lane + 32 * kk);
-              done[kk] = (unsigned)(word[kk] >> 32) == epoch;
-              all &= done[kk];
-            }
-        } while (!all);
+      for (int job = warp; job < jobs; job += CR_WARPS) {
+        const int v = (job >= 2 * P.l) ? 2 : (job >= P.l ? 1 : 0), e = v * lp + (job - v * P.l);
+        const double* src = R.part + (size_t)e * G;
         double t = 0.0;
 #pragma unroll
-        for (int kk = 0; kk < CR_POLL; ++kk)
-          if (lane + 32 * kk < G) t += (double)__uint_as_float((unsigned)word[kk]);
-        t = warp_sum(t);  // xor butterfly: fixed order
-        const unsigned long long out = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint((float)t);
-#pragma unroll
-        for (int kk = 0; kk < CR_POLL; ++kk)  // one private copy per CTA: results[d][cr]
-          if (lane + 32 * kk < G) st_relaxed_u64(R.results + (size_t)(lane + 32 * kk) * ncols + cr, out);
+        for (int k = 0; k < CR_MAX_GRID / 32; ++k)
+          if (lane + 32 * k < G) t += __ldcg(src + lane + 32 * k);
+        t = warp_sum(t);
+        if (lane == 0) red[e] = t;
       }
-      if (warp == CR_WARPS - 1) {
-        const unsigned long long* mine = R.results + (size_t)b * ncols;
-#pragma unroll 1
-        for (int cr = lane; cr < ncols; cr += 32) {
-          unsigned long long word;
-          do {
-            word = ld_relaxed_u64(mine + cr);
-          } while ((unsigned)(word >> 32) != epoch);
-          const int v_of = (cr >= 2 * P.l) ? 2 : (cr >= P.l ? 1 : 0);
-          red[v_of * lp + (cr - v_of * P.l)] = (double)__uint_as_float((unsigned)word);
-        }
-        __syncwarp();
-        cr_stamp(R, iter, 4, (CR_WARPS - 1) * 32);
-      }
+      if (TRACE) cr_stamp(R, iter, 8);
+      __syncthreads();
     }
-    __syncthreads();
+    if (TRACE) cr_stamp(R, iter, 11);
 
-    // ================= scalars (warp 0; every CTA computes identical values from identical inputs) =================
-    if (warp == 0) {
-      if (iter == 0) {  // P.tol < 0: relative to the largest right-hand-side column norm (r = b at this point)
+    // ================= scalars: thread c owns class column c (every CTA computes identical values) =================
+    if (iter == 0) {  // P.tol < 0: relative to the largest right-hand-side column norm (r = b at this point)
+      if (tid == 0) {
         double mx = 0.0;
 #pragma unroll 1
-        for (int c = lane; c < lp; c += 32) mx = fmax(mx, red[2 * lp + c]);
-#pragma unroll 1
-        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
-        tol2 = (P.tol < 0.f) ? (double)P.tol * (double)P.tol * mx : (double)P.tol * (double)P.tol;
+        for (int c = 0; c < lp; ++c) mx = fmax(mx, red[2 * lp + c]);
+        ctrl->tol2 = (P.tol < 0.f) ? (double)P.tol * (double)P.tol * mx : (double)P.tol * (double)P.tol;
       }
-      double mx_all = 0.0, mx_live = 0.0;
-      int bad = 0;
-#pragma unroll 1
-      for (int c = lane; c < lp; c += 32) {
-        const double v = red[2 * lp + c];
-        bad |= (!(v == v) || v > 1.0e300) ? 1 : 0;
-        mx_all = fmax(mx_all, v);
-        if (!frozen[c]) mx_live = fmax(mx_live, v);  // columns that broke down are frozen for good
-      }
-#pragma unroll 1
-      for (int o = 16; o > 0; o >>= 1) {
-        mx_all = fmax(mx_all, __shfl_xor_sync(FULL, mx_all, o));
-        mx_live = fmax(mx_live, __shfl_xor_sync(FULL, mx_live, o));
-        bad |= __shfl_xor_sync(FULL, bad, o);
-      }
-      const bool stop = bad || mx_live <= tol2 || iter >= P.max_iter;
-      cr_stamp(R, iter, 6);
-      if (lane == 0) {
-        ctrl->stop = stop ? 1 : 0;
-        if (stop && b == 0) {
-          if (P.iters_out) *P.iters_out = iter;
-          if (P.resid_out) *P.resid_out = sqrtf((float)mx_all);
-          if (P.status_out) {
-            int st = 0;
-            if (bad) st |= GLL_STATUS_NONFINITE;
-            if (!bad && !(mx_all <= tol2)) st |= GLL_STATUS_CG_NOT_CONVERGED;
-            if (st) atomicOr(P.status_out, st);
-          }
-        }
-      }
-      if (!stop) {
-#pragma unroll 1
-        for (int c = lane; c < lp; c += 32) {
-          // quotients in fp32 (alpha and beta are fp32 anyway); the cancellation-prone difference in fp64
-          const double g_new = red[c], d_new = red[lp + c], rr = red[2 * lp + c];
-          float al = 0.f, be = 0.f;
-          if (!frozen[c] && rr > tol2) {
-            const float bb = (iter == 0) ? 0.f : (float)g_new * inv_g_old[c];
-            const double den = d_new - (double)bb * g_new * (double)inv_a_old[c];
-            if (den > 0.0 && g_new > 0.0) {
-              al = (float)g_new / (float)den;
-              be = bb;
-              inv_a_old[c] = 1.f / al;
-              inv_g_old[c] = 1.f / (float)g_new;
-            } else {
-              frozen[c] = 1;  // breakdown (rounding at the fp32 floor): stop moving this column
-            }
-          }
-          alpha[c] = al;
-          beta[c] = be;
-        }
-      }
-      cr_stamp(R, iter, 7);
+      __syncthreads();
     }
-    __syncthreads();
-    cr_stamp(R, iter, 5);
-    if (ctrl->stop) break;
+    int live = 0, bad = 0;
+    if (tid < lp) {
+      const int c = tid;
+      const double tol2 = ctrl->tol2;
+      // quotients in fp32 (alpha and beta are fp32 anyway); the cancellation-prone difference in fp64
+      const double g_new = red[c], d_new = red[lp + c], rr = red[2 * lp + c];
+      bad = (!(rr == rr) || rr > 1.0e300) ? 1 : 0;
+      float al = 0.f, be = 0.f;
+      if (!frozen[c] && rr > tol2) {  // columns that broke down are frozen for good
+        live = 1;
+        const float bb = (iter == 0) ? 0.f : (float)g_new * inv_g_old[c];
+        const double den = d_new - (double)bb * g_new * (double)inv_a_old[c];
+        if (den > 0.0 && g_new > 0.0) {
+          // approximate reciprocals (MUFU.RCP, deterministic): alpha and beta only have to be the SAME numbers in every
+          // CTA and in the x and r updates, their last bits do not matter to CG
+          const float rg = __fdividef(1.f, (float)g_new);
+          al = __fdividef((float)g_new, (float)den);
+          be = bb;
+          inv_a_old[c] = (float)den * rg;
+          inv_g_old[c] = rg;
+        } else {
+          frozen[c] = 1;  // breakdown (rounding at the fp32 floor): stop moving this column
+        }
+      }
+      alpha[c] = al;
+      beta[c] = be;
+    }
+    const int any_bad = __syncthreads_or(bad);
+    const int any_live = __syncthreads_or(live);
+    if (TRACE) cr_stamp(R, iter, 14);
+    if (any_bad || !any_live || iter >= P.max_iter) {
+      if (b == 0 && tid == 0) write_stats(P, red, lp, iter, any_bad, ctrl->tol2);
+      break;
+    }
     ++iter;
     // ================= vector updates (all on chip), publish the new u =================
-    float* unext = SINGLE ? nullptr : R.ubuf + (size_t)(iter & 1) * P.m * lp;
 #pragma unroll 1
-    for (int it = tid; it < items; it += CR_THREADS) {
-      const int i = it / Q, q = it - i * Q;
+    for (int i = i_first; i < rows; i += istep) {
       const size_t o = (size_t)i * lp + 4 * q;
       const float4 al = *reinterpret_cast<const float4*>(alpha + 4 * q);
       const float4 be = *reinterpret_cast<const float4*>(beta + 4 * q);
@@ -482,50 +418,62 @@ __global__ void __launch_bounds__(CR_THREADS, 1) cg_resident_kernel(CrParams R) 
       *reinterpret_cast<float4*>(rs + o) = r4;
       *reinterpret_cast<float4*>(ps + o) = p4;
       *reinterpret_cast<float4*>(ss + o) = s4;
-      if (!SINGLE) *reinterpret_cast<float4*>(unext + (size_t)(row0 + i) * lp + 4 * q) = scale4(r4, di);
+      if (SINGLE)
+        *reinterpret_cast<float4*>(us + o) = scale4(r4, di);
+      else
+        *reinterpret_cast<float4*>(R.ubuf + (size_t)(row0 + i) * R.ustride + 4 * q) = scale4(r4, di);
     }
+    if (TRACE) cr_stamp(R, iter - 1, 15);
   }
 
   // ---- write the answer ----
 #pragma unroll 1
-  for (int it = tid; it < items; it += CR_THREADS) {
-    const int i = it / Q, q = it - i * Q;
+  for (int i = i_first; i < rows; i += istep) {
     *reinterpret_cast<float4*>(P.x + (size_t)(row0 + i) * lp + 4 * q) = *reinterpret_cast<const float4*>(xs + (size_t)i * lp + 4 * q);
   }
 }
 
-size_t fixed_smem(int rows_cap, int lp) {
-  size_t b = sizeof(float) * (5 * (size_t)rows_cap * lp + 2 * (size_t)rows_cap) + sizeof(int) * ((size_t)rows_cap + 1);
+size_t fixed_smem(int rows_cap, int lp, bool single) {
+  const int E3 = 3 * lp;
+  size_t b = sizeof(float) * ((single ? 6 : 5) * (size_t)rows_cap * lp + 2 * (size_t)rows_cap) + sizeof(int) * ((size_t)rows_cap + 1);
   b = align_up(b, 16);
-  b += sizeof(double) * (3 * (size_t)lp) + sizeof(float) * (3 * (size_t)CR_WARPS * lp + 4 * lp) + sizeof(int) * lp + 16;
+  b += sizeof(double) * (size_t)E3 + sizeof(float) * (4 * (size_t)lp) + sizeof(int) * lp + 16;
   return align_up(b, 16);
 }
 
+int ustride_of(int lp) { return lp <= 4 ? 4 : (lp <= 8 ? 8 : (lp <= 16 ? 16 : lp)); }
+
 struct CrPlan {
-  int ok, grid, rows_cap, csr_cap;
+  int ok, grid, rows_cap, seg_cap;
   size_t smem;
 };
 
-CrPlan plan(int m, int lp) {
+CrPlan plan(int m, int lp, int seg) {
   CrPlan p;
   p.ok = 0;
   const int sms = device_info().sms;
+  const size_t per_seg = align_up(sizeof(int) * seg + sizeof(float) * seg + sizeof(float) * lp, 16);
   int grid;
-  if (fixed_smem(m, lp) + 8 * 1024 <= CR_SMEM_BUDGET * 3 / 4)
-    grid = 1;  // whole system in one SM: no grid-wide exchange at all
+  // whole system in one SM (no grid-wide exchange at all) when the vectors and ~5 segments per row fit
+  if (fixed_smem(m, lp, true) + per_seg * 5 * (size_t)m <= CR_SMEM_BUDGET * 3 / 4)
+    grid = 1;
   else
-    grid = max(2, min(sms, ceil_div(m, 96)));
+    grid = max(2, min(min(sms, CR_MAX_GRID), ceil_div(m, 96)));
+  if (const char* e = getenv("GLL_B200_CG_GRID")) {  // debug: sweep the number of CTAs
+    const int g = atoi(e);
+    if (g >= 2 && g <= min(sms, CR_MAX_GRID) && grid > 1) grid = g;
+  }
   int rows_cap = ceil_div(m, grid);
-  if (grid > 1 && fixed_smem(rows_cap, lp) + 4 * 1024 > CR_SMEM_BUDGET) {
-    grid = sms;
+  if (grid > 1 && fixed_smem(rows_cap, lp, false) + 4 * 1024 > CR_SMEM_BUDGET) {
+    grid = min(sms, CR_MAX_GRID);
     rows_cap = ceil_div(m, grid);
-    if (fixed_smem(rows_cap, lp) + 4 * 1024 > CR_SMEM_BUDGET) return p;  // does not fit on chip: streaming kernel
+    if (fixed_smem(rows_cap, lp, false) + 4 * 1024 > CR_SMEM_BUDGET) return p;  // does not fit on chip: streaming kernel
   }
   p.grid = grid;
   p.rows_cap = rows_cap;
-  const size_t fx = fixed_smem(rows_cap, lp);
-  p.csr_cap = (int)((CR_SMEM_BUDGET - fx) / 8);
-  p.smem = fx + (size_t)p.csr_cap * 8;
+  const size_t fx = fixed_smem(rows_cap, lp, grid == 1);
+  p.seg_cap = (int)((CR_SMEM_BUDGET - fx) / per_seg);
+  p.smem = fx + (size_t)p.seg_cap * per_seg;
   p.ok = 1;
   return p;
 }
@@ -538,41 +486,44 @@ void* cg_get_trace() { return g_cg_trace; }
 
 size_t cg_resident_ws_bytes(int m, int lp) {
   const size_t sms = (size_t)device_info().sms;
-  return align_up(sizeof(float) * 2 * (size_t)m * lp, 256) + align_up(sizeof(unsigned) * sms * sms, 256) +
-         align_up(sizeof(unsigned long long) * 3 * (size_t)lp * sms * 2, 256) + 256;
+  return align_up(sizeof(float) * (size_t)m * ustride_of(lp), 256) + align_up(sizeof(double) * 3 * (size_t)lp * sms, 256) + 256 + 256;
+}
+
+static int cg_seg() {
+  const char* e = getenv("GLL_B200_CG_SEG");  // debug: 8 or 10
+  return (e && atoi(e) == 8) ? 8 : CR_SEG_DEFAULT;
 }
 
 int cg_resident_try(const CgParams& P, void* scratch, cudaStream_t st) {
-  const CrPlan pl = plan(P.m, P.lp);
+  const int seg = cg_seg();
+  const CrPlan pl = plan(P.m, P.lp, seg);
   if (!pl.ok) return 0;
   CrParams R;
   R.cg = P;
   Carver cv(scratch, cg_resident_ws_bytes(P.m, P.lp));
-  R.ubuf = cv.take<float>(2 * (size_t)P.m * P.lp);
   const size_t sms = (size_t)device_info().sms;
-  R.flags = cv.take<unsigned>(sms * sms);
-  R.words = cv.take<unsigned long long>(3 * (size_t)P.lp * sms * 2);
-  R.results = R.words + 3 * (size_t)P.lp * sms;
+  R.ustride = ustride_of(P.lp);
+  R.ubuf = cv.take<float>((size_t)P.m * R.ustride);
+  R.part = cv.take<double>(3 * (size_t)P.lp * sms);
+  R.counter = cv.take<unsigned>(64);
   R.rows_cap = pl.rows_cap;
-  R.csr_cap = pl.csr_cap;
+  R.seg_cap = pl.seg_cap;
   R.trace = g_cg_trace;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GLL_CUDA_CHECK(cudaFuncSetAttribute(cg_resident_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CR_SMEM_BUDGET));
-    GLL_CUDA_CHECK(cudaFuncSetAttribute(cg_resident_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CR_SMEM_BUDGET));
-    attr_set = true;
-  }
+  const void* k_single = seg == 8 ? (const void*)cg_resident_kernel<true, 8, false> : (const void*)cg_resident_kernel<true, 10, false>;
+  const void* k_multi = seg == 8 ? (const void*)cg_resident_kernel<false, 8, false> : (const void*)cg_resident_kernel<false, 10, false>;
+  if (R.trace != nullptr) k_multi = (const void*)cg_resident_kernel<false, 10, true>;  // debug timeline (gll_debug_cg_trace)
+  GLL_CUDA_CHECK(set_max_dynamic_smem_once(k_single, (int)CR_SMEM_BUDGET));
+  GLL_CUDA_CHECK(set_max_dynamic_smem_once(k_multi, (int)CR_SMEM_BUDGET));
   void* args[] = {&R};
   if (pl.grid == 1) {
     GLL_PROF(KID_CG, st);
-    cg_resident_kernel<true><<<1, CR_THREADS, pl.smem, st>>>(R);
-    GLL_LAUNCH_CHECK();
+    GLL_CUDA_CHECK(cudaLaunchKernel(k_single, dim3(1), dim3(CR_THREADS), args, pl.smem, st));
   } else {
-    // flags and words live side by side: one memset clears the epochs of both exchanges
-    GLL_CUDA_CHECK(cudaMemsetAsync(R.flags, 0, (size_t)((char*)(R.results + 3 * (size_t)P.lp * sms) - (char*)R.flags), st));
+    // only the barrier counter needs a defined start value (the partials of padded class columns are never read)
+    GLL_CUDA_CHECK(cudaMemsetAsync(R.counter, 0, 64 * sizeof(unsigned), st));
     GLL_PROF(KID_CG, st);
-    // cooperative launch: all CTAs are co-resident, which the flag exchanges rely on
-    GLL_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)cg_resident_kernel<false>, dim3(pl.grid), dim3(CR_THREADS), args, pl.smem, st));
+    // cooperative launch: all CTAs are co-resident, which the grid barrier relies on
+    GLL_CUDA_CHECK(cudaLaunchCooperativeKernel(k_multi, dim3(pl.grid), dim3(CR_THREADS), args, pl.smem, st));
   }
   return 1;
 }

@@ -439,12 +439,7 @@ int cg_rows_spmv(const int* uu_ptr, const int* uu_col, const float* uu_val, cons
   GLL_REQUIRE(lp <= CG_MAX_LP, "at most 128 classes per solve");
   RowsState S = carve(ws, ws_bytes, row_hi - row_lo, lp);
   const size_t smem = sizeof(double) * RW_WARPS * 3 * (size_t)lp;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GLL_CUDA_CHECK(cudaFuncSetAttribute(rows_spmv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(sizeof(double) * RW_WARPS * 3 * CG_MAX_LP)));
-    attr_set = true;
-  }
+  GLL_CUDA_CHECK(set_max_dynamic_smem_once((const void*)rows_spmv_kernel, (int)(sizeof(double) * RW_WARPS * 3 * CG_MAX_LP)));
   GLL_PROF(KID_CG_ROWS, st);
   rows_spmv_kernel<<<S.grid, RW_THREADS, smem, st>>>(uu_ptr, uu_col, uu_val, diag, lp, row_lo, row_hi, u_full, S, sums,
                                                      make_peers(peers), epoch, ctrl);

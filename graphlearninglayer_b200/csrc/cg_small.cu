@@ -288,14 +288,10 @@ int cg_small_try(const CgParams& P, cudaStream_t st) {
   if (fixed + 4096 > CS_SMEM_BUDGET) return 0;
   const int csr_cap = (int)((CS_SMEM_BUDGET - fixed) / 8);
   const size_t smem = fixed + (size_t)csr_cap * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GLL_CUDA_CHECK(cudaFuncSetAttribute(cg_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM_BUDGET));
-    GLL_CUDA_CHECK(cudaFuncSetAttribute(cg_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM_BUDGET));
-    GLL_CUDA_CHECK(cudaFuncSetAttribute(cg_small_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM_BUDGET));
-    GLL_CUDA_CHECK(cudaFuncSetAttribute(cg_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM_BUDGET));
-    attr_set = true;
-  }
+  GLL_CUDA_CHECK(set_max_dynamic_smem_once((const void*)cg_small_kernel<1>, (int)CS_SMEM_BUDGET));
+  GLL_CUDA_CHECK(set_max_dynamic_smem_once((const void*)cg_small_kernel<2>, (int)CS_SMEM_BUDGET));
+  GLL_CUDA_CHECK(set_max_dynamic_smem_once((const void*)cg_small_kernel<3>, (int)CS_SMEM_BUDGET));
+  GLL_CUDA_CHECK(set_max_dynamic_smem_once((const void*)cg_small_kernel<4>, (int)CS_SMEM_BUDGET));
   unsigned long long* trace = (unsigned long long*)cg_get_trace();
   GLL_PROF(KID_CG, st);
   switch (nit) {

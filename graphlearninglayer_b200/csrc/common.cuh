@@ -62,6 +62,9 @@ struct DeviceInfo {
   int max_smem_optin;
 };
 const DeviceInfo& device_info();
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: opt in once per (kernel, device),
+// thread-safe (a process may drive several GPUs, e.g. the reference's nn.DataParallel, utils.py:547-548).
+cudaError_t set_max_dynamic_smem_once(const void* func, int bytes);
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

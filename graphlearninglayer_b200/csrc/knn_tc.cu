@@ -785,12 +785,8 @@ int knn_tc_candidates(const float* X, const float* sq, const float* rscale, cons
     const char* dbg = getenv("GLL_B200_KNN_DEBUG");
     P.debug = dbg ? atoi(dbg) : 0;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_gram_topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-    GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_gram_topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-    attr_set = true;
-  }
+  GLL_CUDA_CHECK(set_max_dynamic_smem_once((const void*)knn_gram_topk_tc_kernel<false>, (int)TC_SMEM_BYTES));
+  GLL_CUDA_CHECK(set_max_dynamic_smem_once((const void*)knn_gram_topk_tc_kernel<true>, (int)TC_SMEM_BYTES));
   {
     GLL_PROF(KID_GRAM_TOPK_TC, st);
     if (plan.rstep == 2) {

@@ -202,8 +202,6 @@ def test_knn_f16x2_full_size_matches_bf16x3(gll, monkeypatch):
     assert int(info0[_lib.INFO_KNN_FALLBACK_ROWS].item()) == 0 and int(info1[_lib.INFO_KNN_FALLBACK_ROWS].item()) == 0
 
 
-@pytest.mark.skipif(os.environ.get("GLL_B200_EXPERIMENTAL") != "1",
-                    reason="verification kernel written after the round's GPU budget was spent; run with GLL_B200_EXPERIMENTAL=1")
 @pytest.mark.parametrize("split", ["f16x2", "bf16x3"])
 @pytest.mark.parametrize("d", [512, 200])
 def test_tensor_core_accumulator_matches_split_model(gll, monkeypatch, split, d):
@@ -460,6 +458,23 @@ def test_layer_vs_oracle_mid_size(gll, eps, tau):
     f, loss_ref, gout, bw = O.fwd_bwd(X, Y, yq, tau, eps, solver="cg")
     pred, loss, dX = layer_fwd_bwd(pkg, X, Y, yq, tau, eps)
     assert O.max_rel(pred.cpu().numpy(), f.pred) < TOL
+    assert O.max_rel(dX.cpu().numpy(), bw.dX) < TOL
+
+
+@pytest.mark.parametrize("eps,tau", [("auto", 0.0), (1.0, 0.07)])
+def test_layer_vs_oracle_c4_full_size(gll, eps, tau):
+    """BASELINE.json configs[3] at its own size: 2048 labeled + 14336 unlabeled nodes, d = 512, 10 classes, both bandwidth
+    modes (the north star's parity target: pred and dL/dfeatures within 1e-5 relative of the reference path,
+    GLL.py:53,93,146-159; the oracle solves by fp64 CG to 1e-13 because SuperLU needs minutes at this size)."""
+    pkg, _lib = gll
+    X, Y, _, yq = O.synth_inputs(2000, 2048, 14336, 512, 10, 4.5)
+    f, loss_ref, gout, bw = O.fwd_bwd(X, Y, yq, tau, eps, solver="cg")
+    pred, loss, dX = layer_fwd_bwd(pkg, X, Y, yq, tau, eps)
+    info = pkg.last_info()
+    assert info["status"] == 0 and info["knn_fallback_rows"] == 0, info
+    assert info["nnz"] == f.graph.W.nnz                      # same union graph as the oracle's exact search
+    assert O.max_rel(pred.cpu().numpy(), f.pred) < TOL
+    assert abs(loss.item() - loss_ref) < 1e-5 * max(1.0, abs(loss_ref))
     assert O.max_rel(dX.cpu().numpy(), bw.dX) < TOL
 
 
