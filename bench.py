@@ -1,23 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- GLL hot-path benchmark (BASELINE.json metric: GLL fwd+bwd calls/s, CG iterations/s vs HBM roofline).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5|c5s] [--impl b200|reference]
 
 One "step" = one call of the hot path on one synthetic graph:
     pred = LaplaceLearningSparseHard.apply(X, Y, tau, eps); loss = custom_ce_loss(pred, y); loss.backward()
-Workloads (BASELINE.json configs): c2 = 10000 base + 512 batch, d=512, eps='auto' (default: the
-config the metric is quoted on for one GPU); c3 = 4096 + 512; c4 = 2048 + 14336 (CG roofline study).
+Workloads (BASELINE.json configs): c1 = 1000 + 1000, d=128, eps=1 (the reference's CPU-runnable case);
+c2 = 10000 base + 512 batch, d=512, eps='auto' (default: the config the metric is quoted on for one GPU); c3 = 4096 + 512;
+c4 = 2048 + 14336 (CG roofline study); c5 / c5s = ONE graph of 2^20 / 2^17 nodes sharded over the ranks.
 N > 1: every rank runs its own independent graph of the same shape (different seed) -- the layer has no
 parameters, so there is no data-path collective (weak scaling).
 
 value  : calls/s with X, Y resident in HBM, timed per step with CUDA events on the launch stream, L2 flushed
          between steps, max over ranks.
 e2e    : the same call through the public autograd API starting from pinned HOST buffers: H2D of X and Y, the call,
-         D2H of pred and dX, all inside the timed region.
+         D2H of pred and dX, all inside the timed region, ONE CALL AT A TIME (what a training loop sees); the
+         double-buffered HostPipeline figure for independent calls is reported beside it (e2e.pipelined_value).
 roofline / kernels : a second pass of the same K steps with the library's per-kernel CUDA-event brackets on
-         (gll_profile_enable), so the timed `value` pass carries no instrumentation.
+         (gll_profile_enable), so the timed `value` pass carries no instrumentation.  roofline.cg_c4_* (N = 1): the
+         north star's own figure -- CG iterations/s and algorithmic GB/s of the on-chip CG at n = 16384.
+config.c5_* / config.c5s_* : the sharded 1M-node graph (BASELINE.json configs[4]) timed at this N (strong scaling: the same
+         graph at every N) and, at N > 1, the parity of the sharded path against the unsharded layer on real ranks.
 cpu_baseline : the fp64 numpy/scipy oracle (a port of the reference's GLL.py, see oracle/gll_oracle.py) on this
-         box's host cores, rank 0 at N=1 only, bounded sample.
+         box's host cores, rank 0 at N=1 only, bounded sample; plus the reference's own stable_conjgrad semantics
+         (GLL.py:247-276, alias included) timed on the C4 system: cpu_baseline.cg_iters_per_sec.
 --impl reference : only the oracle port, all host threads, same JSON line with "impl": "reference".
 """
 import argparse
@@ -36,6 +42,7 @@ import numpy as np  # noqa: E402
 
 # name: (k_lab, m, d, l, sigma, tau, eps)
 WORKLOADS = {
+    "c1": (1000, 1000, 128, 10, 3.0, 0.0, 1.0),          # BASELINE.json configs[0]: the reference's CPU-runnable case
     "c2": (10000, 512, 512, 10, 4.5, 0.0, "auto"),
     "c3": (4096, 512, 512, 10, 4.5, 0.0, "auto"),
     "c4": (2048, 14336, 512, 10, 4.5, 0.0, "auto"),
@@ -44,6 +51,7 @@ WORKLOADS = {
 }
 SHARDED = ("c5", "c5s")
 WORKLOAD_DESC = {
+    "c1": "LaplaceLearningSparseHard fwd+bwd, 1000 base + 1000 batch, d=128, l=10, eps=1, tau=0, k=25",
     "c2": "GLL classifier head, 10000 base + 512 batch, d=512, l=10, eps='auto', tau=0, k=25",
     "c3": "data-parallel GLL step, 4096 base + 512 batch per rank, d=512, l=10, eps='auto', tau=0, k=25",
     "c4": "large single graph, 2048 base + 14336 unlabeled, d=512, l=10, eps='auto', tau=0, k=25, CG tol 1e-7",
@@ -115,6 +123,24 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path (checker code; never on the GPU product path)
 # ----------------------------------------------------------------------------------------------------------------
+def pin_host_threads():
+    """All host cores for the CPU arm, the same at every N (torchrun exports OMP_NUM_THREADS=1 to its children)."""
+    n = os.cpu_count() or 1
+    try:
+        import torch
+
+        torch.set_num_threads(n)
+    except Exception:
+        pass
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return host_threads()
+
+
 def cpu_calls(workload, seed, n_calls, budget_s):
     from oracle import gll_oracle as O
 
@@ -131,6 +157,21 @@ def cpu_calls(workload, seed, n_calls, budget_s):
     return times
 
 
+def cpu_cg_iters_per_sec(budget_s=20.0):
+    """The reference's own CG (stable_conjgrad, GLL.py:247-276, with its `p = r` alias) on the C4 system L_uu u = B:
+    matvecs per second on the host (SURVEY 8d last row).  Returns (iters/s, matvecs, seconds) or None."""
+    from oracle import gll_oracle as O
+
+    k_lab, m, d, l, sigma, tau, eps = WORKLOADS["c4"]
+    X, Y, _, _ = O.synth_inputs(2000, k_lab, m, d, l, sigma)
+    g = O.build_graph(X, 25, eps)
+    Luu, B, _ = O.laplace_system(g.W, Y, tau)
+    t0 = time.perf_counter()
+    _, its = O.reference_semantics_cg(Luu, B, tol=1e-6, max_iter=2000)  # BASELINE configs[3]: CG to 1e-6 residual
+    dt = time.perf_counter() - t0
+    return its / dt, its, dt
+
+
 def host_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -140,24 +181,43 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+CONFIG_KEYS = ("workload", "l2", "parallelism", "cg_tol", "loss", "what", "c4_calls_per_sec", "c4_ms_per_call",
+               "c5_ms_per_call", "c5_nodes", "c5_cg_partition", "c5_knn_ms", "c5_cg_solve_ms_fwd", "c5_cg_solve_ms_bwd",
+               "c5s_ms_per_call_columns", "c5s_ms_per_call_rows_p2p", "c5s_parity_pred_vs_unsharded",
+               "c5s_parity_dx_vs_unsharded", "c5s_parity_rows_p2p_pred", "c5s_parity_rows_p2p_dx")
+
+
+def make_config(**kw):
+    """Both arms print the same key set (flat scalars: the driver keeps those)."""
+    cfg = {k: None for k in CONFIG_KEYS}
+    cfg.update(kw)
+    return cfg
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    # warm-up calls are run but bounded to one when a call takes seconds
-    warm = cpu_calls(args.workload, 1000, min(args.warmup, 1), 60.0)
+    cores = pin_host_threads()
+    warm = cpu_calls(args.workload, 1000, args.warmup, 120.0)  # honours --warmup (bounded to two minutes)
     times = cpu_calls(args.workload, 1000, args.steps, 1e9)
     total = float(np.sum(times))
     val = len(times) / total
-    cores = host_threads()
+    cb = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+          "sample": f"{len(times)} full fwd+bwd calls of the workload"}
+    if args.workload == "c4" or args.cpu_cg:
+        r = cpu_cg_iters_per_sec()
+        cb.update({"cg_iters_per_sec": r[0], "cg_matvecs": r[1], "cg_seconds": r[2],
+                   "cg_what": "stable_conjgrad semantics (GLL.py:247-276, p = r alias included) on the C4 L_uu, tol 1e-6"})
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": len(warm), "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic gaussian clusters (graphlearninglayer_b200.synth), L2-normalised",
-        "config": {"workload": args.workload + ": " + WORKLOAD_DESC[args.workload],
-                   "what": "oracle port of /root/reference GLL.py (exact kNN instead of annoy, scipy sparse, SuperLU/CG), "
-                           "one process on the host cores; the Python reference itself cannot travel to the GPU box"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{len(times)} full fwd+bwd calls of the workload"},
+        "config": make_config(workload=args.workload + ": " + WORKLOAD_DESC[args.workload],
+                              l2="n/a (host arm)", parallelism="one process, all host threads", cg_tol=1e-13,
+                              loss="custom_ce_loss formula in numpy (losses.py:128-136)",
+                              what="oracle port of /root/reference GLL.py (exact kNN instead of annoy, scipy sparse, SuperLU/CG), "
+                                   "one process on the host cores; the Python reference itself cannot travel to the GPU box"),
+        "cpu_baseline": cb,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -366,6 +426,7 @@ def run_b200(args, rank, world, local_rank):
     _lib.lib.gll_profile_enable(0)
 
     extra = {}
+    c4 = None
     if rank == 0 and world == 1 and args.workload not in ("c4",) + SHARDED and not args.no_large_graph:
         # the CG roofline study (BASELINE.json configs[3]); reported beside the headline, not instead of it
         r4, _, shp4, _, _, _, _ = step_fn("c4", 2000)
@@ -379,7 +440,15 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.synchronize()
         prof4 = _lib.profile_collect()
         _lib.lib.gll_profile_enable(0)
-        extra["large_graph_c4"] = large_graph_report(prof4, shp4, info4, ms4 / 5)
+        c4 = large_graph_report(prof4, shp4, info4, ms4 / 5)
+        extra["large_graph_c4"] = c4
+        del r4
+        torch.cuda.empty_cache()
+
+    # ---- the sharded 1M-node graph (BASELINE.json configs[4]) at this N: strong scaling, plus parity on real ranks ----
+    shard_cfg = {}
+    if not sharded and not args.no_sharded:
+        shard_cfg = sharded_lines(args, rank, world, dev, dist)
 
     if rank == 0:
         peaks = load_peaks()
@@ -410,52 +479,66 @@ def run_b200(args, rank, world, local_rank):
             traffic = json.load(open(tpath)).get(args.workload, {}).get(top)
         roofline = {"kernel": top, "bound": bound, "achieved": ach, "peak": peak, "unit": u,
                     "frac": (ach / peak if ach else None), "traffic": traffic, "peak_source": peak_source,
-                    "algorithmic_work_per_launch": work, "work_unit": unit, "launch_ms": t_s * 1e3}
+                    "algorithmic_work_per_launch": work, "work_unit": unit, "launch_ms": t_s * 1e3,
+                    "share_of_step": (prof[top][0] / args.steps) / step_kernel_ms}
         if bound == "tensor" and top == "knn_gram_topk_tcgen05":
-            # the Gram entry is accumulated from split operands: (hi + lo).hi in fp16 = 2 MMA passes (default), or
-            # hi.hi + lo.hi + hi.lo in bf16 = 3 passes (GLL_B200_KNN_SPLIT=bf16x3); `achieved` counts 2 n^2 d once
-            passes = 3 if os.environ.get("GLL_B200_KNN_SPLIT") == "bf16x3" else 2
-            roofline.update({"mma_passes": passes, "issued": ach * passes, "issued_frac": ach * passes / peak})
+            # the Gram entry is accumulated from split operands: (hi + lo).hi in fp16 = 2 MMA passes; `achieved` counts
+            # 2 n^2 d once
+            roofline.update({"mma_passes": 2, "issued": ach * 2, "issued_frac": ach * 2 / peak})
+        if c4 is not None and "cg" in c4:
+            # the north star's own figure, flat so that the driver's record keeps it: the on-chip CG at n = 16384
+            cg = c4["cg"]
+            roofline.update({"cg_c4_us_per_iter": cg["us_per_iter"], "cg_c4_iters_per_sec": cg["iters_per_sec"],
+                             "cg_c4_bytes_per_iter": cg["bytes_per_iter"], "cg_c4_achieved_gbs": cg["achieved_gbs"],
+                             "cg_c4_frac_of_hbm_peak": cg["frac"], "cg_c4_ms_per_solve": cg["ms_per_solve"],
+                             "cg_c4_iters_fwd": c4["graph"]["cg_iters_fwd"], "cg_c4_iters_bwd": c4["graph"]["cg_iters_bwd"],
+                             "cg_c4_note": "working set (4 MB CSR + vectors) is on chip: an iteration is two grid barriers + one "
+                                           "L1TEX-bound gather, not HBM traffic; see profiles/r02_cg_trace.md"})
         cpu = None
         if world == 1 and not args.no_cpu_baseline and not sharded:
+            cores = pin_host_threads()
             times = cpu_calls(args.workload, 1000, 4, 25.0)
-            cpu = {"value": len(times) / float(np.sum(times)), "unit": UNIT, "cores": host_threads(), "kind": "port",
+            cpu = {"value": len(times) / float(np.sum(times)), "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{len(times)} full fwd+bwd calls of the same workload through oracle/gll_oracle.py (fp64)"}
+            r = cpu_cg_iters_per_sec()
+            cpu.update({"cg_iters_per_sec": r[0], "cg_matvecs": r[1], "cg_seconds": r[2],
+                        "cg_what": "stable_conjgrad semantics (GLL.py:247-276, p = r alias included) on the C4 L_uu, tol 1e-6"})
+        cfg = make_config(
+            workload=args.workload + ": " + WORKLOAD_DESC[args.workload],
+            l2="flushed between timed steps (256 MiB memset outside the event pairs)",
+            parallelism=(f"one graph over {world} rank(s): rows (kNN, backward) + "
+                         + ("class columns (CG, no per-iteration collective)" if args.cg_partition == "columns" else
+                            "rows (CG: NCCL all-gather of the iterate + all-reduce of the dot products per iteration)"
+                            if args.cg_partition == "rows" else
+                            "rows (CG: iterate and dot products exchanged INSIDE the kernels over NVLink peer memory)")
+                         if sharded else f"independent graphs x{world}"),
+            cg_tol=1e-7,
+            loss=("custom_ce_loss as one kernel (graphlearninglayer_b200.losses; formula of losses.py:128-136)"
+                  if args.loss == "fused" else "custom_ce_loss with the reference's PyTorch ops (losses.py:128-136)"),
+            what="libgll_b200.so (sm_100a kernels) through LaplaceLearningSparseHard.apply",
+            **shard_cfg)
+        if c4 is not None:
+            cfg.update(c4_calls_per_sec=c4["calls_per_sec"], c4_ms_per_call=c4["ms_per_call"])
         line = {
             "metric": METRIC, "value": jobs * 1e3 / per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per_step, "higher_is_better": True,
             "scaling": "strong" if sharded else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic gaussian clusters (graphlearninglayer_b200.synth), L2-normalised, one graph per rank",
-            "config": {"workload": args.workload + ": " + WORKLOAD_DESC[args.workload], "l2": "flushed between timed steps "
-                       "(256 MiB memset outside the event pairs)", "parallelism": (f"one graph over {world} rank(s): rows (kNN, backward) + "
-                                       + ("class columns (CG, no per-iteration collective)" if args.cg_partition == "columns" else
-                                          "rows (CG: NCCL all-gather of the iterate + all-reduce of the dot products per iteration)"
-                                          if args.cg_partition == "rows" else
-                                          "rows (CG: iterate and dot products exchanged INSIDE the kernels over NVLink peer memory)")
-                                       if sharded
-                                       else f"independent graphs x{world}"),
-                       "cg_tol": 1e-7,
-                       "loss": ("custom_ce_loss as one kernel (graphlearninglayer_b200.losses; formula of losses.py:128-136)"
-                                if args.loss == "fused" else "custom_ce_loss with the reference's PyTorch ops (losses.py:128-136)"),
-                       "graph": {"nnz": info["nnz"], "nnz_uu": info["nnz_uu"],
-                                                 "cg_iters_fwd": info["cg_iters_fwd"], "cg_iters_bwd": info["cg_iters_bwd"],
-                                                 "knn_fallback_rows": info["knn_fallback_rows"], "status": info["status"],
-                                                 **({"cg_solve_ms_fwd_bwd": info.get("cg_solve_ms")} if sharded else {})}},
-            # e2e: host buffers in, host buffers out, every copy inside the timed region.  Headline = the double-buffered
-            # pipeline (three streams; independent calls overlap their PCIe copies with the neighbours' kernels);
-            # "serial" = one call at a time, copies and kernels back to back on one stream.
-            "e2e": ({"value": jobs * 1e3 / (pipe_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                     "d2h_bytes_per_step": d2h, "ms_per_step": pipe_ms / args.steps,
-                     "mode": "HostPipeline depth 3: H2D(i+1) | kernels(i) | D2H(i-1) on three streams; L2 not flushed "
-                             "(inputs arrive by DMA every step, the in-flight steps touch ~290 MB > L2); bound by the "
-                             "43.5 MB per step crossing PCIe in both directions at once (~54 GB/s in total)",
-                     "serial": {"value": jobs * 1e3 / (e2e_ms / args.steps), "ms_per_step": e2e_ms / args.steps,
-                                "mode": "one call at a time on one stream, L2 flushed between steps"}}
-                    if pipe_ms is not None else
-                    {"value": jobs * 1e3 / (e2e_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps}),
+            "config": cfg,
+            # e2e: host buffers in, host buffers out, every copy inside the timed region, ONE CALL AT A TIME on one stream
+            # (a training loop's calls depend on each other).  pipelined_value: independent calls through HostPipeline
+            # (depth 3: H2D(i+1) | kernels(i) | D2H(i-1) on three streams).
+            "e2e": {"value": jobs * 1e3 / (e2e_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                    "mode": "serial: one call at a time on one stream (H2D, kernels, D2H back to back), L2 flushed between steps",
+                    **({"pipelined_value": jobs * 1e3 / (pipe_ms / args.steps), "pipelined_ms_per_step": pipe_ms / args.steps,
+                        "pipelined_mode": "HostPipeline depth 3, independent calls; bound by the PCIe copies in both directions"}
+                       if pipe_ms is not None else {})},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "fwd_bwd_split_ms": {"forward_and_loss": fwd_ms, "backward": bwd_ms},
+            "graph": {"nnz": info["nnz"], "nnz_uu": info["nnz_uu"], "cg_iters_fwd": info["cg_iters_fwd"],
+                      "cg_iters_bwd": info["cg_iters_bwd"], "knn_fallback_rows": info["knn_fallback_rows"], "status": info["status"],
+                      **({"cg_solve_ms_fwd_bwd": info.get("cg_solve_ms")} if sharded else {})},
             "kernels": kern,
             "cpu_baseline": cpu,
         }
@@ -463,6 +546,92 @@ def run_b200(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def sharded_lines(args, rank, world, dev, dist):
+    """ONE graph over all ranks (graphlearninglayer_b200.sharded): the 1M-node graph of BASELINE.json configs[4] timed at
+    this N with the current kernels (strong scaling: the same graph at every N; N = 1 is the reference point), and at
+    N > 1 the 131072-node graph run sharded on the REAL ranks -- class-column CG and the row-partitioned CG over NVLink peer
+    memory -- against the unsharded layer on rank 0.  Returns flat config entries (identical on every rank)."""
+    import torch
+
+    from graphlearninglayer_b200 import LaplaceLearningSparseHard, sharded as sh
+    from graphlearninglayer_b200.losses import custom_ce_loss
+    from graphlearninglayer_b200.synth import synth_inputs
+
+    out = {}
+
+    def run(shape, partition, calls, seed=1000):
+        k_lab, m, d, l, sigma, tau, eps = WORKLOADS[shape]
+        X, Y, _, yq = synth_inputs(seed, k_lab, m, d, l, sigma)  # the same graph on every rank
+        Xd = torch.as_tensor(X).to(dev).requires_grad_(True)
+        Yd = torch.as_tensor(Y).to(dev)
+        yq_d = torch.as_tensor(yq).to(dev)
+        del X
+
+        def call(layer):
+            Xd.grad = None
+            pred = layer(Xd, Yd, tau, eps)
+            custom_ce_loss(pred, yq_d).backward()
+            return pred.detach()
+
+        def sharded_layer(a, b, c, e):
+            return sh.ShardedLaplaceLearning.apply(a, b, c, e, None, 0, partition)
+
+        pred = call(sharded_layer)  # warm-up (allocator, symmetric memory rendezvous, NCCL channels)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(calls):
+            pred = call(sharded_layer)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / calls
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        info = sh.last_info()
+        return float(t.item()), pred, Xd.grad.detach().clone(), info, (lambda: call(LaplaceLearningSparseHard.apply), Xd)
+
+    def rel(a, b):
+        return float((a - b).abs().max().item() / max(b.abs().max().item(), 1e-300))
+
+    if world > 1:
+        ms_c, pred_c, dx_c, _, (unsharded, Xd) = run("c5s", "columns", 2)
+        out["c5s_ms_per_call_columns"] = ms_c
+        errs = torch.zeros(4, dtype=torch.float64, device=dev)
+        if rank == 0:  # the unsharded layer on one GPU is the yardstick (itself checked against the oracle in tests/)
+            pred_u = unsharded()
+            dx_u = Xd.grad.detach().clone()
+            errs[0], errs[1] = rel(pred_c, pred_u), rel(dx_c, dx_u)
+        del unsharded, Xd
+        try:
+            ms_p, pred_p, dx_p, _, keep = run("c5s", "rows-p2p", 2)
+            del keep
+            out["c5s_ms_per_call_rows_p2p"] = ms_p
+            if rank == 0:
+                errs[2], errs[3] = rel(pred_p, pred_u), rel(dx_p, dx_u)
+        except Exception as e:  # symmetric memory unavailable on this box: say so instead of dying
+            out["c5s_ms_per_call_rows_p2p"] = None
+            if rank == 0:
+                print(f"bench.py: rows-p2p not run: {e}", file=sys.stderr)
+            errs[2] = errs[3] = float("nan")
+        dist.broadcast(errs, 0)
+        e = errs.cpu().tolist()
+        out.update(c5s_parity_pred_vs_unsharded=e[0], c5s_parity_dx_vs_unsharded=e[1], c5s_parity_rows_p2p_pred=e[2],
+                   c5s_parity_rows_p2p_dx=e[3])
+        torch.cuda.empty_cache()
+    if not args.no_c5:
+        ms5, _, _, info5, keep = run("c5", "columns", 2)
+        del keep
+        solve = info5.get("cg_solve_ms") or [None, None]
+        out.update(c5_ms_per_call=ms5, c5_nodes=WORKLOADS["c5"][0] + WORKLOADS["c5"][1], c5_cg_partition="columns",
+                   c5_cg_solve_ms_fwd=solve[-2] if len(solve) >= 2 else None, c5_cg_solve_ms_bwd=solve[-1] if solve else None)
+        torch.cuda.empty_cache()
+    return out
 
 
 def large_graph_report(prof, shp, info, ms_per_call):
@@ -477,7 +646,7 @@ def large_graph_report(prof, shp, info, ms_per_call):
         m, l, Euu = shp["m"], shp["l"], info["nnz_uu"]
         b_iter = 8.0 * Euu + 4.0 * (m + 1) + 44.0 * m * l
         gbs = b_iter * iters / (solves_ms * 1e-3) / 1e9
-        out["cg"] = {"iters_per_sec": iters / (solves_ms * 1e-3), "us_per_iter": 1e3 * solves_ms / iters,
+        out["cg"] = {"iters_per_sec": iters / (solves_ms * 1e-3), "us_per_iter": 1e3 * solves_ms / iters, "ms_per_solve": solves_ms / 2,
                      "bytes_per_iter": b_iter, "achieved_gbs": gbs, "peak_gbs": peaks["hbm_gbs"],
                      "frac": gbs / peaks["hbm_gbs"], "note": "working set is L2-resident at this size (SURVEY 8d)"}
     tot = sum(v[0] for v in prof.values())
@@ -500,6 +669,9 @@ def main():
                          "(all-gather + all-reduce per iteration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-large-graph", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded c5 / c5s lines")
+    ap.add_argument("--no-c5", action="store_true", help="skip the 1M-node graph (keeps the c5s parity lines at N > 1)")
+    ap.add_argument("--cpu-cg", action="store_true", help="reference arm: also time the reference's CG on the C4 system")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     os.environ["GLL_B200_SHARD_CG"] = args.cg_partition

@@ -288,7 +288,8 @@ def _graph_stages(Xc: torch.Tensor, k: int, epsilon):
 def knn_sym_dist(data, k=K_NEIGHBOURS, epsilon="auto"):
     """Same contract as the reference ``knn_sym_dist`` (GLL.py:180-244): numpy (n, d) in, scipy CSR out.
 
-    Returns ``(W, V, mod_V, C, knn_ind)``; for a fixed epsilon ``mod_V`` and ``C`` are None (GLL.py:238).  ``C`` is
+    Returns ``(W, V, mod_V, C, knn_ind)``; for a fixed epsilon ``mod_V`` and ``C`` are the integer 0, the reference's
+    placeholders (GLL.py:229-230; its backward tests ``isinstance(C, int)``, GLL.py:124).  For 'auto', ``C`` is
     returned as a sparse CSR with C[kappa(i), i] = 1 (the reference builds the same matrix through a dense n x n
     array, GLL.py:209-213).  kNN, symmetrisation and the exp() run on the GPU; V and mod_V are the closed-form
     multiples of W (GLL.py:217-218) formed in fp64 on the host for the caller.
@@ -320,7 +321,7 @@ def knn_sym_dist(data, k=K_NEIGHBOURS, epsilon="auto"):
         kappa = g["kappa"].cpu().numpy().astype(np.int64)
         Cm = sp.csr_matrix((np.ones(n), (kappa, np.arange(n))), shape=(n, n))
         return W, V, mod_V, Cm, knn_ind
-    return W, V, None, None, knn_ind
+    return W, V, 0, 0, knn_ind  # placeholders of GLL.py:229-230
 
 
 def stable_conjgrad(A, b, x0=None, max_iter=1e5, tol=1e-10):

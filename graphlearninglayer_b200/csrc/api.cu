@@ -71,7 +71,7 @@ std::atomic<long long> g_launches[KID_COUNT];
 const char* const g_kernel_names[KID_COUNT] = {
     "sqnorm", "knn_gram_topk_simt", "knn_gram_topk_tcgen05", "knn_rerank", "knn_fallback", "graph_count", "scan",
     "graph_fill", "graph_sort_rows", "edge_weights", "uu_fill", "cg_persistent", "pack_unpack", "edge_grad",
-    "row_gather", "convert", "cg_rows", "cg_row_order"};
+    "row_gather", "convert", "cg_rows"};
 }  // namespace
 
 ProfScope::ProfScope(int id_, cudaStream_t st_) : id(id_), st(st_), slot(nullptr) {

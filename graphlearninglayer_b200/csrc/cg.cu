@@ -22,7 +22,6 @@
 namespace gll {
 namespace {
 
-constexpr const char* CG_ORDER_DEFAULT = "0";  // row schedule of the streaming kernel (cg_order.cu): opt-in until measured
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
@@ -173,13 +172,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) cg_persistent_kernel(CgParams P
 
     // ---- phase 1: Ap = A p, partial <p, Ap> ----
     float4 dot[1] = {make_float4(0.f, 0.f, 0.f, 0.f)};
-    // natural order: this CTA's row block; scheduled (P.order): consecutive positions of the schedule are dealt to the warps
-    // of the WHOLE grid, so that all rows in flight belong to one or two clusters and their gathers hit L2 (cg_order.cu)
-    const int k_begin = P.order ? (int)(blockIdx.x * CG_WARPS + warp) : row_begin + warp;
-    const int k_end = P.order ? P.m : row_end;
-    const int k_step = P.order ? (int)(gridDim.x * CG_WARPS) : CG_WARPS;
-    for (int k = k_begin; k < k_end; k += k_step) {
-      const int i = P.order ? __ldg(P.order + k) : k;
+    for (int i = row_begin + warp; i < row_end; i += CG_WARPS) {
       const int e0 = __ldg(P.ptr + i), e1 = __ldg(P.ptr + i + 1);
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
       if (active) {
@@ -297,20 +290,27 @@ int cg_grid(int m) {
 
 }  // namespace
 
+// More than CG_MAX_LP class columns (the reference has no limit): the columns of a multi-right-hand-side CG are independent
+// (per-column alpha / beta, GLL.py:262-269), so the solve runs in chunks of CG_MAX_LP columns on packed copies.
+__global__ void cg_combine_stats_kernel(const int* __restrict__ iters, const float* __restrict__ resid, int chunks, int* iters_out,
+                                        float* resid_out) {
+  int it = 0;
+  float rs = 0.f;
+  for (int c = 0; c < chunks; ++c) {
+    it = max(it, iters[c]);
+    rs = fmaxf(rs, resid[c]);
+  }
+  if (iters_out) *iters_out = it;
+  if (resid_out) *resid_out = rs;
+}
+
 size_t cg_ws_bytes(int m, int l) {
+  if (padded_classes(l) > CG_MAX_LP)
+    return 2 * align_up(sizeof(float) * (size_t)m * CG_MAX_LP, 256) + 2 * 256 * ceil_div(l, CG_MAX_LP) + 1024 + cg_ws_bytes(m, CG_MAX_LP);
   const int lp = padded_classes(l);
   size_t v = align_up(sizeof(float) * (size_t)m * lp, 256);
   return 3 * v + align_up(sizeof(double) * 2 * (2 * CG_MAX_LP) * (size_t)device_info().sms, 256) + 256 + 1024 +
-         cg_resident_ws_bytes(m, lp) + align_up(sizeof(int) * (size_t)m, 256) + cg_order_ws_bytes(m);
-}
-
-// GLL_B200_CG_ORDER: "0" never, "1" when the iterate exceeds what L2 keeps resident, "force" always (tests).
-static int cg_order_mode(int m, int lp) {
-  const char* e = getenv("GLL_B200_CG_ORDER");
-  if (e == nullptr || e[0] == 0) e = CG_ORDER_DEFAULT;
-  if (strcmp(e, "force") == 0) return 1;
-  if (e[0] == '0') return 0;
-  return ((size_t)m * lp * sizeof(float) > ((size_t)96 << 20)) ? 1 : 0;
+         cg_resident_ws_bytes(m, lp);
 }
 
 int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, const float* rhs, int m, int l,
@@ -319,12 +319,33 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
   GLL_REQUIRE(uu_ptr && uu_col && uu_val && diag && rhs && x && ws, "null pointer");
   GLL_REQUIRE(m >= 1 && l >= 1, "bad sizes");
   const int lp = padded_classes(l);
-  GLL_REQUIRE(lp <= CG_MAX_LP, "at most 128 classes per solve");
   if (ws_bytes < cg_ws_bytes(m, l)) {
     set_error("CG workspace too small: %zu < %zu", ws_bytes, cg_ws_bytes(m, l));
     return GLL_ERR_WORKSPACE;
   }
   Carver cv(ws, ws_bytes);
+  if (lp > CG_MAX_LP) {
+    const int chunks = ceil_div(l, CG_MAX_LP);
+    float* rhs_c = cv.take<float>((size_t)m * CG_MAX_LP);
+    float* x_c = cv.take<float>((size_t)m * CG_MAX_LP);
+    int* it_c = cv.take<int>(chunks);
+    float* rs_c = cv.take<float>(chunks);
+    const size_t sub_bytes = cg_ws_bytes(m, CG_MAX_LP);
+    void* sub = cv.take<char>(sub_bytes);
+    GLL_CUDA_CHECK(cudaMemsetAsync(x, 0, sizeof(float) * (size_t)m * lp, st));  // padded class columns read as zero
+    for (int c = 0; c < chunks; ++c) {
+      const int c0 = c * CG_MAX_LP, cnt = min(CG_MAX_LP, l - c0), lpc = padded_classes(cnt);
+      int rc = pack_columns(rhs, m, lp, c0, cnt, rhs_c, lpc, st);
+      if (rc) return rc;
+      rc = cg_run(uu_ptr, uu_col, uu_val, diag, rhs_c, m, cnt, tol, max_iter, x_c, it_c + c, rs_c + c, status_out, sub, sub_bytes, st);
+      if (rc) return rc;
+      rc = unpack_columns(x_c, m, lpc, c0, cnt, x, lp, st);
+      if (rc) return rc;
+    }
+    cg_combine_stats_kernel<<<1, 1, 0, st>>>(it_c, rs_c, chunks, iters_out, resid_out);
+    GLL_LAUNCH_CHECK();
+    return GLL_OK;
+  }
   CgParams P;
   P.ptr = uu_ptr;
   P.col = uu_col;
@@ -346,7 +367,6 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
   P.resid_out = resid_out;
   P.status_out = status_out;
   P.rows_per_block = 0;
-  P.order = nullptr;
   {  // systems that fit on chip (every config except the sharded 1M-node graph) take the shared-memory-resident kernel
     const char* force = getenv("GLL_B200_CG_PATH");  // "streaming" / "resident": testing knobs
     if (force == nullptr || force[0] == 0) {  // minibatch-sized systems: the one-CTA, register-resident kernel
@@ -369,14 +389,6 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
   const size_t smem = cg_smem_bytes(lp);
   GLL_CUDA_CHECK(set_max_dynamic_smem_once((const void*)cg_persistent_kernel, (int)cg_smem_bytes(CG_MAX_LP)));
   GLL_CUDA_CHECK(cudaMemsetAsync(P.barrier, 0, 256, st));
-  if (cg_order_mode(m, lp)) {
-    int* order = cv.take<int>(m);
-    const size_t ob = cg_order_ws_bytes(m);
-    void* ows = cv.take<char>(ob);
-    const int rc = cg_row_order(uu_ptr, uu_col, rhs, m, lp, order, ows, ob, st);
-    if (rc < 0) return rc;
-    P.order = order;
-  }
   void* args[] = {&P};
   GLL_PROF(KID_CG, st);
   GLL_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)cg_persistent_kernel, dim3(grid), dim3(CG_THREADS), args, smem, st));

@@ -19,7 +19,6 @@ struct CgParams {
   float* r;
   float* p;
   float* ap;
-  const int* order;   // streaming kernel: row schedule of the SpMV phase (cg_order.cu), or NULL = natural order
   double* partial;    // [2 buffers][2*lp columns][grid]
   unsigned* barrier;  // zeroed before launch
   int m, l, lp, rows_per_block, max_iter;
@@ -35,10 +34,6 @@ size_t cg_resident_ws_bytes(int m, int lp);
 int cg_resident_try(const CgParams& P, void* scratch, cudaStream_t st);
 void cg_set_trace(void* buf);
 void* cg_get_trace();
-// Row schedule for the streaming kernel (cg_order.cu): rows grouped by the class that dominates their right-hand side.
-size_t cg_order_ws_bytes(int m);
-int cg_row_order(const int* uu_ptr, const int* uu_col, const float* rhs, int m, int lp, int* order, void* ws, size_t ws_bytes,
-                 cudaStream_t st);
 // One-CTA kernel for minibatch-sized systems (cg_small.cu): 1 = took the solve, 0 = not small, < 0 = error.
 int cg_small_try(const CgParams& P, cudaStream_t st);
 

@@ -23,6 +23,7 @@
 //   update          waits for all ranks' sums, adds the mailbox rows in rank order (identical on every rank), proceeds
 // Every wait is for data produced by kernels that the peers launch EARLIER in the same sequence, so the scheme cannot
 // deadlock as long as every rank enqueues the same launches; a spin that lasts longer than 2 s traps (no hung GPU).
+#include <stdlib.h>
 #include <string.h>
 
 #include "cg_common.cuh"
@@ -74,6 +75,7 @@ struct Peers {
   double* mail[MAX_PEERS];  // every rank's mailbox: [2 parities][MAX_PEERS sources][MAIL_ROW]
   unsigned* flags[MAX_PEERS];  // every rank's flags: [0][src] = epoch of src's published u, [1][src] = of src's sums
   int world, rank;          // world == 0: not in peer-memory mode
+  unsigned long long timeout_ns;  // bound of a flag wait (GLL_B200_PEER_TIMEOUT_S, default 60 s)
 };
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   unsigned v;
@@ -83,8 +85,10 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// one thread: until every rank's flag has reached `epoch` (flags only grow); bounded
-__device__ __forceinline__ void wait_all_flags(const unsigned* f, int world, unsigned epoch) {
+// one thread: until every rank's flag has reached `epoch` (flags only grow).  The wait is bounded so that a dead peer or
+// diverged launch sequences end in an error instead of a hung GPU; the bound is long (a peer's HOST may stall for seconds:
+// lazy module loading on its first call, garbage collection, a debugger) and configurable.
+__device__ __forceinline__ void wait_all_flags(const unsigned* f, int world, unsigned epoch, unsigned long long timeout_ns) {
   unsigned long long t0, t1;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   for (int p = 0; p < world; ++p) {
@@ -92,7 +96,7 @@ __device__ __forceinline__ void wait_all_flags(const unsigned* f, int world, uns
     while ((int)(ld_acquire_sys(f + p) - epoch) < 0) {
       if ((++spin & 1023u) == 0) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 2000000000ull) __trap();  // 2 s: a peer died or the launch sequences diverged
+        if (t1 - t0 > timeout_ns) __trap();  // a peer died or the launch sequences diverged
       }
     }
   }
@@ -174,7 +178,7 @@ rows_spmv_kernel(const int* __restrict__ ptr, const int* __restrict__ col, const
   __shared__ bool last;
   if (PR.world > 0) {
     if (ctrl[0] != 0) return;  // the solve has stopped on every rank (same decision everywhere): nothing to wait for
-    if (threadIdx.x == 0) wait_all_flags(PR.flags[PR.rank], PR.world, epoch);  // everybody's u of this iteration is here
+    if (threadIdx.x == 0) wait_all_flags(PR.flags[PR.rank], PR.world, epoch, PR.timeout_ns);  // everybody's u of this iteration is here
     __syncthreads();
   }
   const int Q = lp >> 2, NS = 32 / Q;
@@ -271,7 +275,7 @@ rows_update_kernel(const float* __restrict__ diag, int lp, int row_lo, int row_h
   float* sc_new = S.scal + (size_t)((iter + 1) & 1) * 3 * lp;
   if (ctrl[0] != 0) return;  // an earlier launch stopped the solve (written by that launch, so no race here)
   if (PR.world > 0) {  // every rank's partial sums of this iteration: add the mailbox rows in rank order
-    if (threadIdx.x == 0) wait_all_flags(PR.flags[PR.rank] + MAX_PEERS, PR.world, epoch);
+    if (threadIdx.x == 0) wait_all_flags(PR.flags[PR.rank] + MAX_PEERS, PR.world, epoch, PR.timeout_ns);
     __syncthreads();
     const double* mb = PR.mail[PR.rank] + (size_t)(epoch & 1u) * MAX_PEERS * MAIL_ROW;
     for (int c = threadIdx.x; c < 3 * lp; c += blockDim.x) {
@@ -388,6 +392,12 @@ static Peers make_peers(const gll_peers* pr) {
   Peers P;
   memset(&P, 0, sizeof(P));
   if (pr != nullptr) {
+    static const double timeout_s = [] {
+      const char* e = getenv("GLL_B200_PEER_TIMEOUT_S");
+      const double v = e ? atof(e) : 0.0;
+      return v > 0.0 ? v : 60.0;
+    }();
+    P.timeout_ns = (unsigned long long)(timeout_s * 1e9);
     P.world = pr->world;
     P.rank = pr->rank;
     for (int p = 0; p < pr->world && p < MAX_PEERS; ++p) {

@@ -95,7 +95,7 @@ __device__ __forceinline__ float ordered_to_float(uint32_t u) {
 enum KernelId {
   KID_SQNORM = 0, KID_GRAM_TOPK, KID_GRAM_TOPK_TC, KID_RERANK, KID_KNN_FALLBACK, KID_GRAPH_COUNT, KID_SCAN,
   KID_GRAPH_FILL, KID_GRAPH_SORT, KID_WEIGHTS, KID_UU_FILL, KID_CG, KID_PACK, KID_EDGE_GRAD, KID_ROW_GATHER,
-  KID_CONVERT, KID_CG_ROWS, KID_CG_ORDER, KID_COUNT
+  KID_CONVERT, KID_CG_ROWS, KID_COUNT
 };
 // RAII: counts the launch; when profiling is on, brackets it with two events on the launch stream.
 struct ProfScope {

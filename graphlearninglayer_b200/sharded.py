@@ -201,6 +201,34 @@ def _solve_columns(g, rhs: torch.Tensor, out: torch.Tensor, tol: float, comm: _C
                        "gll_unpack_columns")
 
 
+class _StopPoll:
+    """Stop test of the host-driven CG loops without stalling the device: after every iteration the stop flag is copied
+    into pinned host memory (async, own event); the host looks at the copy made `lag` iterations earlier, whose event has
+    normally completed already.  Every rank looks at the copy of the SAME iteration, so all ranks leave the loop after the
+    same number of launches (and collectives); iterations enqueued after the stop are no-ops on the device."""
+
+    def __init__(self, lag: int):
+        self.lag = max(0, lag)
+        self.ring = torch.zeros(self.lag + 2, dtype=torch.int32).pin_memory()
+        self.events = [None] * (self.lag + 2)
+
+    def push(self, it: int, flag: torch.Tensor) -> None:
+        slot = it % len(self.events)
+        self.ring[slot:slot + 1].copy_(flag, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[slot] = ev
+
+    def stopped(self, it: int, last: bool = False) -> bool:
+        """True once the copy of iteration it - lag (of iteration it itself when `last`) shows the stop flag."""
+        look = it if last else it - self.lag
+        if look < 0:
+            return False
+        slot = look % len(self.events)
+        self.events[slot].synchronize()
+        return int(self.ring[slot]) != 0
+
+
 def m_block(m: int, rank: int, world: int):
     """Unlabeled rows owned by `rank` in the row-partitioned CG: equal blocks of ceil(m/world) rounded up to 32."""
     per = -(-m // world)
@@ -230,8 +258,8 @@ def _solve_rows(g, rhs: torch.Tensor, out: torch.Tensor, tol: float, comm: _Comm
         _lib.check(lib.gll_cg_rows_init(g.diag.data_ptr(), rhs.data_ptr(), g.m, g.l, lo, hi, x_full.data_ptr(), u_full.data_ptr(),
                                         ws.data_ptr(), wsb, s), "gll_cg_rows_init")
     maxit = _cg_maxit()
-    check_every = max(1, int(os.environ.get("GLL_B200_ROWS_CHECK_EVERY", "2")))
     first = comm.ranks[0]
+    poll = _StopPoll(int(os.environ.get("GLL_B200_ROWS_STOP_LAG", "1")))  # every extra iteration costs an all-gather here
     for it in range(maxit + 1):
         comm.all_gather_blocks_(u_full, per)
         for r in comm.ranks:
@@ -245,11 +273,10 @@ def _solve_rows(g, rhs: torch.Tensor, out: torch.Tensor, tol: float, comm: _Comm
             _lib.check(lib.gll_cg_rows_update(g.diag.data_ptr(), g.m, g.l, lo, hi, sums.data_ptr(), it, maxit, tol,
                                               x_full.data_ptr(), u_full.data_ptr(), ctrl.data_ptr(), resid.data_ptr(),
                                               ws.data_ptr(), wsb, s), "gll_cg_rows_update")
-        # the stop flag is identical on every rank (same reduced sums); reading it synchronises, so not every iteration --
-        # iterations after the stop are no-ops on the device
-        if (it + 1) % check_every == 0 or it == maxit:
-            if int(st[first][5][0].item()) != 0:
-                break
+        # the stop flag is identical on every rank (same reduced sums)
+        poll.push(it, st[first][5][0:1])
+        if poll.stopped(it, last=it == maxit):
+            break
     comm.all_gather_blocks_(x_full, per)
     out.copy_(x_full[:g.m])
     ctrl = st[first][5]
@@ -295,7 +322,7 @@ def _solve_rows_p2p(g, rhs: torch.Tensor, out: torch.Tensor, tol: float, comm: _
     """Row-partitioned CG with BOTH collectives fused into the kernels over NVLink peer memory (csrc/cg_rows.cu, peer-memory
     mode): the update kernel stores the new iterate into every rank's copy, the SpMV kernel's last CTA stores the partial
     dot products into every rank's mailbox; epoch flags in peer memory order the kernels across GPUs.  No NCCL call and no
-    host round trip inside the loop (the stop flag is read every second iteration, locally); one all-gather of x at the end."""
+    host stall inside the loop (the stop flag is polled through pinned memory, two iterations behind); one all-gather of x at the end."""
     import ctypes
 
     dev = rhs.device
@@ -315,7 +342,7 @@ def _solve_rows_p2p(g, rhs: torch.Tensor, out: torch.Tensor, tol: float, comm: _
     blk["epoch"] = e0 + maxit + 4  # flags only grow: the next solve starts above everything this one can publish
     _lib.check(lib.gll_cg_rows_init_p2p(g.diag.data_ptr(), rhs.data_ptr(), g.m, g.l, lo, hi, x_full.data_ptr(), P, e0,
                                         ws.data_ptr(), wsb, s), "gll_cg_rows_init_p2p")
-    check_every = max(1, int(os.environ.get("GLL_B200_ROWS_CHECK_EVERY", "2")))
+    poll = _StopPoll(int(os.environ.get("GLL_B200_ROWS_STOP_LAG", "2")))
     for it in range(maxit + 1):
         _lib.check(lib.gll_cg_rows_spmv_p2p(g.uu_ptr.data_ptr(), g.uu_col.data_ptr(), g.uu_val.data_ptr(), g.diag.data_ptr(), g.m,
                                             g.l, lo, hi, P, e0 + it, ctrl.data_ptr(), ws.data_ptr(), wsb, s),
@@ -323,9 +350,9 @@ def _solve_rows_p2p(g, rhs: torch.Tensor, out: torch.Tensor, tol: float, comm: _
         _lib.check(lib.gll_cg_rows_update_p2p(g.diag.data_ptr(), g.m, g.l, lo, hi, it, maxit, tol, x_full.data_ptr(), P, e0 + it,
                                               ctrl.data_ptr(), resid.data_ptr(), ws.data_ptr(), wsb, s),
                    "gll_cg_rows_update_p2p")
-        if (it + 1) % check_every == 0 or it == maxit:
-            if int(ctrl[0].item()) != 0:
-                break
+        poll.push(it, ctrl[0:1])
+        if poll.stopped(it, last=it == maxit):
+            break
     comm.all_gather_blocks_(x_full, per)
     out.copy_(x_full[:g.m])
     iters[rank:rank + 1].copy_(ctrl[1:2])
@@ -359,6 +386,7 @@ def _backward(g, X: torch.Tensor, grad_output: torch.Tensor, comm: _Comm) -> tor
     wt = torch.zeros((n, g.lp), dtype=f32, device=dev)  # GLL.py:104: zero rows for the labeled nodes
     g.iters_bwd = torch.zeros(comm.world, dtype=torch.int32, device=dev)
     _solve(g, rhs, wt[k_lab:], -_cg_tol(), comm, g.iters_bwd)
+    g.wt = wt  # [0; adjoint solution], GLL.py:104 (kept for inspection, like ut)
 
     # ---- K5 rows -> all-gather b -> K6 rows -> all-gather dX ----
     _, _, per = row_block(n, 0, comm.world)

@@ -84,6 +84,31 @@ def exact_knn(X: np.ndarray, k: int = K_DEFAULT, block: int = 2048, slack: int =
     return ind, dist
 
 
+def exact_knn_rows(X: np.ndarray, rows, k: int = K_DEFAULT, slack: int = 8):
+    """exact_knn for a SAMPLE of rows against all points (full-size checks: n = 131072 and up, where the all-rows search
+    would take minutes on the host).  Same candidates / exact recompute / (distance, index) order as exact_knn."""
+    X32 = np.ascontiguousarray(X, dtype=np.float32)
+    rows = np.asarray(rows, dtype=np.int64)
+    n = X32.shape[0]
+    sq = np.einsum("ij,ij->i", X32, X32, dtype=np.float64)
+    Xr = X32[rows].astype(np.float64)
+    kc = min(n, k + slack)
+    d2 = sq[rows, None] + sq[None, :]
+    for s in range(0, n, 16384):  # the fp64 copy of X is only materialised block by block
+        e = min(n, s + 16384)
+        d2[:, s:e] -= 2.0 * (Xr @ X32[s:e].astype(np.float64).T)
+    d2[np.arange(len(rows)), rows] = -1.0
+    cand = np.argpartition(d2, kc - 1, axis=1)[:, :kc]
+    diff = Xr[:, None, :] - X32[cand].astype(np.float64)
+    d2c = np.einsum("ijk,ijk->ij", diff, diff)
+    d2c[cand == rows[:, None]] = -1.0
+    order = np.lexsort((cand, d2c), axis=1)[:, :k]
+    ci = np.take_along_axis(cand, order, axis=1)
+    cd = np.take_along_axis(d2c, order, axis=1)
+    cd[:, 0] = 0.0
+    return ci, np.sqrt(np.maximum(cd, 0.0)).astype(np.float32).astype(np.float64)
+
+
 # --------------------------------------------------------------------------------------
 # graph + weights (GLL.py:180-244)
 # --------------------------------------------------------------------------------------

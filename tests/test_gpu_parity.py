@@ -351,7 +351,7 @@ def test_graph_drops_zero_distance_edges(gll):
 # "": the dispatch by size (here the multi-CTA on-chip kernel); "streaming": the global-memory kernel that only ~1M-row systems
 # reach on their own, forced so that it is covered at a size the CPU checker can solve
 @pytest.mark.parametrize("path", ["", "streaming"])
-@pytest.mark.parametrize("l", [1, 3, 10, 37, 100])
+@pytest.mark.parametrize("l", [1, 3, 10, 37, 100, 150])  # 150 > 128 class columns: solved in column chunks
 def test_cg_vs_direct_solve(gll, monkeypatch, l, path):
     _, _lib = gll
     if path:
@@ -380,32 +380,6 @@ def test_cg_zero_rhs_column_and_maxiter(gll, monkeypatch, path):
     assert O.max_rel(x, ref) < TOL
     x2, it2, _, status2 = run_cg(_lib, f.Luu, f.B, tol=1e-12, max_iter=3)
     assert it2 == 3 and status2 & 1  # GLL_STATUS_CG_NOT_CONVERGED <-> 'max iter reached' (GLL.py:273-274)
-
-
-@pytest.mark.parametrize("l", [3, 10, 100])
-def test_cg_streaming_row_schedule(gll, monkeypatch, l):
-    """The streaming kernel with its SpMV rows scheduled by right-hand-side class (csrc/cg_order.cu; what a 1M-node system
-    gets): every row is still computed from the same operands, so the solve matches the natural order to rounding of the
-    dot products, takes the same number of iterations, and matches the direct solve."""
-    _, _lib = gll
-    monkeypatch.setenv("GLL_B200_CG_PATH", "streaming")
-    X, Y, *_ = O.synth_inputs(3, 160, 1500, 24, l, 1.5)
-    f = O.forward(X, Y, 0.02, 1.0, solver="lu")
-    monkeypatch.setenv("GLL_B200_CG_ORDER", "0")
-    x0, it0, _, st0 = run_cg(_lib, f.Luu, f.B, tol=1e-7)
-    names = _lib.kernel_names()
-    before = _lib.launch_count(names.index("cg_row_order"))
-    monkeypatch.setenv("GLL_B200_CG_ORDER", "force")
-    x1, it1, resid1, st1 = run_cg(_lib, f.Luu, f.B, tol=1e-7)
-    assert _lib.launch_count(names.index("cg_row_order")) == before + 1
-    assert st0 == 0 and st1 == 0 and abs(it1 - it0) <= 1 and resid1 <= 1e-7
-    assert O.max_rel(x1, x0) < 1e-6
-    assert O.max_rel(x1, f.pred) < TOL
-    # a right-hand side with empty rows and a single live column (the adjoint's shape, GLL.py:93)
-    B = np.zeros_like(f.B)
-    B[::3, 0] = -1.0
-    x2, _, _, st2 = run_cg(_lib, f.Luu, B, tol=1e-7)
-    assert st2 == 0 and O.max_rel(x2, O.solve(f.Luu, B, "lu")) < TOL
 
 
 def test_cg_relative_tolerance(gll):
@@ -475,6 +449,18 @@ def test_layer_vs_oracle_c4_full_size(gll, eps, tau):
     assert info["nnz"] == f.graph.W.nnz                      # same union graph as the oracle's exact search
     assert O.max_rel(pred.cpu().numpy(), f.pred) < TOL
     assert abs(loss.item() - loss_ref) < 1e-5 * max(1.0, abs(loss_ref))
+    assert O.max_rel(dX.cpu().numpy(), bw.dX) < TOL
+
+
+def test_layer_more_than_128_classes(gll):
+    """The reference layer has no class limit (GLL.py:53 solves all columns of label_matrix); the CG kernels take 128 class
+    columns per launch, gll_forward / gll_backward chunk the rest."""
+    pkg, _lib = gll
+    X, Y, _, yq = O.synth_inputs(5, 300, 700, 32, 130, 1.5)
+    f, loss_ref, gout, bw = O.fwd_bwd(X, Y, yq, 0.05, "auto", solver="lu")
+    pred, loss, dX = layer_fwd_bwd(pkg, X, Y, yq, 0.05, "auto")
+    assert pkg.last_info()["status"] == 0
+    assert O.max_rel(pred.cpu().numpy(), f.pred) < TOL
     assert O.max_rel(dX.cpu().numpy(), bw.dX) < TOL
 
 
@@ -564,7 +550,7 @@ def test_knn_sym_dist_wrapper(gll):
     assert np.array_equal(np.asarray(Cm.argmax(axis=0)).ravel(), g.kappa)
     assert np.array_equal(knn_ind, g.knn_ind)
     W50, V50, mv, cc, ki = pkg.knn_sym_dist(X, 30, 1.0)  # a different k (utils.py:651 uses 50 at eval; kernel max is 33)
-    assert mv is None and cc is None and ki.shape == (800, 30)
+    assert isinstance(mv, int) and mv == 0 and isinstance(cc, int) and cc == 0 and ki.shape == (800, 30)  # GLL.py:229-230
     g30 = O.build_graph(X, 30, 1.0)
     assert np.array_equal(W50.indices, g30.W.indices) and O.max_rel(W50.data, g30.W.data) < 1e-6
 
@@ -623,6 +609,103 @@ def test_sharded_layer_vs_oracle(gll):
     (-torch.sum(tgt * torch.log(pred + 1e-8)) / pred.shape[0]).backward()
     assert O.max_rel(pred.detach().cpu().numpy(), f.pred) < TOL
     assert O.max_rel(Xt.grad.cpu().numpy(), bw.dX) < TOL
+
+
+def _stagewise_fp64_check(X, Y, yq, g, pred, dX, n_sample=16, seed=0):
+    """Full-size checker for graphs the oracle cannot rebuild in seconds (n >= 131072): every stage of the path is
+    re-evaluated in fp64 on the host FROM THE PREVIOUS STAGE'S DEVICE OUTPUT, on all rows where that is cheap and on a
+    sample of rows where it is not.  Returns a dict of error measures.
+      kNN        sampled rows: fp64 brute force over all n points (O.exact_knn_rows), set equality          GLL.py:181-189
+      eps, W     sampled rows and their neighbours: eps = 25th distance, W = exp(-4 d^2 / eps_i eps_j)      GLL.py:205,216
+      forward    ||L_uu pred - B||_2 / ||B||_2 per class column, L from the device's W in fp64              GLL.py:29-53
+      adjoint    the same for the adjoint solve                                                             GLL.py:93
+      dX         sampled rows: sum_j t_ij (x_i - x_j) from the device's U, w, W, eps, kappa in fp64         GLL.py:104-159
+    """
+    n, d = X.shape
+    k_lab, l = Y.shape
+    out = {}
+    rng = np.random.default_rng(seed)
+    rows_s = np.sort(rng.choice(n, size=n_sample, replace=False))
+    row_ptr = g.row_ptr.cpu().numpy().astype(np.int64)
+    E = int(row_ptr[-1])
+    col = g.col[:E].cpu().numpy().astype(np.int64)
+    dist = g.dist[:E].cpu().numpy().astype(np.float64)
+    w = g.w[:E].cpu().numpy().astype(np.float64)
+    eps = g.eps.cpu().numpy().astype(np.float64)
+    kappa = g.kappa.cpu().numpy().astype(np.int64)
+    knn_idx = g.knn_idx[:n].cpu().numpy().astype(np.int64)
+    # -- kNN on the sample and on the sample's neighbours (needed for eps_j)
+    nb = np.unique(np.concatenate([col[row_ptr[i]:row_ptr[i + 1]] for i in rows_s] + [rows_s]))
+    ref_idx, ref_dist = O.exact_knn_rows(X, nb, 25)
+    pos = {int(r): t for t, r in enumerate(nb)}
+    exact, tie, bad = O.knn_sets_match(knn_idx[nb], ref_idx, ref_dist)
+    out["knn_bad_rows"], out["knn_rows_checked"] = bad, len(nb)
+    eps_ref = ref_dist[:, -1]
+    out["eps_err"] = float(np.max(np.abs(eps[nb] - eps_ref) / eps_ref))
+    werr = 0.0
+    for i in rows_s:
+        e0, e1 = row_ptr[i], row_ptr[i + 1]
+        j = col[e0:e1]
+        dij = np.sqrt(((X[i].astype(np.float64) - X[j].astype(np.float64)) ** 2).sum(axis=1))
+        wref = np.exp(-4.0 * dij * dij / eps_ref[pos[int(i)]] / np.array([eps_ref[pos[int(t)]] for t in j]))
+        werr = max(werr, float(np.max(np.abs(w[e0:e1] - wref) / np.maximum(wref, 1e-30))))
+    out["w_err"] = werr
+    # -- both solves against the device's own weights, fp64
+    W = sp.csr_matrix((w, col, row_ptr), shape=(n, n))
+    Luu, B, _ = O.laplace_system(W, Y, 0.0)
+    P = pred.cpu().numpy()
+    out["fwd_residual"] = float(np.max(np.linalg.norm(Luu @ P - B, axis=0) / np.linalg.norm(B, axis=0)))
+    _, gout = O.ce_loss_and_grad(P, yq)
+    wt = g.wt[:, :l].double().cpu().numpy()
+    ut = g.ut[:, :l].double().cpu().numpy()
+    assert np.abs(ut[k_lab:] - P).max() <= 1e-6 * np.abs(P).max() and np.array_equal(ut[:k_lab], Y.astype(np.float64))
+    gn = np.linalg.norm(gout, axis=0)
+    out["adj_residual"] = float(np.max(np.linalg.norm(Luu @ wt[k_lab:] - gout, axis=0)[gn > 0] / gn.max()))
+    # -- per-edge G, V, modV, b (all rows, chunked) and dX on the sample
+    rows_all = np.repeat(np.arange(n), np.diff(row_ptr))
+    V = -8.0 * w / eps[rows_all] / eps[col]
+    Gv = np.empty(E)
+    for s0 in range(0, E, 1 << 19):
+        s1 = min(E, s0 + (1 << 19))
+        r_, c_ = rows_all[s0:s1], col[s0:s1]
+        Gv[s0:s1] = -np.einsum("ij,ij->i", wt[r_] - wt[c_], ut[r_] - ut[c_])
+    b = np.bincount(rows_all, weights=Gv * (dist * dist * V / (eps[rows_all] ** 2) / 2.0), minlength=n)
+    dXn = dX.cpu().numpy().astype(np.float64)
+    scale = np.abs(dXn).max()
+    derr = 0.0
+    for i in rows_s:
+        e0, e1 = row_ptr[i], row_ptr[i + 1]
+        j = col[e0:e1]
+        t = Gv[e0:e1] * V[e0:e1] - (j == kappa[i]) * b[i] - (kappa[j] == i) * b[j]
+        ref = (t[:, None] * (X[i].astype(np.float64)[None, :] - X[j].astype(np.float64))).sum(axis=0)
+        derr = max(derr, float(np.abs(dXn[i] - ref).max() / scale))
+    out["dx_err"] = derr
+    return out
+
+
+@pytest.mark.parametrize("partition", ["columns", "rows"])
+def test_sharded_c5s_size_stagewise(gll, partition):
+    """BASELINE.json configs[4] at 1/8 of its size (n = 131072 nodes, 8192 labeled, d = 256, 100 classes, eps = 'auto') --
+    the size ONE of eight ranks holds of the 1M-node graph -- sharded over virtual ranks, both CG partitions; the kNN
+    search runs in its large-graph (aligned, whole row tiles per CTA) mode at d = 256."""
+    pkg, _lib = gll
+    from graphlearninglayer_b200 import sharded as sh
+
+    X, Y, _, yq = O.synth_inputs(1000, 8192, 122880, 256, 100, 3.0)
+    Xt = torch.as_tensor(X).cuda().requires_grad_(True)
+    pred = sh.ShardedLaplaceLearning.apply(Xt, torch.as_tensor(Y).cuda(), 0.0, "auto", None, 2, partition)
+    tgt = torch.nn.functional.one_hot(torch.as_tensor(yq).cuda(), pred.shape[1]).to(pred.dtype)
+    (-torch.sum(tgt * torch.log(pred + 1e-8)) / pred.shape[0]).backward()
+    torch.cuda.synchronize()
+    info = sh.last_info()
+    assert info["status"] & ~_lib.STATUS_KNN_FALLBACK == 0 and info["knn_fallback_rows"] == 0, info
+    p = pred.detach().cpu().numpy()
+    assert np.abs(p.sum(axis=1) - 1.0).max() < 5e-5 and p.min() > -1e-5   # tau = 0: rows of the harmonic extension sum to 1
+    r = _stagewise_fp64_check(X, Y, yq, sh._last_graph, pred.detach(), Xt.grad)
+    assert r["knn_bad_rows"] == 0 and r["knn_rows_checked"] > 300, r
+    assert r["eps_err"] < 1e-6 and r["w_err"] < 1e-5, r
+    assert r["fwd_residual"] < 1e-5 and r["adj_residual"] < 1e-5, r
+    assert r["dx_err"] < TOL, r
 
 
 @pytest.mark.parametrize("world", [1, 2, 5])
