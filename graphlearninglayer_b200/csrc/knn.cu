@@ -18,7 +18,7 @@
 #include <math.h>
 #include <stdlib.h>
 
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -43,67 +43,77 @@ __device__ __forceinline__ void max_into(unsigned* addr, unsigned v) {
   if (__ldcg(addr) < v) atomicMax(addr, v);
 }
 
-// |x_i|^2 (fp64 accumulate -> fp32) and the global maximum; when H/L are given also the bf16 split x = hi + lo that
-// feeds the tensor-core Gram kernel (row stride d_pad, zero padded), so X is read once.
+// |x_i|^2 (fp64 accumulate -> fp32) and the global maximum: the SIMT Gram path (tiny graphs) needs nothing else.
 __global__ void __launch_bounds__(256)
-sqnorm_split_kernel(const float* __restrict__ X, int n, int d, int d_pad, float* __restrict__ sq, unsigned* __restrict__ sqmax_bits,
-                    __nv_bfloat16* __restrict__ H, __nv_bfloat16* __restrict__ L, unsigned* __restrict__ thr_g) {
+sqnorm_kernel(const float* __restrict__ X, int n, int d, float* __restrict__ sq, unsigned* __restrict__ sqmax_bits) {
   const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (row >= n) return;
   const float* x = X + (size_t)row * d;
   double s = 0.0;
-  const int cend = (H != nullptr) ? d_pad : d;
-  for (int c = 2 * lane; c < cend; c += 64) {
-    const float x0 = (c < d) ? __ldg(x + c) : 0.f;
-    const float x1 = (c + 1 < d) ? __ldg(x + c + 1) : 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float x0 = __ldg(x + c);
     s += (double)x0 * (double)x0;
-    s += (double)x1 * (double)x1;
-    if (H != nullptr) {
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-      __nv_bfloat162 hv, lv;
-      hv.x = h0;
-      hv.y = h1;
-      lv.x = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-      lv.y = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-      *reinterpret_cast<__nv_bfloat162*>(H + (size_t)row * d_pad + c) = hv;
-      *reinterpret_cast<__nv_bfloat162*>(L + (size_t)row * d_pad + c) = lv;
-    }
   }
   s = warp_sum(s);
   if (lane == 0) {
-    float f = (float)s;
+    const float f = (float)s;
     sq[row] = f;
-    if (thr_g != nullptr) thr_g[row] = 0xFF800000u;  // float_to_ordered(+inf): the row's shared threshold (knn_tc.cu)
     if (f == f) max_into(sqmax_bits, __float_as_uint(f));  // non-negative floats order like their bits
   }
 }
 
 constexpr int F16_TARGET_LOG2 = 8;  // rows are scaled to a norm in [0.58, 1.16) * 2^8
 
-// f16x2 operands (knn_tc.cu), fused with the norms so that X is read from HBM once: row i is scaled by 2^-E_i to a norm
-// in [148, 296) (exact; no fp16 overflow, and fp16's subnormal range lies 2^-22 below the row's own norm),
-// then hi = fp16(z), lo = fp16(z - hi), row stride d_pad, zero padded.  rscale[i] = 2^E_i undoes
-// the scaling in the Gram epilogue.  Also the largest B-side residual rho = max_j |x_j - hi_j 2^E_j|_2 (exact in fp64,
-// rounded up): the Gram kernel computes (hi + lo)_i . hi_j, so its error is |x_i| rho + O(2^-22).
+// fp16 operands of the tensor-core Gram kernel (knn_tc.cu), fused with the norms so that X is read from HBM once: row i is
+// scaled by 2^-E_i to a norm in [148, 296) (exact; no fp16 overflow, and fp16's subnormal range lies 2^-22 below the row's
+// own norm), then hi = fp16(z) and -- two-pass mode only, L != NULL -- lo = fp16(z - hi); row stride d_pad, zero padded.
+// rscale[i] = 2^E_i undoes the scaling in the Gram epilogue.  Also the largest operand residual
+// rho = max_j |x_j - hi_j 2^E_j|_2 (exact in fp64, rounded up), which bounds the Gram error: one pass computes hi_i . hi_j
+// (error <= rho (|x_i| + |x_j| + rho)), two passes (hi + lo)_i . hi_j (error <= |x_i| rho + O(2^-22)); small[5] tells
+// knn_err_bound() which.  NREG > 0: the row (d_pad <= 64 NREG) is held in registers, one sweep over X; NREG = 0: any d, the
+// second sweep hits L1.
+template <int NREG>
 __global__ void __launch_bounds__(256)
 sqnorm_split_f16_kernel(const float* __restrict__ X, int n, int d, int d_pad, float* __restrict__ sq, unsigned* __restrict__ small,
                         __half* __restrict__ H, __half* __restrict__ L, float* __restrict__ rscale, unsigned* __restrict__ thr_g) {
-  const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  if (row >= n) return;
+  // the four global maxima (|x|^2, rho, range of E) are reduced per CTA first: 10 k warps reading and bumping the same
+  // 32-byte sector of L2 one after the other cost more than the rest of the kernel
+  __shared__ unsigned sh_max[4][8];
+  const int row_raw = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  const bool live = row_raw < n;
+  const int row = live ? row_raw : n - 1;  // idle warps of the last CTA recompute the last row and store nothing
   const float* x = X + (size_t)row * d;
+  const bool vec2 = (d & 1) == 0;  // float2 loads need an 8-byte aligned row
+  float2 xr[NREG > 0 ? NREG : 1];
   double s = 0.0;
-  for (int c = 2 * lane; c < d; c += 64) {
-    const float x0 = __ldg(x + c);
-    const float x1 = (c + 1 < d) ? __ldg(x + c + 1) : 0.f;
-    s += (double)x0 * (double)x0;
-    s += (double)x1 * (double)x1;
+  if (NREG > 0) {
+#pragma unroll
+    for (int t = 0; t < NREG; ++t) {
+      const int c = 2 * lane + 64 * t;
+      float2 v = make_float2(0.f, 0.f);
+      if (vec2) {
+        if (c < d) v = __ldg(reinterpret_cast<const float2*>(x + c));
+      } else {
+        if (c < d) v.x = __ldg(x + c);
+        if (c + 1 < d) v.y = __ldg(x + c + 1);
+      }
+      xr[t] = v;
+      s += (double)v.x * (double)v.x;
+      s += (double)v.y * (double)v.y;
+    }
+  } else {
+    for (int c = 2 * lane; c < d; c += 64) {
+      const float x0 = __ldg(x + c);
+      const float x1 = (c + 1 < d) ? __ldg(x + c + 1) : 0.f;
+      s += (double)x0 * (double)x0;
+      s += (double)x1 * (double)x1;
+    }
   }
   s = warp_sum(s);
   // E_i from the row NORM, with the bucket boundaries at |x|^2 = 2^k / 1.5 so that rows normalised to 1 (every caller of the
   // layer) all get the same E whatever their rounding: 2^(2F - 1) <= 1.5 |x_i|^2 < 2^(2F + 1), E = F - 8, hence
   // 148 <= |z_i| < 296.  The target norm 2^8 (not 1) keeps `lo` = z - hi a NORMAL fp16 number for every element above
-  // 2^-11 |x_i|: the split then does not lean on how the tensor core treats fp16 subnormals (with a target of 1, 99.99 % of
-  // the lo values of a 512-dimensional unit row were subnormal); |z_ik| < 296 is far from fp16's 65504.
+  // 2^-11 |x_i| and hi's own subnormal range 2^-22 below the row norm; |z_ik| < 296 is far from fp16's 65504.
   int E = -F16_TARGET_LOG2;
   {
     const unsigned b = __float_as_uint((float)(1.5 * s));
@@ -113,33 +123,59 @@ sqnorm_split_f16_kernel(const float* __restrict__ X, int n, int d, int d_pad, fl
   double r2 = 0.0;
   const float down = ldexpf(1.f, -E);  // |E| <= 60: both factors are normal numbers, the products below are exact
   const double up = ldexp(1.0, E);
-  for (int c = 2 * lane; c < d_pad; c += 64) {  // second sweep over the row: L1 hits
-    const float x0 = (c < d) ? __ldg(x + c) : 0.f;
-    const float x1 = (c + 1 < d) ? __ldg(x + c + 1) : 0.f;
+  auto emit = [&](int c, float x0, float x1) {
     const float z0 = x0 * down, z1 = x1 * down;
     const __half h0 = __float2half_rn(z0), h1 = __float2half_rn(z1);
     const float f0 = __half2float(h0), f1 = __half2float(h1);
-    __half2 hv, lv;
+    __half2 hv;
     hv.x = h0;
     hv.y = h1;
-    lv.x = __float2half_rn(z0 - f0);
-    lv.y = __float2half_rn(z1 - f1);
-    *reinterpret_cast<__half2*>(H + (size_t)row * d_pad + c) = hv;
-    *reinterpret_cast<__half2*>(L + (size_t)row * d_pad + c) = lv;
+    if (live) *reinterpret_cast<__half2*>(H + (size_t)row * d_pad + c) = hv;
+    if (live && L != nullptr) {
+      __half2 lv;
+      lv.x = __float2half_rn(z0 - f0);
+      lv.y = __float2half_rn(z1 - f1);
+      *reinterpret_cast<__half2*>(L + (size_t)row * d_pad + c) = lv;
+    }
     const double e0 = (double)x0 - (double)f0 * up, e1 = (double)x1 - (double)f1 * up;
     r2 += e0 * e0 + e1 * e1;
+  };
+  if (NREG > 0) {
+#pragma unroll
+    for (int t = 0; t < NREG; ++t) {
+      const int c = 2 * lane + 64 * t;
+      if (c < d_pad) emit(c, xr[t].x, xr[t].y);
+    }
+  } else {
+    for (int c = 2 * lane; c < d_pad; c += 64) {  // second sweep over the row: L1 hits
+      const float x0 = (c < d) ? __ldg(x + c) : 0.f;
+      const float x1 = (c + 1 < d) ? __ldg(x + c + 1) : 0.f;
+      emit(c, x0, x1);
+    }
   }
   r2 = warp_sum(r2);
+  const int warp = threadIdx.x >> 5;
   if (lane == 0) {
     const float f = (float)s;
-    sq[row] = f;
-    rscale[row] = ldexpf(1.f, E);
-    if (thr_g != nullptr) thr_g[row] = 0xFF800000u;  // float_to_ordered(+inf): the row's shared threshold (knn_tc.cu)
-    if (f == f) max_into(small, __float_as_uint(f));  // non-negative floats order like their bits
     const float rho = __double2float_ru(sqrt(r2) * 1.000001);
-    if (rho == rho) max_into(small + 2, __float_as_uint(rho));
-    max_into(small + 3, (unsigned)(E + 128));        // range of the row scales: when all rows share one scale (normalised
-    max_into(small + 4, 255u - (unsigned)(E + 128));  // features) the Gram epilogue skips the per-row / per-column factors
+    if (live) {
+      sq[row] = f;
+      rscale[row] = ldexpf(1.f, E);
+      if (thr_g != nullptr) thr_g[row] = 0xFF800000u;  // float_to_ordered(+inf): the row's shared threshold (knn_tc.cu)
+      if (row == 0) small[5] = (L != nullptr) ? 1u : 2u;  // operand sides whose rounding rho has to cover (knn_err_bound)
+    }
+    sh_max[0][warp] = (f == f) ? __float_as_uint(f) : 0u;      // non-negative floats order like their bits
+    sh_max[1][warp] = (rho == rho) ? __float_as_uint(rho) : 0u;
+    sh_max[2][warp] = (unsigned)(E + 128);         // range of the row scales: when all rows share one scale (normalised
+    sh_max[3][warp] = 255u - (unsigned)(E + 128);  // features) the Gram epilogue skips the per-row / per-column factors
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned v = sh_max[lane >> 3][lane & 7];  // lane = 8 * quantity + warp
+    unsigned m = v;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(FULL, m, o));
+    if ((lane & 7) == 0) max_into(small + (lane == 0 ? 0 : 1 + (lane >> 3)), m);  // small[0], [2], [3], [4]
   }
 }
 
@@ -356,11 +392,15 @@ __device__ __forceinline__ double exact_d2_reg(const double (&xr)[16], const flo
   return warp_sum(part);
 }
 
-// |d~^2_ij - d^2_ij| <= err_coef (|x_i|^2 + max|x|^2) + 2 |x_i| rho.  small[0] = bits of max_j |x_j|^2, small[2] = bits of
-// rho, the largest one-sided operand residual of the f16x2 Gram path (0 on the other paths).
+// |d~^2_ij - d^2_ij| <= err_coef (|x_i|^2 + max|x|^2) + 2 * [rho term].  small[0] = bits of max_j |x_j|^2, small[2] = bits of
+// rho = max_j |x_j - hi_j 2^E_j|_2, the largest residual of the fp16 operands (0 on the SIMT path), small[5] = how many
+// operand sides carry it: two passes, (hi + lo)_i . hi_j: |x_i| rho; one pass, hi_i . hi_j:
+// |x_i . x_j - hi_i . hi_j| <= |x_i - hi_i| |x_j| + |hi_i| |x_j - hi_j| <= rho (|x_j| + |x_i| + rho).
 __device__ __forceinline__ double knn_err_bound(float err_coef, float sqi, const unsigned* __restrict__ small) {
   const double sqm = (double)__uint_as_float(small[0]), rho = (double)__uint_as_float(small[2]);
-  return (double)err_coef * ((double)sqi + sqm) + 2.0 * sqrt((double)sqi) * rho * 1.000001;
+  const double xi = sqrt((double)sqi);
+  const double rterm = (small[5] == 2u) ? rho * (xi + sqrt(sqm) + rho) : xi * rho;
+  return (double)err_coef * ((double)sqi + sqm) + 2.0 * rterm * 1.000001;
 }
 
 template <bool VEC4>
@@ -368,7 +408,7 @@ __global__ void __launch_bounds__(RERANK_WARPS * 32)
 knn_rerank_kernel(const float* __restrict__ X, const float* __restrict__ sq, const unsigned* __restrict__ sqmax_bits,
                   int n, int d, int k, int row_end, CandLayout lay, const u64* __restrict__ cand, float err_coef,
                   int* __restrict__ knn_idx, float* __restrict__ knn_dist, int* __restrict__ flag_count,
-                  int* __restrict__ flag_rows) {
+                  int* __restrict__ flag_rows, int force_rows) {
   extern __shared__ __align__(16) float xs[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = lay.row_begin + blockIdx.x * RERANK_WARPS + warp;
@@ -448,6 +488,7 @@ knn_rerank_kernel(const float* __restrict__ X, const float* __restrict__ sq, con
     double dk = __shfl_sync(FULL, myd2, __ffs(who) - 1);
     ok = ((double)lower - errb > dk) || (lower == INFINITY);
   }
+  if (i - lay.row_begin < force_rows) ok = false;  // GLL_B200_KNN_FORCE_FALLBACK (tests): treat the first rows as unproven
   if (!ok && lane == 0) {
     int p = atomicAdd(flag_count, 1);
     flag_rows[p] = i;
@@ -530,6 +571,116 @@ knn_fallback_kernel(const float* __restrict__ X, int n, int d, int k, const int*
       __syncthreads();
     }
     __syncthreads();
+  }
+}
+
+// ---- brute-force fallback for k - 1 <= 32, fast for FEW rows: the flagged rows' column ranges are dealt to all CTAs ----
+// (a flagged row used to be one CTA's job: 171 ms for two rows of a 1M-node graph.)  Task t = (flagged row f, column chunk c)
+// with C = max(1, G / nflag) chunks per row; every task leaves the 32 smallest (exact fp64 distance, index) pairs of its
+// chunk; with C == 1 that is the row's answer, otherwise knn_fallback_merge_kernel merges the C lists of a row.
+template <bool VEC4>
+__global__ void __launch_bounds__(FB_WARPS * 32)
+knn_fallback_scan_kernel(const float* __restrict__ X, int n, int d, int k, const int* __restrict__ flag_count,
+                         const int* __restrict__ flag_rows, int* __restrict__ knn_idx, float* __restrict__ knn_dist,
+                         int* __restrict__ info, double* __restrict__ part_d, int* __restrict__ part_j) {
+  extern __shared__ __align__(16) float xs[];
+  __shared__ double sd[FB_WARPS][32];
+  __shared__ int sj[FB_WARPS][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nflag = *flag_count;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && info != nullptr) {
+    info[GLL_INFO_KNN_FALLBACK_ROWS] = nflag;
+    if (nflag > 0) atomicOr(&info[GLL_INFO_STATUS], GLL_STATUS_KNN_FALLBACK);
+  }
+  if (nflag == 0) return;
+  const int G = gridDim.x, C = max(1, G / nflag);
+  const long long T = (long long)nflag * C;
+  for (long long t = blockIdx.x; t < T; t += G) {
+    const int f = (int)(t / C), c = (int)(t - (long long)f * C);
+    const int i = flag_rows[f];
+    const int j0 = (int)((long long)n * c / C), j1 = (int)((long long)n * (c + 1) / C);
+    __syncthreads();  // the previous task's readers of xs / sd / sj are done
+    for (int q = threadIdx.x; q < d; q += blockDim.x) xs[q] = X[(size_t)i * d + q];
+    __syncthreads();
+    double md = INFINITY, thr_d = INFINITY;
+    int mj = 0x7fffffff, thr_j = 0x7fffffff;
+    for (int j = j0 + warp; j < j1; j += FB_WARPS) {
+      if (j == i) continue;
+      const double v = exact_d2<VEC4>(xs, X + (size_t)j * d, d, lane);
+      if (v < thr_d || (v == thr_d && j < thr_j)) {  // warp-uniform: only pairs that enter the list pay for the insertion
+        list_insert_d(md, mj, v, j, lane);
+        thr_d = __shfl_sync(FULL, md, 31);
+        thr_j = __shfl_sync(FULL, mj, 31);
+      }
+    }
+    sd[warp][lane] = md;
+    sj[warp][lane] = mj;
+    __syncthreads();
+    if (warp == 0) {
+      for (int w = 1; w < FB_WARPS; ++w)
+        for (int e = 0; e < 32; ++e) {
+          const int xj = sj[w][e];
+          if (xj == 0x7fffffff) break;
+          const double xd = sd[w][e];
+          if (!(xd < thr_d || (xd == thr_d && xj < thr_j))) break;  // the list is sorted: nothing behind can enter either
+          list_insert_d(md, mj, xd, xj, lane);
+          thr_d = __shfl_sync(FULL, md, 31);
+          thr_j = __shfl_sync(FULL, mj, 31);
+        }
+      if (C == 1) {
+        if (lane < k - 1 && mj != 0x7fffffff) {
+          knn_idx[(size_t)i * k + 1 + lane] = mj;
+          knn_dist[(size_t)i * k + 1 + lane] = (float)sqrt(md);
+        }
+        if (lane == 0) {
+          knn_idx[(size_t)i * k] = i;
+          knn_dist[(size_t)i * k] = 0.f;
+        }
+      } else {
+        part_d[(size_t)t * 32 + lane] = md;
+        part_j[(size_t)t * 32 + lane] = mj;
+      }
+    }
+  }
+}
+
+// one warp per flagged row merges the row's C chunk lists (no-op when the scan kernel already wrote the answers)
+__global__ void __launch_bounds__(FB_WARPS * 32)
+knn_fallback_merge_kernel(int k, int scan_grid, const int* __restrict__ flag_count, const int* __restrict__ flag_rows,
+                          int* __restrict__ knn_idx, float* __restrict__ knn_dist, const double* __restrict__ part_d,
+                          const int* __restrict__ part_j) {
+  const int nflag = *flag_count;
+  if (nflag == 0) return;
+  const int C = max(1, scan_grid / nflag);
+  if (C == 1) return;
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * FB_WARPS + (threadIdx.x >> 5), nw = gridDim.x * FB_WARPS;
+  for (int f = gw; f < nflag; f += nw) {
+    const int i = flag_rows[f];
+    double md = part_d[(size_t)f * C * 32 + lane], thr_d;
+    int mj = part_j[(size_t)f * C * 32 + lane], thr_j;
+    thr_d = __shfl_sync(FULL, md, 31);
+    thr_j = __shfl_sync(FULL, mj, 31);
+    for (int c = 1; c < C; ++c) {
+      const double ld = part_d[((size_t)f * C + c) * 32 + lane];
+      const int lj = part_j[((size_t)f * C + c) * 32 + lane];
+      for (int e = 0; e < 32; ++e) {
+        const double xd = __shfl_sync(FULL, ld, e);
+        const int xj = __shfl_sync(FULL, lj, e);
+        if (xj == 0x7fffffff || !(xd < thr_d || (xd == thr_d && xj < thr_j))) break;  // sorted list
+        list_insert_d(md, mj, xd, xj, lane);
+        thr_d = __shfl_sync(FULL, md, 31);
+        thr_j = __shfl_sync(FULL, mj, 31);
+      }
+    }
+    if (lane < k - 1 && mj != 0x7fffffff) {
+      knn_idx[(size_t)i * k + 1 + lane] = mj;
+      knn_dist[(size_t)i * k + 1 + lane] = (float)sqrt(md);
+    }
+    if (lane == 0) {
+      knn_idx[(size_t)i * k] = i;
+      knn_dist[(size_t)i * k] = 0.f;
+    }
   }
 }
 
@@ -627,20 +778,25 @@ knn_rerank64_kernel(const float* __restrict__ X, const float* __restrict__ sq, c
 
 }  // namespace
 
+int knn_fallback_grid() { return 2 * device_info().sms; }
+size_t knn_fallback_scratch_bytes() { return align_up((size_t)knn_fallback_grid() * 32 * (sizeof(double) + sizeof(int)), 256); }
+
 int knn_finish(const float* X, const float* sq, const unsigned* sqmax_bits, int n, int d, int k, int row_begin, int row_end,
                CandLayout lay, const u64* cand, float err_coef, int* knn_idx, float* knn_dist, int* flag_count, int* flag_rows,
-               int* info, cudaStream_t st) {
+               int* info, void* fb_scratch, cudaStream_t st) {
   const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
   size_t smem = sizeof(float) * (size_t)RERANK_WARPS * d;
   lay.row_begin = row_begin;
   int blocks = ceil_div(row_end - row_begin, RERANK_WARPS);
+  int force_rows = 0;
+  if (const char* e = getenv("GLL_B200_KNN_FORCE_FALLBACK")) force_rows = atoi(e);
   if (vec4) {
     if (smem > 48 * 1024)
       GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
       GLL_PROF(KID_RERANK, st);
       knn_rerank_kernel<true><<<blocks, RERANK_WARPS * 32, smem, st>>>(X, sq, sqmax_bits, n, d, k, row_end, lay, cand,
-                                                                      err_coef, knn_idx, knn_dist, flag_count, flag_rows);
+                                                                      err_coef, knn_idx, knn_dist, flag_count, flag_rows, force_rows);
     }
   } else {
     if (smem > 48 * 1024)
@@ -648,19 +804,26 @@ int knn_finish(const float* X, const float* sq, const unsigned* sqmax_bits, int 
     {
       GLL_PROF(KID_RERANK, st);
       knn_rerank_kernel<false><<<blocks, RERANK_WARPS * 32, smem, st>>>(X, sq, sqmax_bits, n, d, k, row_end, lay, cand,
-                                                                       err_coef, knn_idx, knn_dist, flag_count, flag_rows);
+                                                                       err_coef, knn_idx, knn_dist, flag_count, flag_rows, force_rows);
     }
   }
   GLL_LAUNCH_CHECK();
   size_t fsmem = sizeof(float) * (size_t)d;
-  int fblocks = device_info().sms;
   if (getenv("GLL_B200_KNN_DEBUG") != nullptr) return GLL_OK;  // timing experiments: every row would be "unproven"
   {
+    // rows whose completeness proof failed: exact brute force, the rows' column ranges dealt to all CTAs
+    const int fblocks = knn_fallback_grid();
+    double* part_d = reinterpret_cast<double*>(fb_scratch);
+    int* part_j = reinterpret_cast<int*>(part_d + (size_t)fblocks * 32);
     GLL_PROF(KID_KNN_FALLBACK, st);
     if (vec4)
-      knn_fallback_kernel<true><<<fblocks, FB_WARPS * 32, fsmem, st>>>(X, n, d, k, flag_count, flag_rows, knn_idx, knn_dist, info);
+      knn_fallback_scan_kernel<true><<<fblocks, FB_WARPS * 32, fsmem, st>>>(X, n, d, k, flag_count, flag_rows, knn_idx, knn_dist, info,
+                                                                           part_d, part_j);
     else
-      knn_fallback_kernel<false><<<fblocks, FB_WARPS * 32, fsmem, st>>>(X, n, d, k, flag_count, flag_rows, knn_idx, knn_dist, info);
+      knn_fallback_scan_kernel<false><<<fblocks, FB_WARPS * 32, fsmem, st>>>(X, n, d, k, flag_count, flag_rows, knn_idx, knn_dist, info,
+                                                                            part_d, part_j);
+    GLL_LAUNCH_CHECK();
+    knn_fallback_merge_kernel<<<8, FB_WARPS * 32, 0, st>>>(k, fblocks, flag_count, flag_rows, knn_idx, knn_dist, part_d, part_j);
   }
   GLL_LAUNCH_CHECK();
   return GLL_OK;
@@ -730,18 +893,30 @@ size_t knn_ws_bytes(int n, int d, int k, int row_begin, int row_end) {
   b += align_up(sizeof(unsigned) * (size_t)n, 256);                     // per-row shared thresholds
   b += align_up(sizeof(float) * (size_t)n, 256);                        // per-row operand scale (f16x2 split)
   if (k > KC + 1) b += 2 * align_up(sizeof(u64) * rows * KC, 256) + align_up(sizeof(u64) * (size_t)n, 256);  // merged lists, excl
+  b += knn_fallback_scratch_bytes() + 256;                              // chunk lists of the brute-force fallback
   return b + 1024;
 }
 
-namespace {
-__global__ void fill_ones_kernel(float* p, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = 1.f;
+// fp16 operand split + norms: rows of up to 1024 padded columns stay in registers (one sweep over X)
+static int launch_split_f16(const float* X, int n, int d, const TcPlan& plan, float* sq, unsigned* small, char* tc_ws, float* rscale,
+                            unsigned* thr_g, cudaStream_t st) {
+  __half* H = reinterpret_cast<__half*>(tc_ws);
+  __half* L = (plan.passes == 2) ? reinterpret_cast<__half*>(tc_ws + align_up((size_t)n * plan.d_pad * 2, 256)) : nullptr;
+  const int grid = ceil_div((long long)n * 32, 256);
+  if (plan.d_pad <= 256)
+    sqnorm_split_f16_kernel<4><<<grid, 256, 0, st>>>(X, n, d, plan.d_pad, sq, small, H, L, rscale, thr_g);
+  else if (plan.d_pad <= 512)
+    sqnorm_split_f16_kernel<8><<<grid, 256, 0, st>>>(X, n, d, plan.d_pad, sq, small, H, L, rscale, thr_g);
+  else if (plan.d_pad <= 1024)
+    sqnorm_split_f16_kernel<16><<<grid, 256, 0, st>>>(X, n, d, plan.d_pad, sq, small, H, L, rscale, thr_g);
+  else
+    sqnorm_split_f16_kernel<0><<<grid, 256, 0, st>>>(X, n, d, plan.d_pad, sq, small, H, L, rscale, thr_g);
+  GLL_LAUNCH_CHECK();
+  return GLL_OK;
 }
-}  // namespace
 
 // Verification entry (gll_debug_gram_tile): operand split of the whole matrix as knn_run does it, then the raw tensor-core
-// accumulator of unit (row_tile, col_tile) and the rows' operand scale (2^E_i; 1 for the bf16 split).
+// accumulator of unit (row_tile, col_tile) and the rows' operand scale 2^E_i.
 int knn_debug_gram_tile(const float* X, int n, int d, int row_tile, int col_tile, float* acc_out, float* rscale_out, void* ws,
                         size_t ws_bytes, cudaStream_t st) {
   GLL_REQUIRE(X && acc_out && rscale_out && ws, "null pointer");
@@ -758,17 +933,9 @@ int knn_debug_gram_tile(const float* X, int n, int d, int row_tile, int col_tile
   unsigned* small = cv.take<unsigned>(64);
   char* tc_ws = cv.take<char>(knn_tc_ws_upper(n, d));
   float* rscale = cv.take<float>(n);
-  __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(tc_ws);
-  __nv_bfloat16* L = reinterpret_cast<__nv_bfloat16*>(tc_ws + align_up((size_t)n * plan.d_pad * 2, 256));
   GLL_CUDA_CHECK(cudaMemsetAsync(small, 0, 256, st));
-  if (plan.f16x2) {
-    sqnorm_split_f16_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(X, n, d, plan.d_pad, sq, small, reinterpret_cast<__half*>(H),
-                                                                              reinterpret_cast<__half*>(L), rscale, nullptr);
-  } else {
-    sqnorm_split_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(X, n, d, plan.d_pad, sq, small, H, L, nullptr);
-    fill_ones_kernel<<<ceil_div(n, 256), 256, 0, st>>>(rscale, n);
-  }
-  GLL_LAUNCH_CHECK();
+  const int rcs = launch_split_f16(X, n, d, plan, sq, small, tc_ws, rscale, nullptr, st);
+  if (rcs) return rcs;
   GLL_CUDA_CHECK(cudaMemcpyAsync(rscale_out, rscale, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
   return knn_tc_debug_tile(plan, n, tc_ws, row_tile, col_tile, acc_out, st);
 }
@@ -796,7 +963,8 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
   int* flag_rows = cv.take<int>(rows);
   char* tc_ws = cv.take<char>(knn_tc_ws_upper(n, d));
   unsigned* thr_g = cv.take<unsigned>(n);
-  float* rscale = cv.take<float>(n);  // per-row power-of-two scale of the f16x2 operand split
+  float* rscale = cv.take<float>(n);  // per-row power-of-two scale of the fp16 operands
+  void* fb_scratch = cv.take<char>(knn_fallback_scratch_bytes());
   {
     const char* sh = getenv("GLL_B200_KNN_SHARE");  // "0": every candidate set keeps its own threshold (experiments)
     if (sh && sh[0] == '0') thr_g = nullptr;
@@ -805,22 +973,17 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
   CandLayout lay;
   float err_coef;
   const TcPlan plan = knn_tc_plan(n, d, row_begin, row_end);
-  __nv_bfloat16 *H = nullptr, *L = nullptr;
-  if (plan.ok) {
-    H = reinterpret_cast<__nv_bfloat16*>(tc_ws);
-    L = reinterpret_cast<__nv_bfloat16*>(tc_ws + align_up((size_t)n * plan.d_pad * 2, 256));
-  }
   GLL_CUDA_CHECK(cudaMemsetAsync(small, 0, 256, st));
   {
     GLL_PROF(KID_SQNORM, st);
-    if (plan.ok && plan.f16x2) {
-      sqnorm_split_f16_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(X, n, d, plan.d_pad, sq, small, reinterpret_cast<__half*>(H),
-                                                                                reinterpret_cast<__half*>(L), rscale, thr_g);
+    if (plan.ok) {
+      const int rcs = launch_split_f16(X, n, d, plan, sq, small, tc_ws, rscale, thr_g, st);
+      if (rcs) return rcs;
     } else {
-      sqnorm_split_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(X, n, d, plan.ok ? plan.d_pad : d, sq, sqmax_bits, H, L, thr_g);
+      sqnorm_kernel<<<ceil_div((long long)n * 32, 256), 256, 0, st>>>(X, n, d, sq, sqmax_bits);
+      GLL_LAUNCH_CHECK();
     }
   }
-  GLL_LAUNCH_CHECK();
 
   if (k > KC + 1) {
     // ---- k in (33, 64]: two rounds of the tensor-core search, the second admits only keys beyond the first round's 32nd ----
@@ -836,25 +999,25 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
     lay.units = plan.units;
     lay.row_begin = row_begin;
     const int mblocks = ceil_div(rows, RERANK_WARPS);
-    int rc = knn_tc_candidates(X, sq, plan.f16x2 ? rscale : nullptr, small, n, d, row_end, plan, tc_ws, cand, nullptr, thr_g, st);
+    int rc = knn_tc_candidates(X, sq, rscale, small, n, d, row_end, plan, tc_ws, cand, nullptr, thr_g, st);
     if (rc) return rc;
     {
       GLL_PROF(KID_RERANK, st);
       knn_merge_kernel<<<mblocks, RERANK_WARPS * 32, 0, st>>>(row_end, lay, cand, merged1, excl);
     }
     GLL_LAUNCH_CHECK();
-    rc = knn_tc_candidates(X, sq, plan.f16x2 ? rscale : nullptr, small, n, d, row_end, plan, tc_ws, cand, excl, nullptr, st);  // second round: own thresholds
+    rc = knn_tc_candidates(X, sq, rscale, small, n, d, row_end, plan, tc_ws, cand, excl, nullptr, st);  // second round: own thresholds
     if (rc) return rc;
     {
       GLL_PROF(KID_RERANK, st);
       knn_merge_kernel<<<mblocks, RERANK_WARPS * 32, 0, st>>>(row_end, lay, cand, merged2, nullptr);
     }
     GLL_LAUNCH_CHECK();
-    return knn_finish64(X, sq, sqmax_bits, n, d, k, row_begin, row_end, merged1, merged2, knn_tc_err_coef(d, plan.f16x2), knn_idx, knn_dist,
+    return knn_finish64(X, sq, sqmax_bits, n, d, k, row_begin, row_end, merged1, merged2, knn_tc_err_coef(d, plan.passes), knn_idx, knn_dist,
                         flag_count, flag_rows, info, st);
   }
   if (plan.ok) {  // tcgen05 / TMA Gram GEMM with the fused top-k epilogue
-    int rc = knn_tc_candidates(X, sq, plan.f16x2 ? rscale : nullptr, small, n, d, row_end, plan, tc_ws, cand, nullptr, thr_g, st);
+    int rc = knn_tc_candidates(X, sq, rscale, small, n, d, row_end, plan, tc_ws, cand, nullptr, thr_g, st);
     if (rc) return rc;
     lay.stride = plan.max_splits;
     lay.tc = plan.aligned ? 2 : 1;
@@ -862,7 +1025,7 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
     lay.col_tiles = plan.col_tiles;
     lay.grid = plan.grid;
     lay.units = plan.units;
-    err_coef = knn_tc_err_coef(d, plan.f16x2);
+    err_coef = knn_tc_err_coef(d, plan.passes);
   } else {  // fp32 SIMT Gram (tiny graphs, or forced by GLL_B200_KNN_PATH=simt)
     int cps;
     const int splits = simt_splits(n, rows, &cps);
@@ -892,7 +1055,7 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
     err_coef = (float)(((double)d * u / (1.0 - (double)d * u) + 4.0 * u) * 1.0001);
   }
   return knn_finish(X, sq, sqmax_bits, n, d, k, row_begin, row_end, lay, cand, err_coef, knn_idx, knn_dist, flag_count, flag_rows,
-                    info, st);
+                    info, fb_scratch, st);
 }
 
 }  // namespace gll

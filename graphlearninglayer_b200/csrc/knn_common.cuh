@@ -70,16 +70,16 @@ __device__ __forceinline__ void list_merge_set(u64& mine, u64 c, int lane) {
 // Tensor-core candidate generation (knn_tc.cu).  plan.ok == 0: shape or configuration not handled, use the SIMT path.
 struct TcPlan {
   int ok, d_pad, kblocks, row_tiles, col_tiles, grid, max_splits, rt0, aligned, rstep;  // row_tiles counts row GROUPS of rstep tiles
-  int f16x2;        // 1: operands are the fp16 split of the rows of X, each scaled by a power of two, and the Gram entry is (hi + lo).hi (two MMA passes)
+  int passes;       // MMA passes over the fp16 operands (rows of X scaled by a power of two): 1 = hi.hi, 2 = (hi + lo).hi
   long long units;
-  size_t ws_bytes;  // 16-bit hi / lo copies of X
+  size_t ws_bytes;  // fp16 hi / lo copies of X
 };
 
 TcPlan knn_tc_plan(int n, int d, int row_begin, int row_end);
 size_t knn_tc_ws_upper(int n, int d);
 int knn_tc_candidates(const float* X, const float* sq, const float* rscale, const unsigned* small, int n, int d, int row_end, const TcPlan& plan,
                       void* tc_ws, u64* cand, const u64* excl, unsigned* thr_g, cudaStream_t st);
-float knn_tc_err_coef(int d, int f16x2);
+float knn_tc_err_coef(int d, int passes);
 // verification: raw accumulator of one (row tile, column tile) unit, acc_out[128][256] (knn_gram_tile_debug_kernel)
 int knn_tc_debug_tile(const TcPlan& plan, int n, void* tc_ws, int rt, int ct, float* acc_out, cudaStream_t st);
 
@@ -96,6 +96,6 @@ struct CandLayout {
 int knn_finish(const float* X, const float* sq, const unsigned* sqmax_bits, int n, int d, int k, int row_begin, int row_end,
                CandLayout lay,
                const u64* cand, float err_coef, int* knn_idx, float* knn_dist, int* flag_count, int* flag_rows,
-               int* info, cudaStream_t st);
+               int* info, void* fb_scratch, cudaStream_t st);
 
 }  // namespace gll

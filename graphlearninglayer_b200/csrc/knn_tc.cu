@@ -1,22 +1,23 @@
-// K1 on the tensor cores: candidate generation for the exact kNN search as a tcgen05 / TMA Gram GEMM with a fused
-// per-row top-KC epilogue (replaces the annoy search behind gl.weightmatrix.knnsearch, GLL.py:181-189).
+// K1, tensor-core variant -- the pairwise-distance contraction behind knnsearch (GLL.py:181-189) as a tcgen05 / TMA GEMM
+// with the per-row top-32 selection fused into the epilogue; the n x n matrix never leaves the SM.
 //
-// Arithmetic.  One 16-bit pass cannot order neighbours whose squared distances differ by ~1e-3, so the operands are split.
-// Default "f16x2": every row is scaled by an exact power of two to a norm in [148, 296) and split z = hi + lo into two
-// fp16 numbers (sqnorm_split_f16_kernel, knn.cu); the Gram entry is accumulated in fp32 TMEM as (hi_i + lo_i).hi_j -- TWO
-// MMA passes that share the B tile, whose lo half is never loaded.  The A side is exact to ~2^-21 (even if fp16 subnormals
-// were flushed: at that norm lo is a normal number for every element that matters); the one-sided B residual
-// rho = max_j |x_j - hi_j 2^E_j| is measured by the split kernel and enters the error bound (knn_err_bound, knn.cu).
-// Option GLL_B200_KNN_SPLIT=bf16x3: x = hi + lo in bf16, hi.hi + lo.hi + hi.lo, three passes (split residual 3 * 2^-18).
-// Either way the result is only used to pick KC = 32 candidates per row; knn_finish() (knn.cu) recomputes the survivors
-// exactly, proves that no true neighbour was missed (error budget knn_tc_err_coef + rho) and redoes unprovable rows by
-// brute force, so the emitted neighbour lists do not depend on tensor-core rounding.
+// Arithmetic.  The GEMM only SELECTS 32 candidates per row; knn_rerank (knn.cu) recomputes them exactly in fp64, proves
+// that no true neighbour was missed and redoes unprovable rows by brute force, so the emitted neighbour lists do not
+// depend on tensor-core rounding.  Every row is scaled by an exact power of two to a norm in [148, 296) (no fp16
+// overflow for any feature scale; rows normalised to 1 -- every caller of the layer -- all get the same scale) and
+// rounded to fp16: z = hi (+ lo).  Default, ONE pass: Gram = hi_i . hi_j.  Its error is bounded rigorously by the measured
+// operand residual rho = max_j |x_j - hi_j 2^E_j|_2 (~0.3 * 2^-11 |x_j|, exact in fp64, computed by the split kernel):
+// |x_i.x_j - hi_i.hi_j| <= rho (|x_i| + |x_j| + rho), which for unit rows is 5.6e-4 in d^2 -- the same size as the fp32
+// accumulation budget (with its 4x margin) that the proof carries anyway, and well below the 24th -> 32nd neighbour gaps
+// (3e-3 .. 9e-3 at C2).  GLL_B200_KNN_SPLIT=f16x2: Gram = (hi_i + lo_i) . hi_j in TWO passes (A side exact to 2^-22, the
+// bound keeps the one-sided 2 |x_i| rho): twice the MMA work for a bound that is 30 % tighter; kept for data whose neighbour
+// gaps sit between the two bounds.  (Round 1's three-pass bf16 split is gone: same lists, 50 % more MMAs.)
 //
 // Kernel (one persistent CTA per SM, 10 warps, warp-specialised):
-//   warp 0   TMA producer: per 32-wide K block one stage = {A_hi, A_lo (128 rows), B_hi (256 rows)} = 32 KB, four stages
-//            (bf16x3: + B_lo = 48 KB, three stages), 64-byte swizzle
-//   warp 1   MMA issuer: one elected lane issues 4 (bf16x3: 6) tcgen05.mma per stage (operand pairs x 2 K=16 steps) into one
-//            of two 128 x 256 fp32 accumulators in TMEM (all 512 columns; double buffered against the epilogue)
+//   warp 0   TMA producer: per 32-wide K block one stage = {A_hi (128 rows), B_hi (256 rows)} = 24 KB (two passes: + A_lo
+//            = 32 KB), four stages, 64-byte swizzle
+//   warp 1   MMA issuer: one elected lane issues 2 (two passes: 4) tcgen05.mma per stage (2 K=16 steps per operand pair)
+//            into one of two 128 x 256 fp32 accumulators in TMEM (all 512 columns; double buffered against the epilogue)
 //   warps 2-9 epilogue, two per SM sub-partition: warps w and w+4 read the same TMEM lane quarter (the same 32 rows) and
 //            take one half of the unit's 256 columns each.  tcgen05.ld gives each thread ONE row, 32 columns at a time;
 //            d~^2 = |xi|^2 + |xj|^2 - 2 acc (times the rows' scales) is compared with the row's threshold (a register): one
@@ -24,13 +25,15 @@
 //            candidate set for its column half: an unsorted 32-slot array in shared memory (slot-major, so the 32 threads
 //            of a warp never bank-conflict), 4 groups of 8 slots whose maxima are cached in registers; a survivor replaces
 //            the overall maximum and only that group is rescanned.  All rows of a warp insert concurrently.  The insertion
-//            is one long dependent chain, which is why a sub-partition gets two warps.  The n x n matrix never leaves the SM.
+//            is one long dependent chain, which is why a sub-partition gets two warps.
 //   thresholds  a row's sets (column halves, other CTAs on the same row tile) publish their 32nd-best through a per-row
-//            word in L2 and prune against each other's bound: fewer insertions, same union of candidates.
+//            word in L2 (atomicMin on the ordered-integer image of the float) and prune against each other's bound.
 // Work = (row tile, column tile) units in row-major order, split evenly and contiguously over the CTAs, so a CTA keeps
 // one row tile's sets on chip for many column tiles; sets are flushed to cand[row][slot][KC] when the row tile changes.
+// PAIR (clusters of two CTAs on the same column tile, B tile fetched once and multicast): with one pass the kernel needs
+// 89 bytes of operands per clock and SM from L2, which the multicast cuts to 59.
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cudaTypedefs.h>
 #include <math.h>
 #include <stdlib.h>
@@ -41,31 +44,27 @@
 namespace gll {
 namespace {
 
-// Stage = one K block of {A_hi, A_lo, B_hi, B_lo}: 48 KB at a K block of 32 (64-byte swizzle); the f16x2 split leaves B_lo
-// out and fits four 32 KB stages into the same space.  Three 48 KB stages already ran the MMA pipe at 98 % of the cuBLAS
-// peak when the epilogue does nothing (GLL_B200_KNN_DEBUG=2), and leave room for the candidate sets of EIGHT epilogue warps.
-constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 32, TC_STAGES = 3, TC_MAX_STAGES = 4;
+// Stage = one K block (32 wide, 64-byte swizzle) of {A_hi, A_lo, B_hi} = 32 KB (two passes: (hi + lo).hi) or {A_hi, B_hi} =
+// 24 KB (one pass: hi.hi); four stages, which leaves room for the candidate sets of EIGHT epilogue warps.
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 32, TC_MAX_STAGES = 4;
 constexpr int TC_EPI_WARPS = 8;                        // two per TMEM lane quarter: each takes one half of the 256 columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 8 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;          // 16 KB
-constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // 48 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + TC_B_BYTES;  // 32 KB (the one-pass stage uses the first 24 KB)
 constexpr int TC_CHUNK = 32;                           // columns per tcgen05.ld
 constexpr int TC_TMEM_COLS = 512, TC_ACC_STRIDE = 256;
 
-constexpr size_t TC_OFF_LD = (size_t)TC_STAGES * TC_STAGE_BYTES;             // float [8 warps][KC entries][32 rows]
+constexpr size_t TC_OFF_LD = (size_t)TC_MAX_STAGES * TC_STAGE_BYTES;         // float [8 warps][KC entries][32 rows]
 constexpr size_t TC_OFF_LI = TC_OFF_LD + TC_EPI_WARPS * KC * 32 * 4;         // int   [8 warps][KC entries][32 rows]
 constexpr size_t TC_OFF_SQJ = TC_OFF_LI + TC_EPI_WARPS * KC * 32 * 4;        // float [TC_BN]  |x_j|^2 of the unit's columns
 constexpr size_t TC_OFF_BAR = TC_OFF_SQJ + 2 * TC_BN * 4;                    // (then float [TC_BN] -2 rscale_j) mbarriers + tmem pointer
 constexpr size_t TC_SMEM_BYTES = TC_OFF_BAR + 128 + 1024;                    // + slack for manual 1024 B alignment
 static_assert(TC_SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(TC_MAX_STAGES * (TC_STAGE_BYTES - TC_B_BYTES) <= TC_STAGES * TC_STAGE_BYTES, "f16x2 stages fit in the same space");
 static_assert(8 * (2 * TC_MAX_STAGES + 4) <= 96, "mbarriers end where the TMEM pointer slot begins");
 static_assert(2 * TC_BN <= TC_TMEM_COLS && TC_ACC_STRIDE >= TC_BN, "two accumulators must fit in TMEM");
 
-// M = 128, N = 256, A/B bf16 K-major, D fp32 (layout: cute::UMMA::InstrDescriptor)
-constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-// the same shape with fp16 operands (A / B format fields 0): the f16x2 split
+// M = 128, N = 256, A/B fp16 K-major (format fields 0), D fp32 (layout: cute::UMMA::InstrDescriptor)
 constexpr uint32_t TC_IDESC_F16 = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -138,7 +137,7 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -146,7 +145,7 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// K-major operand tile whose rows are one swizzle atom wide (TC_BK bf16 = 64 B), 8-row groups 8 rows apart
+// K-major operand tile whose rows are one swizzle atom wide (TC_BK fp16 = 64 B), 8-row groups 8 rows apart
 // (cute::UMMA::SmemDescriptor; layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
   constexpr uint64_t sbo = (uint64_t)(8 * TC_BK * 2) >> 4, layout = (TC_BK == 64) ? 2 : 4;
@@ -189,8 +188,8 @@ struct TcParams {
   unsigned* thr_g;    // [n] per-row threshold shared by every candidate set of the row (ordered-uint of the float), or NULL
   int debug;          // GLL_B200_KNN_DEBUG (timing experiments only, results are wrong): 1 no insertions, 2 no TMEM drain
   const u64* excl;    // optional [n]: per row, only keys > excl[row] are candidates (second round of a k > 33 search)
-  int f16x2;          // operands are fp16(x_i 2^-E_i): Gram = (hi + lo).hi in two MMA passes, B_lo is never loaded
-  const float* rscale;  // [n] 2^E_i (f16x2) or NULL: the accumulator holds x_i.x_j / (rscale_i rscale_j)
+  int passes;         // operands are fp16(x_i 2^-E_i): 1 = hi.hi, 2 = (hi + lo).hi (B_lo never exists)
+  const float* rscale;  // [n] 2^E_i: the accumulator holds x_i.x_j / (rscale_i rscale_j)
   const unsigned* small;  // small[3], small[4]: range of E_i over the rows (written by sqnorm_split_f16_kernel)
 };
 
@@ -204,7 +203,7 @@ __host__ __device__ inline int tc_cta_of_unit(long long u, int G, long long unit
 template <bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_constant__ CUtensorMap mapAL,
-                        const __grid_constant__ CUtensorMap mapBH, const __grid_constant__ CUtensorMap mapBL, TcParams P) {
+                        const __grid_constant__ CUtensorMap mapBH, TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // 128B-swizzled operand tiles need 1024 B alignment
@@ -225,9 +224,10 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     u_end = (long long)(b + 1) * P.units / G;
   }
 
-  // f16x2 stages hold {A_hi, A_lo, B_hi} = 32 KB, so FOUR of them fit where three 48 KB stages of the bf16x3 split do
-  const int nstages = P.f16x2 ? TC_MAX_STAGES : TC_STAGES;
-  const uint32_t stage_bytes = P.f16x2 ? (uint32_t)(TC_STAGE_BYTES - TC_B_BYTES) : (uint32_t)TC_STAGE_BYTES;
+  const int nstages = TC_MAX_STAGES;
+  const bool two = P.passes == 2;
+  const uint32_t a_bytes = two ? 2u * TC_A_BYTES : (uint32_t)TC_A_BYTES;  // A_hi (+ A_lo)
+  const uint32_t stage_bytes = a_bytes + (uint32_t)TC_B_BYTES;
   const uint32_t bar_full = base + (uint32_t)TC_OFF_BAR;        // [TC_MAX_STAGES]
   const uint32_t bar_empty = bar_full + 8 * TC_MAX_STAGES;      // [TC_MAX_STAGES]
   const uint32_t bar_tfull = bar_empty + 8 * TC_MAX_STAGES;     // [2]
@@ -238,7 +238,6 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     tma_prefetch_desc(&mapAH);
     tma_prefetch_desc(&mapAL);
     tma_prefetch_desc(&mapBH);
-    tma_prefetch_desc(&mapBL);
     for (int s = 0; s < TC_MAX_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, PAIR ? 2 : 1);  // PAIR: both CTAs' MMAs must have consumed the stage
@@ -273,18 +272,15 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
         for (int kk = 0; kk < KB; ++kk) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
           const uint32_t full = bar_full + 8 * stage;
-          const uint32_t s0 = base + (uint32_t)stage * stage_bytes;
+          const uint32_t s0 = base + (uint32_t)stage * TC_STAGE_BYTES;
           mbar_arrive_expect_tx(full, stage_bytes);
           tma_load_2d(s0, &mapAH, full, kk * TC_BK, rt * TC_BM);
-          tma_load_2d(s0 + TC_A_BYTES, &mapAL, full, kk * TC_BK, rt * TC_BM);
-          if (PAIR) {  // my half of the B tiles (128 of the 256 rows), delivered to both CTAs (128-row boxes: the A maps)
+          if (two) tma_load_2d(s0 + TC_A_BYTES, &mapAL, full, kk * TC_BK, rt * TC_BM);
+          if (PAIR) {  // my half of the B tile (128 of the 256 rows), delivered to both CTAs (128-row boxes: the A map)
             const uint32_t half = (uint32_t)crank * (TC_B_BYTES / 2);
-            tma_load_2d_mc(s0 + 2 * TC_A_BYTES + half, &mapAH, full, kk * TC_BK, ct * TC_BN + crank * (TC_BN / 2), 3);
-            if (!P.f16x2)
-              tma_load_2d_mc(s0 + 2 * TC_A_BYTES + TC_B_BYTES + half, &mapAL, full, kk * TC_BK, ct * TC_BN + crank * (TC_BN / 2), 3);
+            tma_load_2d_mc(s0 + a_bytes + half, &mapAH, full, kk * TC_BK, ct * TC_BN + crank * (TC_BN / 2), 3);
           } else {
-            tma_load_2d(s0 + 2 * TC_A_BYTES, &mapBH, full, kk * TC_BK, ct * TC_BN);
-            if (!P.f16x2) tma_load_2d(s0 + 2 * TC_A_BYTES + TC_B_BYTES, &mapBL, full, kk * TC_BK, ct * TC_BN);
+            tma_load_2d(s0 + a_bytes, &mapBH, full, kk * TC_BK, ct * TC_BN);
           }
           if (++stage == nstages) {
             stage = 0;
@@ -297,8 +293,8 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     // ================================================= MMA issuer ===================================================
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
-    const int nprod = P.f16x2 ? 2 : 3;
-    const uint32_t idesc = P.f16x2 ? TC_IDESC_F16 : TC_IDESC;
+    const int nprod = P.passes;
+    const uint32_t idesc = TC_IDESC_F16;
     for (long long u = u_begin; u < u_end; ++u) {
       mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);  // the epilogue has drained this accumulator
       tc_fence_after();
@@ -307,16 +303,16 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
         mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t s0 = base + (uint32_t)stage * stage_bytes;
+          const uint32_t s0 = base + (uint32_t)stage * TC_STAGE_BYTES;
           const uint64_t dAH = tc_smem_desc(s0), dAL = tc_smem_desc(s0 + TC_A_BYTES);
-          const uint64_t dBH = tc_smem_desc(s0 + 2 * TC_A_BYTES), dBL = tc_smem_desc(s0 + 2 * TC_A_BYTES + TC_B_BYTES);
+          const uint64_t dBH = tc_smem_desc(s0 + a_bytes);
 #pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            if (g >= nprod) break;  // f16x2: hi.hi and lo.hi only
-            const uint64_t da = (g == 1) ? dAL : dAH, db = (g == 2) ? dBL : dBH;  // hi.hi, lo.hi, hi.lo
+          for (int g = 0; g < 2; ++g) {
+            if (g >= nprod) break;  // one pass: hi.hi only
+            const uint64_t da = (g == 1) ? dAL : dAH, db = dBH;  // hi.hi, lo.hi
 #pragma unroll
             for (int k4 = 0; k4 < TC_BK / 16; ++k4)  // +32 B (two 16 B units) per K=16 step inside the swizzle atom
-              tc_mma_bf16(d_tmem, da + (uint64_t)(2 * k4), db + (uint64_t)(2 * k4), idesc, (uint32_t)((kk | g | k4) != 0));
+              tc_mma_f16(d_tmem, da + (uint64_t)(2 * k4), db + (uint64_t)(2 * k4), idesc, (uint32_t)((kk | g | k4) != 0));
           }
           if (PAIR)
             tc_commit_mc(bar_empty + 8 * stage, 3);  // frees the stage in BOTH CTAs (the peer multicasts into mine)
@@ -576,8 +572,8 @@ constexpr size_t TCD_SMEM_BYTES = TCD_OFF_BAR + 64 + 1024;
 
 __global__ void __launch_bounds__(128, 1)
 knn_gram_tile_debug_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_constant__ CUtensorMap mapAL,
-                           const __grid_constant__ CUtensorMap mapBH, const __grid_constant__ CUtensorMap mapBL, int kblocks, int rt,
-                           int ct, int f16x2, float* __restrict__ out) {
+                           const __grid_constant__ CUtensorMap mapBH, int kblocks, int rt, int ct, int passes,
+                           float* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -598,27 +594,27 @@ knn_gram_tile_debug_kernel(const __grid_constant__ CUtensorMap mapAH, const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t stage_bytes = f16x2 ? (uint32_t)(TC_STAGE_BYTES - TC_B_BYTES) : (uint32_t)TC_STAGE_BYTES;
-  const int nprod = f16x2 ? 2 : 3;
-  const uint32_t idesc = f16x2 ? TC_IDESC_F16 : TC_IDESC;
+  const uint32_t a_bytes = passes == 2 ? 2u * TC_A_BYTES : (uint32_t)TC_A_BYTES;
+  const uint32_t stage_bytes = a_bytes + (uint32_t)TC_B_BYTES;
+  const int nprod = passes;
+  const uint32_t idesc = TC_IDESC_F16;
   uint32_t phase = 0;
   for (int kk = 0; kk < kblocks; ++kk) {
     if (threadIdx.x == 0) {
       mbar_arrive_expect_tx(bar_full, stage_bytes);
       tma_load_2d(base, &mapAH, bar_full, kk * TC_BK, rt * TC_BM);
-      tma_load_2d(base + TC_A_BYTES, &mapAL, bar_full, kk * TC_BK, rt * TC_BM);
-      tma_load_2d(base + 2 * TC_A_BYTES, &mapBH, bar_full, kk * TC_BK, ct * TC_BN);
-      if (!f16x2) tma_load_2d(base + 2 * TC_A_BYTES + TC_B_BYTES, &mapBL, bar_full, kk * TC_BK, ct * TC_BN);
+      if (passes == 2) tma_load_2d(base + TC_A_BYTES, &mapAL, bar_full, kk * TC_BK, rt * TC_BM);
+      tma_load_2d(base + a_bytes, &mapBH, bar_full, kk * TC_BK, ct * TC_BN);
     }
     mbar_wait(bar_full, phase);
     tc_fence_after();
     if (threadIdx.x == 0) {
       const uint64_t dAH = tc_smem_desc(base), dAL = tc_smem_desc(base + TC_A_BYTES);
-      const uint64_t dBH = tc_smem_desc(base + 2 * TC_A_BYTES), dBL = tc_smem_desc(base + 2 * TC_A_BYTES + TC_B_BYTES);
+      const uint64_t dBH = tc_smem_desc(base + a_bytes);
       for (int g = 0; g < nprod; ++g) {
-        const uint64_t da = (g == 1) ? dAL : dAH, db = (g == 2) ? dBL : dBH;
+        const uint64_t da = (g == 1) ? dAL : dAH, db = dBH;
         for (int k4 = 0; k4 < TC_BK / 16; ++k4)
-          tc_mma_bf16(tmem_base, da + (uint64_t)(2 * k4), db + (uint64_t)(2 * k4), idesc, (uint32_t)((kk | g | k4) != 0));
+          tc_mma_f16(tmem_base, da + (uint64_t)(2 * k4), db + (uint64_t)(2 * k4), idesc, (uint32_t)((kk | g | k4) != 0));
       }
       tc_commit(bar_mma);
     }
@@ -657,7 +653,7 @@ PFN_cuTensorMapEncodeTiled get_encode_fn() {
   return fn;
 }
 
-int make_map(CUtensorMap* m, const void* base, int n, int d_pad, int box_rows, int f16) {
+int make_map(CUtensorMap* m, const void* base, int n, int d_pad, int box_rows) {
   PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -667,7 +663,7 @@ int make_map(CUtensorMap* m, const void* base, int n, int d_pad, int box_rows, i
   const cuuint64_t gstride[1] = {(cuuint64_t)d_pad * 2};
   const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, (TC_BK == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -713,57 +709,56 @@ TcPlan knn_tc_plan(int n, int d, int row_begin, int row_end) {
     }
     p.max_splits = 2 * ms;  // two candidate sets (column halves) per CTA and row
   }
-  p.ws_bytes = 2 * align_up((size_t)n * p.d_pad * 2, 256);
+  p.ws_bytes = 2 * align_up((size_t)n * p.d_pad * 2, 256);  // hi and (two passes) lo
   p.ok = (p.max_splits <= KNN_MAX_SPLITS) ? 1 : 0;
-  // Operand split.  "f16x2": fp16 hi/lo of the scaled features, Gram = (hi + lo).hi -- two MMA passes; the one-sided
-  // residual (~2^-12 |x_j|, measured per call) enters the completeness proof.  "bf16x3": hi.hi + lo.hi + hi.lo, three
-  // passes, residual 2^-18.  Both only SELECT candidates; the emitted lists are exact either way.
+  // MMA passes over the fp16 operands: 1 = hi.hi (default), 2 = (hi + lo).hi (GLL_B200_KNN_SPLIT=f16x2).  Both only SELECT
+  // candidates; the emitted lists are exact either way (the measured residual rho enters the completeness proof).
   const char* sp = getenv("GLL_B200_KNN_SPLIT");
-  p.f16x2 = (sp && strcmp(sp, "bf16x3") == 0) ? 0 : 1;  // default f16x2 (a third fewer MMAs; same lists, same proof)
+  p.passes = (sp && strcmp(sp, "f16x2") == 0) ? 2 : 1;
   return p;
 }
 
 size_t knn_tc_ws_upper(int n, int d) { return 2 * align_up((size_t)n * (size_t)(ceil_div(d, TC_BK) * TC_BK) * 2, 256) + 512; }
 
-// |d~^2 - d^2| <= coef * (|xi|^2 + |xj|^2): split residual 3*2^-18, fp32 accumulation over 3*d/16 MMA steps of unknown
-// internal rounding (budgeted at 2^-21 per step and per 16-term tree), final fp32 expression 4u; then a 4x margin.
-// f16x2: rows are scaled to a norm of at least 148, so the A side is x_i = (hi + lo) 2^E_i + r_i with
-// |r_ik| <= 2^-22 |x_ik| wherever lo is a normal fp16 number and |r_ik| < 2^-14 2^E_i <= 2^-21.2 |x_i| elsewhere -- even if the
-// tensor core flushed fp16 subnormals to zero: |r_i| <= (2^-22 + 2^-21.2 sqrt(d)) |x_i|, 2 |r_i| |x_j| <= (1 + sqrt(d)) 2^-21 (|xi|^2 + |xj|^2) / 2, budgeted without the 1/2;
-// two MMA passes; the B-side residual is NOT in this coefficient -- it is measured (rho) and added by knn_err_bound().
-float knn_tc_err_coef(int d, int f16x2) {
-  const double steps = (f16x2 ? 2.0 : 3.0) * ceil_div(d, 16) + 8.0;
-  const double split = f16x2 ? (1.0 + sqrt((double)d)) / 2097152.0 * 1.01 : 3.0 / 262144.0;
+// |d~^2 - d^2| <= coef (|xi|^2 + max|x|^2) + [the rho term of knn_err_bound()].  coef budgets what rho does not measure:
+//  * fp16 SUBNORMAL operand elements, in case the multiplier flushed them: rows are scaled to a norm of at least 148, so an
+//    element below fp16's normal range is below 2^-14 2^E_i <= 2^-21.2 |x_i|; over d elements that is at most
+//    2^-21.2 sqrt(d) |x_i| per operand whose rounding is not already in rho (two passes: the A side, whose hi + lo is exact
+//    to 2^-22 |x_ik| elsewhere; one pass: budgeted for both sides, although rho measures hi's own rounding exactly);
+//  * fp32 accumulation over passes * d/16 MMA steps of unknown internal rounding (2^-21 per step and per 16-term tree);
+//  * the final fp32 expression, 4u;  then a 4x margin.
+float knn_tc_err_coef(int d, int passes) {
+  const double steps = (double)passes * ceil_div(d, 16) + 8.0;
+  const double split = (passes == 1 ? 2.0 : 1.0) * (1.0 + sqrt((double)d)) / 2097152.0 * 1.01;
   const double e = split + steps * 4.76837158203125e-7 + 4.0 * 5.9604644775390625e-8;
   return (float)(4.0 * e);
 }
 
 int knn_tc_debug_tile(const TcPlan& plan, int n, void* tc_ws, int rt, int ct, float* acc_out, cudaStream_t st) {
-  __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(tc_ws);
-  __nv_bfloat16* L = reinterpret_cast<__nv_bfloat16*>((char*)tc_ws + align_up((size_t)n * plan.d_pad * 2, 256));
-  CUtensorMap mAH, mAL, mBH, mBL;
+  __half* H = reinterpret_cast<__half*>(tc_ws);
+  __half* L = reinterpret_cast<__half*>((char*)tc_ws + align_up((size_t)n * plan.d_pad * 2, 256));
+  CUtensorMap mAH, mAL, mBH;
   int rc;
-  if ((rc = make_map(&mAH, H, n, plan.d_pad, TC_BM, plan.f16x2))) return rc;
-  if ((rc = make_map(&mAL, L, n, plan.d_pad, TC_BM, plan.f16x2))) return rc;
-  if ((rc = make_map(&mBH, H, n, plan.d_pad, TC_BN, plan.f16x2))) return rc;
-  if ((rc = make_map(&mBL, L, n, plan.d_pad, TC_BN, plan.f16x2))) return rc;
-  GLL_CUDA_CHECK(cudaFuncSetAttribute(knn_gram_tile_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCD_SMEM_BYTES));
-  knn_gram_tile_debug_kernel<<<1, 128, TCD_SMEM_BYTES, st>>>(mAH, mAL, mBH, mBL, plan.kblocks, rt, ct, plan.f16x2, acc_out);
+  if ((rc = make_map(&mAH, H, n, plan.d_pad, TC_BM))) return rc;
+  if ((rc = make_map(&mAL, L, n, plan.d_pad, TC_BM))) return rc;
+  if ((rc = make_map(&mBH, H, n, plan.d_pad, TC_BN))) return rc;
+  GLL_CUDA_CHECK(set_max_dynamic_smem_once((const void*)knn_gram_tile_debug_kernel, (int)TCD_SMEM_BYTES));
+  knn_gram_tile_debug_kernel<<<1, 128, TCD_SMEM_BYTES, st>>>(mAH, mAL, mBH, plan.kblocks, rt, ct, plan.passes, acc_out);
   GLL_LAUNCH_CHECK();
   return GLL_OK;
 }
 
 int knn_tc_candidates(const float* X, const float* sq, const float* rscale, const unsigned* small, int n, int d, int row_end, const TcPlan& plan,
                       void* tc_ws, u64* cand, const u64* excl, unsigned* thr_g, cudaStream_t st) {
-  __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(tc_ws);
-  __nv_bfloat16* L = reinterpret_cast<__nv_bfloat16*>((char*)tc_ws + align_up((size_t)n * plan.d_pad * 2, 256));
-  // H and L (bf16 hi / lo split of X, row stride d_pad) were written by sqnorm_split_kernel (knn.cu)
-  CUtensorMap mAH, mAL, mBH, mBL;
+  __half* H = reinterpret_cast<__half*>(tc_ws);
+  __half* L = reinterpret_cast<__half*>((char*)tc_ws + align_up((size_t)n * plan.d_pad * 2, 256));
+  // H and L (fp16 hi / lo of the scaled rows, row stride d_pad) were written by sqnorm_split_f16_kernel (knn.cu); with one
+  // pass L is never touched (the map is encoded over the same allocation)
+  CUtensorMap mAH, mAL, mBH;
   int rc;
-  if ((rc = make_map(&mAH, H, n, plan.d_pad, TC_BM, plan.f16x2))) return rc;
-  if ((rc = make_map(&mAL, L, n, plan.d_pad, TC_BM, plan.f16x2))) return rc;
-  if ((rc = make_map(&mBH, H, n, plan.d_pad, TC_BN, plan.f16x2))) return rc;
-  if ((rc = make_map(&mBL, L, n, plan.d_pad, TC_BN, plan.f16x2))) return rc;
+  if ((rc = make_map(&mAH, H, n, plan.d_pad, TC_BM))) return rc;
+  if ((rc = make_map(&mAL, L, n, plan.d_pad, TC_BM))) return rc;
+  if ((rc = make_map(&mBH, H, n, plan.d_pad, TC_BN))) return rc;
   TcParams P;
   P.n = n;
   P.kblocks = plan.kblocks;
@@ -778,7 +773,7 @@ int knn_tc_candidates(const float* X, const float* sq, const float* rscale, cons
   P.cand = cand;
   P.excl = excl;
   P.thr_g = thr_g;
-  P.f16x2 = plan.f16x2;
+  P.passes = plan.passes;
   P.rscale = rscale;
   P.small = small;
   {
@@ -803,9 +798,9 @@ int knn_tc_candidates(const float* X, const float* sq, const float* rscale, cons
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      GLL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, knn_gram_topk_tc_kernel<true>, mAH, mAL, mBH, mBL, P));
+      GLL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, knn_gram_topk_tc_kernel<true>, mAH, mAL, mBH, P));
     } else {
-      knn_gram_topk_tc_kernel<false><<<plan.grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mAH, mAL, mBH, mBL, P);
+      knn_gram_topk_tc_kernel<false><<<plan.grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mAH, mAL, mBH, P);
     }
   }
   GLL_LAUNCH_CHECK();

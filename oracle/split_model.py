@@ -3,7 +3,8 @@
 The product kernel (graphlearninglayer_b200/csrc/knn.cu: sqnorm_split_f16_kernel; knn_tc.cu: knn_gram_topk_tc_kernel,
 knn_tc_err_coef; knn.cu: knn_err_bound) replaces the distances behind ``gl.weightmatrix.knnsearch`` (GLL.py:181-189) by
 approximate ones that only SELECT candidates; exactness of the emitted lists rests on a proven bound
-``|d~^2_ij - d^2_ij| <= coef (|x_i|^2 + max|x|^2) + 2 |x_i| rho``.  This file restates the split and the bound in numpy so
+``|d~^2_ij - d^2_ij| <= coef (|x_i|^2 + max|x|^2) + 2 R`` with ``R = rho (|x_i| + max|x| + rho)`` for the default one-pass
+Gram ``hi_i . hi_j`` and ``R = |x_i| rho`` for the two-pass ``(hi_i + lo_i) . hi_j``.  This file restates the split and the bound in numpy so
 that tests/test_split_bound.py can check the bound itself on the CPU, for feature scales and shapes the GPU tests cannot
 sweep.  The fp32 accumulation order inside the tensor core is not modelled (it has its own budget inside ``coef``); the
 Gram entries here are the exact fp64 products of the split operands, and, as a second variant, numpy's fp32 matmul.
@@ -30,7 +31,7 @@ def scale_exponent(sq64: np.ndarray) -> np.ndarray:
     return E
 
 
-def split_f16x2(X: np.ndarray):
+def split_f16(X: np.ndarray):
     """Returns hi, lo (float16, scaled rows), E (int), sq (float32 |x_i|^2) and rho (float32, rounded up)."""
     X = np.ascontiguousarray(X, dtype=np.float32)
     s = (X.astype(np.float64) ** 2).sum(axis=1)
@@ -55,10 +56,13 @@ def flush_fp16_subnormals(h: np.ndarray) -> np.ndarray:
     return out
 
 
-def approx_d2_f16x2(hi, lo, E, sq, fp32_accumulate: bool = False, flush_subnormals: bool = False) -> np.ndarray:
-    """d~^2_ij = |x_i|^2 + (|x_j|^2 + (acc 2^E_i)(-2 2^E_j)) with acc = (hi_i + lo_i) . hi_j, as the epilogue forms it."""
+def approx_d2_f16(hi, lo, E, sq, passes: int = 1, fp32_accumulate: bool = False, flush_subnormals: bool = False) -> np.ndarray:
+    """d~^2_ij = |x_i|^2 + (|x_j|^2 + (acc 2^E_i)(-2 2^E_j)) as the epilogue forms it, with acc = hi_i . hi_j (one pass) or
+    (hi_i + lo_i) . hi_j (two passes)."""
     if flush_subnormals:
         hi, lo = flush_fp16_subnormals(hi), flush_fp16_subnormals(lo)
+    if passes == 1:
+        lo = np.zeros_like(lo)
     if fp32_accumulate:
         a = hi.astype(np.float32) @ hi.astype(np.float32).T + lo.astype(np.float32) @ hi.astype(np.float32).T
         acc = a.astype(np.float32)
@@ -72,18 +76,20 @@ def approx_d2_f16x2(hi, lo, E, sq, fp32_accumulate: bool = False, flush_subnorma
     return (key + sq[:, None]).astype(np.float32)
 
 
-def err_coef(d: int, f16x2: bool = True) -> float:
+def err_coef(d: int, passes: int = 1) -> float:
     """knn_tc_err_coef (knn_tc.cu)."""
-    steps = (2.0 if f16x2 else 3.0) * math.ceil(d / 16) + 8.0
-    split = (1.0 + math.sqrt(d)) / 2097152.0 * 1.01 if f16x2 else 3.0 / 262144.0
+    steps = passes * math.ceil(d / 16) + 8.0
+    split = (2.0 if passes == 1 else 1.0) * (1.0 + math.sqrt(d)) / 2097152.0 * 1.01
     e = split + steps * 4.76837158203125e-7 + 4.0 * 5.9604644775390625e-8
     return float(np.float32(4.0 * e))
 
 
-def err_bound(d: int, sq: np.ndarray, rho) -> np.ndarray:
+def err_bound(d: int, sq: np.ndarray, rho, passes: int = 1) -> np.ndarray:
     """knn_err_bound (knn.cu), per row i."""
     sq64 = sq.astype(np.float64)
-    return err_coef(d) * (sq64 + float(sq.max())) + 2.0 * np.sqrt(sq64) * float(rho) * 1.000001
+    xi, xm, r = np.sqrt(sq64), math.sqrt(float(sq.max())), float(rho)
+    rterm = r * (xi + xm + r) if passes == 1 else xi * r
+    return err_coef(d, passes) * (sq64 + float(sq.max())) + 2.0 * rterm * 1.000001
 
 
 def exact_d2(X: np.ndarray) -> np.ndarray:
@@ -91,36 +97,6 @@ def exact_d2(X: np.ndarray) -> np.ndarray:
     g = Xd @ Xd.T
     s = (Xd ** 2).sum(axis=1)
     return s[:, None] + s[None, :] - 2.0 * g  # fp64 Gram form: its own error (1e-16 relative to the norms) is far below the bounds tested
-
-
-# ---------------------------------------------------------------------------------------------------------------------------
-# the optional three-pass split (GLL_B200_KNN_SPLIT=bf16x3; sqnorm_split_kernel in knn.cu)
-# ---------------------------------------------------------------------------------------------------------------------------
-def to_bf16(x32: np.ndarray) -> np.ndarray:
-    """Round-to-nearest-even float32 -> bfloat16, returned as float32 (what __float2bfloat16_rn produces)."""
-    u = np.ascontiguousarray(x32, dtype=np.float32).view(np.uint32).astype(np.uint64)
-    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
-    return r.astype(np.uint32).view(np.float32)
-
-
-def approx_d2_bf16x3(X: np.ndarray, fp32_accumulate: bool = False) -> np.ndarray:
-    """d~^2_ij = |x_i|^2 + (|x_j|^2 - 2 acc), acc = hi_i.hi_j + lo_i.hi_j + hi_i.lo_j."""
-    X = np.ascontiguousarray(X, dtype=np.float32)
-    sq = (X.astype(np.float64) ** 2).sum(axis=1).astype(np.float32)
-    hi = to_bf16(X)
-    lo = to_bf16(X - hi)
-    if fp32_accumulate:
-        acc = (hi @ hi.T + lo @ hi.T + hi @ lo.T).astype(np.float32)
-    else:
-        h, l = hi.astype(np.float64), lo.astype(np.float64)
-        acc = (h @ h.T + l @ h.T + h @ l.T).astype(np.float32)
-    key = (acc.astype(np.float64) * -2.0 + sq[None, :].astype(np.float64)).astype(np.float32)
-    return (key + sq[:, None]).astype(np.float32), sq
-
-
-def err_bound_bf16x3(d: int, sq: np.ndarray) -> np.ndarray:
-    sq64 = sq.astype(np.float64)
-    return err_coef(d, f16x2=False) * (sq64 + float(sq.max()))
 
 
 # ---------------------------------------------------------------------------------------------------------------------------

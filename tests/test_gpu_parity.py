@@ -129,10 +129,10 @@ KNN_SHAPES = [(0, 300, 500, 64, 10, 2.0), (3, 37, 91, 19, 3, 1.0), (1, 1000, 100
 
 
 def _set_knn_path(monkeypatch, path):
-    """simt: fp32 SIMT Gram; tc: tcgen05 Gram with the bf16 hi/lo split (three MMA passes); tc-f16x2: tcgen05 Gram with the
-    scaled fp16 split, (hi + lo).hi (two passes)."""
+    """simt: fp32 SIMT Gram; tc: tcgen05 Gram on the scaled fp16 rows, hi.hi (one MMA pass, the default); tc-f16x2: the same
+    with the A side split, (hi + lo).hi (two passes)."""
     monkeypatch.setenv("GLL_B200_KNN_PATH", "tc" if path.startswith("tc") else path)
-    monkeypatch.setenv("GLL_B200_KNN_SPLIT", "f16x2" if path == "tc-f16x2" else "bf16x3")
+    monkeypatch.setenv("GLL_B200_KNN_SPLIT", "f16x2" if path == "tc-f16x2" else "f16x1")
 
 
 @pytest.mark.parametrize("path", ["simt", "tc", "tc-f16x2"])  # every Gram path must give the exact lists
@@ -171,8 +171,9 @@ def test_knn_duplicates_and_tiny_n(gll, monkeypatch, path):
     assert np.array_equal(np.sort(idx2.cpu().numpy(), axis=1), np.tile(np.arange(25), (25, 1)))
 
 
+@pytest.mark.parametrize("path", ["tc", "tc-f16x2"])
 @pytest.mark.parametrize("scale", [1.0, 3.0e4, 2.0e-6, "ragged"])
-def test_knn_f16x2_split_any_feature_scale(gll, monkeypatch, scale):
+def test_knn_f16_split_any_feature_scale(gll, monkeypatch, scale, path):
     """The fp16 split scales X by a power of two derived from max |x_i|^2, so features far outside fp16's range (or rows of very
     different norms) must give the same exact lists as the SIMT path, with (almost) no rows sent to the brute-force fallback."""
     _, _lib = gll
@@ -183,15 +184,16 @@ def test_knn_f16x2_split_any_feature_scale(gll, monkeypatch, scale):
         X = (X * np.float32(scale)).astype(np.float32)
     _set_knn_path(monkeypatch, "simt")
     i_s, d_s, _ = run_knn(_lib, X)
-    _set_knn_path(monkeypatch, "tc-f16x2")
+    _set_knn_path(monkeypatch, path)
     i_h, d_h, info = run_knn(_lib, X)
     assert torch.equal(i_s, i_h) and torch.equal(d_s, d_h)
     if scale != "ragged":  # rows 1e6 apart in norm: small rows are legitimately unprovable against the largest row's error
         assert int(info[_lib.INFO_KNN_FALLBACK_ROWS].item()) < 0.02 * X.shape[0]
 
 
-def test_knn_f16x2_full_size_matches_bf16x3(gll, monkeypatch):
-    """C2 size: the two operand splits select the same exact lists, neither needs the fallback."""
+def test_knn_one_pass_full_size_matches_two_pass(gll, monkeypatch):
+    """C2 size: one MMA pass (hi.hi, the default) and two ((hi + lo).hi) select the same exact lists, neither needs the
+    fallback."""
     _, _lib = gll
     X, *_ = O.synth_inputs(1, 10000, 512, 512, 10, 4.5)
     _set_knn_path(monkeypatch, "tc")
@@ -199,19 +201,33 @@ def test_knn_f16x2_full_size_matches_bf16x3(gll, monkeypatch):
     _set_knn_path(monkeypatch, "tc-f16x2")
     i1, d1, info1 = run_knn(_lib, X)
     assert torch.equal(i0, i1) and torch.equal(d0, d1)
-    assert int(info0[_lib.INFO_KNN_FALLBACK_ROWS].item()) == 0 and int(info1[_lib.INFO_KNN_FALLBACK_ROWS].item()) == 0
+    # one pass carries a bound of ~1.3e-3 on d^2 against ~8e-4 for two: a handful of rows out of 10512 may need the fallback
+    assert int(info0[_lib.INFO_KNN_FALLBACK_ROWS].item()) <= 4 and int(info1[_lib.INFO_KNN_FALLBACK_ROWS].item()) == 0
 
 
-@pytest.mark.parametrize("split", ["f16x2", "bf16x3"])
+@pytest.mark.parametrize("forced", [1, 3, 700, 5000])
+def test_knn_fallback_rows_dealt_over_all_ctas(gll, monkeypatch, forced):
+    """Rows whose completeness proof fails are redone by exact brute force; few rows are split into column chunks over all
+    CTAs and merged (1, 3: chunked; 700, 5000: one or more rows per CTA).  Forced here for the first rows: same lists."""
+    _, _lib = gll
+    X, *_ = O.synth_inputs(12, 3000, 1777, 200, 10, 3.5)
+    i0, d0, info0 = run_knn(_lib, X)
+    monkeypatch.setenv("GLL_B200_KNN_FORCE_FALLBACK", str(forced))
+    i1, d1, info1 = run_knn(_lib, X)
+    assert int(info1[_lib.INFO_KNN_FALLBACK_ROWS].item()) >= min(forced, X.shape[0])
+    assert torch.equal(i0, i1) and torch.equal(d0, d1)
+
+
+@pytest.mark.parametrize("passes", [1, 2])
 @pytest.mark.parametrize("d", [512, 200])
-def test_tensor_core_accumulator_matches_split_model(gll, monkeypatch, split, d):
-    """What the tensor core accumulates for one (row tile, column tile) unit against the numpy model of the operand split
-    (oracle/split_model.py), within the fp32-accumulation budget of knn_tc_err_coef.  In particular: fp16 SUBNORMAL `lo`
-    operands must take part (most of them are subnormal for unit rows), or the f16x2 bound would not hold on the device."""
+def test_tensor_core_accumulator_matches_split_model(gll, monkeypatch, passes, d):
+    """What the tensor core accumulates for one (row tile, column tile) unit against the numpy model of the fp16 operands
+    (oracle/split_model.py), within the fp32-accumulation budget of knn_tc_err_coef -- one pass (hi.hi) and two
+    ((hi + lo).hi; fp16 SUBNORMAL `lo` operands must take part there)."""
     from oracle import split_model as S
 
     _, _lib = gll
-    _set_knn_path(monkeypatch, "tc-f16x2" if split == "f16x2" else "tc")
+    _set_knn_path(monkeypatch, "tc-f16x2" if passes == 2 else "tc")
     X, *_ = O.synth_inputs(13, 600, 680, d, 10, 4.5)
     n = X.shape[0]
     rt, ct = 3, 2
@@ -224,21 +240,13 @@ def test_tensor_core_accumulator_matches_split_model(gll, monkeypatch, split, d)
                                             torch.cuda.current_stream().cuda_stream), "gll_debug_gram_tile")
     torch.cuda.synchronize()
     rows, cols = np.arange(rt * 128, rt * 128 + 128), np.arange(ct * 256, ct * 256 + 256)
-    if split == "f16x2":
-        hi, lo, E, sq, rho = S.split_f16x2(X)
-        assert np.array_equal(rscale.cpu().numpy(), np.ldexp(np.float32(1), E).astype(np.float32))
-        a, b = (hi.astype(np.float64) + lo.astype(np.float64))[rows], hi.astype(np.float64)[cols]
-        want = a @ b.T
-        passes = 2
-    else:
-        assert bool((rscale == 1).all())
-        hi = S.to_bf16(X)
-        lo = S.to_bf16(X - hi)
-        h, l = hi.astype(np.float64), lo.astype(np.float64)
-        want = h[rows] @ h[cols].T + l[rows] @ h[cols].T + h[rows] @ l[cols].T
-        a, b = h[rows], h[cols]
+    hi, lo, E, sq, rho = S.split_f16(X)
+    assert np.array_equal(rscale.cpu().numpy(), np.ldexp(np.float32(1), E).astype(np.float32))
+    a = (hi.astype(np.float64) + (lo.astype(np.float64) if passes == 2 else 0.0))[rows]
+    b = hi.astype(np.float64)[cols]
+    want = a @ b.T
     got = acc.cpu().numpy().astype(np.float64)
-    steps = passes * int(np.ceil(d / 16)) + 8 if split == "f16x2" else 3 * int(np.ceil(d / 16)) + 8
+    steps = passes * int(np.ceil(d / 16)) + 8
     budget = steps * 2.0 ** -22 * ((a ** 2).sum(axis=1)[:, None] + (b ** 2).sum(axis=1)[None, :])  # un-margined share of the coefficient
     err = np.abs(got - want)
     assert float((err / budget).max()) <= 1.0, float((err / budget).max())
@@ -445,7 +453,7 @@ def test_layer_vs_oracle_c4_full_size(gll, eps, tau):
     f, loss_ref, gout, bw = O.fwd_bwd(X, Y, yq, tau, eps, solver="cg")
     pred, loss, dX = layer_fwd_bwd(pkg, X, Y, yq, tau, eps)
     info = pkg.last_info()
-    assert info["status"] == 0 and info["knn_fallback_rows"] == 0, info
+    assert info["status"] & ~_lib.STATUS_KNN_FALLBACK == 0 and info["knn_fallback_rows"] <= 8, info  # rows redone exactly
     assert info["nnz"] == f.graph.W.nnz                      # same union graph as the oracle's exact search
     assert O.max_rel(pred.cpu().numpy(), f.pred) < TOL
     assert abs(loss.item() - loss_ref) < 1e-5 * max(1.0, abs(loss_ref))
@@ -698,7 +706,7 @@ def test_sharded_c5s_size_stagewise(gll, partition):
     (-torch.sum(tgt * torch.log(pred + 1e-8)) / pred.shape[0]).backward()
     torch.cuda.synchronize()
     info = sh.last_info()
-    assert info["status"] & ~_lib.STATUS_KNN_FALLBACK == 0 and info["knn_fallback_rows"] == 0, info
+    assert info["status"] & ~_lib.STATUS_KNN_FALLBACK == 0 and info["knn_fallback_rows"] <= 16, info
     p = pred.detach().cpu().numpy()
     assert np.abs(p.sum(axis=1) - 1.0).max() < 5e-5 and p.min() > -1e-5   # tau = 0: rows of the harmonic extension sum to 1
     r = _stagewise_fp64_check(X, Y, yq, sh._last_graph, pred.detach(), Xt.grad)

@@ -11,8 +11,8 @@ sys.path.insert(0, ".")
 from graphlearninglayer_b200 import _lib
 lib = _lib.lib
 n, d = int(sys.argv[1]), int(sys.argv[2])
-g = torch.Generator().manual_seed(0)
-X = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1).cuda()
+from graphlearninglayer_b200.synth import synth_inputs
+X = torch.as_tensor(synth_inputs(1000, n - 512, 512, d, 10, 4.5)[0]).cuda()  # the benchmark's Gaussian clusters
 idx = torch.empty((n, 25), dtype=torch.int32, device="cuda"); dist = torch.empty((n, 25), device="cuda")
 info = torch.zeros(_lib.INFO_WORDS, dtype=torch.int32, device="cuda")
 wsb = lib.gll_knn_workspace_bytes(n, d, 25); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
@@ -29,13 +29,11 @@ print({k: round(v[0] / v[1], 4) for k, v in p.items()}, "fallback_rows", int(inf
 '''
 
 n, d = (sys.argv[1:3] + ["10512", "512"])[:2] if len(sys.argv) >= 3 else ("10512", "512")
-F16 = {"GLL_B200_KNN_SPLIT": "f16x2"}
-ENVS = ({}, {"GLL_B200_KNN_DEBUG": "1"}, {"GLL_B200_KNN_DEBUG": "2"}, {"GLL_B200_KNN_PAIR": "1"},
-        {"GLL_B200_KNN_PAIR": "1", "GLL_B200_KNN_DEBUG": "2"}, F16, dict(F16, GLL_B200_KNN_DEBUG="1"),
-        dict(F16, GLL_B200_KNN_DEBUG="2"))
-if os.environ.get("KNN_EXPERIMENT_ENVS") == "split":  # only the two operand splits
-    ENVS = ({"GLL_B200_KNN_SPLIT": "bf16x3"}, F16, dict(F16, GLL_B200_KNN_DEBUG="1"), dict(F16, GLL_B200_KNN_DEBUG="2"),
-            dict(F16, GLL_B200_KNN_PAIR="1"), dict(F16, GLL_B200_KNN_PAIR="1", GLL_B200_KNN_DEBUG="2"))
+F2 = {"GLL_B200_KNN_SPLIT": "f16x2"}
+PAIR = {"GLL_B200_KNN_PAIR": "1"}
+# one pass (default) / with CTA pairs / two passes, each also without insertions (DEBUG=1) and as MMA + TMA pipeline alone (2)
+ENVS = ({}, {"GLL_B200_KNN_DEBUG": "1"}, {"GLL_B200_KNN_DEBUG": "2"}, PAIR, dict(PAIR, GLL_B200_KNN_DEBUG="1"),
+        dict(PAIR, GLL_B200_KNN_DEBUG="2"), F2, dict(F2, GLL_B200_KNN_DEBUG="2"), dict(F2, **PAIR))
 if os.environ.get("KNN_EXPERIMENT_ENVS") == "default":  # the default configuration, and without the set insertions
     ENVS = ({}, {"GLL_B200_KNN_DEBUG": "1"})
 for env in ENVS:
