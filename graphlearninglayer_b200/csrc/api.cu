@@ -69,9 +69,8 @@ std::vector<ProfRec*> g_prof_recs;
 std::atomic<int> g_prof_on{0};
 std::atomic<long long> g_launches[KID_COUNT];
 const char* const g_kernel_names[KID_COUNT] = {
-    "sqnorm", "knn_gram_topk_simt", "knn_gram_topk_tcgen05", "knn_rerank", "knn_fallback", "graph_count", "scan",
-    "graph_fill", "graph_sort_rows", "edge_weights", "uu_fill", "cg_persistent", "pack_unpack", "edge_grad",
-    "row_gather", "convert", "cg_rows"};
+    "sqnorm", "knn_gram_topk_simt", "knn_gram_topk_tcgen05", "knn_rerank", "knn_fallback", "graph_build", "edge_weights",
+    "cg_persistent", "pack_unpack", "edge_grad", "row_gather", "convert", "cg_rows"};
 }  // namespace
 
 ProfScope::ProfScope(int id_, cudaStream_t st_) : id(id_), st(st_), slot(nullptr) {
@@ -96,8 +95,12 @@ ProfScope::~ProfScope() {
 
 namespace {
 
-__global__ void pack_grad_kernel(const void* __restrict__ g, int is_f64, int m, int l, int lp, float* __restrict__ rhs) {
+// rhs = grad_output padded to lp class columns (fp32); optionally also wt[0 : zero_count] = 0 (the labeled rows of the
+// padded adjoint solution, GLL.py:104) so that the backward needs no separate memset
+__global__ void pack_grad_kernel(const void* __restrict__ g, int is_f64, int m, int l, int lp, float* __restrict__ rhs,
+                                 float* __restrict__ zero_ptr, long long zero_count) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long z = t; z < zero_count; z += (long long)gridDim.x * blockDim.x) zero_ptr[z] = 0.f;
   if (t >= (long long)m * lp) return;
   int r = (int)(t / lp), c = (int)(t % lp);
   float v = 0.f;
@@ -243,9 +246,9 @@ int unpack_columns(const float* src, int rows, int lp_src, int c0, int cnt, floa
   return GLL_OK;
 }
 
-int pack_grad(const void* g, int is_f64, int m, int l, int lp, float* rhs, cudaStream_t st) {
+int pack_grad(const void* g, int is_f64, int m, int l, int lp, float* rhs, cudaStream_t st, float* zero_ptr, long long zero_count) {
   GLL_PROF(KID_PACK, st);
-  pack_grad_kernel<<<ceil_div((long long)m * lp, 256), 256, 0, st>>>(g, is_f64, m, l, lp, rhs);
+  pack_grad_kernel<<<ceil_div((long long)m * lp, 256), 256, 0, st>>>(g, is_f64, m, l, lp, rhs, zero_ptr, zero_count);
   GLL_LAUNCH_CHECK();
   return GLL_OK;
 }
@@ -354,9 +357,7 @@ size_t gll_cg_workspace_bytes(int m, int l) { return cg_ws_bytes(m, l); }
 
 size_t gll_workspace_bytes(int n, int d, int k, int l, int k_lab) {
   size_t b = knn_ws_bytes(n, d, k, 0, n);
-  size_t t = graph_ws_bytes(n, k);
-  if (t > b) b = t;
-  t = weights_ws_bytes(n, k);
+  size_t t = graph_weights_ws_bytes(n, k);
   if (t > b) b = t;
   t = cg_ws_bytes(n - k_lab > 0 ? n - k_lab : 1, l);
   if (t > b) b = t;
@@ -555,19 +556,16 @@ int gll_forward(const float* X, const float* Y, int n, int d, int k, int l, int 
   GLL_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int) * GLL_INFO_WORDS, st));
   int rc = knn_run(X, n, d, k, 0, n, (int*)(S + L.knn_idx), (float*)(S + L.knn_dist), info, workspace, workspace_bytes, st);
   if (rc) return rc;
-  rc = graph_run((int*)(S + L.knn_idx), (float*)(S + L.knn_dist), n, k, (int*)(S + L.row_ptr), (int*)(S + L.col),
-                 (float*)(S + L.dist), info, workspace, workspace_bytes, st);
-  if (rc) return rc;
-  rc = weights_run((int*)(S + L.knn_idx), (float*)(S + L.knn_dist), (int*)(S + L.row_ptr), (int*)(S + L.col),
-                   (float*)(S + L.dist), Y, n, k, l, k_lab, eps_auto, eps_fixed, tau, (float*)(S + L.eps),
-                   (int*)(S + L.kappa), (float*)(S + L.w), (float*)(S + L.deg), (int*)(S + L.uu_ptr), (int*)(S + L.uu_col),
-                   (float*)(S + L.uu_val), (float*)(S + L.diag), (float*)(S + L.rhs), (float*)(S + L.ut), info, workspace,
-                   workspace_bytes, st);
+  rc = graph_weights_run((int*)(S + L.knn_idx), (float*)(S + L.knn_dist), Y, n, k, l, k_lab, eps_auto, eps_fixed, tau,
+                         (int*)(S + L.row_ptr), (int*)(S + L.col), (float*)(S + L.dist), (float*)(S + L.eps), (int*)(S + L.kappa),
+                         (float*)(S + L.w), (float*)(S + L.deg), (int*)(S + L.uu_ptr), (int*)(S + L.uu_col), (float*)(S + L.uu_val),
+                         (float*)(S + L.diag), (float*)(S + L.rhs), (float*)(S + L.ut), info, workspace, workspace_bytes, st);
   if (rc) return rc;
   float* u_out = (float*)(S + L.ut) + (size_t)k_lab * lp;
   rc = cg_run((int*)(S + L.uu_ptr), (int*)(S + L.uu_col), (float*)(S + L.uu_val), (float*)(S + L.diag),
               (float*)(S + L.rhs), m, l, cg_tol, cg_max_iter, u_out, info + GLL_INFO_CG_ITERS_FWD,
-              (float*)(info + GLL_INFO_CG_RESID_FWD), info + GLL_INFO_STATUS, workspace, workspace_bytes, st);
+              (float*)(info + GLL_INFO_CG_RESID_FWD), info + GLL_INFO_STATUS, workspace, workspace_bytes, st,
+              (unsigned*)(info + 12));  // info[12..13]: the on-chip CG's barrier words (zeroed with info, rewound by the kernel)
   if (rc) return rc;
   return unpack_pred(u_out, m, l, lp, pred_out, pred_is_f64, st);
 }
@@ -587,12 +585,12 @@ int gll_backward(const float* X, const void* grad_out, int grad_is_f64, int n, i
   int* info = (int*)(S + L.info);
   const int m = n - k_lab, lp = padded_classes(l);
   float* wt = (float*)(S + L.wt);
-  if (k_lab > 0) GLL_CUDA_CHECK(cudaMemsetAsync(wt, 0, sizeof(float) * (size_t)k_lab * lp, st));  // GLL.py:104
-  int rc = pack_grad(grad_out, grad_is_f64, m, l, lp, (float*)(S + L.rhs), st);
+  int rc = pack_grad(grad_out, grad_is_f64, m, l, lp, (float*)(S + L.rhs), st, wt, (long long)k_lab * lp);  // GLL.py:104
   if (rc) return rc;
   rc = cg_run((int*)(S + L.uu_ptr), (int*)(S + L.uu_col), (float*)(S + L.uu_val), (float*)(S + L.diag),
               (float*)(S + L.rhs), m, l, cg_tol, cg_max_iter, wt + (size_t)k_lab * lp, info + GLL_INFO_CG_ITERS_BWD,
-              (float*)(info + GLL_INFO_CG_RESID_BWD), info + GLL_INFO_STATUS, workspace, workspace_bytes, st);
+              (float*)(info + GLL_INFO_CG_RESID_BWD), info + GLL_INFO_STATUS, workspace, workspace_bytes, st,
+              (unsigned*)(info + 12));
   if (rc) return rc;
   return backward_edges_run(X, n, d, l, k_lab, eps_auto, (int*)(S + L.row_ptr), (int*)(S + L.col), (float*)(S + L.dist),
                             (float*)(S + L.w), (float*)(S + L.eps), (int*)(S + L.kappa), (float*)(S + L.ut), wt,

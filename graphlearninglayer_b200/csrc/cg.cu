@@ -315,7 +315,7 @@ size_t cg_ws_bytes(int m, int l) {
 
 int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, const float* rhs, int m, int l,
            float tol, int max_iter, float* x, int* iters_out, float* resid_out, int* status_out, void* ws, size_t ws_bytes,
-           cudaStream_t st) {
+           cudaStream_t st, unsigned* ext_counter) {
   GLL_REQUIRE(uu_ptr && uu_col && uu_val && diag && rhs && x && ws, "null pointer");
   GLL_REQUIRE(m >= 1 && l >= 1, "bad sizes");
   const int lp = padded_classes(l);
@@ -337,7 +337,8 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
       const int c0 = c * CG_MAX_LP, cnt = min(CG_MAX_LP, l - c0), lpc = padded_classes(cnt);
       int rc = pack_columns(rhs, m, lp, c0, cnt, rhs_c, lpc, st);
       if (rc) return rc;
-      rc = cg_run(uu_ptr, uu_col, uu_val, diag, rhs_c, m, cnt, tol, max_iter, x_c, it_c + c, rs_c + c, status_out, sub, sub_bytes, st);
+      rc = cg_run(uu_ptr, uu_col, uu_val, diag, rhs_c, m, cnt, tol, max_iter, x_c, it_c + c, rs_c + c, status_out, sub, sub_bytes, st,
+                  ext_counter);
       if (rc) return rc;
       rc = unpack_columns(x_c, m, lpc, c0, cnt, x, lp, st);
       if (rc) return rc;
@@ -367,6 +368,7 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
   P.resid_out = resid_out;
   P.status_out = status_out;
   P.rows_per_block = 0;
+  P.ext_counter = ext_counter;
   {  // systems that fit on chip (every config except the sharded 1M-node graph) take the shared-memory-resident kernel
     const char* force = getenv("GLL_B200_CG_PATH");  // "streaming" / "resident": testing knobs
     if (force == nullptr || force[0] == 0) {  // minibatch-sized systems: the one-CTA, register-resident kernel

@@ -21,6 +21,8 @@ struct CgParams {
   float* ap;
   double* partial;    // [2 buffers][2*lp columns][grid]
   unsigned* barrier;  // zeroed before launch
+  unsigned* ext_counter;  // optional [2], zero on entry: the on-chip kernel's grid barrier and exit ticket.  The kernel leaves
+                          // both zero again, so one memset per forward (the info block) serves the forward AND the adjoint solve
   int m, l, lp, rows_per_block, max_iter;
   float tol;
   int* iters_out;

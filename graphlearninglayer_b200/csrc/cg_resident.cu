@@ -397,6 +397,13 @@ __global__ void __launch_bounds__(CR_THREADS, 1) cg_resident_kernel(CrParams R) 
     if (TRACE) cr_stamp(R, iter, 14);
     if (any_bad || !any_live || iter >= P.max_iter) {
       if (b == 0 && tid == 0) write_stats(P, red, lp, iter, any_bad, ctrl->tol2);
+      if (!SINGLE && P.ext_counter != nullptr && tid == 0) {
+        // exit ticket: every CTA is past its last barrier wait when it gets here, so the last one may rewind both words
+        if (atomicAdd(P.ext_counter + 1, 1u) == (unsigned)G - 1u) {
+          P.ext_counter[0] = 0u;
+          P.ext_counter[1] = 0u;
+        }
+      }
       break;
     }
     ++iter;
@@ -506,6 +513,7 @@ int cg_resident_try(const CgParams& P, void* scratch, cudaStream_t st) {
   R.ubuf = cv.take<float>((size_t)P.m * R.ustride);
   R.part = cv.take<double>(3 * (size_t)P.lp * sms);
   R.counter = cv.take<unsigned>(64);
+  if (P.ext_counter != nullptr) R.counter = P.ext_counter;
   R.rows_cap = pl.rows_cap;
   R.seg_cap = pl.seg_cap;
   R.trace = g_cg_trace;
@@ -520,7 +528,7 @@ int cg_resident_try(const CgParams& P, void* scratch, cudaStream_t st) {
     GLL_CUDA_CHECK(cudaLaunchKernel(k_single, dim3(1), dim3(CR_THREADS), args, pl.smem, st));
   } else {
     // only the barrier counter needs a defined start value (the partials of padded class columns are never read)
-    GLL_CUDA_CHECK(cudaMemsetAsync(R.counter, 0, 64 * sizeof(unsigned), st));
+    if (P.ext_counter == nullptr) GLL_CUDA_CHECK(cudaMemsetAsync(R.counter, 0, 64 * sizeof(unsigned), st));
     GLL_PROF(KID_CG, st);
     // cooperative launch: all CTAs are co-resident, which the grid barrier relies on
     GLL_CUDA_CHECK(cudaLaunchCooperativeKernel(k_multi, dim3(pl.grid), dim3(CR_THREADS), args, pl.smem, st));

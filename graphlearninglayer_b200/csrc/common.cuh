@@ -93,9 +93,8 @@ __device__ __forceinline__ float ordered_to_float(uint32_t u) {
 
 // ---- per-kernel launch counter and optional CUDA-event timing (gll_profile_* in the C ABI) ----
 enum KernelId {
-  KID_SQNORM = 0, KID_GRAM_TOPK, KID_GRAM_TOPK_TC, KID_RERANK, KID_KNN_FALLBACK, KID_GRAPH_COUNT, KID_SCAN,
-  KID_GRAPH_FILL, KID_GRAPH_SORT, KID_WEIGHTS, KID_UU_FILL, KID_CG, KID_PACK, KID_EDGE_GRAD, KID_ROW_GATHER,
-  KID_CONVERT, KID_CG_ROWS, KID_COUNT
+  KID_SQNORM = 0, KID_GRAM_TOPK, KID_GRAM_TOPK_TC, KID_RERANK, KID_KNN_FALLBACK, KID_GRAPH, KID_WEIGHTS, KID_CG, KID_PACK,
+  KID_EDGE_GRAD, KID_ROW_GATHER, KID_CONVERT, KID_CG_ROWS, KID_COUNT
 };
 // RAII: counts the launch; when profiling is on, brackets it with two events on the launch stream.
 struct ProfScope {
@@ -123,10 +122,16 @@ int weights_run(const int* knn_idx, const float* knn_dist, const int* row_ptr, c
                 float* eps, int* kappa, float* w, float* deg, int* uu_ptr, int* uu_col, float* uu_val,
                 float* diag, float* rhs, float* ut, int* info, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t weights_ws_bytes(int n, int k);
+// K2 + K3 in one cooperative launch (graph.cu)
+int graph_weights_run(const int* knn_idx, const float* knn_dist, const float* Y, int n, int k, int l, int k_lab, int eps_auto,
+                      float eps_fixed, float tau, int* row_ptr, int* col, float* dist, float* eps, int* kappa, float* w, float* deg,
+                      int* uu_ptr, int* uu_col, float* uu_val, float* diag, float* rhs, float* ut, int* info, void* ws, size_t ws_bytes,
+                      cudaStream_t st);
+size_t graph_weights_ws_bytes(int n, int k);
 
 int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, const float* rhs, int m,
            int l, float tol, int max_iter, float* x, int* iters_out, float* resid_out, int* status_out, void* ws,
-           size_t ws_bytes, cudaStream_t st);
+           size_t ws_bytes, cudaStream_t st, unsigned* ext_counter = nullptr);
 size_t cg_ws_bytes(int m, int l);
 
 // row-partitioned CG (cg_rows.cu): stage launchers.  peers == NULL: the host runs the NCCL collectives between them;
@@ -152,12 +157,10 @@ int backward_edges_run(const float* X, int n, int d, int l, int k_lab, int eps_a
 int pack_columns(const float* src, int rows, int lp_src, int c0, int cnt, float* dst, int lp_dst, cudaStream_t st);
 int unpack_columns(const float* src, int rows, int lp_src, int c0, int cnt, float* dst, int lp_dst, cudaStream_t st);
 
-// exclusive prefix sum of int32 counts[0..n) into out[0..n] (out[n] = total). scratch: scan_ws_bytes(n).
-size_t scan_ws_bytes(int n);
-int exclusive_scan(const int* counts, int n, int* out, void* scratch, cudaStream_t st);
 
 // small utility kernels (api.cu)
-int pack_grad(const void* g, int is_f64, int m, int l, int lp, float* rhs, cudaStream_t st);
+int pack_grad(const void* g, int is_f64, int m, int l, int lp, float* rhs, cudaStream_t st, float* zero_ptr = nullptr,
+              long long zero_count = 0);
 int unpack_pred(const float* ut_u, int m, int l, int lp, void* pred, int is_f64, cudaStream_t st);
 
 inline int padded_classes(int l) { return (l + 3) / 4 * 4; }

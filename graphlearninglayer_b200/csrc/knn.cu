@@ -577,15 +577,17 @@ knn_fallback_kernel(const float* __restrict__ X, int n, int d, int k, const int*
 // ---- brute-force fallback for k - 1 <= 32, fast for FEW rows: the flagged rows' column ranges are dealt to all CTAs ----
 // (a flagged row used to be one CTA's job: 171 ms for two rows of a 1M-node graph.)  Task t = (flagged row f, column chunk c)
 // with C = max(1, G / nflag) chunks per row; every task leaves the 32 smallest (exact fp64 distance, index) pairs of its
-// chunk; with C == 1 that is the row's answer, otherwise knn_fallback_merge_kernel merges the C lists of a row.
+// chunk; with C == 1 that is the row's answer, otherwise the last CTA to finish merges the C lists of every row.
 template <bool VEC4>
 __global__ void __launch_bounds__(FB_WARPS * 32)
 knn_fallback_scan_kernel(const float* __restrict__ X, int n, int d, int k, const int* __restrict__ flag_count,
                          const int* __restrict__ flag_rows, int* __restrict__ knn_idx, float* __restrict__ knn_dist,
-                         int* __restrict__ info, double* __restrict__ part_d, int* __restrict__ part_j) {
+                         int* __restrict__ info, double* __restrict__ part_d, int* __restrict__ part_j,
+                         unsigned* __restrict__ ticket) {
   extern __shared__ __align__(16) float xs[];
   __shared__ double sd[FB_WARPS][32];
   __shared__ int sj[FB_WARPS][32];
+  __shared__ int last_cta;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nflag = *flag_count;
   if (blockIdx.x == 0 && threadIdx.x == 0 && info != nullptr) {
@@ -642,28 +644,25 @@ knn_fallback_scan_kernel(const float* __restrict__ X, int n, int d, int k, const
       }
     }
   }
-}
-
-// one warp per flagged row merges the row's C chunk lists (no-op when the scan kernel already wrote the answers)
-__global__ void __launch_bounds__(FB_WARPS * 32)
-knn_fallback_merge_kernel(int k, int scan_grid, const int* __restrict__ flag_count, const int* __restrict__ flag_rows,
-                          int* __restrict__ knn_idx, float* __restrict__ knn_dist, const double* __restrict__ part_d,
-                          const int* __restrict__ part_j) {
-  const int nflag = *flag_count;
-  if (nflag == 0) return;
-  const int C = max(1, scan_grid / nflag);
   if (C == 1) return;
-  const int lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * FB_WARPS + (threadIdx.x >> 5), nw = gridDim.x * FB_WARPS;
-  for (int f = gw; f < nflag; f += nw) {
+  // the last CTA to finish merges the C chunk lists of every flagged row (one warp per row; nflag < G rows, G lists in all)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last_cta = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!last_cta) return;
+  __threadfence();
+  for (int f = warp; f < nflag; f += FB_WARPS) {
     const int i = flag_rows[f];
-    double md = part_d[(size_t)f * C * 32 + lane], thr_d;
-    int mj = part_j[(size_t)f * C * 32 + lane], thr_j;
-    thr_d = __shfl_sync(FULL, md, 31);
-    thr_j = __shfl_sync(FULL, mj, 31);
+    double md = __ldcg(part_d + (size_t)f * C * 32 + lane);
+    int mj = __ldcg(part_j + (size_t)f * C * 32 + lane);
+    double thr_d = __shfl_sync(FULL, md, 31);
+    int thr_j = __shfl_sync(FULL, mj, 31);
     for (int c = 1; c < C; ++c) {
-      const double ld = part_d[((size_t)f * C + c) * 32 + lane];
-      const int lj = part_j[((size_t)f * C + c) * 32 + lane];
+      const double ld = __ldcg(part_d + ((size_t)f * C + c) * 32 + lane);
+      const int lj = __ldcg(part_j + ((size_t)f * C + c) * 32 + lane);
       for (int e = 0; e < 32; ++e) {
         const double xd = __shfl_sync(FULL, ld, e);
         const int xj = __shfl_sync(FULL, lj, e);
@@ -683,6 +682,7 @@ knn_fallback_merge_kernel(int k, int scan_grid, const int* __restrict__ flag_cou
     }
   }
 }
+
 
 // ---------------------------------------------------------------------------------------------------------
 // k in (33, 64]: two candidate rounds of 32 (the second excludes the first by key), merged and re-ranked together.
@@ -815,15 +815,14 @@ int knn_finish(const float* X, const float* sq, const unsigned* sqmax_bits, int 
     const int fblocks = knn_fallback_grid();
     double* part_d = reinterpret_cast<double*>(fb_scratch);
     int* part_j = reinterpret_cast<int*>(part_d + (size_t)fblocks * 32);
+    unsigned* ticket = reinterpret_cast<unsigned*>(flag_count) + 7;  // small[8]: zeroed with flag_count at the start of the search
     GLL_PROF(KID_KNN_FALLBACK, st);
     if (vec4)
       knn_fallback_scan_kernel<true><<<fblocks, FB_WARPS * 32, fsmem, st>>>(X, n, d, k, flag_count, flag_rows, knn_idx, knn_dist, info,
-                                                                           part_d, part_j);
+                                                                           part_d, part_j, ticket);
     else
       knn_fallback_scan_kernel<false><<<fblocks, FB_WARPS * 32, fsmem, st>>>(X, n, d, k, flag_count, flag_rows, knn_idx, knn_dist, info,
-                                                                            part_d, part_j);
-    GLL_LAUNCH_CHECK();
-    knn_fallback_merge_kernel<<<8, FB_WARPS * 32, 0, st>>>(k, fblocks, flag_count, flag_rows, knn_idx, knn_dist, part_d, part_j);
+                                                                            part_d, part_j, ticket);
   }
   GLL_LAUNCH_CHECK();
   return GLL_OK;

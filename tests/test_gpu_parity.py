@@ -472,6 +472,31 @@ def test_layer_more_than_128_classes(gll):
     assert O.max_rel(dX.cpu().numpy(), bw.dX) < TOL
 
 
+def test_graphed_step_replays_the_layer(gll):
+    """forward + loss + backward captured into CUDA graphs once and replayed on NEW inputs of the same shape: bit-equal to
+    the eager call (the library's launches carry no host-side data dependence)."""
+    pkg, _lib = gll
+    from graphlearninglayer_b200.graphed import GraphedStep
+    from graphlearninglayer_b200.losses import custom_ce_loss
+
+    k_lab, m, d, l = 700, 500, 64, 10
+    step = GraphedStep(k_lab + m, d, k_lab, l, "cuda", tau=0.0, epsilon="auto")
+    for seed in (3, 4):
+        X, Y, _, yq = O.synth_inputs(seed, k_lab, m, d, l, 2.0)
+        Xt = torch.as_tensor(X).cuda().requires_grad_(True)
+        Yt, yt = torch.as_tensor(Y).cuda(), torch.as_tensor(yq).cuda()
+        pred = pkg.LaplaceLearningSparseHard.apply(Xt, Yt, 0.0, "auto")
+        loss = custom_ce_loss(pred, yt)
+        loss.backward()
+        before = _lib.launch_count()
+        loss_g = step(torch.as_tensor(X).cuda(), Yt, yt)
+        assert _lib.launch_count() == before          # nothing was launched through the API: the graphs replayed
+        assert torch.equal(step.pred, pred.detach()) and torch.equal(step.dX, Xt.grad)
+        assert loss_g.item() == loss.item()
+    f, loss_ref, gout, bw = O.fwd_bwd(X, Y, yq, 0.0, "auto", solver="lu")
+    assert O.max_rel(step.pred.cpu().numpy(), f.pred) < TOL and O.max_rel(step.dX.cpu().numpy(), bw.dX) < TOL
+
+
 def test_layer_full_size_properties(gll):
     """C4 size (2048 + 14336, d=512): invariants of SURVEY 4 that need no oracle."""
     pkg, _lib = gll
