@@ -76,6 +76,11 @@ def _load():
     sig("gll_cg_solve", i32, [vp, vp, vp, vp, vp, i32, i32, f32, i32, vp, vp, vp, vp, vp, sz, vp])
     sig("gll_backward_edges", i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
     sig("gll_debug_gram_tile", i32, [vp, i32, i32, i32, i32, vp, vp, vp, sz, vp])
+    sig("gll_base_cache_bytes", sz, [i32])
+    sig("gll_base_cache_workspace_bytes", sz, [i32, i32])
+    sig("gll_base_cache_build", i32, [vp, i32, i32, vp, vp, sz, vp])
+    sig("gll_knn_cached_workspace_bytes", sz, [i32, i32, i32, i32])
+    sig("gll_knn_cached", i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp])
     sig("gll_knn_rows_workspace_bytes", sz, [i32, i32, i32, i32, i32])
     sig("gll_knn_rows", i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp])
     sig("gll_backward_edges_rows", i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp])
@@ -115,7 +120,8 @@ EXPORTS = ["gll_last_error", "gll_version", "gll_device_sm_count", "gll_kernel_c
            "gll_cg_rows_workspace_bytes", "gll_cg_rows_init", "gll_cg_rows_spmv", "gll_cg_rows_update", "gll_ce_loss", "gll_ce_loss_workspace_bytes",
            "gll_cg_rows_peer_mail_bytes", "gll_cg_rows_peer_flag_bytes", "gll_cg_rows_init_p2p", "gll_cg_rows_spmv_p2p",
            "gll_cg_rows_update_p2p", "gll_csr_residual_f64", "gll_normalize_rows",
-           "gll_normalize_rows_backward", "gll_debug_gram_tile"]
+           "gll_normalize_rows_backward", "gll_debug_gram_tile", "gll_base_cache_bytes", "gll_base_cache_workspace_bytes",
+           "gll_base_cache_build", "gll_knn_cached_workspace_bytes", "gll_knn_cached"]
 
 
 def check(rc: int, what: str) -> None:

@@ -369,6 +369,17 @@ int gll_knn(const float* X, int n, int d, int k, int* knn_idx, float* knn_dist, 
   return knn_run(X, n, d, k, 0, n, knn_idx, knn_dist, info, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+size_t gll_base_cache_bytes(int n_base) { return knn_base_cache_bytes(n_base); }
+size_t gll_base_cache_workspace_bytes(int n_base, int d) { return knn_ws_bytes(n_base, d, 25, 0, n_base); }
+int gll_base_cache_build(const float* Xbase, int n_base, int d, void* cache, void* workspace, size_t workspace_bytes, void* stream) {
+  return knn_base_cache_build(Xbase, n_base, d, cache, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+size_t gll_knn_cached_workspace_bytes(int n, int d, int k, int n_base) { return knn_cached_ws_bytes(n, d, k, n_base); }
+int gll_knn_cached(const float* X, int n, int d, int k, int n_base, const void* cache, int* knn_idx, float* knn_dist, int* info,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  return knn_run_cached(X, n, d, k, n_base, cache, knn_idx, knn_dist, info, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 int gll_debug_gram_tile(const float* X, int n, int d, int row_tile, int col_tile, float* acc_out, float* rscale_out, void* workspace,
                         size_t workspace_bytes, void* stream) {
   return knn_debug_gram_tile(X, n, d, row_tile, col_tile, acc_out, rscale_out, workspace, workspace_bytes, (cudaStream_t)stream);

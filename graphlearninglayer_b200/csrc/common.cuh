@@ -110,6 +110,12 @@ struct ProfScope {
 int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int* knn_idx, float* knn_dist, int* info,
             void* ws, size_t ws_bytes, cudaStream_t st);
 size_t knn_ws_bytes(int n, int d, int k, int row_begin, int row_end);
+// base-set reuse across evaluation batches (knn.cu)
+size_t knn_base_cache_bytes(int n_base);
+int knn_base_cache_build(const float* Xbase, int n_base, int d, void* cache, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t knn_cached_ws_bytes(int n, int d, int k, int n_base);
+int knn_run_cached(const float* X, int n, int d, int k, int n_base, const void* cache, int* knn_idx, float* knn_dist, int* info,
+                   void* ws, size_t ws_bytes, cudaStream_t st);
 int knn_debug_gram_tile(const float* X, int n, int d, int row_tile, int col_tile, float* acc_out, float* rscale_out, void* ws,
                         size_t ws_bytes, cudaStream_t st);
 

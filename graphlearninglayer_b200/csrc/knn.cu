@@ -595,7 +595,7 @@ knn_fallback_scan_kernel(const float* __restrict__ X, int n, int d, int k, const
     if (nflag > 0) atomicOr(&info[GLL_INFO_STATUS], GLL_STATUS_KNN_FALLBACK);
   }
   if (nflag == 0) return;
-  const int G = gridDim.x, C = max(1, G / nflag);
+  const int G = gridDim.x, C = max(1, min(64, G / nflag));  // at most 64 chunks per row (what the merge handles quickly)
   const long long T = (long long)nflag * C;
   for (long long t = blockIdx.x; t < T; t += G) {
     const int f = (int)(t / C), c = (int)(t - (long long)f * C);
@@ -606,13 +606,23 @@ knn_fallback_scan_kernel(const float* __restrict__ X, int n, int d, int k, const
     __syncthreads();
     double md = INFINITY, thr_d = INFINITY;
     int mj = 0x7fffffff, thr_j = 0x7fffffff;
-    for (int j = j0 + warp; j < j1; j += FB_WARPS) {
-      if (j == i) continue;
-      const double v = exact_d2<VEC4>(xs, X + (size_t)j * d, d, lane);
-      if (v < thr_d || (v == thr_d && j < thr_j)) {  // warp-uniform: only pairs that enter the list pay for the insertion
-        list_insert_d(md, mj, v, j, lane);
-        thr_d = __shfl_sync(FULL, md, 31);
-        thr_j = __shfl_sync(FULL, mj, 31);
+    // four columns per trip: their row loads and butterflies are independent (one column at a time is a chain of L2 round trips)
+    for (int jb = j0 + 4 * warp; jb < j1; jb += 4 * FB_WARPS) {
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = min(jb + u, j1 - 1);  // clamped duplicates are dropped below
+        v[u] = exact_d2<VEC4>(xs, X + (size_t)j * d, d, lane);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = jb + u;
+        if (j >= j1 || j == i) continue;
+        if (v[u] < thr_d || (v[u] == thr_d && j < thr_j)) {  // warp-uniform: only pairs that enter the list pay for the insertion
+          list_insert_d(md, mj, v[u], j, lane);
+          thr_d = __shfl_sync(FULL, md, 31);
+          thr_j = __shfl_sync(FULL, mj, 31);
+        }
       }
     }
     sd[warp][lane] = md;
@@ -645,7 +655,8 @@ knn_fallback_scan_kernel(const float* __restrict__ X, int n, int d, int k, const
     }
   }
   if (C == 1) return;
-  // the last CTA to finish merges the C chunk lists of every flagged row (one warp per row; nflag < G rows, G lists in all)
+  // the last CTA to finish merges the C chunk lists of every flagged row: its eight warps take C / 8 lists each (the loads of
+  // a warp's lists are issued together), then warp 0 merges the eight partial lists
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -654,31 +665,52 @@ knn_fallback_scan_kernel(const float* __restrict__ X, int n, int d, int k, const
   __syncthreads();
   if (!last_cta) return;
   __threadfence();
-  for (int f = warp; f < nflag; f += FB_WARPS) {
+  for (int f = 0; f < nflag; ++f) {
     const int i = flag_rows[f];
-    double md = __ldcg(part_d + (size_t)f * C * 32 + lane);
-    int mj = __ldcg(part_j + (size_t)f * C * 32 + lane);
-    double thr_d = __shfl_sync(FULL, md, 31);
-    int thr_j = __shfl_sync(FULL, mj, 31);
-    for (int c = 1; c < C; ++c) {
-      const double ld = __ldcg(part_d + ((size_t)f * C + c) * 32 + lane);
-      const int lj = __ldcg(part_j + ((size_t)f * C + c) * 32 + lane);
-      for (int e = 0; e < 32; ++e) {
-        const double xd = __shfl_sync(FULL, ld, e);
-        const int xj = __shfl_sync(FULL, lj, e);
-        if (xj == 0x7fffffff || !(xd < thr_d || (xd == thr_d && xj < thr_j))) break;  // sorted list
-        list_insert_d(md, mj, xd, xj, lane);
-        thr_d = __shfl_sync(FULL, md, 31);
-        thr_j = __shfl_sync(FULL, mj, 31);
+    double md = INFINITY, thr_d = INFINITY;
+    int mj = 0x7fffffff, thr_j = 0x7fffffff;
+    for (int c0 = warp; c0 < C; c0 += 4 * FB_WARPS) {
+      double ld[4];
+      int lj[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u * FB_WARPS;
+        ld[u] = (c < C) ? __ldcg(part_d + ((size_t)f * C + c) * 32 + lane) : INFINITY;
+        lj[u] = (c < C) ? __ldcg(part_j + ((size_t)f * C + c) * 32 + lane) : 0x7fffffff;
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        for (int e = 0; e < 32; ++e) {
+          const double xd = __shfl_sync(FULL, ld[u], e);
+          const int xj = __shfl_sync(FULL, lj[u], e);
+          if (xj == 0x7fffffff || !(xd < thr_d || (xd == thr_d && xj < thr_j))) break;  // sorted list
+          list_insert_d(md, mj, xd, xj, lane);
+          thr_d = __shfl_sync(FULL, md, 31);
+          thr_j = __shfl_sync(FULL, mj, 31);
+        }
     }
-    if (lane < k - 1 && mj != 0x7fffffff) {
-      knn_idx[(size_t)i * k + 1 + lane] = mj;
-      knn_dist[(size_t)i * k + 1 + lane] = (float)sqrt(md);
-    }
-    if (lane == 0) {
-      knn_idx[(size_t)i * k] = i;
-      knn_dist[(size_t)i * k] = 0.f;
+    __syncthreads();
+    sd[warp][lane] = md;
+    sj[warp][lane] = mj;
+    __syncthreads();
+    if (warp == 0) {
+      for (int w = 1; w < FB_WARPS; ++w)
+        for (int e = 0; e < 32; ++e) {
+          const int xj = sj[w][e];
+          const double xd = sd[w][e];
+          if (xj == 0x7fffffff || !(xd < thr_d || (xd == thr_d && xj < thr_j))) break;
+          list_insert_d(md, mj, xd, xj, lane);
+          thr_d = __shfl_sync(FULL, md, 31);
+          thr_j = __shfl_sync(FULL, mj, 31);
+        }
+      if (lane < k - 1 && mj != 0x7fffffff) {
+        knn_idx[(size_t)i * k + 1 + lane] = mj;
+        knn_dist[(size_t)i * k + 1 + lane] = (float)sqrt(md);
+      }
+      if (lane == 0) {
+        knn_idx[(size_t)i * k] = i;
+        knn_dist[(size_t)i * k] = 0.f;
+      }
     }
   }
 }
@@ -1055,6 +1087,181 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
   }
   return knn_finish(X, sq, sqmax_bits, n, d, k, row_begin, row_end, lay, cand, err_coef, knn_idx, knn_dist, flag_count, flag_rows,
                     info, fb_scratch, st);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Base-set reuse across evaluation batches (utils.py:596-621: test_network calls the layer on
+// [base; test batch] with the SAME base rows for every batch).  The base-base part of the search -- n_base^2 of the
+// (n_base + m)^2 pairs -- is done once: per base row the 32 best base columns (approximate keys, as the Gram kernel
+// selects them).  Per call only the batch rows are searched against all columns and the base rows against the batch
+// columns, each base row starting from its cached threshold; the merged candidates go through the usual exact re-rank
+// and completeness proof (approximate distances only have to satisfy the error bound, whichever launch produced them),
+// so the lists are the ones gll_knn gives on the concatenated matrix.
+// ------------------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void base_thr_init_kernel(const u64* __restrict__ cache, const float* __restrict__ sq, int rows, unsigned* __restrict__ thr_g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const u64 last = cache[(size_t)i * KC + KC - 1];
+  float thr = INFINITY;
+  if (last != KEY_INF) {
+    // the epilogue compares d~^2 - |x_i|^2 with the threshold; the cached key holds fl(d~^2): undo the addition rounding UP
+    // (a looser threshold only admits a few more candidates)
+    thr = __fadd_ru(key_dist(last), -sq[i]);
+    thr = fmaf(fabsf(thr), 4.0e-7f, thr) + 1.0e-30f;
+  }
+  thr_g[i] = float_to_ordered(thr);
+}
+
+// rows < r0: cached base list + the sets of the base x batch-columns launch; rows >= r0: the sets of the full-row launch
+__global__ void __launch_bounds__(RERANK_WARPS * 32)
+knn_merge_cached_kernel(int r0, int n, CandLayout layA, const u64* __restrict__ candA, CandLayout layB, const u64* __restrict__ candB,
+                        const u64* __restrict__ cache, u64* __restrict__ merged) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * RERANK_WARPS + warp;
+  if (i >= n) return;
+  const bool base = i < r0;
+  const CandLayout& lay = base ? layB : layA;
+  const u64* cand = base ? candB : candA;
+  u64 mine = base ? cache[(size_t)i * KC + lane] : KEY_INF;
+  int splits = lay.stride;
+  if (lay.tc == 1) {
+    const long long rt = (i - lay.row_begin) / lay.row_tile;
+    const int b0 = (int)(((rt * lay.col_tiles + 1) * lay.grid - 1) / lay.units);
+    const int b1 = (int)((((rt + 1) * lay.col_tiles) * lay.grid - 1) / lay.units);
+    splits = 2 * (b1 - b0 + 1);
+  }
+  for (int s = 0; s < splits; ++s) list_merge_set(mine, cand[((size_t)i * lay.stride + s) * KC + lane], lane);
+  merged[(size_t)i * KC + lane] = mine;
+}
+
+CandLayout layout_of(const TcPlan& plan, int row_begin) {
+  CandLayout lay;
+  lay.stride = plan.max_splits;
+  lay.tc = plan.aligned ? 2 : 1;
+  lay.row_tile = 128 * plan.rstep;
+  lay.col_tiles = plan.col_tiles;
+  lay.grid = plan.grid;
+  lay.units = plan.units;
+  lay.row_begin = row_begin;
+  return lay;
+}
+
+}  // namespace
+
+size_t knn_base_cache_bytes(int n_base) { return align_up(sizeof(u64) * (size_t)n_base * KC, 256); }
+
+int knn_base_cache_build(const float* Xb, int nb, int d, void* cache, void* ws, size_t ws_bytes, cudaStream_t st) {
+  GLL_REQUIRE(Xb && cache && ws, "null pointer");
+  GLL_REQUIRE(nb >= KC + 1 && d >= 1, "bad sizes");
+  if (ws_bytes < knn_ws_bytes(nb, d, 25, 0, nb)) {
+    set_error("kNN workspace too small: %zu < %zu", ws_bytes, knn_ws_bytes(nb, d, 25, 0, nb));
+    return GLL_ERR_WORKSPACE;
+  }
+  const TcPlan plan = knn_tc_plan(nb, d, 0, nb);
+  GLL_REQUIRE(plan.ok, "the base-set cache needs the tensor-core search (n_base >= 256)");
+  Carver cv(ws, ws_bytes);
+  float* sq = cv.take<float>(nb);
+  unsigned* small = cv.take<unsigned>(64);
+  u64* cand = cv.take<u64>((size_t)nb * plan.max_splits * KC);
+  char* tc_ws = cv.take<char>(knn_tc_ws_upper(nb, d));
+  unsigned* thr_g = cv.take<unsigned>(nb);
+  float* rscale = cv.take<float>(nb);
+  GLL_CUDA_CHECK(cudaMemsetAsync(small, 0, 256, st));
+  int rc;
+  {
+    GLL_PROF(KID_SQNORM, st);
+    rc = launch_split_f16(Xb, nb, d, plan, sq, small, tc_ws, rscale, thr_g, st);
+  }
+  if (rc) return rc;
+  rc = knn_tc_candidates(Xb, sq, rscale, small, nb, d, nb, plan, tc_ws, cand, nullptr, thr_g, st);
+  if (rc) return rc;
+  {
+    GLL_PROF(KID_RERANK, st);
+    knn_merge_kernel<<<ceil_div(nb, RERANK_WARPS), RERANK_WARPS * 32, 0, st>>>(nb, layout_of(plan, 0), cand, (u64*)cache, nullptr);
+  }
+  GLL_LAUNCH_CHECK();
+  return GLL_OK;
+}
+
+size_t knn_cached_ws_bytes(int n, int d, int k, int nb) {
+  (void)k;
+  const int r0 = nb / 128 * 128;
+  const TcPlan pa = knn_tc_plan(n, d, r0, n), pb = knn_tc_plan(n, d, 0, r0 > 0 ? r0 : 128, nb);
+  size_t b = 0;
+  b += align_up(sizeof(float) * (size_t)n, 256) + 256;
+  b += align_up(sizeof(u64) * (size_t)(n - r0) * (size_t)(pa.ok ? pa.max_splits : 1) * KC, 256);
+  b += align_up(sizeof(u64) * (size_t)r0 * (size_t)(pb.ok ? pb.max_splits : 1) * KC, 256);
+  b += align_up(sizeof(int) * (size_t)n, 256);
+  b += knn_tc_ws_upper(n, d);
+  b += 2 * align_up(sizeof(unsigned) * (size_t)n, 256);
+  b += align_up(sizeof(u64) * (size_t)n * KC, 256);
+  b += knn_fallback_scratch_bytes() + 256;
+  return b + 2048;
+}
+
+int knn_run_cached(const float* X, int n, int d, int k, int nb, const void* cache_v, int* knn_idx, float* knn_dist, int* info, void* ws,
+                   size_t ws_bytes, cudaStream_t st) {
+  GLL_REQUIRE(X && cache_v && knn_idx && knn_dist && ws, "null pointer");
+  GLL_REQUIRE(k >= 2 && k <= KC + 1, "the base-set cache serves k <= 33");
+  GLL_REQUIRE(nb >= KC + 1 && nb < n && d >= 1, "need 32 < n_base < n");
+  if (ws_bytes < knn_cached_ws_bytes(n, d, k, nb)) {
+    set_error("kNN workspace too small: %zu < %zu", ws_bytes, knn_cached_ws_bytes(n, d, k, nb));
+    return GLL_ERR_WORKSPACE;
+  }
+  const u64* cache = (const u64*)cache_v;
+  const int r0 = nb / 128 * 128;  // base rows [r0, n_base) ride along with the batch rows (row ranges start on a tile)
+  const TcPlan pa = knn_tc_plan(n, d, r0, n);
+  GLL_REQUIRE(pa.ok, "tensor-core plan not available for this shape");
+  TcPlan pb;
+  memset(&pb, 0, sizeof(pb));
+  if (r0 > 0) {
+    pb = knn_tc_plan(n, d, 0, r0, nb);
+    GLL_REQUIRE(pb.ok, "tensor-core plan not available for this shape");
+  }
+  Carver cv(ws, ws_bytes);
+  float* sq = cv.take<float>(n);
+  unsigned* small = cv.take<unsigned>(64);
+  int* flag_count = reinterpret_cast<int*>(small + 1);
+  u64* candA_store = cv.take<u64>((size_t)(n - r0) * pa.max_splits * KC);
+  u64* candA = candA_store - (size_t)r0 * pa.max_splits * KC;  // indexed by GLOBAL row
+  u64* candB = cv.take<u64>((size_t)r0 * (pb.ok ? pb.max_splits : 1) * KC);
+  int* flag_rows = cv.take<int>(n);
+  char* tc_ws = cv.take<char>(knn_tc_ws_upper(n, d));
+  unsigned* thr_g = cv.take<unsigned>(n);
+  float* rscale = cv.take<float>(n);
+  u64* merged = cv.take<u64>((size_t)n * KC);
+  void* fb_scratch = cv.take<char>(knn_fallback_scratch_bytes());
+  GLL_CUDA_CHECK(cudaMemsetAsync(small, 0, 256, st));
+  int rc;
+  {
+    GLL_PROF(KID_SQNORM, st);
+    rc = launch_split_f16(X, n, d, pa, sq, small, tc_ws, rscale, thr_g, st);
+    if (rc) return rc;
+    if (r0 > 0) base_thr_init_kernel<<<ceil_div(r0, 256), 256, 0, st>>>(cache, sq, r0, thr_g);
+    GLL_LAUNCH_CHECK();
+  }
+  rc = knn_tc_candidates(X, sq, rscale, small, n, d, n, pa, tc_ws, candA, nullptr, thr_g, st);
+  if (rc) return rc;
+  if (r0 > 0) {
+    rc = knn_tc_candidates(X, sq, rscale, small, n, d, r0, pb, tc_ws, candB, nullptr, thr_g, st);
+    if (rc) return rc;
+  }
+  {
+    GLL_PROF(KID_RERANK, st);
+    knn_merge_cached_kernel<<<ceil_div(n, RERANK_WARPS), RERANK_WARPS * 32, 0, st>>>(r0, n, layout_of(pa, r0), candA, layout_of(pb, 0), candB,
+                                                                                   cache, merged);
+  }
+  GLL_LAUNCH_CHECK();
+  CandLayout lay;
+  lay.stride = 1;
+  lay.tc = 0;
+  lay.row_tile = lay.col_tiles = lay.grid = 0;
+  lay.units = 0;
+  return knn_finish(X, sq, small, n, d, k, 0, n, lay, merged, knn_tc_err_coef(d, pa.passes), knn_idx, knn_dist, flag_count, flag_rows, info,
+                    fb_scratch, st);
 }
 
 }  // namespace gll

@@ -70,12 +70,13 @@ __device__ __forceinline__ void list_merge_set(u64& mine, u64 c, int lane) {
 // Tensor-core candidate generation (knn_tc.cu).  plan.ok == 0: shape or configuration not handled, use the SIMT path.
 struct TcPlan {
   int ok, d_pad, kblocks, row_tiles, col_tiles, grid, max_splits, rt0, aligned, rstep;  // row_tiles counts row GROUPS of rstep tiles
+  int ct0, col_begin;  // column range [col_begin, n): first column tile; columns before col_begin inside it are masked
   int passes;       // MMA passes over the fp16 operands (rows of X scaled by a power of two): 1 = hi.hi, 2 = (hi + lo).hi
   long long units;
   size_t ws_bytes;  // fp16 hi / lo copies of X
 };
 
-TcPlan knn_tc_plan(int n, int d, int row_begin, int row_end);
+TcPlan knn_tc_plan(int n, int d, int row_begin, int row_end, int col_begin = 0);
 size_t knn_tc_ws_upper(int n, int d);
 int knn_tc_candidates(const float* X, const float* sq, const float* rscale, const unsigned* small, int n, int d, int row_end, const TcPlan& plan,
                       void* tc_ws, u64* cand, const u64* excl, unsigned* thr_g, cudaStream_t st);

@@ -180,6 +180,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 struct TcParams {
   int n, kblocks, col_tiles, max_splits;
   int rt0, row_end;   // first row tile of this call's row range, one past its last row
+  int ct0, col_begin; // first column tile / first column of this call's column range (columns before col_begin are masked)
   int aligned;        // 1: every CTA owns whole row tiles (all CTAs sweep the column tiles in lockstep: B tiles hit in L2)
   int row_tiles;
   long long units;
@@ -268,7 +269,7 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
       int stage = 0;
       uint32_t phase = 0;
       for (long long u = u_begin; u < u_end; ++u) {
-        const int rt = P.rt0 + RSTEP * (int)(u / C) + crank, ct = (int)(u % C);
+        const int rt = P.rt0 + RSTEP * (int)(u / C) + crank, ct = P.ct0 + (int)(u % C);
         for (int kk = 0; kk < KB; ++kk) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
           const uint32_t full = bar_full + 8 * stage;
@@ -381,7 +382,7 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     };
 
     for (long long u = u_begin; u < u_end; ++u) {
-      const int rt = P.rt0 + RSTEP * (int)(u / C) + crank, ct = (int)(u % C);
+      const int rt = P.rt0 + RSTEP * (int)(u / C) + crank, ct = P.ct0 + (int)(u % C);
       if (rt != cur_rt) {
         if (cur_rt >= 0) flush(cur_rt);
 #pragma unroll
@@ -403,7 +404,7 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
       const int c_begin = ct * TC_BN;
       // stage |x_j|^2 of the unit's 256 columns for all four epilogue warps (+inf masks columns beyond n)
       epi_bar_sync();  // everybody is done with the previous unit's values
-      sqj_s[et] = (c_begin + et < P.n) ? __ldg(P.sq + c_begin + et) : INFINITY;
+      sqj_s[et] = (c_begin + et < P.n && c_begin + et >= P.col_begin) ? __ldg(P.sq + c_begin + et) : INFINITY;
       cj_s[et] = (P.rscale != nullptr && c_begin + et < P.n) ? -2.f * __ldg(P.rscale + c_begin + et) : -2.f;
       epi_bar_sync();
       // once per unit (sharing every 32 columns instead measured the same): take what the row's other sets have published
@@ -675,7 +676,7 @@ int make_map(CUtensorMap* m, const void* base, int n, int d_pad, int box_rows) {
 
 }  // namespace
 
-TcPlan knn_tc_plan(int n, int d, int row_begin, int row_end) {
+TcPlan knn_tc_plan(int n, int d, int row_begin, int row_end, int col_begin) {
   TcPlan p;
   memset(&p, 0, sizeof(p));
   const char* force = getenv("GLL_B200_KNN_PATH");  // "simt" or "tc": testing knob, both paths are exact
@@ -687,7 +688,9 @@ TcPlan knn_tc_plan(int n, int d, int row_begin, int row_end) {
   p.rt0 = row_begin / TC_BM;
   const int row_tiles = ceil_div(row_end - row_begin, TC_BM);
   const int sms = device_info().sms;
-  p.col_tiles = ceil_div(n, TC_BN);
+  p.ct0 = col_begin / TC_BN;
+  p.col_begin = col_begin;
+  p.col_tiles = ceil_div(n, TC_BN) - p.ct0;
   p.aligned = (row_tiles >= 4 * sms) ? 1 : 0;  // big graphs: whole row tiles per CTA, one candidate set per row
   // GLL_B200_KNN_PAIR=1: CTA pairs (clusters of 2) that share the B tiles by TMA multicast.  Measured on B200 it cuts the
   // L2 -> shared-memory operand traffic by a third but not the run time (the kernel is bound by the epilogue's insertions
@@ -698,6 +701,9 @@ TcPlan knn_tc_plan(int n, int d, int row_begin, int row_end) {
   p.units = (long long)p.row_tiles * p.col_tiles;
   const int owners = sms / p.rstep;
   p.grid = (int)((p.units < (long long)owners) ? p.units : (long long)owners);  // owners (CTAs or CTA pairs)
+  // few row tiles (a batch-rows-only search): a row tile may be shared by at most KNN_MAX_SPLITS / 2 owners (two candidate
+  // sets per owner and row), so the grid shrinks rather than the plan failing
+  if (!p.aligned) p.grid = max(1, min(p.grid, p.row_tiles * (KNN_MAX_SPLITS / 2 - 1)));
   if (p.aligned) {
     p.max_splits = 2;  // the two column halves of the epilogue (knn_tc.cu: `half`)
   } else {
@@ -767,6 +773,8 @@ int knn_tc_candidates(const float* X, const float* sq, const float* rscale, cons
   P.units = plan.units;
   P.rt0 = plan.rt0;
   P.row_end = row_end;
+  P.ct0 = plan.ct0;
+  P.col_begin = plan.col_begin;
   P.aligned = plan.aligned;
   P.row_tiles = plan.row_tiles;
   P.sq = sq;

@@ -156,10 +156,23 @@ int gll_backward_edges(const float* X, int n, int d, int l, int k_lab, int eps_a
  * arrays.  row_begin should be a multiple of 128 (otherwise the SIMT Gram path is taken). */
 /* Verification only: the raw fp32 accumulator acc_out[128][256] that the tensor-core kNN kernel forms for rows
  * [128 row_tile, +128) against columns [256 col_tile, +256) from the split operands (mode of GLL_B200_KNN_SPLIT), and the
- * operands' per-row scale rscale_out[n] (the accumulator holds x_i.x_j / (rscale_i rscale_j); all ones for the bf16 split).
+ * operands' per-row scale rscale_out[n] (the accumulator holds x_i.x_j / (rscale_i rscale_j)).
  * tests compare it with the numpy model of the split (oracle/split_model.py).  workspace: gll_knn_workspace_bytes(n, d, 25). */
 int gll_debug_gram_tile(const float* X, int n, int d, int row_tile, int col_tile, float* acc_out, float* rscale_out,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* Base-set reuse across evaluation batches (utils.py:596-621, test_network: the layer is called on [base; test batch]
+ * with the SAME base rows for every batch).  gll_base_cache_build searches the n_base base rows among
+ * themselves once and keeps, per base row, its 32 best base columns (cache: gll_base_cache_bytes(n_base) bytes of device
+ * memory owned by the caller).  gll_knn_cached is gll_knn(X, n, ...) for X = [base (n_base rows, the ones the cache was built
+ * from); batch] that searches only the batch rows against all columns and the base rows against the batch columns; the
+ * emitted lists are identical to gll_knn's (same exact re-rank and completeness proof).  n_base >= 256, k <= 33. */
+size_t gll_base_cache_bytes(int n_base);
+size_t gll_base_cache_workspace_bytes(int n_base, int d);
+int gll_base_cache_build(const float* Xbase, int n_base, int d, void* cache, void* workspace, size_t workspace_bytes,
+                         void* stream);
+size_t gll_knn_cached_workspace_bytes(int n, int d, int k, int n_base);
+int gll_knn_cached(const float* X, int n, int d, int k, int n_base, const void* cache, int* knn_idx, float* knn_dist,
+                   int* info, void* workspace, size_t workspace_bytes, void* stream);
 size_t gll_knn_rows_workspace_bytes(int n, int d, int k, int row_begin, int row_end);
 int gll_knn_rows(const float* X, int n, int d, int k, int row_begin, int row_end, int* knn_idx, float* knn_dist, int* info,
                  void* workspace, size_t workspace_bytes, void* stream);

@@ -497,6 +497,32 @@ def test_graphed_step_replays_the_layer(gll):
     assert O.max_rel(step.pred.cpu().numpy(), f.pred) < TOL and O.max_rel(step.dX.cpu().numpy(), bw.dX) < TOL
 
 
+@pytest.mark.parametrize("eps,tau", [("auto", 0.0), (1.0, 0.07)])
+def test_base_set_evaluator_equals_full_search(gll, eps, tau):
+    """utils.py:596-621 (test_network): the same base rows in every call, only the batch changes.  The evaluator searches the
+    base set among itself ONCE; per batch its predictions and kNN lists must be bit-identical to the layer / gll_knn on the
+    concatenated matrix (n_base = 1500 is not a multiple of the 128-row tile; batches of different sizes)."""
+    pkg, _lib = gll
+    from graphlearninglayer_b200.evalcache import BaseSetEvaluator
+
+    Xall, Y, _, _ = O.synth_inputs(17, 1500, 1100, 96, 10, 2.5)
+    base = torch.as_tensor(Xall[:1500]).cuda()
+    Yt = torch.as_tensor(Y).cuda()
+    ev = BaseSetEvaluator(base, Yt, tau=tau, epsilon=eps)
+    for lo, hi in ((1500, 1800), (1800, 2311), (2311, 2600)):
+        batch = torch.as_tensor(Xall[lo:hi]).cuda()
+        pred = ev(batch)
+        full = torch.cat((base, batch), 0)
+        with torch.no_grad():
+            ref = pkg.LaplaceLearningSparseHard.apply(full, Yt, tau, eps)
+        i_ref, d_ref, _ = run_knn(_lib, full.cpu().numpy())
+        assert torch.equal(ev.knn_idx, i_ref) and torch.equal(ev.knn_dist, d_ref)
+        assert pred.dtype == ref.dtype and torch.equal(pred, ref)
+        assert int(ev.info[_lib.INFO_STATUS].item()) & ~_lib.STATUS_KNN_FALLBACK == 0
+    f = O.forward(np.concatenate([Xall[:1500], Xall[2311:2600]]), Y, tau, eps, solver="lu")
+    assert O.max_rel(pred.cpu().numpy(), f.pred) < TOL
+
+
 def test_layer_full_size_properties(gll):
     """C4 size (2048 + 14336, d=512): invariants of SURVEY 4 that need no oracle."""
     pkg, _lib = gll
