@@ -44,27 +44,37 @@
 namespace gll {
 namespace {
 
-// Stage = one K block (32 wide, 64-byte swizzle) of {A_hi, A_lo, B_hi} = 32 KB (two passes: (hi + lo).hi) or {A_hi, B_hi} =
-// 24 KB (one pass: hi.hi); four stages, which leaves room for the candidate sets of EIGHT epilogue warps.
-constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 32, TC_MAX_STAGES = 4;
+// Stage = one K block (32 wide, 64-byte swizzle): {A_hi, B_hi} = 24 KB for one pass, + A_lo = 32 KB for two; a CTA of a pair
+// stages half of B: 16 / 24 KB.  The ring takes all the shared memory the candidate sets of the EIGHT epilogue warps leave
+// (152 KB): what bounds the one-pass kernel is the TMA round trip (~1600 cycles from "stage free" to "stage full") against
+// the MMA time its stages cover (271 cycles each): 4 stages of 24 KB ran the MMA/TMA pipeline at 58 % of the MMA rate
+// whatever the bytes per stage (profiles/r02k_knn_experiments_c2.txt), 6 to 9 stages cover the round trip.
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_MAX_STAGES = 9;
+constexpr size_t TC_STAGE_REGION = 152 * 1024;
+// CTA pairs (cta_group::2, M = 256).  Measured (profiles/r02q_knn_experiments.txt): 4-7 % faster on the 1M-node graph (whole
+// row tiles per CTA, drain-bound epilogue: fewer operand bytes and TMA issues per SM), no difference at 10-16 k nodes (bound
+// by the candidate insertions).  Default: on in the large-graph mode only; GLL_B200_KNN_PAIR=0/1 forces it.
 constexpr int TC_EPI_WARPS = 8;                        // two per TMEM lane quarter: each takes one half of the 256 columns
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS + 32;  // + the second TMA producer warp
+constexpr int TC_WARP_PRODUCER_B = 2 + TC_EPI_WARPS;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 8 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;          // 16 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + TC_B_BYTES;  // 32 KB (the one-pass stage uses the first 24 KB)
 constexpr int TC_CHUNK = 32;                           // columns per tcgen05.ld
 constexpr int TC_TMEM_COLS = 512, TC_ACC_STRIDE = 256;
 
-constexpr size_t TC_OFF_LD = (size_t)TC_MAX_STAGES * TC_STAGE_BYTES;         // float [8 warps][KC entries][32 rows]
+constexpr size_t TC_OFF_LD = TC_STAGE_REGION;                                // float [8 warps][KC entries][32 rows]
 constexpr size_t TC_OFF_LI = TC_OFF_LD + TC_EPI_WARPS * KC * 32 * 4;         // int   [8 warps][KC entries][32 rows]
 constexpr size_t TC_OFF_SQJ = TC_OFF_LI + TC_EPI_WARPS * KC * 32 * 4;        // float [TC_BN]  |x_j|^2 of the unit's columns
 constexpr size_t TC_OFF_BAR = TC_OFF_SQJ + 2 * TC_BN * 4;                    // (then float [TC_BN] -2 rscale_j) mbarriers + tmem pointer
-constexpr size_t TC_SMEM_BYTES = TC_OFF_BAR + 128 + 1024;                    // + slack for manual 1024 B alignment
+constexpr size_t TC_OFF_TMEM = TC_OFF_BAR + 8 * (2 * TC_MAX_STAGES + 4);     // the TMEM base address slot
+constexpr size_t TC_SMEM_BYTES = TC_OFF_TMEM + 16 + 1024;                    // + slack for manual 1024 B alignment
 static_assert(TC_SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(8 * (2 * TC_MAX_STAGES + 4) <= 96, "mbarriers end where the TMEM pointer slot begins");
+static_assert(TC_STAGE_REGION / (2 * TC_A_BYTES) >= 1 && TC_STAGE_REGION % 1024 == 0, "stage ring");
 static_assert(2 * TC_BN <= TC_TMEM_COLS && TC_ACC_STRIDE >= TC_BN, "two accumulators must fit in TMEM");
 
 // M = 128, N = 256, A/B fp16 K-major (format fields 0), D fp32 (layout: cute::UMMA::InstrDescriptor)
+constexpr uint32_t TC_IDESC_F16_PAIR = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);  // M = 256
 constexpr uint32_t TC_IDESC_F16 = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -108,12 +118,33 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
       : "memory");
 }
-// Same load delivered to the CTAs of the cluster selected by `mask` (same shared-memory offset and barrier offset in each)
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, uint16_t mask) {
+// ---- CTA pair (cta_group::2): one tcgen05.mma of M = 256 spans two SMs of a TPC; each CTA holds its 128 rows of A and
+// its 128 rows (= accumulator columns) of B in its own shared memory, the accumulator rows land in each CTA's own TMEM.
+// Bit 24 of a shared-window address selects the CTA of the pair (cute: Sm100MmaPeerBitMask): cleared = the leader (rank 0).
+constexpr uint32_t TC_PEER_MASK = 0xFEFFFFFFu;
+// TMA load into MY shared memory whose completion bytes are counted by the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y), "h"(mask)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & TC_PEER_MASK), "r"(x), "r"(y)
       : "memory");
+}
+// arrive on the LEADER's mbarrier at this offset (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & TC_PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same offset in both CTAs once the pair's MMAs issued so far have retired
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -131,11 +162,6 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// arrive on the barrier at the same offset in every CTA of `mask` once the MMAs issued so far have retired
-__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-               : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -194,13 +220,17 @@ struct TcParams {
   const unsigned* small;  // small[3], small[4]: range of E_i over the rows (written by sqnorm_split_f16_kernel)
 };
 
+__host__ __device__ inline uint32_t a_bytes_of(int passes) { return passes == 2 ? 2u * TC_A_BYTES : (uint32_t)TC_A_BYTES; }  // A_hi (+ A_lo)
+
 // CTA that owns unit u when `units` units are dealt contiguously to G CTAs (CTA b owns [b*units/G, (b+1)*units/G))
 __host__ __device__ inline int tc_cta_of_unit(long long u, int G, long long units) { return (int)(((u + 1) * G - 1) / units); }
 
 // ---------------------------------------------------------------------------------------------- the GEMM + top-k kernel
-// PAIR: launched as clusters of two CTAs that process the SAME column tile for two adjacent row tiles; each CTA fetches
-// half of the B tiles and multicasts it to both, so the L2 -> shared-memory operand traffic per CTA drops from 96 to 64 KB
-// per stage (this kernel is bound by that traffic on mid-size graphs).  The MMAs stay per-CTA (cta_group::1).
+// PAIR: launched as clusters of two CTAs (one TPC) that process the SAME column tile for two adjacent row tiles with ONE
+// tcgen05.mma.cta_group::2 of M = 256: each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256
+// columns), so the operand bytes a CTA pulls from L2 drop by a third -- which is what bounds the one-pass kernel
+// (measured: ~70 GB/s per SM whatever the stage count, profiles/r02k_knn_experiments_c2.txt).  The leader CTA issues the
+// MMAs; both CTAs run their own TMA producer and their own epilogue on their own 128 accumulator rows.
 template <bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_constant__ CUtensorMap mapAL,
@@ -225,35 +255,43 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     u_end = (long long)(b + 1) * P.units / G;
   }
 
-  const int nstages = TC_MAX_STAGES;
+  const uint32_t stage_stride = a_bytes_of(P.passes) + (uint32_t)(PAIR ? TC_B_BYTES / 2 : TC_B_BYTES);  // = bytes this CTA loads per stage
+  const int nstages = min(TC_MAX_STAGES, (int)(TC_STAGE_REGION / stage_stride));
   const bool two = P.passes == 2;
   const uint32_t a_bytes = two ? 2u * TC_A_BYTES : (uint32_t)TC_A_BYTES;  // A_hi (+ A_lo)
-  const uint32_t stage_bytes = a_bytes + (uint32_t)TC_B_BYTES;
+  const uint32_t stage_bytes = a_bytes + (uint32_t)(PAIR ? TC_B_BYTES / 2 : TC_B_BYTES);  // what THIS CTA loads per stage
   const uint32_t bar_full = base + (uint32_t)TC_OFF_BAR;        // [TC_MAX_STAGES]
   const uint32_t bar_empty = bar_full + 8 * TC_MAX_STAGES;      // [TC_MAX_STAGES]
   const uint32_t bar_tfull = bar_empty + 8 * TC_MAX_STAGES;     // [2]
   const uint32_t bar_tempty = bar_tfull + 16;                   // [2]
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + TC_OFF_BAR + 96);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + TC_OFF_TMEM);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapAH);
     tma_prefetch_desc(&mapAL);
     tma_prefetch_desc(&mapBH);
     for (int s = 0; s < TC_MAX_STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, PAIR ? 2 : 1);  // PAIR: both CTAs' MMAs must have consumed the stage
+      mbar_init(bar_full + 8 * s, 2);   // the two producer warps
+      mbar_init(bar_empty + 8 * s, 1);  // PAIR: the leader's commit arrives on both CTAs' barriers
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, TC_EPI_WARPS);  // one arrival per epilogue warp
+      mbar_init(bar_tempty + 8 * a, PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS);  // one arrival per epilogue warp (PAIR: of both CTAs, on the leader)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + (uint32_t)TC_OFF_BAR + 96),
-                 "r"((uint32_t)TC_TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {  // the same warp of both CTAs, the same destination offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + (uint32_t)TC_OFF_TMEM),
+                   "r"((uint32_t)TC_TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + (uint32_t)TC_OFF_TMEM),
+                   "r"((uint32_t)TC_TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   if (PAIR)
@@ -263,25 +301,40 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ================================================= TMA producer =================================================
+  if (warp == 0 || warp == TC_WARP_PRODUCER_B) {
+    // ================================================= TMA producers ================================================
+    // One cp.async.bulk.tensor takes its issuing thread ~280 cycles (measured: the MMA/TMA pipeline alone ran at 690 / 860 /
+    // 1120 cycles per K block with 2 / 3 / 4 loads per block, whatever the stage count or the bytes per load), so a single
+    // producer thread cannot feed one-pass K blocks (2 MMAs = 366 cycles): warp 0 loads the A tiles, a second producer warp
+    // the B tile; both arrive on the stage's barrier with their own byte counts.
     if (lane == 0) {
+      const bool is_a = warp == 0;
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t my_bytes = is_a ? a_bytes : stage_bytes - a_bytes;
       for (long long u = u_begin; u < u_end; ++u) {
         const int rt = P.rt0 + RSTEP * (int)(u / C) + crank, ct = P.ct0 + (int)(u % C);
         for (int kk = 0; kk < KB; ++kk) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
           const uint32_t full = bar_full + 8 * stage;
-          const uint32_t s0 = base + (uint32_t)stage * TC_STAGE_BYTES;
-          mbar_arrive_expect_tx(full, stage_bytes);
-          tma_load_2d(s0, &mapAH, full, kk * TC_BK, rt * TC_BM);
-          if (two) tma_load_2d(s0 + TC_A_BYTES, &mapAL, full, kk * TC_BK, rt * TC_BM);
-          if (PAIR) {  // my half of the B tile (128 of the 256 rows), delivered to both CTAs (128-row boxes: the A map)
-            const uint32_t half = (uint32_t)crank * (TC_B_BYTES / 2);
-            tma_load_2d_mc(s0 + a_bytes + half, &mapAH, full, kk * TC_BK, ct * TC_BN + crank * (TC_BN / 2), 3);
+          const uint32_t s0 = base + (uint32_t)stage * stage_stride;
+          if (PAIR) {
+            // both CTAs' loads of this stage are counted by the LEADER's barrier (its MMA warp is the only consumer)
+            if (crank == 0) mbar_arrive_expect_tx(full, 2u * my_bytes);
+            if (is_a) {
+              tma_load_2d_pair(s0, &mapAH, full, kk * TC_BK, rt * TC_BM);
+              if (two) tma_load_2d_pair(s0 + TC_A_BYTES, &mapAL, full, kk * TC_BK, rt * TC_BM);
+            } else {  // my half of the B tile: 128 of its 256 rows (128-row boxes: the A map)
+              tma_load_2d_pair(s0 + a_bytes, &mapAH, full, kk * TC_BK, ct * TC_BN + crank * (TC_BN / 2));
+            }
           } else {
-            tma_load_2d(s0 + a_bytes, &mapBH, full, kk * TC_BK, ct * TC_BN);
+            mbar_arrive_expect_tx(full, my_bytes);
+            if (is_a) {
+              tma_load_2d(s0, &mapAH, full, kk * TC_BK, rt * TC_BM);
+              if (two) tma_load_2d(s0 + TC_A_BYTES, &mapAL, full, kk * TC_BK, rt * TC_BM);
+            } else {
+              tma_load_2d(s0 + a_bytes, &mapBH, full, kk * TC_BK, ct * TC_BN);
+            }
           }
           if (++stage == nstages) {
             stage = 0;
@@ -291,12 +344,12 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
       }
     }
   } else if (warp == 1) {
-    // ================================================= MMA issuer ===================================================
+    // ================================================= MMA issuer (PAIR: the leader CTA only) =========================
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     const int nprod = P.passes;
-    const uint32_t idesc = TC_IDESC_F16;
-    for (long long u = u_begin; u < u_end; ++u) {
+    const uint32_t idesc = PAIR ? TC_IDESC_F16_PAIR : TC_IDESC_F16;
+    for (long long u = (PAIR && crank != 0) ? u_end : u_begin; u < u_end; ++u) {
       mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);  // the epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_ACC_STRIDE;
@@ -304,7 +357,7 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
         mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t s0 = base + (uint32_t)stage * TC_STAGE_BYTES;
+          const uint32_t s0 = base + (uint32_t)stage * stage_stride;
           const uint64_t dAH = tc_smem_desc(s0), dAL = tc_smem_desc(s0 + TC_A_BYTES);
           const uint64_t dBH = tc_smem_desc(s0 + a_bytes);
 #pragma unroll
@@ -312,14 +365,20 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
             if (g >= nprod) break;  // one pass: hi.hi only
             const uint64_t da = (g == 1) ? dAL : dAH, db = dBH;  // hi.hi, lo.hi
 #pragma unroll
-            for (int k4 = 0; k4 < TC_BK / 16; ++k4)  // +32 B (two 16 B units) per K=16 step inside the swizzle atom
-              tc_mma_f16(d_tmem, da + (uint64_t)(2 * k4), db + (uint64_t)(2 * k4), idesc, (uint32_t)((kk | g | k4) != 0));
+            for (int k4 = 0; k4 < TC_BK / 16; ++k4) {  // +32 B (two 16 B units) per K=16 step inside the swizzle atom
+              if (PAIR)
+                tc_mma_f16_pair(d_tmem, da + (uint64_t)(2 * k4), db + (uint64_t)(2 * k4), idesc, (uint32_t)((kk | g | k4) != 0));
+              else
+                tc_mma_f16(d_tmem, da + (uint64_t)(2 * k4), db + (uint64_t)(2 * k4), idesc, (uint32_t)((kk | g | k4) != 0));
+            }
           }
-          if (PAIR)
-            tc_commit_mc(bar_empty + 8 * stage, 3);  // frees the stage in BOTH CTAs (the peer multicasts into mine)
-          else
+          if (PAIR) {
+            tc_commit_pair(bar_empty + 8 * stage);                 // frees the stage in BOTH CTAs when these MMAs retire
+            if (kk == KB - 1) tc_commit_pair(bar_tfull + 8 * acc);  // accumulator complete, in both CTAs' TMEM
+          } else {
             tc_commit(bar_empty + 8 * stage);      // frees the smem stage when these MMAs retire
-          if (kk == KB - 1) tc_commit(bar_tfull + 8 * acc);  // accumulator complete
+            if (kk == KB - 1) tc_commit(bar_tfull + 8 * acc);  // accumulator complete
+          }
         }
         __syncwarp();
         if (++stage == nstages) {
@@ -402,7 +461,9 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
         }
       }
       const int c_begin = ct * TC_BN;
-      // stage |x_j|^2 of the unit's 256 columns for all four epilogue warps (+inf masks columns beyond n)
+      // stage |x_j|^2 of the unit's 256 columns for all eight epilogue warps (+inf masks columns outside the column range).
+      // (Fetching these one unit ahead into a second buffer -- one barrier and one L2 round trip less per unit -- measured no
+      // faster, and a threshold that is one unit older costs insertions: both tried twice, not kept.)
       epi_bar_sync();  // everybody is done with the previous unit's values
       sqj_s[et] = (c_begin + et < P.n && c_begin + et >= P.col_begin) ? __ldg(P.sq + c_begin + et) : INFINITY;
       cj_s[et] = (P.rscale != nullptr && c_begin + et < P.n) ? -2.f * __ldg(P.rscale + c_begin + et) : -2.f;
@@ -525,7 +586,12 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
       if (P.debug >= 2) {  // timing experiment: hand the accumulator back untouched
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        if (lane == 0) {
+          if (PAIR)
+            mbar_arrive_leader(bar_tempty + 8 * acc);
+          else
+            mbar_arrive(bar_tempty + 8 * acc);
+        }
       } else
         tc_ld_issue(taddr + q0 * TC_CHUNK, rawA);
 #pragma unroll 1
@@ -539,7 +605,12 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
         } else {  // this warp's half of the accumulator is in registers or consumed: hand it back to the MMA warp early
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+          if (lane == 0) {
+            if (PAIR)
+              mbar_arrive_leader(bar_tempty + 8 * acc);  // the leader's MMA warp waits for both CTAs' epilogues
+            else
+              mbar_arrive(bar_tempty + 8 * acc);
+          }
         }
         process(rawB, q + 1);
       }
@@ -560,7 +631,10 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS) : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS) : "memory");
   }
 }
 
@@ -692,11 +766,10 @@ TcPlan knn_tc_plan(int n, int d, int row_begin, int row_end, int col_begin) {
   p.col_begin = col_begin;
   p.col_tiles = ceil_div(n, TC_BN) - p.ct0;
   p.aligned = (row_tiles >= 4 * sms) ? 1 : 0;  // big graphs: whole row tiles per CTA, one candidate set per row
-  // GLL_B200_KNN_PAIR=1: CTA pairs (clusters of 2) that share the B tiles by TMA multicast.  Measured on B200 it cuts the
-  // L2 -> shared-memory operand traffic by a third but not the run time (the kernel is bound by the epilogue's insertions
-  // at C2/C4 and already at 83 % of the MMA peak at C5), so it stays opt-in.
+  // GLL_B200_KNN_PAIR: CTA pairs (clusters of 2, tcgen05.mma.cta_group::2 with M = 256): a third fewer operand bytes per CTA.
   const char* pr = getenv("GLL_B200_KNN_PAIR");
-  p.rstep = (pr && pr[0] == '1' && !p.aligned && row_tiles >= 2) ? 2 : 1;
+  const bool pair = pr ? (pr[0] == '1') : (p.aligned != 0);
+  p.rstep = (pair && row_tiles >= 2 && sms >= 2) ? 2 : 1;
   p.row_tiles = ceil_div(row_tiles, p.rstep);  // row groups: the unit of work is (row group, column tile)
   p.units = (long long)p.row_tiles * p.col_tiles;
   const int owners = sms / p.rstep;

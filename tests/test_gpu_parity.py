@@ -270,8 +270,9 @@ def test_knn_paths_agree_and_tc_is_used(gll, monkeypatch):
     assert int(info[_lib.INFO_KNN_FALLBACK_ROWS].item()) < 0.02 * X.shape[0]
 
 
-def test_knn_cta_pair_multicast_variant(gll, monkeypatch):
-    """Opt-in cluster-of-2 variant of the tensor-core kernel (TMA multicast of the B tiles): identical lists."""
+def test_knn_cta_pair_variant(gll, monkeypatch):
+    """Cluster-of-2 variant of the tensor-core kernel (tcgen05.mma.cta_group::2, M = 256: each CTA stages its 128 rows of A and
+    half of the B tile): identical lists."""
     _, _lib = gll
     X, *_ = O.synth_inputs(12, 3000, 1777, 200, 10, 3.5)
     monkeypatch.setenv("GLL_B200_KNN_PATH", "tc")
