@@ -497,9 +497,9 @@ def run_b200(args, rank, world, local_rank):
                     "algorithmic_work_per_launch": work, "work_unit": unit, "launch_ms": t_s * 1e3,
                     "share_of_step": (prof[top][0] / args.steps) / step_kernel_ms}
         if bound == "tensor" and top == "knn_gram_topk_tcgen05":
-            # the Gram entry is accumulated from split operands: (hi + lo).hi in fp16 = 2 MMA passes; `achieved` counts
-            # 2 n^2 d once
-            roofline.update({"mma_passes": 2, "issued": ach * 2, "issued_frac": ach * 2 / peak})
+            # one fp16 MMA pass (hi.hi) by default, two ((hi + lo).hi) with GLL_B200_KNN_SPLIT=f16x2; `achieved` counts 2 n^2 d once
+            passes = 2 if os.environ.get("GLL_B200_KNN_SPLIT") == "f16x2" else 1
+            roofline.update({"mma_passes": passes, "issued": ach * passes, "issued_frac": ach * passes / peak})
         if c4 is not None and "cg" in c4:
             # the north star's own figure, flat so that the driver's record keeps it: the on-chip CG at n = 16384
             cg = c4["cg"]

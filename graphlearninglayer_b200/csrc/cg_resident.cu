@@ -97,7 +97,8 @@ __device__ __forceinline__ void cr_stamp(const CrParams& R, int pass, int phase)
 
 struct Ctrl {
   double tol2;  // squared absolute tolerance, fixed in pass 0
-  int pad[2];
+  int flags;    // bit 0: some column still moves, bit 1: non-finite residual (set by the column threads, cleared every pass)
+  int pad;
 };
 
 // Rare path: a row block whose segments do not fit in shared memory walks the CSR in global memory, one thread per
@@ -308,13 +309,14 @@ __global__ void __launch_bounds__(CR_THREADS, 1) cg_resident_kernel(CrParams R) 
     __syncthreads();
     if (TRACE) cr_stamp(R, iter, 5);
     // ================= partial <r,u>, <w,u>, <r,r>: one warp per (product, class column), one butterfly each =========
+    if (tid == 0) ctrl->flags = 0;  // read last before the previous pass's vector update; set again after barrier (A)
 #pragma unroll 1
     for (int job = warp; job < jobs; job += CR_WARPS) {
       const int v = (job >= 2 * P.l) ? 2 : (job >= P.l ? 1 : 0), cc = job - v * P.l;
       const float* av = (v == 1) ? ws : rs;
       double t = 0.0;
-#pragma unroll 1
-      for (int i0 = 0; i0 < rows; i0 += 32) {  // warp-uniform trip count
+#pragma unroll 4
+      for (int i0 = 0; i0 < rows; i0 += 32) {  // warp-uniform trip count; unrolled: the shared-memory loads go out together
         const int i = i0 + lane;
         if (i < rows) {
           const float r = rs[(size_t)i * lp + cc];
@@ -392,8 +394,9 @@ __global__ void __launch_bounds__(CR_THREADS, 1) cg_resident_kernel(CrParams R) 
       alpha[c] = al;
       beta[c] = be;
     }
-    const int any_bad = __syncthreads_or(bad);
-    const int any_live = __syncthreads_or(live);
+    if (live | bad) atomicOr(&ctrl->flags, live | (bad << 1));
+    __syncthreads();
+    const int any_live = ctrl->flags & 1, any_bad = ctrl->flags & 2;
     if (TRACE) cr_stamp(R, iter, 14);
     if (any_bad || !any_live || iter >= P.max_iter) {
       if (b == 0 && tid == 0) write_stats(P, red, lp, iter, any_bad, ctrl->tol2);

@@ -511,6 +511,30 @@ __device__ __forceinline__ void list_insert_d(double& md, int& mj, double xd, in
   }
 }
 
+// Merge the ascending 32-list (od, oj) into the ascending 32-list (md, mj), one (distance, index) pair per lane, padding
+// (INFINITY, 0x7fffffff) at the end: min(A[i], B[31 - i]) holds the 32 smallest of the union as a bitonic sequence, five
+// compare-exchange steps put it in order.  Replaces up to 32 serial insertions per list.
+__device__ __forceinline__ bool pair_less(double ad, int aj, double bd, int bj) { return ad < bd || (ad == bd && aj < bj); }
+__device__ __forceinline__ void dlist_merge_sorted(double& md, int& mj, double od, int oj, int lane) {
+  const double rd = __shfl_sync(FULL, od, 31 - lane);
+  const int rj = __shfl_sync(FULL, oj, 31 - lane);
+  if (pair_less(rd, rj, md, mj)) {
+    md = rd;
+    mj = rj;
+  }
+#pragma unroll
+  for (int j = 16; j >= 1; j >>= 1) {
+    const double pd = __shfl_xor_sync(FULL, md, j);
+    const int pj = __shfl_xor_sync(FULL, mj, j);
+    const bool keep_min = (lane & j) == 0;
+    const bool p_less = pair_less(pd, pj, md, mj);
+    if (p_less == keep_min) {
+      md = pd;
+      mj = pj;
+    }
+  }
+}
+
 template <bool VEC4>
 __global__ void __launch_bounds__(FB_WARPS * 32)
 knn_fallback_kernel(const float* __restrict__ X, int n, int d, int k, const int* __restrict__ flag_count,
@@ -595,7 +619,7 @@ knn_fallback_scan_kernel(const float* __restrict__ X, int n, int d, int k, const
     if (nflag > 0) atomicOr(&info[GLL_INFO_STATUS], GLL_STATUS_KNN_FALLBACK);
   }
   if (nflag == 0) return;
-  const int G = gridDim.x, C = max(1, min(64, G / nflag));  // at most 64 chunks per row (what the merge handles quickly)
+  const int G = gridDim.x, C = max(1, min(128, G / nflag));  // <= 128 chunks per row: the serial merge stays short
   const long long T = (long long)nflag * C;
   for (long long t = blockIdx.x; t < T; t += G) {
     const int f = (int)(t / C), c = (int)(t - (long long)f * C);
@@ -629,16 +653,7 @@ knn_fallback_scan_kernel(const float* __restrict__ X, int n, int d, int k, const
     sj[warp][lane] = mj;
     __syncthreads();
     if (warp == 0) {
-      for (int w = 1; w < FB_WARPS; ++w)
-        for (int e = 0; e < 32; ++e) {
-          const int xj = sj[w][e];
-          if (xj == 0x7fffffff) break;
-          const double xd = sd[w][e];
-          if (!(xd < thr_d || (xd == thr_d && xj < thr_j))) break;  // the list is sorted: nothing behind can enter either
-          list_insert_d(md, mj, xd, xj, lane);
-          thr_d = __shfl_sync(FULL, md, 31);
-          thr_j = __shfl_sync(FULL, mj, 31);
-        }
+      for (int w = 1; w < FB_WARPS; ++w) dlist_merge_sorted(md, mj, sd[w][lane], sj[w][lane], lane);
       if (C == 1) {
         if (lane < k - 1 && mj != 0x7fffffff) {
           knn_idx[(size_t)i * k + 1 + lane] = mj;
@@ -665,10 +680,38 @@ knn_fallback_scan_kernel(const float* __restrict__ X, int n, int d, int k, const
   __syncthreads();
   if (!last_cta) return;
   __threadfence();
+  if (C <= 16) {  // many flagged rows, few chunks each: one warp per row
+    for (int f = warp; f < nflag; f += FB_WARPS) {
+      const int i = flag_rows[f];
+      double md = INFINITY;
+      int mj = 0x7fffffff;
+      for (int c0 = 0; c0 < C; c0 += 4) {
+        double ld[4];
+        int lj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u;
+          ld[u] = (c < C) ? __ldcg(part_d + ((size_t)f * C + c) * 32 + lane) : INFINITY;
+          lj[u] = (c < C) ? __ldcg(part_j + ((size_t)f * C + c) * 32 + lane) : 0x7fffffff;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dlist_merge_sorted(md, mj, ld[u], lj[u], lane);
+      }
+      if (lane < k - 1 && mj != 0x7fffffff) {
+        knn_idx[(size_t)i * k + 1 + lane] = mj;
+        knn_dist[(size_t)i * k + 1 + lane] = (float)sqrt(md);
+      }
+      if (lane == 0) {
+        knn_idx[(size_t)i * k] = i;
+        knn_dist[(size_t)i * k] = 0.f;
+      }
+    }
+    return;
+  }
   for (int f = 0; f < nflag; ++f) {
     const int i = flag_rows[f];
-    double md = INFINITY, thr_d = INFINITY;
-    int mj = 0x7fffffff, thr_j = 0x7fffffff;
+    double md = INFINITY;
+    int mj = 0x7fffffff;
     for (int c0 = warp; c0 < C; c0 += 4 * FB_WARPS) {
       double ld[4];
       int lj[4];
@@ -679,30 +722,14 @@ knn_fallback_scan_kernel(const float* __restrict__ X, int n, int d, int k, const
         lj[u] = (c < C) ? __ldcg(part_j + ((size_t)f * C + c) * 32 + lane) : 0x7fffffff;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        for (int e = 0; e < 32; ++e) {
-          const double xd = __shfl_sync(FULL, ld[u], e);
-          const int xj = __shfl_sync(FULL, lj[u], e);
-          if (xj == 0x7fffffff || !(xd < thr_d || (xd == thr_d && xj < thr_j))) break;  // sorted list
-          list_insert_d(md, mj, xd, xj, lane);
-          thr_d = __shfl_sync(FULL, md, 31);
-          thr_j = __shfl_sync(FULL, mj, 31);
-        }
+      for (int u = 0; u < 4; ++u) dlist_merge_sorted(md, mj, ld[u], lj[u], lane);
     }
     __syncthreads();
     sd[warp][lane] = md;
     sj[warp][lane] = mj;
     __syncthreads();
     if (warp == 0) {
-      for (int w = 1; w < FB_WARPS; ++w)
-        for (int e = 0; e < 32; ++e) {
-          const int xj = sj[w][e];
-          const double xd = sd[w][e];
-          if (xj == 0x7fffffff || !(xd < thr_d || (xd == thr_d && xj < thr_j))) break;
-          list_insert_d(md, mj, xd, xj, lane);
-          thr_d = __shfl_sync(FULL, md, 31);
-          thr_j = __shfl_sync(FULL, mj, 31);
-        }
+      for (int w = 1; w < FB_WARPS; ++w) dlist_merge_sorted(md, mj, sd[w][lane], sj[w][lane], lane);
       if (lane < k - 1 && mj != 0x7fffffff) {
         knn_idx[(size_t)i * k + 1 + lane] = mj;
         knn_dist[(size_t)i * k + 1 + lane] = (float)sqrt(md);

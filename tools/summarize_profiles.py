@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
 OUT = os.path.join(ROOT, "profiles")
 GO = os.path.join(ROOT, "gpurun_out")
 
@@ -34,7 +34,7 @@ def launches(path, out):
     tot = sum(sum(v) for v in per.values())
     with open(out, "w") as f:
         f.write(f"# ncu launch list ({os.path.basename(path)}): gpu__time_duration.sum per kernel, cold-cache and serialised\n")
-        f.write("# command: python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-large-graph (all launches, warm-up included)\n\n")
+        f.write("# command: python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-large-graph --no-sharded --no-cuda-graph (all launches, warm-up included)\n\n")
         f.write("| kernel | launches | mean us | total us | share |\n|---|---|---|---|---|\n")
         for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
             f.write(f"| {k} | {len(v)} | {sum(v) / len(v) / 1e3:.2f} | {sum(v) / 1e3:.1f} | {100 * sum(v) / tot:.1f}% |\n")
@@ -43,7 +43,7 @@ def launches(path, out):
 
 NAME_MAP = {"knn_gram_topk_tc_kernel": "knn_gram_topk_tcgen05", "knn_rerank_kernel": "knn_rerank", "cg_resident_kernel": "cg_persistent",
             "cg_persistent_kernel": "cg_persistent", "cg_small_kernel": "cg_persistent", "row_gather_kernel": "row_gather",
-            "row_gather_warp_kernel": "row_gather", "edge_grad_kernel": "edge_grad"}
+            "row_gather_warp_kernel": "row_gather", "edge_grad_kernel": "edge_grad", "graph_weights_kernel": "graph_build"}
 TRAFFIC = {}
 
 
