@@ -386,7 +386,11 @@ def run_b200(args, rank, world, local_rank):
         return tot_ms
 
     sharded = args.workload in SHARDED
-    resident, e2e, shp, h2d, d2h, e2e_pipelined, split = step_fn(args.workload, 1000 if sharded else ranks.rank_seed(1000, rank))
+    # weak scaling measures the machine, not the data: every rank runs the SAME synthetic graph (seed 1000), each on its own
+    # GPU with its own buffers.  (Different seeds change a rank's step by up to 8 %: a seed whose graph has rows that need the
+    # exact brute-force fallback pays ~0.02 ms per such row, and the job waits for its slowest rank.)
+    seed = 1000 if (sharded or not args.rank_seeds) else ranks.rank_seed(1000, rank)
+    resident, e2e, shp, h2d, d2h, e2e_pipelined, split = step_fn(args.workload, seed)
     jobs = 1 if sharded else world  # graphs finished per step by the whole job
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -539,7 +543,8 @@ def run_b200(args, rank, world, local_rank):
             "metric": METRIC, "value": jobs * 1e3 / per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per_step, "higher_is_better": True,
             "scaling": "strong" if sharded else "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic gaussian clusters (graphlearninglayer_b200.synth), L2-normalised, one graph per rank",
+            "dtype": "f32", "data": "synthetic gaussian clusters (graphlearninglayer_b200.synth), L2-normalised, one graph per rank "
+                                    + ("(a different seed per rank)" if args.rank_seeds else "(the same seed on every rank)"),
             "config": cfg,
             # e2e: host buffers in, host buffers out, every copy inside the timed region, ONE CALL AT A TIME on one stream
             # (a training loop's calls depend on each other).  pipelined_value: independent calls through HostPipeline
@@ -685,6 +690,7 @@ def main():
                          "(all-gather + all-reduce per iteration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-large-graph", action="store_true")
+    ap.add_argument("--rank-seeds", action="store_true", help="N > 1: a different synthetic graph per rank (default: the same graph)")
     ap.add_argument("--no-cuda-graph", action="store_true", help="`value` from eager launches instead of CUDA graph replay")
     ap.add_argument("--no-sharded", action="store_true", help="skip the sharded c5 / c5s lines")
     ap.add_argument("--no-c5", action="store_true", help="skip the 1M-node graph (keeps the c5s parity lines at N > 1)")

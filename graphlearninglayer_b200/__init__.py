@@ -6,10 +6,16 @@ The names resolve lazily so that ``python -m graphlearninglayer_b200.build`` can
 exists; the first access loads libgll_b200.so through ctypes and fails loudly if it is missing or stale.  There is no
 CPU or PyTorch fallback.
 """
-__all__ = ["LaplaceLearningSparseHard", "LaplaceLearningSparseHardNormalized", "knn_sym_dist", "stable_conjgrad", "last_info", "GLL"]
+__all__ = ["LaplaceLearningSparseHard", "LaplaceLearningSparseHardNormalized", "knn_sym_dist", "stable_conjgrad", "last_info", "GLL",
+           "GraphedStep", "BaseSetEvaluator"]
+_ELSEWHERE = {"GraphedStep": ".graphed", "BaseSetEvaluator": ".evalcache"}
 
 
 def __getattr__(name):
+    if name in _ELSEWHERE:
+        import importlib
+
+        return getattr(importlib.import_module(_ELSEWHERE[name], __name__), name)
     if name in __all__:
         import importlib
 
