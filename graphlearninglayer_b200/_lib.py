@@ -60,6 +60,7 @@ def _load():
     sig("gll_launch_count", C.c_longlong, [i32])
     sig("gll_profile_enable", None, [i32])
     sig("gll_debug_cg_trace", None, [vp])
+    sig("gll_debug_knn_trace", None, [vp])
     sig("gll_profile_collect", i32, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)])
     sig("gll_padded_classes", i32, [i32])
     sig("gll_max_edges", sz, [i32, i32])
@@ -112,7 +113,7 @@ lib = _load()
 
 #: every symbol include/gll_b200.h declares (tests check the .so exports all of them)
 EXPORTS = ["gll_last_error", "gll_version", "gll_device_sm_count", "gll_kernel_count", "gll_kernel_name",
-           "gll_launch_count", "gll_profile_enable", "gll_profile_collect", "gll_debug_cg_trace", "gll_padded_classes", "gll_max_edges",
+           "gll_launch_count", "gll_profile_enable", "gll_profile_collect", "gll_debug_cg_trace", "gll_debug_knn_trace", "gll_padded_classes", "gll_max_edges",
            "gll_state_layout", "gll_workspace_bytes", "gll_knn_workspace_bytes", "gll_graph_workspace_bytes",
            "gll_weights_workspace_bytes", "gll_cg_workspace_bytes", "gll_knn", "gll_graph_build", "gll_edge_weights",
            "gll_cg_solve", "gll_backward_edges", "gll_forward", "gll_backward", "gll_knn_rows_workspace_bytes", "gll_knn_rows",

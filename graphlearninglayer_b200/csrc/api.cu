@@ -313,6 +313,7 @@ long long gll_launch_count(int id) {
   return t;
 }
 void gll_debug_cg_trace(void* device_buf) { cg_set_trace(device_buf); }
+void gll_debug_knn_trace(void* device_buf) { knn_tc_set_trace(device_buf); }
 void gll_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
 int gll_profile_collect(double* ms_sum, long long* count) {
   std::vector<ProfRec*> recs;

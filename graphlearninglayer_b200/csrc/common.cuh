@@ -116,6 +116,7 @@ int knn_base_cache_build(const float* Xbase, int n_base, int d, void* cache, voi
 size_t knn_cached_ws_bytes(int n, int d, int k, int n_base);
 int knn_run_cached(const float* X, int n, int d, int k, int n_base, const void* cache, int* knn_idx, float* knn_dist, int* info,
                    void* ws, size_t ws_bytes, cudaStream_t st);
+void knn_tc_set_trace(void* device_buf);  // debug timeline of the Gram kernel's CTA 0 (knn_tc.cu)
 int knn_debug_gram_tile(const float* X, int n, int d, int row_tile, int col_tile, float* acc_out, float* rscale_out, void* ws,
                         size_t ws_bytes, cudaStream_t st);
 

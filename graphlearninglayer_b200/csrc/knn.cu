@@ -1128,7 +1128,8 @@ int knn_run(const float* X, int n, int d, int k, int row_begin, int row_end, int
 // ------------------------------------------------------------------------------------------------------------------------
 namespace {
 
-__global__ void base_thr_init_kernel(const u64* __restrict__ cache, const float* __restrict__ sq, int rows, unsigned* __restrict__ thr_g) {
+__global__ void base_thr_init_kernel(const u64* __restrict__ cache, const float* __restrict__ sq, const unsigned* __restrict__ small, int rows,
+                                     unsigned* __restrict__ thr_g) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows) return;
   const u64 last = cache[(size_t)i * KC + KC - 1];
@@ -1136,8 +1137,9 @@ __global__ void base_thr_init_kernel(const u64* __restrict__ cache, const float*
   if (last != KEY_INF) {
     // the epilogue compares d~^2 - |x_i|^2 with the threshold; the cached key holds fl(d~^2): undo the addition rounding UP
     // (a looser threshold only admits a few more candidates)
+    // ... and the roundings of the epilogue's own arithmetic on shifted values (knn_tc.cu: a few ulps of max|x|^2)
     thr = __fadd_ru(key_dist(last), -sq[i]);
-    thr = fmaf(fabsf(thr), 4.0e-7f, thr) + 1.0e-30f;
+    thr = fmaf(fabsf(thr), 4.0e-7f, thr) + 2.0e-6f * __uint_as_float(small[0]) + 1.0e-30f;
   }
   thr_g[i] = float_to_ordered(thr);
 }
@@ -1267,7 +1269,7 @@ int knn_run_cached(const float* X, int n, int d, int k, int nb, const void* cach
     GLL_PROF(KID_SQNORM, st);
     rc = launch_split_f16(X, n, d, pa, sq, small, tc_ws, rscale, thr_g, st);
     if (rc) return rc;
-    if (r0 > 0) base_thr_init_kernel<<<ceil_div(r0, 256), 256, 0, st>>>(cache, sq, r0, thr_g);
+    if (r0 > 0) base_thr_init_kernel<<<ceil_div(r0, 256), 256, 0, st>>>(cache, sq, small, r0, thr_g);
     GLL_LAUNCH_CHECK();
   }
   rc = knn_tc_candidates(X, sq, rscale, small, n, d, n, pa, tc_ws, candA, nullptr, thr_g, st);

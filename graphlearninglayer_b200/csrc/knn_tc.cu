@@ -65,9 +65,9 @@ constexpr int TC_TMEM_COLS = 512, TC_ACC_STRIDE = 256;
 
 constexpr size_t TC_OFF_LD = TC_STAGE_REGION;                                // float [8 warps][KC entries][32 rows]
 constexpr size_t TC_OFF_LI = TC_OFF_LD + TC_EPI_WARPS * KC * 32 * 4;         // int   [8 warps][KC entries][32 rows]
-constexpr size_t TC_OFF_SQJ = TC_OFF_LI + TC_EPI_WARPS * KC * 32 * 4;        // float [TC_BN]  |x_j|^2 of the unit's columns
-constexpr size_t TC_OFF_BAR = TC_OFF_SQJ + 2 * TC_BN * 4;                    // (then float [TC_BN] -2 rscale_j) mbarriers + tmem pointer
-constexpr size_t TC_OFF_TMEM = TC_OFF_BAR + 8 * (2 * TC_MAX_STAGES + 4);     // the TMEM base address slot
+constexpr size_t TC_OFF_SQJ = TC_OFF_LI + TC_EPI_WARPS * KC * 32 * 4;        // float [8 warps][{|x_j|^2 + Cs, -2 rscale_j}][128 columns]
+constexpr size_t TC_OFF_BAR = TC_OFF_SQJ + TC_EPI_WARPS * TC_BN * 4;         // mbarriers + tmem pointer
+constexpr size_t TC_OFF_TMEM = TC_OFF_BAR + 8 * (2 * TC_MAX_STAGES + 6);     // the TMEM base address slot
 constexpr size_t TC_SMEM_BYTES = TC_OFF_TMEM + 16 + 1024;                    // + slack for manual 1024 B alignment
 static_assert(TC_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(TC_STAGE_REGION / (2 * TC_A_BYTES) >= 1 && TC_STAGE_REGION % 1024 == 0, "stage ring");
@@ -78,6 +78,20 @@ constexpr uint32_t TC_IDESC_F16_PAIR = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17
 constexpr uint32_t TC_IDESC_F16 = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
+// One elected lane of a CONVERGED warp.  The TMA and MMA loops below are run by all 32 lanes with warp-uniform operands
+// and only the issue itself sits under this predicate: operands then live in uniform registers.  Under `if (lane == 0)`
+// the compiler treats them as per-thread values and wraps every UTMALDG / UTCHMMA into an ELECT + 5 x R2UR + branch
+// "waterfall" (~170 cycles per tcgen05.mma, ~280 per cp.async.bulk.tensor: the MMA warp, not the tensor pipe or L2, paced
+// the kernel -- tools/knn_trace.py, profiles/r02zc_mma_trace.txt).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -216,9 +230,12 @@ struct TcParams {
   int debug;          // GLL_B200_KNN_DEBUG (timing experiments only, results are wrong): 1 no insertions, 2 no TMEM drain
   const u64* excl;    // optional [n]: per row, only keys > excl[row] are candidates (second round of a k > 33 search)
   int passes;         // operands are fp16(x_i 2^-E_i): 1 = hi.hi, 2 = (hi + lo).hi (B_lo never exists)
+  int ares;           // 1: all K blocks of the row tile's A operand stay in shared memory while the CTA sweeps column tiles
   const float* rscale;  // [n] 2^E_i: the accumulator holds x_i.x_j / (rscale_i rscale_j)
   const unsigned* small;  // small[3], small[4]: range of E_i over the rows (written by sqnorm_split_f16_kernel)
+  unsigned long long* trace;  // debug timeline of CTA 0 (gll_debug_knn_trace, tools/knn_trace.py), or NULL
 };
+constexpr int TC_TRACE_UNITS = 1024, TC_TRACE_PHASES = 8, TC_TRACE_WARPS = 4;  // MMA warp, epilogue warps 2 and 6, producer A
 
 __host__ __device__ inline uint32_t a_bytes_of(int passes) { return passes == 2 ? 2u * TC_A_BYTES : (uint32_t)TC_A_BYTES; }  // A_hi (+ A_lo)
 
@@ -246,6 +263,10 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
   const int G = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x, b = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int RSTEP = PAIR ? 2 : 1;  // row tiles per unit
   const int C = P.col_tiles, KB = P.kblocks;
+  const bool tracing = P.trace != nullptr && blockIdx.x == 0 && lane == 0;
+  auto stamp = [&](int w, long long ui, int ph, long long val) {
+    if (tracing && ui < TC_TRACE_UNITS) P.trace[((size_t)w * TC_TRACE_UNITS + ui) * TC_TRACE_PHASES + ph] = (unsigned long long)val;
+  };
   long long u_begin, u_end;
   if (P.aligned) {
     u_begin = ((long long)b * P.row_tiles / G) * C;
@@ -255,15 +276,23 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     u_end = (long long)(b + 1) * P.units / G;
   }
 
-  const uint32_t stage_stride = a_bytes_of(P.passes) + (uint32_t)(PAIR ? TC_B_BYTES / 2 : TC_B_BYTES);  // = bytes this CTA loads per stage
-  const int nstages = min(TC_MAX_STAGES, (int)(TC_STAGE_REGION / stage_stride));
   const bool two = P.passes == 2;
-  const uint32_t a_bytes = two ? 2u * TC_A_BYTES : (uint32_t)TC_A_BYTES;  // A_hi (+ A_lo)
-  const uint32_t stage_bytes = a_bytes + (uint32_t)(PAIR ? TC_B_BYTES / 2 : TC_B_BYTES);  // what THIS CTA loads per stage
+  const uint32_t a_bytes = two ? 2u * TC_A_BYTES : (uint32_t)TC_A_BYTES;  // A_hi (+ A_lo) of one K block
+  const uint32_t b_bytes = (uint32_t)(PAIR ? TC_B_BYTES / 2 : TC_B_BYTES);  // what THIS CTA loads of a B tile's K block
+  // ares (A resident): the KB blocks of the row tile's A operand sit at the start of the stage region for as long as the CTA
+  // stays on the row tile and the ring only carries B -- on the 1M-node graph (4096 column tiles per row tile) this halves
+  // the operand bytes a CTA pulls from L2, which is what paces the MMA/TMA pipeline there (~40 B per clock and SM).
+  const bool ares = P.ares != 0;
+  const uint32_t ring_base = base + (ares ? (uint32_t)KB * a_bytes : 0u);
+  const uint32_t stage_stride = ares ? b_bytes : a_bytes + b_bytes;  // = bytes this CTA loads per stage
+  const int nstages = min(TC_MAX_STAGES, (int)(((uint32_t)TC_STAGE_REGION - (ring_base - base)) / stage_stride));
+  const uint32_t stage_bytes = stage_stride;
   const uint32_t bar_full = base + (uint32_t)TC_OFF_BAR;        // [TC_MAX_STAGES]
   const uint32_t bar_empty = bar_full + 8 * TC_MAX_STAGES;      // [TC_MAX_STAGES]
   const uint32_t bar_tfull = bar_empty + 8 * TC_MAX_STAGES;     // [2]
   const uint32_t bar_tempty = bar_tfull + 16;                   // [2]
+  const uint32_t bar_afull = bar_tempty + 16;                   // ares: the resident A operand has landed
+  const uint32_t bar_afree = bar_afull + 8;                     // ares: every MMA that reads the resident A operand has retired
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + TC_OFF_TMEM);
 
   if (warp == 0 && lane == 0) {
@@ -271,13 +300,15 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     tma_prefetch_desc(&mapAL);
     tma_prefetch_desc(&mapBH);
     for (int s = 0; s < TC_MAX_STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 2);   // the two producer warps
+      mbar_init(bar_full + 8 * s, ares ? 1 : 2);  // the two producer warps (ares: the B producer alone)
       mbar_init(bar_empty + 8 * s, 1);  // PAIR: the leader's commit arrives on both CTAs' barriers
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS);  // one arrival per epilogue warp (PAIR: of both CTAs, on the leader)
     }
+    mbar_init(bar_afull, 1);
+    mbar_init(bar_afree, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -307,35 +338,76 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     // 1120 cycles per K block with 2 / 3 / 4 loads per block, whatever the stage count or the bytes per load), so a single
     // producer thread cannot feed one-pass K blocks (2 MMAs = 366 cycles): warp 0 loads the A tiles, a second producer warp
     // the B tile; both arrive on the stage's barrier with their own byte counts.
-    if (lane == 0) {
+    if (ares && warp == 0) {
+      // resident A: one load of all K blocks per row tile, after the MMAs of the previous row tile have retired
+      int r_idx = (int)(u_begin / C), c_idx = (int)(u_begin % C);
+      uint32_t ph_free = 0;
+      for (long long u = u_begin; u < u_end;) {
+        const int rt = P.rt0 + RSTEP * r_idx + crank;
+        if (u != u_begin) {
+          mbar_wait(bar_afree, ph_free);
+          ph_free ^= 1u;
+        }
+        if (elect_one()) {
+          if (PAIR) {  // both CTAs' loads are counted by the LEADER's barrier (its MMA warp is the only consumer)
+            if (crank == 0) mbar_arrive_expect_tx(bar_afull, 2u * (uint32_t)KB * a_bytes);
+            for (int kk = 0; kk < KB; ++kk) {
+              tma_load_2d_pair(base + (uint32_t)kk * a_bytes, &mapAH, bar_afull, kk * TC_BK, rt * TC_BM);
+              if (two) tma_load_2d_pair(base + (uint32_t)kk * a_bytes + TC_A_BYTES, &mapAL, bar_afull, kk * TC_BK, rt * TC_BM);
+            }
+          } else {
+            mbar_arrive_expect_tx(bar_afull, (uint32_t)KB * a_bytes);
+            for (int kk = 0; kk < KB; ++kk) {
+              tma_load_2d(base + (uint32_t)kk * a_bytes, &mapAH, bar_afull, kk * TC_BK, rt * TC_BM);
+              if (two) tma_load_2d(base + (uint32_t)kk * a_bytes + TC_A_BYTES, &mapAL, bar_afull, kk * TC_BK, rt * TC_BM);
+            }
+          }
+        }
+        __syncwarp();
+        u += C - c_idx;  // on to the CTA's next row tile
+        c_idx = 0;
+        ++r_idx;
+      }
+    } else {
       const bool is_a = warp == 0;
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t my_bytes = is_a ? a_bytes : stage_bytes - a_bytes;
+      const uint32_t my_bytes = is_a ? a_bytes : b_bytes;
+      const uint32_t b_off = ares ? 0u : a_bytes;  // where the B block sits inside a stage
+      int r_idx = (int)(u_begin / C), c_idx = (int)(u_begin % C);  // the unit's row-tile ordinal and column tile, kept incrementally
       for (long long u = u_begin; u < u_end; ++u) {
-        const int rt = P.rt0 + RSTEP * (int)(u / C) + crank, ct = P.ct0 + (int)(u % C);
+        const int rt = P.rt0 + RSTEP * r_idx + crank, ct = P.ct0 + c_idx;
+        if (++c_idx == C) {
+          c_idx = 0;
+          ++r_idx;
+        }
+        if (is_a && tracing) stamp(3, u - u_begin, 0, clock64());
         for (int kk = 0; kk < KB; ++kk) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+          if (is_a && tracing && kk == KB - 1) stamp(3, u - u_begin, 1, clock64());
           const uint32_t full = bar_full + 8 * stage;
-          const uint32_t s0 = base + (uint32_t)stage * stage_stride;
-          if (PAIR) {
-            // both CTAs' loads of this stage are counted by the LEADER's barrier (its MMA warp is the only consumer)
-            if (crank == 0) mbar_arrive_expect_tx(full, 2u * my_bytes);
-            if (is_a) {
-              tma_load_2d_pair(s0, &mapAH, full, kk * TC_BK, rt * TC_BM);
-              if (two) tma_load_2d_pair(s0 + TC_A_BYTES, &mapAL, full, kk * TC_BK, rt * TC_BM);
-            } else {  // my half of the B tile: 128 of its 256 rows (128-row boxes: the A map)
-              tma_load_2d_pair(s0 + a_bytes, &mapAH, full, kk * TC_BK, ct * TC_BN + crank * (TC_BN / 2));
-            }
-          } else {
-            mbar_arrive_expect_tx(full, my_bytes);
-            if (is_a) {
-              tma_load_2d(s0, &mapAH, full, kk * TC_BK, rt * TC_BM);
-              if (two) tma_load_2d(s0 + TC_A_BYTES, &mapAL, full, kk * TC_BK, rt * TC_BM);
+          const uint32_t s0 = ring_base + (uint32_t)stage * stage_stride;
+          if (elect_one()) {
+            if (PAIR) {
+              // both CTAs' loads of this stage are counted by the LEADER's barrier (its MMA warp is the only consumer)
+              if (crank == 0) mbar_arrive_expect_tx(full, 2u * my_bytes);
+              if (is_a) {
+                tma_load_2d_pair(s0, &mapAH, full, kk * TC_BK, rt * TC_BM);
+                if (two) tma_load_2d_pair(s0 + TC_A_BYTES, &mapAL, full, kk * TC_BK, rt * TC_BM);
+              } else {  // my half of the B tile: 128 of its 256 rows (128-row boxes: the A map)
+                tma_load_2d_pair(s0 + b_off, &mapAH, full, kk * TC_BK, ct * TC_BN + crank * (TC_BN / 2));
+              }
             } else {
-              tma_load_2d(s0 + a_bytes, &mapBH, full, kk * TC_BK, ct * TC_BN);
+              mbar_arrive_expect_tx(full, my_bytes);
+              if (is_a) {
+                tma_load_2d(s0, &mapAH, full, kk * TC_BK, rt * TC_BM);
+                if (two) tma_load_2d(s0 + TC_A_BYTES, &mapAL, full, kk * TC_BK, rt * TC_BM);
+              } else {
+                tma_load_2d(s0 + b_off, &mapBH, full, kk * TC_BK, ct * TC_BN);
+              }
             }
           }
+          __syncwarp();
           if (++stage == nstages) {
             stage = 0;
             phase ^= 1u;
@@ -349,17 +421,34 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
     uint32_t phase = 0, acc_phase = 0;
     const int nprod = P.passes;
     const uint32_t idesc = PAIR ? TC_IDESC_F16_PAIR : TC_IDESC_F16;
+    int c_idx = (int)(u_begin % C);
+    uint32_t ph_afull = 0;
+    bool need_a = ares;
     for (long long u = (PAIR && crank != 0) ? u_end : u_begin; u < u_end; ++u) {
+      if (tracing) stamp(0, u - u_begin, 0, clock64());
       mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);  // the epilogue has drained this accumulator
+      if (need_a) {  // first unit of a row tile: the resident A operand
+        mbar_wait(bar_afull, ph_afull);
+        ph_afull ^= 1u;
+        need_a = false;
+      }
+      const bool row_done = (++c_idx == C);  // last unit of the row tile
+      if (row_done) c_idx = 0;
       tc_fence_after();
+      if (tracing) stamp(0, u - u_begin, 1, clock64());
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_ACC_STRIDE;
       for (int kk = 0; kk < KB; ++kk) {
         mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t s0 = base + (uint32_t)stage * stage_stride;
-          const uint64_t dAH = tc_smem_desc(s0), dAL = tc_smem_desc(s0 + TC_A_BYTES);
-          const uint64_t dBH = tc_smem_desc(s0 + a_bytes);
+        if (tracing && kk == 0) stamp(0, u - u_begin, 2, clock64());
+        if (tracing && kk == KB - 1) stamp(0, u - u_begin, 3, clock64());
+        if (tracing && kk == 1) stamp(0, u - u_begin, 4, clock64());
+        if (tracing && kk == 2) stamp(0, u - u_begin, 5, clock64());
+        const uint32_t s0 = ring_base + (uint32_t)stage * stage_stride;
+        const uint32_t sa = ares ? base + (uint32_t)kk * a_bytes : s0;
+        const uint64_t dAH = tc_smem_desc(sa), dAL = tc_smem_desc(sa + TC_A_BYTES);
+        const uint64_t dBH = tc_smem_desc(ares ? s0 : s0 + a_bytes);
+        if (elect_one()) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             if (g >= nprod) break;  // one pass: hi.hi only
@@ -372,49 +461,65 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
                 tc_mma_f16(d_tmem, da + (uint64_t)(2 * k4), db + (uint64_t)(2 * k4), idesc, (uint32_t)((kk | g | k4) != 0));
             }
           }
+          // the resident A operand may be overwritten once the row tile's last MMAs have retired (committed BEFORE the
+          // accumulator: when the epilogue of the CTA's last unit is through, nothing is in flight towards the peer any more)
+          const bool a_done = ares && row_done && kk == KB - 1 && u + 1 < u_end;
           if (PAIR) {
             tc_commit_pair(bar_empty + 8 * stage);                 // frees the stage in BOTH CTAs when these MMAs retire
+            if (a_done) tc_commit_pair(bar_afree);
             if (kk == KB - 1) tc_commit_pair(bar_tfull + 8 * acc);  // accumulator complete, in both CTAs' TMEM
           } else {
             tc_commit(bar_empty + 8 * stage);      // frees the smem stage when these MMAs retire
+            if (a_done) tc_commit(bar_afree);
             if (kk == KB - 1) tc_commit(bar_tfull + 8 * acc);  // accumulator complete
           }
         }
         __syncwarp();
+        if (tracing && kk == 0) stamp(0, u - u_begin, 6, clock64());        // the first K block's MMAs and commit are issued
+        if (tracing && kk == KB - 1) stamp(0, u - u_begin, 7, clock64());   // ... and the last one's
         if (++stage == nstages) {
           stage = 0;
           phase ^= 1u;
         }
       }
+      if (row_done) need_a = ares;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
   } else {
     // ================================================= epilogue =====================================================
     // Every SM sub-partition hosts TWO epilogue warps (w and w + 4: same TMEM lane quarter, i.e. the same 32 rows); each
-    // scans one half of the unit's 256 columns into its OWN candidate set, so a row has two sets per CTA.  The insertion
-    // path is one long dependent chain (ncu: 0.18 IPC with a single warp per sub-partition): the second warp fills the gaps.
+    // scans one half of the unit's 256 columns into its OWN candidate set, so a row has two sets per CTA.  The warps are
+    // independent of each other: each stages the column norms of its own 128 columns (no CTA-wide barrier), so a warp that
+    // runs insertion rounds delays nobody but itself, and only through the accumulator hand-off (tools/knn_trace.py: with a
+    // barrier per unit every round of any warp cost all eight ~600 cycles).
     const int quarter = warp & 3;          // TMEM lanes [32*quarter, +32) are the ones this warp may read
     const int half = (warp - 2) >> 2;      // which 128 columns of the unit
     const int eset = half * 4 + quarter;   // the warp's block of candidate sets
-    float* Ld = reinterpret_cast<float*>(smem + TC_OFF_LD) + (size_t)eset * KC * 32 + lane;  // my row: Ld[e * 32]
+    // A row's set: 32 slots of PACKED keys = (bits of the shifted value v' with the low five mantissa bits cleared) | slot, and
+    // the column index beside it.  v' = d~^2 - |x_i|^2 + Cs with Cs = 2 max|x|^2 is positive, so unsigned order of the keys =
+    // order of the values, ties by slot: ONE integer max finds the largest entry AND where it sits.  Clearing five bits costs
+    // nothing in rigour: every threshold is a stored (cleared) value, a rejected column has v' >= threshold >= the final set
+    // maximum as stored, and the stored values are what goes to the re-rank kernel (whose proof only needs "every column
+    // that is not a candidate has an approximate distance >= the 32nd candidate's").
+    uint32_t* Lk = reinterpret_cast<uint32_t*>(smem + TC_OFF_LD) + (size_t)eset * KC * 32 + lane;  // my row: Lk[e * 32]
     int* Li = reinterpret_cast<int*>(smem + TC_OFF_LI) + (size_t)eset * KC * 32 + lane;
+    constexpr uint32_t KEY_EMPTY = 0x7f800000u;  // +inf
     int acc = 0, cur_rt = -1, gi = 0;
-    float gm[4];  // maximum of slots [8t, 8t+8) of my row's candidate set
-    int gp[4];    // ... and where it sits
+    uint32_t gk[4];  // largest key of slots [8t, 8t+8) of my row's set
     uint32_t acc_phase = 0;
-    // Ranking inside a row only needs key = |x_j|^2 - 2 x_i.x_j; |x_i|^2 is added when the set is flushed.
     // thr = min(smax, tlim): smax = largest entry of MY set (inf until it is full), tlim = what the row's other sets --
     // the partner warp's column half, other CTAs working on the same row tile -- have published through thr_g (L2).
     // Any set's 32nd-best bounds the row's overall 32nd-best from above, so entries >= tlim can never be needed; the
     // union of the row's sets still holds the overall 32 best, and sets fill far more slowly (fewer insertions).
     float thr = INFINITY, smax = INFINITY, tlim = INFINITY, published = INFINITY;
+    bool fresh_set = false;  // the set is empty: the first 32 columns go straight into the 32 slots
     u64 excl_row = 0ull;   // second-round searches: skip everything the first round already holds
     float sqi_row = 0.f;
-    float* sqj_s = reinterpret_cast<float*>(smem + TC_OFF_SQJ);
-    const int et = (warp - 2) * 32 + lane;  // 0..255 over the epilogue warps
+    // this warp's staging area: |x_j|^2 + Cs of its 128 columns, then -2 rscale_j
+    float* sq_w = reinterpret_cast<float*>(smem + TC_OFF_SQJ) + (size_t)(warp - 2) * TC_BN;
+    float* cj_w = sq_w + TC_BN / 2;
     // d~^2 - |x_i|^2 = |x_j|^2 + (acc ri) cj with cj = -2 rscale_j, ri = rscale_i (powers of two: exact; 1 without scaling)
-    float* cj_s = sqj_s + TC_BN;
     float ri = 1.f;
     // all rows share one scale (the usual case: normalised features; always without scaling): v = |x_j|^2 + cu acc
     bool uniform = true;
@@ -424,35 +529,68 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
       uniform = (emax == 255u - eminc);
       cu = -ldexpf(2.f, 2 * ((int)emax - 128));
     }
+    const float Cs = 2.f * __uint_as_float(__ldg(P.small + 0));  // v + Cs >= max|x|^2 - (error bound) > 0
+    // value that goes to the candidate lists: fl(fl(v' - Cs) + |x_i|^2), monotone in v'
+    auto unshift = [&](float vs, float sqr) { return (vs - Cs) + sqr; };
 
     auto flush = [&](int rt) {
       __syncwarp();
       const int slot = 2 * (P.aligned ? 0 : b - tc_cta_of_unit((long long)((rt - P.rt0) / RSTEP) * C, G, P.units)) + half;
-      const float* wd = Ld - lane;
+      const uint32_t* wk = Lk - lane;
       const int* wi = Li - lane;
       for (int r = 0; r < 32; ++r) {  // lane = slot index e here; 256 B coalesced store per row
         const int row = rt * TC_BM + quarter * 32 + r;
-        const float dd = wd[lane * 32 + r];
+        const uint32_t kk = wk[lane * 32 + r];
         const float sqr = (row < P.n) ? __ldg(P.sq + row) : 0.f;
-        const u64 key = (dd == INFINITY) ? KEY_INF : make_key(dd + sqr, wi[lane * 32 + r]);
+        const u64 key = (kk >= KEY_EMPTY) ? KEY_INF : make_key(unshift(__uint_as_float(kk & ~31u), sqr), wi[lane * 32 + r]);
         if (row < P.row_end) P.cand[((size_t)row * P.max_splits + slot) * KC + lane] = key;
       }
       __syncwarp();
     };
 
+    // |x_j|^2 + Cs (and -2 rscale_j) of my four columns of a unit, +inf masking columns outside the column range.  The values
+    // of unit u + 1 are fetched into registers at the top of unit u and staged at the top of unit u + 1: their L2 round trip
+    // is never in the epilogue's critical path (the kernel is bound by the epilogue).
+    const int mycol = half * (TC_BN / 2) + 4 * lane;
+    auto col_sq = [&](int ctile) {
+      const int j = ctile * TC_BN + mycol;
+      float4 r;
+      r.x = (j + 0 < P.n && j + 0 >= P.col_begin) ? __ldg(P.sq + j + 0) : INFINITY;  // (Cs is added when the values are staged:
+      r.y = (j + 1 < P.n && j + 1 >= P.col_begin) ? __ldg(P.sq + j + 1) : INFINITY;  //  nothing here may wait for the loads)
+      r.z = (j + 2 < P.n && j + 2 >= P.col_begin) ? __ldg(P.sq + j + 2) : INFINITY;
+      r.w = (j + 3 < P.n && j + 3 >= P.col_begin) ? __ldg(P.sq + j + 3) : INFINITY;
+      return r;
+    };
+    auto col_cj = [&](int ctile) {
+      const int j = ctile * TC_BN + mycol;
+      float4 r;
+      r.x = (j + 0 < P.n) ? __ldg(P.rscale + j + 0) : 1.f;  // (times -2 when staged)
+      r.y = (j + 1 < P.n) ? __ldg(P.rscale + j + 1) : 1.f;
+      r.z = (j + 2 < P.n) ? __ldg(P.rscale + j + 2) : 1.f;
+      r.w = (j + 3 < P.n) ? __ldg(P.rscale + j + 3) : 1.f;
+      return r;
+    };
+    int r_idx = (int)(u_begin / C), c_idx = (int)(u_begin % C);  // kept incrementally: no 64-bit divisions per unit
+    float4 nsq = make_float4(0.f, 0.f, 0.f, 0.f), ncj = nsq;
+    if (u_begin < u_end) {
+      nsq = col_sq(P.ct0 + c_idx);
+      if (!uniform) ncj = col_cj(P.ct0 + c_idx);
+    }
     for (long long u = u_begin; u < u_end; ++u) {
-      const int rt = P.rt0 + RSTEP * (int)(u / C) + crank, ct = P.ct0 + (int)(u % C);
+      const int rt = P.rt0 + RSTEP * r_idx + crank, ct = P.ct0 + c_idx;
+      if (++c_idx == C) {
+        c_idx = 0;
+        ++r_idx;
+      }
       if (rt != cur_rt) {
         if (cur_rt >= 0) flush(cur_rt);
 #pragma unroll
-        for (int e = 0; e < KC; ++e) Ld[e * 32] = INFINITY;
+        for (int e = 0; e < KC; ++e) Lk[e * 32] = KEY_EMPTY | (uint32_t)e;
         cur_rt = rt;
         thr = smax = tlim = published = INFINITY;
+        fresh_set = (P.excl == nullptr);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          gm[t] = INFINITY;
-          gp[t] = 8 * t;
-        }
+        for (int t = 0; t < 4; ++t) gk[t] = KEY_EMPTY | (uint32_t)(8 * t + 7);
         gi = rt * TC_BM + quarter * 32 + lane;
         ri = (P.rscale != nullptr && gi < P.n) ? __ldg(P.rscale + gi) : 1.f;
         if (P.excl != nullptr) {
@@ -461,34 +599,48 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
         }
       }
       const int c_begin = ct * TC_BN;
-      // stage |x_j|^2 of the unit's 256 columns for all eight epilogue warps (+inf masks columns outside the column range).
-      // (Fetching these one unit ahead into a second buffer -- one barrier and one L2 round trip less per unit -- measured no
-      // faster, and a threshold that is one unit older costs insertions: both tried twice, not kept.)
-      epi_bar_sync();  // everybody is done with the previous unit's values
-      sqj_s[et] = (c_begin + et < P.n && c_begin + et >= P.col_begin) ? __ldg(P.sq + c_begin + et) : INFINITY;
-      cj_s[et] = (P.rscale != nullptr && c_begin + et < P.n) ? -2.f * __ldg(P.rscale + c_begin + et) : -2.f;
-      epi_bar_sync();
-      // once per unit (sharing every 32 columns instead measured the same): take what the row's other sets have published
-      if (P.thr_g != nullptr && gi < P.n) {  // ordered + 1 = the next float up: ties with another set's bound stay admissible
-        tlim = fminf(tlim, ordered_to_float(__ldcg(P.thr_g + gi) + 1u));
-        thr = fminf(smax, tlim);
+      const int tw = !tracing ? -1 : (warp == 2) ? 1 : (warp == 6) ? 2 : -1;  // (tracing: lane 0 of CTA 0, debug runs only)
+      int nround = 0;
+      if (tw > 0) stamp(tw, u - u_begin, 0, clock64());
+      if (tw == 1 && ((u - u_begin) & 1023) == 0) {  // coarse timeline of the whole CTA: SM clock and wall clock every 1024 units
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        stamp(1, (u - u_begin) >> 10, 6, (long long)gt);
+        stamp(1, (u - u_begin) >> 10, 7, clock64());
       }
+      // stage this unit's column values (fetched one unit ago), then put the next unit's in flight
+      __syncwarp();  // every lane is done with the previous unit's values
+      *reinterpret_cast<float4*>(sq_w + 4 * lane) = make_float4(nsq.x + Cs, nsq.y + Cs, nsq.z + Cs, nsq.w + Cs);
+      if (!uniform) *reinterpret_cast<float4*>(cj_w + 4 * lane) = make_float4(-2.f * ncj.x, -2.f * ncj.y, -2.f * ncj.z, -2.f * ncj.w);
+      __syncwarp();
+      if (u + 1 < u_end) {
+        nsq = col_sq(P.ct0 + c_idx);
+        if (!uniform) ncj = col_cj(P.ct0 + c_idx);
+      }
+      // ... and what the row's other sets have published (once per unit; folded in after the first 32 columns, when the
+      // load has landed)
+      unsigned tg = 0xffffffffu;
+      if (P.thr_g != nullptr && gi < P.n) tg = __ldcg(P.thr_g + gi);
+      if (tw > 0) stamp(tw, u - u_begin, 1, clock64());
       // does this warp's row range meet this unit's column range?  (only then can a column be the row itself)
       const int wrow0 = rt * TC_BM + quarter * 32;
       const bool diag = (c_begin < wrow0 + 32) && (c_begin + TC_BN > wrow0);
 
+      if (tw > 0) stamp(tw, u - u_begin, 2, clock64());
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
+      if (tw > 0) stamp(tw, u - u_begin, 3, clock64());
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * TC_ACC_STRIDE;
       uint32_t rawA[TC_CHUNK], rawB[TC_CHUNK];
-      auto process = [&](const uint32_t (&raw)[TC_CHUNK], int q) {
-        const int j0 = c_begin + q * TC_CHUNK;
+      // qq = chunk of this warp's column half (0..3)
+      auto process = [&](const uint32_t (&raw)[TC_CHUNK], int qq) {
+        const int j0 = c_begin + half * (TC_BN / 2) + qq * TC_CHUNK;
         float v[TC_CHUNK];
         uint32_t hits = 0;
         if (uniform) {  // every row has the same scale: one FMA per element (same value, the factors are powers of two)
 #pragma unroll
           for (int c4 = 0; c4 < TC_CHUNK / 4; ++c4) {
-            const float4 s4 = *reinterpret_cast<const float4*>(sqj_s + q * TC_CHUNK + 4 * c4);  // warp-wide broadcast
+            const float4 s4 = *reinterpret_cast<const float4*>(sq_w + qq * TC_CHUNK + 4 * c4);  // warp-wide broadcast
             v[4 * c4 + 0] = fmaf(__uint_as_float(raw[4 * c4 + 0]), cu, s4.x);
             v[4 * c4 + 1] = fmaf(__uint_as_float(raw[4 * c4 + 1]), cu, s4.y);
             v[4 * c4 + 2] = fmaf(__uint_as_float(raw[4 * c4 + 2]), cu, s4.z);
@@ -497,8 +649,8 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
         } else {
 #pragma unroll
           for (int c4 = 0; c4 < TC_CHUNK / 4; ++c4) {
-            const float4 s4 = *reinterpret_cast<const float4*>(sqj_s + q * TC_CHUNK + 4 * c4);  // warp-wide broadcast
-            const float4 c4v = *reinterpret_cast<const float4*>(cj_s + q * TC_CHUNK + 4 * c4);
+            const float4 s4 = *reinterpret_cast<const float4*>(sq_w + qq * TC_CHUNK + 4 * c4);  // warp-wide broadcast
+            const float4 c4v = *reinterpret_cast<const float4*>(cj_w + qq * TC_CHUNK + 4 * c4);
             v[4 * c4 + 0] = fmaf(ri * __uint_as_float(raw[4 * c4 + 0]), c4v.x, s4.x);
             v[4 * c4 + 1] = fmaf(ri * __uint_as_float(raw[4 * c4 + 1]), c4v.y, s4.y);
             v[4 * c4 + 2] = fmaf(ri * __uint_as_float(raw[4 * c4 + 2]), c4v.z, s4.z);
@@ -509,6 +661,26 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
 #pragma unroll
           for (int c = 0; c < TC_CHUNK; ++c)
             if (j0 + c == gi) v[c] = INFINITY;  // self is slot 0 by construction (knn_finish)
+        }
+        if (fresh_set) {  // warp-uniform: the first 32 columns of a new row tile fill the 32 slots directly
+          fresh_set = false;
+          if (P.debug >= 1) return;
+          uint32_t kv[TC_CHUNK];
+#pragma unroll
+          for (int c = 0; c < TC_CHUNK; ++c) {
+            kv[c] = (__float_as_uint(v[c]) & ~31u) | (uint32_t)c;
+            Lk[c * 32] = kv[c];
+            Li[c * 32] = j0 + c;
+          }
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const uint32_t a = max(max(kv[8 * t], kv[8 * t + 1]), max(kv[8 * t + 2], kv[8 * t + 3]));
+            const uint32_t bq = max(max(kv[8 * t + 4], kv[8 * t + 5]), max(kv[8 * t + 6], kv[8 * t + 7]));
+            gk[t] = max(a, bq);
+          }
+          smax = __uint_as_float(max(max(gk[0], gk[1]), max(gk[2], gk[3])) & ~31u);
+          thr = fminf(smax, tlim);
+          return;
         }
         // Steady state: no column of the chunk beats any row's threshold.  One min per element and one vote decide that; the
         // per-column hit mask (three instructions per element) is only built for chunks that do have a survivor.  On the
@@ -523,6 +695,7 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
         }
         // ---- every row (thread) inserts its own survivors; rows proceed concurrently ----
         while (__any_sync(FULL, hits != 0)) {
+          ++nround;
           if (hits) {
             const int c = __ffs(hits) - 1;
             hits &= hits - 1;
@@ -537,44 +710,26 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
             for (int t = 0; t < 4; ++t) s4[t] = (c & 4) ? s8[2 * t + 1] : s8[2 * t];
             const float s2a = (c & 8) ? s4[1] : s4[0], s2b = (c & 8) ? s4[3] : s4[2];
             const float dsel = (c & 16) ? s2b : s2a;
-            // second round: the key is rebuilt exactly as the first round flushed it (dd + |x_i|^2, index), so the
-            // lexicographic test excludes precisely the first round's set
-            const bool fresh = (P.excl == nullptr) || (make_key(dsel + sqi_row, j0 + c) > excl_row);
+            const uint32_t kbits = __float_as_uint(dsel) & ~31u;
+            // second round: the key is rebuilt exactly as the first round flushed it, so the lexicographic test excludes
+            // precisely the first round's set
+            const bool fresh = (P.excl == nullptr) || (make_key(unshift(__uint_as_float(kbits), sqi_row), j0 + c) > excl_row);
             if (dsel < thr && fresh) {  // thr may have tightened since the scan
-              // the row's 32 slots are 4 groups of 8 with the group maxima (value, slot) cached in registers: replace
-              // the overall maximum, rescan only its group (8 shared-memory loads instead of 32).  First maximum wins ties.
-              const bool h01 = gm[1] > gm[0], h23 = gm[3] > gm[2];
-              const float m01 = h01 ? gm[1] : gm[0], m23 = h23 ? gm[3] : gm[2];
-              const int p01 = h01 ? gp[1] : gp[0], p23 = h23 ? gp[3] : gp[2];
-              const bool hi = m23 > m01;
-              const int g = hi ? (h23 ? 3 : 2) : (h01 ? 1 : 0);
-              const int pos = hi ? p23 : p01;
-              Ld[pos * 32] = dsel;
+              // replace the set's largest entry (one integer max over the four cached group maxima names it), reload its
+              // group of eight and take the group's new maximum
+              const uint32_t top = max(max(gk[0], gk[1]), max(gk[2], gk[3]));
+              const int pos = (int)(top & 31u);
+              Lk[pos * 32] = kbits | (uint32_t)pos;
               Li[pos * 32] = j0 + c;
-              float tv[8];
+              const uint32_t* grp = Lk + (pos & ~7) * 32;
+              uint32_t tk[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) tv[e] = Ld[(g * 8 + e) * 32];
-              // ... and the group's new maximum by a three-level tournament (lower slot wins ties, as a scan would)
-              float a4[4];
-              int i4[4];
+              for (int e = 0; e < 8; ++e) tk[e] = grp[e * 32];
+              const uint32_t mx = max(max(max(tk[0], tk[1]), max(tk[2], tk[3])), max(max(tk[4], tk[5]), max(tk[6], tk[7])));
+              const int g = pos >> 3;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const bool h = tv[2 * e + 1] > tv[2 * e];
-                a4[e] = h ? tv[2 * e + 1] : tv[2 * e];
-                i4[e] = h ? 2 * e + 1 : 2 * e;
-              }
-              const bool ha = a4[1] > a4[0], hb = a4[3] > a4[2];
-              const float a2a = ha ? a4[1] : a4[0], a2b = hb ? a4[3] : a4[2];
-              const int i2a = ha ? i4[1] : i4[0], i2b = hb ? i4[3] : i4[2];
-              const bool hc = a2b > a2a;
-              const float mx = hc ? a2b : a2a;
-              const int mp = g * 8 + (hc ? i2b : i2a);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                gm[t] = (t == g) ? mx : gm[t];
-                gp[t] = (t == g) ? mp : gp[t];
-              }
-              smax = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+              for (int t = 0; t < 4; ++t) gk[t] = (t == g) ? mx : gk[t];
+              smax = __uint_as_float(max(max(gk[0], gk[1]), max(gk[2], gk[3])) & ~31u);
               thr = fminf(smax, tlim);
             }
           }
@@ -582,40 +737,51 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
       };
       // two register sets: the TMEM load of the next 32 columns is in flight while the current ones are processed
       constexpr int QH = TC_BN / TC_CHUNK / 2;  // chunks per warp (its half of the columns)
-      const int q0 = half * QH;
-      if (P.debug >= 2) {  // timing experiment: hand the accumulator back untouched
+      static_assert(QH == 4, "the chunk loop below is written for four chunks per warp");
+      const uint32_t tcol = taddr + (uint32_t)(half * (TC_BN / 2));
+      auto hand_back = [&]() {  // this warp's half of the accumulator is in registers or consumed: the MMA warp may reuse it
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           if (PAIR)
-            mbar_arrive_leader(bar_tempty + 8 * acc);
+            mbar_arrive_leader(bar_tempty + 8 * acc);  // the leader's MMA warp waits for both CTAs' epilogues
           else
             mbar_arrive(bar_tempty + 8 * acc);
         }
-      } else
-        tc_ld_issue(taddr + q0 * TC_CHUNK, rawA);
-#pragma unroll 1
-      for (int q = q0; q < ((P.debug >= 2) ? 0 : q0 + QH); q += 2) {
+      };
+      if (P.debug >= 2) {  // timing experiment: hand the accumulator back untouched
+        hand_back();
+      } else {
+        tc_ld_issue(tcol, rawA);
         tc_ld_wait(rawA);
-        tc_ld_issue(taddr + (q + 1) * TC_CHUNK, rawB);
-        process(rawA, q);
-        tc_ld_wait(rawB);
-        if (q + 2 < q0 + QH) {
-          tc_ld_issue(taddr + (q + 2) * TC_CHUNK, rawA);
-        } else {  // this warp's half of the accumulator is in registers or consumed: hand it back to the MMA warp early
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (PAIR)
-              mbar_arrive_leader(bar_tempty + 8 * acc);  // the leader's MMA warp waits for both CTAs' epilogues
-            else
-              mbar_arrive(bar_tempty + 8 * acc);
+        tc_ld_issue(tcol + TC_CHUNK, rawB);
+        process(rawA, 0);
+        if (tg != 0xffffffffu) {
+          // another set's bound, shifted (rounded up) and moved to the START OF THE NEXT five-bit bucket: a column whose
+          // stored value would tie with that set's largest entry stays admissible (it may have the smaller index: the
+          // merged lists and the second round of a k > 33 search order candidates by (value, index))
+          const float t_sh = __fadd_ru(ordered_to_float(tg + 1u), Cs);
+          if (t_sh < INFINITY) {  // nothing published yet: +inf (or the NaN one past it)
+            tlim = fminf(tlim, __uint_as_float((__float_as_uint(t_sh) | 31u) + 1u));
+            thr = fminf(smax, tlim);
           }
         }
-        process(rawB, q + 1);
+        tc_ld_wait(rawB);
+        tc_ld_issue(tcol + 2 * TC_CHUNK, rawA);
+        process(rawB, 1);
+        tc_ld_wait(rawA);
+        tc_ld_issue(tcol + 3 * TC_CHUNK, rawB);
+        process(rawA, 2);
+        tc_ld_wait(rawB);
+        hand_back();
+        process(rawB, 3);
+      }
+      if (tw > 0) {
+        stamp(tw, u - u_begin, 4, clock64());
+        stamp(tw, u - u_begin, 5, nround);
       }
       if (P.thr_g != nullptr && gi < P.n && smax < published) {  // my set is full and its bound improved during this unit
-        atomicMin(P.thr_g + gi, float_to_ordered(smax));
+        atomicMin(P.thr_g + gi, float_to_ordered(__fadd_ru(smax, -Cs)));  // unshifted, rounded up: still an upper bound
         published = smax;
       }
       acc ^= 1;
@@ -809,7 +975,9 @@ size_t knn_tc_ws_upper(int n, int d) { return 2 * align_up((size_t)n * (size_t)(
 float knn_tc_err_coef(int d, int passes) {
   const double steps = (double)passes * ceil_div(d, 16) + 8.0;
   const double split = (passes == 1 ? 2.0 : 1.0) * (1.0 + sqrt((double)d)) / 2097152.0 * 1.01;
-  const double e = split + steps * 4.76837158203125e-7 + 4.0 * 5.9604644775390625e-8;
+  // 12 ulps: the roundings of the epilogue (|x_j|^2 + Cs, the FMA at the magnitude of the shifted value, un-shifting and
+  // adding |x_i|^2 when a set is flushed: <= 15 * 2^-24 max|x|^2 together, against 4 * 12 * 2^-24 (|x_i|^2 + max|x|^2) here)
+  const double e = split + steps * 4.76837158203125e-7 + 12.0 * 5.9604644775390625e-8;
   return (float)(4.0 * e);
 }
 
@@ -826,6 +994,9 @@ int knn_tc_debug_tile(const TcPlan& plan, int n, void* tc_ws, int rt, int ct, fl
   GLL_LAUNCH_CHECK();
   return GLL_OK;
 }
+
+static unsigned long long* g_knn_trace = nullptr;  // debug only: [TC_TRACE_WARPS][TC_TRACE_UNITS][TC_TRACE_PHASES] of CTA 0
+void knn_tc_set_trace(void* device_buf) { g_knn_trace = reinterpret_cast<unsigned long long*>(device_buf); }
 
 int knn_tc_candidates(const float* X, const float* sq, const float* rscale, const unsigned* small, int n, int d, int row_end, const TcPlan& plan,
                       void* tc_ws, u64* cand, const u64* excl, unsigned* thr_g, cudaStream_t st) {
@@ -860,6 +1031,15 @@ int knn_tc_candidates(const float* X, const float* sq, const float* rscale, cons
   {
     const char* dbg = getenv("GLL_B200_KNN_DEBUG");
     P.debug = dbg ? atoi(dbg) : 0;
+  }
+  P.trace = g_knn_trace;
+  {
+    // resident A operand: when all K blocks of a row tile and at least three B stages fit the stage region (d <= 384 with CTA
+    // pairs and one pass); default in the large-graph mode (a row tile is swept over all column tiles), GLL_B200_KNN_ARES=0/1
+    const size_t need = (size_t)plan.kblocks * a_bytes_of(plan.passes) + 3u * (size_t)(plan.rstep == 2 ? TC_B_BYTES / 2 : TC_B_BYTES);
+    const bool fits = need <= TC_STAGE_REGION;
+    const char* e = getenv("GLL_B200_KNN_ARES");
+    P.ares = (fits && (e ? atoi(e) != 0 : plan.aligned != 0)) ? 1 : 0;
   }
   GLL_CUDA_CHECK(set_max_dynamic_smem_once((const void*)knn_gram_topk_tc_kernel<false>, (int)TC_SMEM_BYTES));
   GLL_CUDA_CHECK(set_max_dynamic_smem_once((const void*)knn_gram_topk_tc_kernel<true>, (int)TC_SMEM_BYTES));

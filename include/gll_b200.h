@@ -62,6 +62,9 @@ int gll_profile_collect(double* ms_sum, long long* count);
 /* Debug aid: when device_buf != NULL the on-chip CG kernel writes %globaltimer stamps [cta][16 passes][8 phases]
  * (uint64) into it; NULL switches the trace off.  Not for production use. */
 void gll_debug_cg_trace(void* device_buf);
+/* Debug aid: SM-clock timeline of CTA 0 of the tensor-core Gram kernel, [4 warps][1024 units][8 phases] uint64
+ * (MMA warp, two epilogue warps, TMA producer; tools/knn_trace.py); NULL switches it off.  Not for production use. */
+void gll_debug_knn_trace(void* device_buf);
 
 /* Class columns are padded to a multiple of 4 so that every class row is float4-addressable. */
 int gll_padded_classes(int l);

@@ -80,7 +80,7 @@ def err_coef(d: int, passes: int = 1) -> float:
     """knn_tc_err_coef (knn_tc.cu)."""
     steps = passes * math.ceil(d / 16) + 8.0
     split = (2.0 if passes == 1 else 1.0) * (1.0 + math.sqrt(d)) / 2097152.0 * 1.01
-    e = split + steps * 4.76837158203125e-7 + 4.0 * 5.9604644775390625e-8
+    e = split + steps * 4.76837158203125e-7 + 12.0 * 5.9604644775390625e-8
     return float(np.float32(4.0 * e))
 
 

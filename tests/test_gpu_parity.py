@@ -283,6 +283,28 @@ def test_knn_cta_pair_variant(gll, monkeypatch):
     assert torch.equal(i0, i1) and torch.equal(d0, d1)
 
 
+@pytest.mark.parametrize("pair", ["0", "1"])
+@pytest.mark.parametrize("split", ["", "f16x2"])
+@pytest.mark.parametrize("d", [64, 200])
+def test_knn_resident_a_operand(gll, monkeypatch, pair, split, d):
+    """Resident-A mode of the tensor-core kernel (the K blocks of a row tile's A operand stay in shared memory while the CTA
+    sweeps column tiles; default on large graphs only): forced on a graph whose CTAs change row tiles several times, with
+    and without CTA pairs, one and two MMA passes -- identical lists."""
+    _, _lib = gll
+    X, *_ = O.synth_inputs(13, 3000, 2900, d, 10, 3.5)
+    monkeypatch.setenv("GLL_B200_KNN_PATH", "tc")
+    monkeypatch.setenv("GLL_B200_KNN_PAIR", pair)
+    if split:
+        monkeypatch.setenv("GLL_B200_KNN_SPLIT", split)
+    monkeypatch.setenv("GLL_B200_KNN_ARES", "0")
+    i0, d0, _ = run_knn(_lib, X)
+    monkeypatch.setenv("GLL_B200_KNN_ARES", "1")
+    i1, d1, _ = run_knn(_lib, X)
+    assert torch.equal(i0, i1) and torch.equal(d0, d1)
+    ref_idx, _ = O.exact_knn_rows(X, np.arange(0, X.shape[0], 53), 25)
+    assert np.array_equal(i1.cpu().numpy()[::53], ref_idx)
+
+
 def test_knn_full_size_properties(gll):
     """C4 size (n=16384, d=512): properties that need no oracle: self first, sorted distances, symmetric distances on
     mutual pairs, distances equal to a torch fp64 recomputation on the chosen pairs, and k-th distance <= any

@@ -32,6 +32,9 @@ print({k: round(v[0] / v[1], 3) for k, v in p.items()}, "issued PFLOP/s", round(
 '''
 ENVS = ({}, {"GLL_B200_KNN_DEBUG": "1"}, {"GLL_B200_KNN_DEBUG": "2"}, {"GLL_B200_KNN_SPLIT": "f16x2"},
         {"GLL_B200_KNN_SPLIT": "f16x2", "GLL_B200_KNN_DEBUG": "2"})
+if os.environ.get("KNN_EXPERIMENT_ENVS") == "pair":  # CTA pairs (default here) against single CTAs, each also as the pipeline alone
+    ENVS = ({}, {"GLL_B200_KNN_DEBUG": "1"}, {"GLL_B200_KNN_DEBUG": "2"}, {"GLL_B200_KNN_PAIR": "0"},
+            {"GLL_B200_KNN_PAIR": "0", "GLL_B200_KNN_DEBUG": "2"})
 if os.environ.get("KNN_EXPERIMENT_ENVS") == "default":  # the default configuration, and without the set insertions
     ENVS = ({}, {"GLL_B200_KNN_DEBUG": "1"})
 for env in ENVS:
