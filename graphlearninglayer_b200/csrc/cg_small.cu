@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) cg_small_kernel(CgParams P, int
   int* ccol = lptr + (m + 1);                                                 // [csr_cap]
   float* cval = reinterpret_cast<float*>(ccol + csr_cap);                     // [csr_cap]
 
+  if (trace != nullptr && threadIdx.x == 0) trace[15 * 8 + 7] = (unsigned long long)clock64();  // kernel entry
   const int nnz = __ldg(P.ptr + m);
   const bool cached = nnz <= csr_cap;
   for (int i = tid; i <= m; i += CS_THREADS) lptr[i] = __ldg(P.ptr + i);
@@ -124,8 +125,10 @@ __global__ void __launch_bounds__(CS_THREADS, 1) cg_small_kernel(CgParams P, int
       // copy per address space of the CSR: otherwise every gather re-derives the shared-memory window (S2UR in the loop)
       auto walk = [&](const int* __restrict__ cj, const float* __restrict__ cv) {
         const int e1 = lptr[row[0] + 1];
+        int e = lptr[row[0]];
+        if (trace != nullptr && threadIdx.x == 0 && iter < 15) trace[iter * 8 + 7] = (unsigned long long)clock64() + (unsigned long long)((e + e1) & 0);
 #pragma unroll 2
-        for (int e = lptr[row[0]]; e < e1; ++e) {
+        for (; e < e1; ++e) {
           const float we = cv[e];
           const uint32_t uj = us_s + (uint32_t)(cj[e] * lp) * 4u;
 #pragma unroll

@@ -13,25 +13,30 @@
 // bound keeps the one-sided 2 |x_i| rho): twice the MMA work for a bound that is 30 % tighter; kept for data whose neighbour
 // gaps sit between the two bounds.  (Round 1's three-pass bf16 split is gone: same lists, 50 % more MMAs.)
 //
-// Kernel (one persistent CTA per SM, 10 warps, warp-specialised):
-//   warp 0   TMA producer: per 32-wide K block one stage = {A_hi (128 rows), B_hi (256 rows)} = 24 KB (two passes: + A_lo
-//            = 32 KB), four stages, 64-byte swizzle
-//   warp 1   MMA issuer: one elected lane issues 2 (two passes: 4) tcgen05.mma per stage (2 K=16 steps per operand pair)
-//            into one of two 128 x 256 fp32 accumulators in TMEM (all 512 columns; double buffered against the epilogue)
+// Kernel (one persistent CTA per SM, 11 warps, warp-specialised; every issue loop is run by a CONVERGED warp with
+// warp-uniform operands and elect.sync around the issue itself, see elect_one()):
+//   warp 0   TMA producer of the A operand: per 64-wide K block A_hi (128 rows, 16 KB; two passes: + A_lo), 128-byte swizzle
+//   warp 10  TMA producer of the B operand: B_hi (256 rows, 32 KB; a CTA of a pair stages its half) into the same stage
+//   warp 1   MMA issuer: 4 (two passes: 8) tcgen05.mma of K = 16 per stage into one of two 128 x 256 fp32 accumulators in
+//            TMEM (all 512 columns; double buffered against the epilogue)
 //   warps 2-9 epilogue, two per SM sub-partition: warps w and w+4 read the same TMEM lane quarter (the same 32 rows) and
 //            take one half of the unit's 256 columns each.  tcgen05.ld gives each thread ONE row, 32 columns at a time;
-//            d~^2 = |xi|^2 + |xj|^2 - 2 acc (times the rows' scales) is compared with the row's threshold (a register): one
+//            v' = |xj|^2 + Cs - 2 acc (times the rows' scales) is compared with the row's threshold (a register): one
 //            min per element and one vote decide whether the chunk holds any survivor at all.  A thread owns its row's
-//            candidate set for its column half: an unsorted 32-slot array in shared memory (slot-major, so the 32 threads
-//            of a warp never bank-conflict), 4 groups of 8 slots whose maxima are cached in registers; a survivor replaces
-//            the overall maximum and only that group is rescanned.  All rows of a warp insert concurrently.  The insertion
-//            is one long dependent chain, which is why a sub-partition gets two warps.
+//            candidate set for its column half: an unsorted 32-slot array of packed (value | slot) keys in shared memory
+//            (slot-major, so the 32 threads of a warp never bank-conflict), 4 groups of 8 slots whose largest keys are
+//            cached in registers; a survivor replaces the overall maximum and only that group is rescanned.  All rows of a
+//            warp insert concurrently.  The insertion is one long dependent chain (~75 instructions, ~430 cycles per round
+//            of a warp), which is why a sub-partition gets two warps.  The warps never synchronise with each other.
 //   thresholds  a row's sets (column halves, other CTAs on the same row tile) publish their 32nd-best through a per-row
 //            word in L2 (atomicMin on the ordered-integer image of the float) and prune against each other's bound.
 // Work = (row tile, column tile) units in row-major order, split evenly and contiguously over the CTAs, so a CTA keeps
 // one row tile's sets on chip for many column tiles; sets are flushed to cand[row][slot][KC] when the row tile changes.
-// PAIR (clusters of two CTAs on the same column tile, B tile fetched once and multicast): with one pass the kernel needs
-// 89 bytes of operands per clock and SM from L2, which the multicast cuts to 59.
+// PAIR: clusters of two CTAs on the same column tile, one tcgen05.mma.cta_group::2 of M = 256.
+// What bounds it (tools/knn_trace.py; profiles/r02w_knn_trace_before.txt -> r02zd_knn_trace_after.txt): the EPILOGUE.  Reading a
+// 128 x 256 fp32 accumulator out of TMEM takes ~2200 cycles (64 B per clock and SM) -- as long as its MMAs at d = 256 --
+// plus the insertion rounds; the MMA/TMA pipeline alone runs a unit of d = 256 in ~3000 cycles (SS-mode operand reads from
+// shared memory, not L2 bytes: a resident A operand changes nothing), the whole kernel in ~3800.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cudaTypedefs.h>
@@ -44,11 +49,9 @@
 namespace gll {
 namespace {
 
-// Stage = one K block (32 wide, 64-byte swizzle): {A_hi, B_hi} = 24 KB for one pass, + A_lo = 32 KB for two; a CTA of a pair
-// stages half of B: 16 / 24 KB.  The ring takes all the shared memory the candidate sets of the EIGHT epilogue warps leave
-// (152 KB): what bounds the one-pass kernel is the TMA round trip (~1600 cycles from "stage free" to "stage full") against
-// the MMA time its stages cover (271 cycles each): 4 stages of 24 KB ran the MMA/TMA pipeline at 58 % of the MMA rate
-// whatever the bytes per stage (profiles/r02k_knn_experiments_c2.txt), 6 to 9 stages cover the round trip.
+// Stage = one 64-wide K block (128-byte swizzle): {A_hi 16 KB, B_hi 32 KB} for one pass, + A_lo 16 KB for two; a CTA of a
+// pair stages half of B.  The ring takes all the shared memory the candidate sets of the EIGHT epilogue warps leave (152 KB:
+// three 48 KB stages; five 16 KB B stages behind a resident 64 KB A operand at d = 256 with pairs).
 constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_MAX_STAGES = 9;
 constexpr size_t TC_STAGE_REGION = 152 * 1024;
 // CTA pairs (cta_group::2, M = 256).  Measured (profiles/r02q_knn_experiments.txt): 4-7 % faster on the 1M-node graph (whole
@@ -57,9 +60,9 @@ constexpr size_t TC_STAGE_REGION = 152 * 1024;
 constexpr int TC_EPI_WARPS = 8;                        // two per TMEM lane quarter: each takes one half of the 256 columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS + 32;  // + the second TMA producer warp
 constexpr int TC_WARP_PRODUCER_B = 2 + TC_EPI_WARPS;
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 8 KB
-constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;          // 16 KB
-constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + TC_B_BYTES;  // 32 KB (the one-pass stage uses the first 24 KB)
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;          // 32 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + TC_B_BYTES;  // 64 KB (the one-pass stage uses 48 KB)
 constexpr int TC_CHUNK = 32;                           // columns per tcgen05.ld
 constexpr int TC_TMEM_COLS = 512, TC_ACC_STRIDE = 256;
 
@@ -334,10 +337,8 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
 
   if (warp == 0 || warp == TC_WARP_PRODUCER_B) {
     // ================================================= TMA producers ================================================
-    // One cp.async.bulk.tensor takes its issuing thread ~280 cycles (measured: the MMA/TMA pipeline alone ran at 690 / 860 /
-    // 1120 cycles per K block with 2 / 3 / 4 loads per block, whatever the stage count or the bytes per load), so a single
-    // producer thread cannot feed one-pass K blocks (2 MMAs = 366 cycles): warp 0 loads the A tiles, a second producer warp
-    // the B tile; both arrive on the stage's barrier with their own byte counts.
+    // Warp 0 loads the A tiles, a second producer warp the B tile; both arrive on the stage's barrier with their own byte
+    // counts.  (The split dates from the lane-0 issue form, where one cp.async.bulk.tensor cost its thread ~280 cycles.)
     if (ares && warp == 0) {
       // resident A: one load of all K blocks per row tile, after the MMAs of the previous row tile have retired
       int r_idx = (int)(u_begin / C), c_idx = (int)(u_begin % C);

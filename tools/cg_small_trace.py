@@ -16,7 +16,8 @@ torch.cuda.synchronize()
 _lib.lib.gll_debug_cg_trace(None)
 t = trace.cpu().numpy().reshape(16, 8).astype(np.float64)
 t = (t - t[0, 0]) / 1965.0
-names = ["loop top", "A done+sync", "B sums done", "C scalars done", "A spmv done(t0)", "A stores done(t0)", "A stores done(t511)"]
+names = ["loop top", "A done+sync", "B sums done", "C scalars done", "A spmv done(t0)", "A stores done(t0)", "A stores done(t511)", "A row range read(t0)"]
+print(f"kernel entry -> first loop top: {-t[15, 7]:.2f} us")
 for p in range(8):
-    print("pass", p, "  ".join(f"{names[ph]}: {t[p, ph]:.2f}" for ph in (0, 4, 5, 6, 1, 2, 3) if t[p, ph] > -1e6))
+    print("pass", p, "  ".join(f"{names[ph]}: {t[p, ph]:.2f}" for ph in (0, 7, 4, 5, 6, 1, 2, 3) if t[p, ph] > -1e6))
 print(pkg.last_info())
