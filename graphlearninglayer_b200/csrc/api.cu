@@ -574,12 +574,11 @@ int gll_forward(const float* X, const float* Y, int n, int d, int k, int l, int 
                          (float*)(S + L.diag), (float*)(S + L.rhs), (float*)(S + L.ut), info, workspace, workspace_bytes, st);
   if (rc) return rc;
   float* u_out = (float*)(S + L.ut) + (size_t)k_lab * lp;
-  rc = cg_run((int*)(S + L.uu_ptr), (int*)(S + L.uu_col), (float*)(S + L.uu_val), (float*)(S + L.diag),
-              (float*)(S + L.rhs), m, l, cg_tol, cg_max_iter, u_out, info + GLL_INFO_CG_ITERS_FWD,
-              (float*)(info + GLL_INFO_CG_RESID_FWD), info + GLL_INFO_STATUS, workspace, workspace_bytes, st,
-              (unsigned*)(info + 12));  // info[12..13]: the on-chip CG's barrier words (zeroed with info, rewound by the kernel)
-  if (rc) return rc;
-  return unpack_pred(u_out, m, l, lp, pred_out, pred_is_f64, st);
+  const CgIo io = {nullptr, 0, pred_out, pred_is_f64};  // Pred (GLL.py:66) is written by the solver itself
+  return cg_run((int*)(S + L.uu_ptr), (int*)(S + L.uu_col), (float*)(S + L.uu_val), (float*)(S + L.diag),
+                (float*)(S + L.rhs), m, l, cg_tol, cg_max_iter, u_out, info + GLL_INFO_CG_ITERS_FWD,
+                (float*)(info + GLL_INFO_CG_RESID_FWD), info + GLL_INFO_STATUS, workspace, workspace_bytes, st,
+                (unsigned*)(info + 12), &io);  // info[12..13]: the on-chip CG's barrier words (zeroed with info, rewound by the kernel)
 }
 
 int gll_backward(const float* X, const void* grad_out, int grad_is_f64, int n, int d, int k, int l, int k_lab, int eps_auto,
@@ -597,12 +596,13 @@ int gll_backward(const float* X, const void* grad_out, int grad_is_f64, int n, i
   int* info = (int*)(S + L.info);
   const int m = n - k_lab, lp = padded_classes(l);
   float* wt = (float*)(S + L.wt);
-  int rc = pack_grad(grad_out, grad_is_f64, m, l, lp, (float*)(S + L.rhs), st, wt, (long long)k_lab * lp);  // GLL.py:104
-  if (rc) return rc;
-  rc = cg_run((int*)(S + L.uu_ptr), (int*)(S + L.uu_col), (float*)(S + L.uu_val), (float*)(S + L.diag),
-              (float*)(S + L.rhs), m, l, cg_tol, cg_max_iter, wt + (size_t)k_lab * lp, info + GLL_INFO_CG_ITERS_BWD,
-              (float*)(info + GLL_INFO_CG_RESID_BWD), info + GLL_INFO_STATUS, workspace, workspace_bytes, st,
-              (unsigned*)(info + 12));
+  // GLL.py:104: the solver reads the incoming gradient itself; the labeled rows of the padded adjoint solution (zeros) are
+  // never read -- edge_grad substitutes them
+  const CgIo io = {grad_out, grad_is_f64 ? 2 : 1, nullptr, 0};
+  int rc = cg_run((int*)(S + L.uu_ptr), (int*)(S + L.uu_col), (float*)(S + L.uu_val), (float*)(S + L.diag),
+                  (float*)(S + L.rhs), m, l, cg_tol, cg_max_iter, wt + (size_t)k_lab * lp, info + GLL_INFO_CG_ITERS_BWD,
+                  (float*)(info + GLL_INFO_CG_RESID_BWD), info + GLL_INFO_STATUS, workspace, workspace_bytes, st,
+                  (unsigned*)(info + 12), &io);
   if (rc) return rc;
   return backward_edges_run(X, n, d, l, k_lab, eps_auto, (int*)(S + L.row_ptr), (int*)(S + L.col), (float*)(S + L.dist),
                             (float*)(S + L.w), (float*)(S + L.eps), (int*)(S + L.kappa), (float*)(S + L.ut), wt,

@@ -30,7 +30,9 @@ edge_grad_kernel(int row_begin, int row_end, int lp, int k_lab, int eps_auto, co
       const float4* uj = reinterpret_cast<const float4*>(ut + (size_t)j * lp);
       const float4* wj = reinterpret_cast<const float4*>(wt + (size_t)j * lp);
       for (int c = 0; c < Q; ++c) {
-        const float4 a = __ldg(wi + c), b = __ldg(wj + c), u = __ldg(ui + c), v = __ldg(uj + c);
+        // the adjoint solution of a labeled row is zero by definition (GLL.py:104): never read from wt
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 a = (i >= k_lab) ? __ldg(wi + c) : z4, b = (j >= k_lab) ? __ldg(wj + c) : z4, u = __ldg(ui + c), v = __ldg(uj + c);
         G -= ((double)a.x - (double)b.x) * ((double)u.x - (double)v.x);
         G -= ((double)a.y - (double)b.y) * ((double)u.y - (double)v.y);
         G -= ((double)a.z - (double)b.z) * ((double)u.z - (double)v.z);

@@ -315,16 +315,22 @@ size_t cg_ws_bytes(int m, int l) {
 
 int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, const float* rhs, int m, int l,
            float tol, int max_iter, float* x, int* iters_out, float* resid_out, int* status_out, void* ws, size_t ws_bytes,
-           cudaStream_t st, unsigned* ext_counter) {
+           cudaStream_t st, unsigned* ext_counter, const CgIo* io) {
   GLL_REQUIRE(uu_ptr && uu_col && uu_val && diag && rhs && x && ws, "null pointer");
-  GLL_REQUIRE(m >= 1 && l >= 1, "bad sizes");
   const int lp = padded_classes(l);
   if (ws_bytes < cg_ws_bytes(m, l)) {
     set_error("CG workspace too small: %zu < %zu", ws_bytes, cg_ws_bytes(m, l));
     return GLL_ERR_WORKSPACE;
   }
   Carver cv(ws, ws_bytes);
+  // Layer-side conversions (GLL.py:66 float64 output, GLL.py:104 the incoming gradient): the on-chip kernels read / write the
+  // caller's arrays themselves; the chunked and the streaming path run the two small kernels around the solve.
+  const bool has_src = io != nullptr && io->rhs_src != nullptr, has_copy = io != nullptr && io->x_copy != nullptr;
   if (lp > CG_MAX_LP) {
+    if (has_src) {
+      const int rc = pack_grad(io->rhs_src, io->rhs_kind == 2, m, l, lp, const_cast<float*>(rhs), st);
+      if (rc) return rc;
+    }
     const int chunks = ceil_div(l, CG_MAX_LP);
     float* rhs_c = cv.take<float>((size_t)m * CG_MAX_LP);
     float* x_c = cv.take<float>((size_t)m * CG_MAX_LP);
@@ -345,7 +351,7 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
     }
     cg_combine_stats_kernel<<<1, 1, 0, st>>>(it_c, rs_c, chunks, iters_out, resid_out);
     GLL_LAUNCH_CHECK();
-    return GLL_OK;
+    return has_copy ? unpack_pred(x, m, l, lp, io->x_copy, io->x_copy_f64, st) : GLL_OK;
   }
   CgParams P;
   P.ptr = uu_ptr;
@@ -369,6 +375,10 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
   P.status_out = status_out;
   P.rows_per_block = 0;
   P.ext_counter = ext_counter;
+  P.rhs_src = io ? io->rhs_src : nullptr;
+  P.rhs_kind = io ? io->rhs_kind : 0;
+  P.x_copy = io ? io->x_copy : nullptr;
+  P.x_copy_f64 = io ? io->x_copy_f64 : 0;
   {  // systems that fit on chip (every config except the sharded 1M-node graph) take the shared-memory-resident kernel
     const char* force = getenv("GLL_B200_CG_PATH");  // "streaming" / "resident": testing knobs
     if (force == nullptr || force[0] == 0) {  // minibatch-sized systems: the one-CTA, register-resident kernel
@@ -383,6 +393,12 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
       if (rc == 1) return GLL_OK;
     }
   }
+  if (has_src) {  // streaming kernel: conversions as separate kernels
+    const int rc = pack_grad(io->rhs_src, io->rhs_kind == 2, m, l, lp, const_cast<float*>(rhs), st);
+    if (rc) return rc;
+    P.rhs_src = nullptr;
+  }
+  P.x_copy = nullptr;
   const int grid = cg_grid(m);
   const int S = 32 / (lp / 4);
   int rpb = ceil_div(m, grid);
@@ -394,7 +410,7 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
   void* args[] = {&P};
   GLL_PROF(KID_CG, st);
   GLL_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)cg_persistent_kernel, dim3(grid), dim3(CG_THREADS), args, smem, st));
-  return GLL_OK;
+  return has_copy ? unpack_pred(x, m, l, lp, io->x_copy, io->x_copy_f64, st) : GLL_OK;
 }
 
 }  // namespace gll

@@ -28,7 +28,41 @@ struct CgParams {
   int* iters_out;
   float* resid_out;
   int* status_out;
+  // Fused input / output conversions of the layer (on-chip kernels; cg_run runs the separate kernels for the others):
+  const void* rhs_src;  // if set: the right-hand side is this [m][l] array (rhs_kind 1: fp32, 2: fp64) instead of rhs [m][lp]
+  int rhs_kind;
+  void* x_copy;         // if set: the solution is also written as an [m][l] array (fp64 if x_copy_f64, else fp32)
+  int x_copy_f64;
 };
+
+// right-hand side of class quad q of a row, from the padded fp32 array or straight from the caller's [m][l] array
+__device__ __forceinline__ float4 cg_load_rhs4(const CgParams& P, int row, int q) {
+  if (P.rhs_src == nullptr) return __ldg(reinterpret_cast<const float4*>(P.rhs + (size_t)row * P.lp + 4 * q));
+  float v[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int col = 4 * q + c;
+    v[c] = 0.f;
+    if (col < P.l)
+      v[c] = (P.rhs_kind == 2) ? (float)__ldg(reinterpret_cast<const double*>(P.rhs_src) + (size_t)row * P.l + col)
+                               : __ldg(reinterpret_cast<const float*>(P.rhs_src) + (size_t)row * P.l + col);
+  }
+  return make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void cg_store_copy4(const CgParams& P, int row, int q, const float4& x) {
+  if (P.x_copy == nullptr) return;
+  const float v[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int col = 4 * q + c;
+    if (col < P.l) {
+      if (P.x_copy_f64)
+        reinterpret_cast<double*>(P.x_copy)[(size_t)row * P.l + col] = (double)v[c];
+      else
+        reinterpret_cast<float*>(P.x_copy)[(size_t)row * P.l + col] = v[c];
+    }
+  }
+}
 
 // Resident variant (cg_resident.cu): returns 1 if it took the solve, 0 if the system does not fit on chip, <0 on error.
 // scratch must hold cg_resident_ws_bytes(m, lp) bytes.

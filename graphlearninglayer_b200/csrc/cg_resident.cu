@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) cg_resident_kernel(CrParams R) 
 #pragma unroll 1
   for (int i = i_first; i < rows; i += istep) {
     const size_t o = (size_t)i * lp + 4 * q;
-    const float4 bq = __ldg(reinterpret_cast<const float4*>(P.rhs + (size_t)(row0 + i) * lp + 4 * q));
+    const float4 bq = cg_load_rhs4(P, row0 + i, q);
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     *reinterpret_cast<float4*>(xs + o) = z;
     *reinterpret_cast<float4*>(rs + o) = bq;
@@ -439,7 +439,9 @@ __global__ void __launch_bounds__(CR_THREADS, 1) cg_resident_kernel(CrParams R) 
   // ---- write the answer ----
 #pragma unroll 1
   for (int i = i_first; i < rows; i += istep) {
-    *reinterpret_cast<float4*>(P.x + (size_t)(row0 + i) * lp + 4 * q) = *reinterpret_cast<const float4*>(xs + (size_t)i * lp + 4 * q);
+    const float4 x4 = *reinterpret_cast<const float4*>(xs + (size_t)i * lp + 4 * q);
+    *reinterpret_cast<float4*>(P.x + (size_t)(row0 + i) * lp + 4 * q) = x4;
+    cg_store_copy4(P, row0 + i, q, x4);
   }
 }
 

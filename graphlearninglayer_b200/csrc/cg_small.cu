@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) cg_small_kernel(CgParams P, int
     on[k] = quad[k] < Q && row[k] < m;
     dg[k] = on[k] ? __ldg(P.diag + row[k]) : 1.f;
     dinv[k] = on[k] ? 1.f / dg[k] : 0.f;
-    r[k] = on[k] ? __ldg(reinterpret_cast<const float4*>(P.rhs + (size_t)row[k] * lp + 4 * quad[k])) : f4zero();
+    r[k] = on[k] ? cg_load_rhs4(P, row[k], quad[k]) : f4zero();
     x[k] = p[k] = s[k] = w[k] = f4zero();
     uoff[k] = (quad[k] < Q) ? 4 * quad[k] : 0;
     if (quad[k] < Q) *reinterpret_cast<float4*>(us + (size_t)row[k] * lp + 4 * quad[k]) = f4scale(r[k], dinv[k]);
@@ -214,10 +214,13 @@ __global__ void __launch_bounds__(CS_THREADS, 1) cg_small_kernel(CgParams P, int
               // the cancellation-prone difference in fp64, the quotients in fp32 (alpha and beta are fp32 anyway)
               const double den = (double)d_new - (double)bb * (double)g_new * (double)inv_a_old[j];
               if (den > 0.0 && g_new > 0.f) {
-                al = g_new / (float)den;
+                // approximate reciprocals (MUFU.RCP, deterministic), as in cg_resident.cu: the last bits of alpha / beta do
+                // not matter to CG, three IEEE divisions in this one-warp section cost ~0.2 us per pass
+                const float rg = __fdividef(1.f, g_new);
+                al = __fdividef(g_new, (float)den);
                 be = bb;
-                inv_a_old[j] = 1.f / al;
-                inv_g_old[j] = 1.f / g_new;
+                inv_a_old[j] = (float)den * rg;
+                inv_g_old[j] = rg;
               } else {
                 frozen[j] = true;  // breakdown at the fp32 floor: stop moving this column
               }
@@ -256,7 +259,10 @@ __global__ void __launch_bounds__(CS_THREADS, 1) cg_small_kernel(CgParams P, int
 
 #pragma unroll
   for (int k = 0; k < NIT; ++k)
-    if (on[k]) *reinterpret_cast<float4*>(P.x + (size_t)row[k] * lp + 4 * quad[k]) = x[k];
+    if (on[k]) {
+      *reinterpret_cast<float4*>(P.x + (size_t)row[k] * lp + 4 * quad[k]) = x[k];
+      cg_store_copy4(P, row[k], quad[k], x[k]);
+    }
   if (tid == 0) {  // warp 0 holds the stop state
     if (P.iters_out) *P.iters_out = iter;
     if (P.resid_out) *P.resid_out = sqrtf(mx_all);

@@ -136,9 +136,17 @@ int graph_weights_run(const int* knn_idx, const float* knn_dist, const float* Y,
                       cudaStream_t st);
 size_t graph_weights_ws_bytes(int n, int k);
 
+// optional fused conversions of the layer: rhs_src = the caller's [m][l] right-hand side (rhs_kind 1 fp32 / 2 fp64; `rhs` is then
+// scratch), x_copy = an extra [m][l] copy of the solution (fp64 if x_copy_f64)
+struct CgIo {
+  const void* rhs_src;
+  int rhs_kind;
+  void* x_copy;
+  int x_copy_f64;
+};
 int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, const float* rhs, int m,
            int l, float tol, int max_iter, float* x, int* iters_out, float* resid_out, int* status_out, void* ws,
-           size_t ws_bytes, cudaStream_t st, unsigned* ext_counter = nullptr);
+           size_t ws_bytes, cudaStream_t st, unsigned* ext_counter = nullptr, const CgIo* io = nullptr);
 size_t cg_ws_bytes(int m, int l);
 
 // row-partitioned CG (cg_rows.cu): stage launchers.  peers == NULL: the host runs the NCCL collectives between them;
