@@ -599,18 +599,20 @@ def sharded_lines(args, rank, world, dev, dist):
         def sharded_layer(a, b, c, e):
             return sh.ShardedLaplaceLearning.apply(a, b, c, e, None, 0, partition)
 
-        pred = call(sharded_layer)  # warm-up (allocator, symmetric memory rendezvous, NCCL channels)
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for _ in range(calls):
+        for _ in range(2):  # warm-up (allocator, symmetric memory rendezvous, NCCL channels and their lazily grown buffers)
             pred = call(sharded_layer)
-        ev1.record()
-        torch.cuda.synchronize()
-        ms = ev0.elapsed_time(ev1) / calls
+        per_call = []
+        for _ in range(calls):  # one event pair per call, barrier in front; the MEDIAN call is reported (a first call after an
+            torch.cuda.synchronize()  # allocator trim or an NCCL buffer growth takes 3-5x the steady time)
+            if dist is not None:
+                dist.barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            pred = call(sharded_layer)
+            ev1.record()
+            torch.cuda.synchronize()
+            per_call.append(ev0.elapsed_time(ev1))
+        ms = sorted(per_call)[len(per_call) // 2]
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -621,7 +623,7 @@ def sharded_lines(args, rank, world, dev, dist):
         return float((a - b).abs().max().item() / max(b.abs().max().item(), 1e-300))
 
     if world > 1:
-        ms_c, pred_c, dx_c, _, (unsharded, Xd) = run("c5s", "columns", 2)
+        ms_c, pred_c, dx_c, _, (unsharded, Xd) = run("c5s", "columns", 3)
         out["c5s_ms_per_call_columns"] = ms_c
         errs = torch.zeros(4, dtype=torch.float64, device=dev)
         if rank == 0:  # the unsharded layer on one GPU is the yardstick (itself checked against the oracle in tests/)
@@ -630,7 +632,7 @@ def sharded_lines(args, rank, world, dev, dist):
             errs[0], errs[1] = rel(pred_c, pred_u), rel(dx_c, dx_u)
         del unsharded, Xd
         try:
-            ms_p, pred_p, dx_p, _, keep = run("c5s", "rows-p2p", 2)
+            ms_p, pred_p, dx_p, _, keep = run("c5s", "rows-p2p", 3)
             del keep
             out["c5s_ms_per_call_rows_p2p"] = ms_p
             if rank == 0:
@@ -646,7 +648,7 @@ def sharded_lines(args, rank, world, dev, dist):
                    c5s_parity_rows_p2p_dx=e[3])
         torch.cuda.empty_cache()
     if not args.no_c5:
-        ms5, _, _, info5, keep = run("c5", "columns", 2)
+        ms5, _, _, info5, keep = run("c5", "columns", 3)
         del keep
         solve = info5.get("cg_solve_ms") or [None, None]
         out.update(c5_ms_per_call=ms5, c5_nodes=WORKLOADS["c5"][0] + WORKLOADS["c5"][1], c5_cg_partition="columns",

@@ -914,6 +914,21 @@ def test_knn_large_k_with_duplicates(gll):
     assert np.array_equal(idx.cpu().numpy()[50:120, :50], ref_ind[50:120])  # ties resolved by index in both
 
 
+@pytest.mark.parametrize("k", [25, 50])
+def test_knn_lattice_points_massive_ties(gll, monkeypatch, k):
+    """Features on a small integer lattice: squared distances take a handful of values, so nearly every candidate decision is a
+    value tie (within one row's set, between the sets of a row, between the two rounds of a k > 33 search).  The lists must be
+    the oracle's -- ties by index -- whatever the packed, truncated keys of the tensor-core epilogue do with equal values."""
+    _, _lib = gll
+    monkeypatch.setenv("GLL_B200_KNN_PATH", "tc")
+    rng = np.random.default_rng(11)
+    X = rng.integers(0, 3, size=(3000, 10)).astype(np.float32)
+    ref_ind, ref_dist = O.exact_knn(X, k, slack=600)
+    idx, dist, info = run_knn(_lib, X, k)
+    assert np.array_equal(dist.cpu().numpy(), ref_dist.astype(np.float32))
+    assert np.array_equal(idx.cpu().numpy(), ref_ind)
+
+
 def test_eval_path_like_utils_laplace(gll):
     """The reference's evaluation routine (utils.py:570-593) run on our drop-in wrappers: k = 50 graph, Jacobi-scaled
     system, stable_conjgrad to 1e-10, argmax accuracy -- against the same steps on the fp64 oracle."""
