@@ -25,3 +25,11 @@ _lib.lib.gll_profile_enable(1); _lib.profile_collect()
 call(LaplaceLearningSparseHard.apply); torch.cuda.synchronize()
 p = _lib.profile_collect(); _lib.lib.gll_profile_enable(0)
 print("unsharded kernels", {k: (round(v[0], 2), v[1]) for k, v in p.items()})
+ts = []
+for i in range(6):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter(); e0.record(); call(LaplaceLearningSparseHard.apply); e1.record(); t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    ts.append((round(e0.elapsed_time(e1), 2), round((t1 - t0) * 1e3, 2)))
+print("unsharded (device ms, host enqueue ms):", ts)
