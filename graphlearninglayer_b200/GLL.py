@@ -14,7 +14,10 @@ Knobs (environment, read at call time):
     GLL_B200_CG_MAXIT     default 5000
     GLL_B200_PRED_DTYPE   'float64' (default: the reference returns float64, GLL.py:66) or 'float32'
     GLL_B200_CHECK        '1': read the device status word after every call (one host sync) and warn like the
-                          reference does (GLL.py:240-241 epsilon ~ 0; GLL.py:273-274 'max iter reached')
+                          reference does (GLL.py:240-241 epsilon ~ 0; GLL.py:273-274 'max iter reached').
+                          Default: DEFERRED -- the status word is copied to pinned memory behind the call and looked at
+                          when a later call finds the copy complete (no host sync; the warning comes one call late).
+                          '0': never (also skipped while a CUDA graph is being captured).
 """
 from __future__ import annotations
 
@@ -87,6 +90,37 @@ def _warn_from_status(info: torch.Tensor, where: str) -> None:
         warnings.warn(f"non-finite values in the {where} solve (singular L_uu or epsilon = 0)")
 
 
+class _DeferredStatus:
+    """One pinned slot per device: the previous call's status word, copied asynchronously; read when its event has completed."""
+    slots: dict = {}
+
+    def __init__(self):
+        self.host = torch.zeros(_lib.INFO_WORDS, dtype=torch.int32).pin_memory()
+        self.event: Optional[torch.cuda.Event] = None
+        self.where = ""
+
+
+def _check_status(info: torch.Tensor, where: str) -> None:
+    mode = os.environ.get("GLL_B200_CHECK", "")
+    if mode == "1":
+        _warn_from_status(info, where)
+        return
+    if mode == "0" or torch.cuda.is_current_stream_capturing():
+        return
+    key = (info.device.index, torch.cuda.current_stream(info.device).cuda_stream)
+    slot = _DeferredStatus.slots.get(key)
+    if slot is None:
+        slot = _DeferredStatus.slots[key] = _DeferredStatus()
+    if slot.event is not None:
+        if not slot.event.query():
+            return  # the previous copy has not landed yet: keep it, look again at the next call
+        _warn_from_status(slot.host, slot.where)
+    slot.host.copy_(info, non_blocking=True)
+    slot.where = where
+    slot.event = torch.cuda.Event()
+    slot.event.record(torch.cuda.current_stream(info.device))
+
+
 class _State:
     """Buffers kept between forward and backward (replaces the scipy objects on ctx, GLL.py:69-70)."""
     __slots__ = ("buf", "layout", "n", "d", "k", "l", "k_lab", "eps_auto")
@@ -137,8 +171,7 @@ def _forward_impl(X: torch.Tensor, label_matrix: torch.Tensor, tau, epsilon, k: 
     _lib.check(rc, "gll_forward")
     global _last_info
     _last_info = st.view("info", torch.int32, _lib.INFO_WORDS)
-    if os.environ.get("GLL_B200_CHECK") == "1":
-        _warn_from_status(_last_info, "forward")
+    _check_status(_last_info, "forward")
     return pred, st, Xc
 
 
@@ -160,8 +193,7 @@ def _backward_impl(st: _State, Xc: torch.Tensor, grad_output: torch.Tensor) -> t
                               st.eps_auto, -_cg_tol(), _cg_maxit(), st.buf.data_ptr(), dX.data_ptr(), ws.data_ptr(),
                               ws_bytes, _stream_ptr(dev))
     _lib.check(rc, "gll_backward")
-    if os.environ.get("GLL_B200_CHECK") == "1":
-        _warn_from_status(st.view("info", torch.int32, _lib.INFO_WORDS), "adjoint")
+    _check_status(st.view("info", torch.int32, _lib.INFO_WORDS), "adjoint")
     return dX
 
 

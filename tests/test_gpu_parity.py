@@ -615,6 +615,17 @@ def test_eps_tiny_warns(gll, monkeypatch):
         pkg.LaplaceLearningSparseHard.apply(torch.as_tensor(X).cuda(), torch.as_tensor(Y).cuda())
         torch.cuda.synchronize()
     assert any("Epsilon in KNN" in str(x.message) for x in w)
+    # default mode: no host sync inside the call; the status word is copied behind it and the warning comes with a later call
+    monkeypatch.delenv("GLL_B200_CHECK")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        pkg.LaplaceLearningSparseHard.apply(torch.as_tensor(X).cuda(), torch.as_tensor(Y).cuda())
+        torch.cuda.synchronize()
+        first = [x for x in w if "Epsilon in KNN" in str(x.message)]
+        pkg.LaplaceLearningSparseHard.apply(torch.as_tensor(X).cuda(), torch.as_tensor(Y).cuda())
+        torch.cuda.synchronize()
+        pkg.LaplaceLearningSparseHard.apply(torch.as_tensor(X).cuda(), torch.as_tensor(Y).cuda())
+    assert any("Epsilon in KNN" in str(x.message) for x in w) and len(first) <= 1
 
 
 # ----------------------------------------------------------------------------------------------------------------
