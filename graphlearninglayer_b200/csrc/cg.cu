@@ -380,9 +380,13 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
   P.x_copy = io ? io->x_copy : nullptr;
   P.x_copy_f64 = io ? io->x_copy_f64 : 0;
   {  // systems that fit on chip (every config except the sharded 1M-node graph) take the shared-memory-resident kernel
-    const char* force = getenv("GLL_B200_CG_PATH");  // "streaming" / "resident": testing knobs
-    if (force == nullptr || force[0] == 0) {  // minibatch-sized systems: the one-CTA, register-resident kernel
-      const int rc = cg_small_try(P, st);
+    const char* force = getenv("GLL_B200_CG_PATH");  // "streaming" / "resident" / "small": testing knobs
+    const bool only_small = force != nullptr && strcmp(force, "small") == 0;
+    if (force == nullptr || force[0] == 0 || only_small) {  // minibatch-sized systems: the latency-organised kernels
+      int rc = only_small ? 0 : cg_cluster_try(P, st);  // one cluster of eight CTAs (64 <= m <= 2048, a few items per thread)
+      if (rc < 0) return rc;
+      if (rc == 1) return GLL_OK;
+      rc = cg_small_try(P, st);  // one CTA, a thread per row (m <= 512)
       if (rc < 0) return rc;
       if (rc == 1) return GLL_OK;
     }

@@ -72,5 +72,7 @@ void cg_set_trace(void* buf);
 void* cg_get_trace();
 // One-CTA kernel for minibatch-sized systems (cg_small.cu): 1 = took the solve, 0 = not small, < 0 = error.
 int cg_small_try(const CgParams& P, cudaStream_t st);
+// Cluster variant for the same minibatch-sized systems (cg_cluster.cu): one cluster of eight CTAs, exchanges through DSMEM.
+int cg_cluster_try(const CgParams& P, cudaStream_t st);
 
 }  // namespace gll

@@ -379,9 +379,10 @@ def test_graph_drops_zero_distance_edges(gll):
 # ----------------------------------------------------------------------------------------------------------------
 # K4: CG
 # ----------------------------------------------------------------------------------------------------------------
-# "": the dispatch by size (here the multi-CTA on-chip kernel); "streaming": the global-memory kernel that only ~1M-row systems
-# reach on their own, forced so that it is covered at a size the CPU checker can solve
-@pytest.mark.parametrize("path", ["", "streaming"])
+# "": the dispatch by size (here: the eight-CTA cluster kernel up to 12 class columns, the multi-CTA on-chip kernel beyond);
+# "resident": the multi-CTA on-chip kernel for every l; "streaming": the global-memory kernel that only ~1M-row systems reach on
+# their own, forced so that it is covered at a size the CPU checker can solve
+@pytest.mark.parametrize("path", ["", "streaming", "resident"])
 @pytest.mark.parametrize("l", [1, 3, 10, 37, 100, 150])  # 150 > 128 class columns: solved in column chunks
 def test_cg_vs_direct_solve(gll, monkeypatch, l, path):
     _, _lib = gll
@@ -399,9 +400,9 @@ def test_cg_vs_direct_solve(gll, monkeypatch, l, path):
 @pytest.mark.parametrize("path", ["", "streaming", "small"])
 def test_cg_zero_rhs_column_and_maxiter(gll, monkeypatch, path):
     _, _lib = gll
-    if path == "streaming":
-        monkeypatch.setenv("GLL_B200_CG_PATH", path)
-    X, Y, *_ = O.synth_inputs(5, 100, 400 if path == "small" else 900, 16, 4, 1.5)  # <= 512 rows: the one-CTA kernel
+    if path:
+        monkeypatch.setenv("GLL_B200_CG_PATH", path)  # "": the cluster kernel; "small": the one-CTA kernel (<= 512 rows)
+    X, Y, *_ = O.synth_inputs(5, 100, 400 if path == "small" else 900, 16, 4, 1.5)
     f = O.forward(X, Y, 0.05, 1.0, solver="lu")
     B = f.B.copy()
     B[:, 2] = 0.0  # a frozen column from the start (the per-column mask of GLL.py:262-263 must not divide 0/0)
