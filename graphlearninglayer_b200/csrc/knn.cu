@@ -79,95 +79,120 @@ sqnorm_split_f16_kernel(const float* __restrict__ X, int n, int d, int d_pad, fl
   // the four global maxima (|x|^2, rho, range of E) are reduced per CTA first: 10 k warps reading and bumping the same
   // 32-byte sector of L2 one after the other cost more than the rest of the kernel
   __shared__ unsigned sh_max[4][8];
-  const int row_raw = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  const bool live = row_raw < n;
-  const int row = live ? row_raw : n - 1;  // idle warps of the last CTA recompute the last row and store nothing
-  const float* x = X + (size_t)row * d;
+  // A warp takes TWO rows (NREG > 0) and has both rows' loads in flight before it touches either: the kernel is one HBM round
+  // trip plus two butterflies per row, and with a row per warp the C2 grid was 1.1 waves of CTAs (25 us cold for 32 MB).
+  constexpr int RPW = (NREG > 0) ? 2 : 1;
+  const int warp_g = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   const bool vec2 = (d & 1) == 0;  // float2 loads need an 8-byte aligned row
-  float2 xr[NREG > 0 ? NREG : 1];
-  double s = 0.0;
-  if (NREG > 0) {
+  float2 xr[RPW][NREG > 0 ? NREG : 1];
+  int rows_i[RPW];
+  bool lives[RPW];
 #pragma unroll
-    for (int t = 0; t < NREG; ++t) {
-      const int c = 2 * lane + 64 * t;
-      float2 v = make_float2(0.f, 0.f);
-      if (vec2) {
-        if (c < d) v = __ldg(reinterpret_cast<const float2*>(x + c));
-      } else {
-        if (c < d) v.x = __ldg(x + c);
-        if (c + 1 < d) v.y = __ldg(x + c + 1);
+  for (int q = 0; q < RPW; ++q) {
+    const int row_raw = warp_g * RPW + q;
+    lives[q] = row_raw < n;
+    rows_i[q] = lives[q] ? row_raw : n - 1;  // idle slots of the last CTA recompute the last row and store nothing
+    if (NREG > 0) {
+      const float* x = X + (size_t)rows_i[q] * d;
+#pragma unroll
+      for (int t = 0; t < NREG; ++t) {
+        const int c = 2 * lane + 64 * t;
+        float2 v = make_float2(0.f, 0.f);
+        if (vec2) {
+          if (c < d) v = __ldg(reinterpret_cast<const float2*>(x + c));
+        } else {
+          if (c < d) v.x = __ldg(x + c);
+          if (c + 1 < d) v.y = __ldg(x + c + 1);
+        }
+        xr[q][t] = v;
       }
-      xr[t] = v;
-      s += (double)v.x * (double)v.x;
-      s += (double)v.y * (double)v.y;
-    }
-  } else {
-    for (int c = 2 * lane; c < d; c += 64) {
-      const float x0 = __ldg(x + c);
-      const float x1 = (c + 1 < d) ? __ldg(x + c + 1) : 0.f;
-      s += (double)x0 * (double)x0;
-      s += (double)x1 * (double)x1;
     }
   }
-  s = warp_sum(s);
-  // E_i from the row NORM, with the bucket boundaries at |x|^2 = 2^k / 1.5 so that rows normalised to 1 (every caller of the
-  // layer) all get the same E whatever their rounding: 2^(2F - 1) <= 1.5 |x_i|^2 < 2^(2F + 1), E = F - 8, hence
-  // 148 <= |z_i| < 296.  The target norm 2^8 (not 1) keeps `lo` = z - hi a NORMAL fp16 number for every element above
-  // 2^-11 |x_i| and hi's own subnormal range 2^-22 below the row norm; |z_ik| < 296 is far from fp16's 65504.
-  int E = -F16_TARGET_LOG2;
-  {
-    const unsigned b = __float_as_uint((float)(1.5 * s));
-    const int ex = (int)((b >> 23) & 0xFFu);
-    if (b != 0u && ex != 0xFF) E = min(60, max(-60, ((ex - 127 + 1) >> 1) - F16_TARGET_LOG2));  // arithmetic shift = floor
-  }
-  double r2 = 0.0;
-  const float down = ldexpf(1.f, -E);  // |E| <= 60: both factors are normal numbers, the products below are exact
-  const double up = ldexp(1.0, E);
-  auto emit = [&](int c, float x0, float x1) {
-    const float z0 = x0 * down, z1 = x1 * down;
-    const __half h0 = __float2half_rn(z0), h1 = __float2half_rn(z1);
-    const float f0 = __half2float(h0), f1 = __half2float(h1);
-    __half2 hv;
-    hv.x = h0;
-    hv.y = h1;
-    if (live) *reinterpret_cast<__half2*>(H + (size_t)row * d_pad + c) = hv;
-    if (live && L != nullptr) {
-      __half2 lv;
-      lv.x = __float2half_rn(z0 - f0);
-      lv.y = __float2half_rn(z1 - f1);
-      *reinterpret_cast<__half2*>(L + (size_t)row * d_pad + c) = lv;
-    }
-    const double e0 = (double)x0 - (double)f0 * up, e1 = (double)x1 - (double)f1 * up;
-    r2 += e0 * e0 + e1 * e1;
-  };
-  if (NREG > 0) {
+  unsigned mx_f = 0u, mx_rho = 0u, mx_e = 0u, mx_ne = 0u;
 #pragma unroll
-    for (int t = 0; t < NREG; ++t) {
-      const int c = 2 * lane + 64 * t;
-      if (c < d_pad) emit(c, xr[t].x, xr[t].y);
+  for (int q = 0; q < RPW; ++q) {
+    const int row = rows_i[q];
+    const bool live = lives[q];
+    const float* x = X + (size_t)row * d;
+    double s = 0.0;
+    if (NREG > 0) {
+#pragma unroll
+      for (int t = 0; t < NREG; ++t) {
+        s += (double)xr[q][t].x * (double)xr[q][t].x;
+        s += (double)xr[q][t].y * (double)xr[q][t].y;
+      }
+    } else {
+      for (int c = 2 * lane; c < d; c += 64) {
+        const float x0 = __ldg(x + c);
+        const float x1 = (c + 1 < d) ? __ldg(x + c + 1) : 0.f;
+        s += (double)x0 * (double)x0;
+        s += (double)x1 * (double)x1;
+      }
     }
-  } else {
-    for (int c = 2 * lane; c < d_pad; c += 64) {  // second sweep over the row: L1 hits
-      const float x0 = (c < d) ? __ldg(x + c) : 0.f;
-      const float x1 = (c + 1 < d) ? __ldg(x + c + 1) : 0.f;
-      emit(c, x0, x1);
+    s = warp_sum(s);
+    // E_i from the row NORM, with the bucket boundaries at |x|^2 = 2^k / 1.5 so that rows normalised to 1 (every caller of the
+    // layer) all get the same E whatever their rounding: 2^(2F - 1) <= 1.5 |x_i|^2 < 2^(2F + 1), E = F - 8, hence
+    // 148 <= |z_i| < 296.  The target norm 2^8 (not 1) keeps `lo` = z - hi a NORMAL fp16 number for every element above
+    // 2^-11 |x_i| and hi's own subnormal range 2^-22 below the row norm; |z_ik| < 296 is far from fp16's 65504.
+    int E = -F16_TARGET_LOG2;
+    {
+      const unsigned b = __float_as_uint((float)(1.5 * s));
+      const int ex = (int)((b >> 23) & 0xFFu);
+      if (b != 0u && ex != 0xFF) E = min(60, max(-60, ((ex - 127 + 1) >> 1) - F16_TARGET_LOG2));  // arithmetic shift = floor
     }
-  }
-  r2 = warp_sum(r2);
-  const int warp = threadIdx.x >> 5;
-  if (lane == 0) {
+    double r2 = 0.0;
+    const float down = ldexpf(1.f, -E);  // |E| <= 60: both factors are normal numbers, the products below are exact
+    const double up = ldexp(1.0, E);
+    auto emit = [&](int c, float x0, float x1) {
+      const float z0 = x0 * down, z1 = x1 * down;
+      const __half h0 = __float2half_rn(z0), h1 = __float2half_rn(z1);
+      const float f0 = __half2float(h0), f1 = __half2float(h1);
+      __half2 hv;
+      hv.x = h0;
+      hv.y = h1;
+      if (live) *reinterpret_cast<__half2*>(H + (size_t)row * d_pad + c) = hv;
+      if (live && L != nullptr) {
+        __half2 lv;
+        lv.x = __float2half_rn(z0 - f0);
+        lv.y = __float2half_rn(z1 - f1);
+        *reinterpret_cast<__half2*>(L + (size_t)row * d_pad + c) = lv;
+      }
+      const double e0 = (double)x0 - (double)f0 * up, e1 = (double)x1 - (double)f1 * up;
+      r2 += e0 * e0 + e1 * e1;
+    };
+    if (NREG > 0) {
+#pragma unroll
+      for (int t = 0; t < NREG; ++t) {
+        const int c = 2 * lane + 64 * t;
+        if (c < d_pad) emit(c, xr[q][t].x, xr[q][t].y);
+      }
+    } else {
+      for (int c = 2 * lane; c < d_pad; c += 64) {  // second sweep over the row: L1 hits
+        const float x0 = (c < d) ? __ldg(x + c) : 0.f;
+        const float x1 = (c + 1 < d) ? __ldg(x + c + 1) : 0.f;
+        emit(c, x0, x1);
+      }
+    }
+    r2 = warp_sum(r2);
     const float f = (float)s;
     const float rho = __double2float_ru(sqrt(r2) * 1.000001);
-    if (live) {
+    if (lane == 0 && live) {
       sq[row] = f;
       rscale[row] = ldexpf(1.f, E);
       if (thr_g != nullptr) thr_g[row] = 0xFF800000u;  // float_to_ordered(+inf): the row's shared threshold (knn_tc.cu)
       if (row == 0) small[5] = (L != nullptr) ? 1u : 2u;  // operand sides whose rounding rho has to cover (knn_err_bound)
     }
-    sh_max[0][warp] = (f == f) ? __float_as_uint(f) : 0u;      // non-negative floats order like their bits
-    sh_max[1][warp] = (rho == rho) ? __float_as_uint(rho) : 0u;
-    sh_max[2][warp] = (unsigned)(E + 128);         // range of the row scales: when all rows share one scale (normalised
-    sh_max[3][warp] = 255u - (unsigned)(E + 128);  // features) the Gram epilogue skips the per-row / per-column factors
+    mx_f = max(mx_f, (f == f) ? __float_as_uint(f) : 0u);      // non-negative floats order like their bits
+    mx_rho = max(mx_rho, (rho == rho) ? __float_as_uint(rho) : 0u);
+    mx_e = max(mx_e, (unsigned)(E + 128));         // range of the row scales: when all rows share one scale (normalised
+    mx_ne = max(mx_ne, 255u - (unsigned)(E + 128));  // features) the Gram epilogue skips the per-row / per-column factors
+  }
+  const int warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    sh_max[0][warp] = mx_f;
+    sh_max[1][warp] = mx_rho;
+    sh_max[2][warp] = mx_e;
+    sh_max[3][warp] = mx_ne;
   }
   __syncthreads();
   if (warp == 0) {
@@ -960,7 +985,7 @@ static int launch_split_f16(const float* X, int n, int d, const TcPlan& plan, fl
                             unsigned* thr_g, cudaStream_t st) {
   __half* H = reinterpret_cast<__half*>(tc_ws);
   __half* L = (plan.passes == 2) ? reinterpret_cast<__half*>(tc_ws + align_up((size_t)n * plan.d_pad * 2, 256)) : nullptr;
-  const int grid = ceil_div((long long)n * 32, 256);
+  const int grid = ceil_div((long long)ceil_div(n, plan.d_pad <= 1024 ? 2 : 1) * 32, 256);  // two rows per warp when the row fits registers
   if (plan.d_pad <= 256)
     sqnorm_split_f16_kernel<4><<<grid, 256, 0, st>>>(X, n, d, plan.d_pad, sq, small, H, L, rscale, thr_g);
   else if (plan.d_pad <= 512)
