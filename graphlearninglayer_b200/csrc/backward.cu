@@ -15,8 +15,10 @@ edge_grad_kernel(int row_begin, int row_end, int lp, int k_lab, int eps_auto, co
                  const float* __restrict__ dist, const float* __restrict__ w, const float* __restrict__ eps,
                  const float* __restrict__ ut, const float* __restrict__ wt, float* __restrict__ gv,
                  float* __restrict__ bvec) {
-  const int i = row_begin + (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  if (i >= row_end) return;
+  // rows are taken from the END: the unlabeled rows come last (GLL.py:11) and are the only ones whose edges all carry work, so
+  // they start first instead of forming the kernel's tail
+  const int i = row_end - 1 - (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (i < row_begin) return;
   const int e0 = row_ptr[i], e1 = row_ptr[i + 1];
   const double ei = (double)eps[i];
   const float4* ui = reinterpret_cast<const float4*>(ut + (size_t)i * lp);
@@ -146,8 +148,10 @@ row_gather_warp_kernel(const float* __restrict__ X, int row_begin, int row_end, 
                        const int* __restrict__ col, const int* __restrict__ kappa, const float* __restrict__ gv,
                        const float* __restrict__ bvec, float* __restrict__ dX) {
   const int lane = threadIdx.x & 31;
-  const int i = row_begin + blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (i >= row_end) return;
+  // rows are taken from the END: an unlabeled row (they come last, GLL.py:11) gathers ~30 neighbour rows one after the other,
+  // a labeled row one or two -- started last, the long chains were the kernel's tail (35 us at C2 for 60 MB of gathers)
+  const int i = row_end - 1 - (blockIdx.x * 4 + (threadIdx.x >> 5));
+  if (i < row_begin) return;
   const int cols = d >> 2;
   const int e0 = __ldg(row_ptr + i), e1 = __ldg(row_ptr + i + 1);
   const int ki = eps_auto ? __ldg(kappa + i) : -1;
