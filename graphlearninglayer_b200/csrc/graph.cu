@@ -24,6 +24,7 @@
 #include <math.h>
 #include <string.h>
 
+#include "cg_common.cuh"
 #include "common.cuh"
 
 namespace gll {
@@ -32,6 +33,7 @@ namespace {
 constexpr int GF_THREADS = 1024;
 
 struct GfParams {
+  unsigned long long* trace;  // debug timeline (gll_debug_cg_trace buffer): trace[64 + phase] = %globaltimer at the phase's end
   // inputs
   const int* knn_idx;
   const float* knn_dist;
@@ -162,6 +164,9 @@ __device__ __forceinline__ bool is_edge(int i, int j, float dd, int n) { return 
 
 __global__ void __launch_bounds__(GF_THREADS, 1) graph_weights_kernel(GfParams P) {
   __shared__ int sm[33];
+  // debug timeline (tools/graph_trace.py): CTA 0, thread 0, %globaltimer (256 ns steps) at the end of every phase
+#define GF_STAMP(slot) do { if (P.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); P.trace[64 + (slot)] = t_; } } while (0)
+  GF_STAMP(0);
   const int n = P.n, k = P.k;
   const long long nthreads = (long long)gridDim.x * GF_THREADS, gtid = (long long)blockIdx.x * GF_THREADS + threadIdx.x;
   const long long total = (long long)n * k;
@@ -200,12 +205,14 @@ __global__ void __launch_bounds__(GF_THREADS, 1) graph_weights_kernel(GfParams P
       if (lane == 0 && carry) atomicAdd(&P.len[i], carry);
     }
     gf_barrier(P.counter, target);
+    GF_STAMP(1);
     ++ph;
   }
   // ---- 1: row_ptr ----
   if (ph == 1 && ph < P.phase_end) {
     grid_scan(P.len, n, P.row_ptr, P.tile_sums, P.counter, target, sm);
     gf_barrier(P.counter, target);
+    GF_STAMP(2);
     ++ph;
   }
   // ---- 2: forward edges of row i fill the head of the row in kNN order, reverse edges the tail through a cursor ----
@@ -226,6 +233,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) graph_weights_kernel(GfParams P
       }
     }
     gf_barrier(P.counter, target);
+    GF_STAMP(3);
     ++ph;
   }
   // ---- 3: warp per row: rank sort by column (columns are unique within a row), then the row's weights ----
@@ -318,6 +326,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) graph_weights_kernel(GfParams P
       }
     }
     if (P.phase_end > 4) gf_barrier(P.counter, target);
+    GF_STAMP(4);
     ++ph;
   }
   // ---- 4: uu_ptr ----
@@ -325,6 +334,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) graph_weights_kernel(GfParams P
   if (ph == 4 && ph < P.phase_end) {
     grid_scan(P.uu_cnt, m, P.uu_ptr, P.tile_sums, P.counter, target, sm);
     gf_barrier(P.counter, target);
+    GF_STAMP(5);
     ++ph;
   }
   // ---- 5: compact off-diagonal CSR of L_uu (columns rebased to the unlabeled block) ----
@@ -340,6 +350,8 @@ __global__ void __launch_bounds__(GF_THREADS, 1) graph_weights_kernel(GfParams P
       }
     }
   }
+  GF_STAMP(6);
+#undef GF_STAMP
 }
 
 int gf_grid() { return device_info().sms; }
@@ -392,6 +404,7 @@ int graph_run(const int* knn_idx, const float* knn_dist, int n, int k, int* row_
   }
   GfParams P;
   memset(&P, 0, sizeof(P));
+  P.trace = (unsigned long long*)cg_get_trace();
   Carver cv(ws, ws_bytes);
   void* common;
   int rc = carve_graph(P, cv, n, k, &common, st);
@@ -445,6 +458,7 @@ int weights_run(const int* knn_idx, const float* knn_dist, const int* row_ptr, c
   }
   GfParams P;
   memset(&P, 0, sizeof(P));
+  P.trace = (unsigned long long*)cg_get_trace();
   Carver cv(ws, ws_bytes);
   P.uu_cnt = cv.take<int>(n + 1);
   void* common = cv.take<char>(gf_common_bytes());
@@ -478,6 +492,7 @@ int graph_weights_run(const int* knn_idx, const float* knn_dist, const float* Y,
   }
   GfParams P;
   memset(&P, 0, sizeof(P));
+  P.trace = (unsigned long long*)cg_get_trace();
   Carver cv(ws, ws_bytes);
   void* common;
   int rc = carve_graph(P, cv, n, k, &common, st);
