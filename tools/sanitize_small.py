@@ -16,8 +16,19 @@ def run(layer, seed, k_lab, m, d, l, eps, tau, extra=()):
 
 for path in ("tc", "simt"):
     os.environ["GLL_B200_KNN_PATH"] = path
-    run(pkg.LaplaceLearningSparseHard.apply, 0, 150, 390, 72, 7, "auto", 0.0)      # single-CTA CG, ragged tiles
+    run(pkg.LaplaceLearningSparseHard.apply, 0, 150, 390, 72, 7, "auto", 0.0)      # cluster CG (eight CTAs, DSMEM), ragged tiles
     run(pkg.LaplaceLearningSparseHard.apply, 1, 100, 2100, 40, 10, 1.0, 0.07)     # multi-CTA on-chip CG
+    run(pkg.LaplaceLearningSparseHard.apply, 4, 300, 1500, 64, 10, "auto", 0.0)    # cluster CG, two items per thread
+os.environ["GLL_B200_CG_PATH"] = "small"
+run(pkg.LaplaceLearningSparseHard.apply, 0, 150, 390, 72, 7, "auto", 0.0)          # one-CTA CG
+del os.environ["GLL_B200_CG_PATH"]
+for ares in ("0", "1"):
+    os.environ["GLL_B200_KNN_ARES"] = ares
+    os.environ["GLL_B200_KNN_PAIR"] = ares
+    run(pkg.LaplaceLearningSparseHard.apply, 5, 200, 1300, 96, 6, "auto", 0.0)     # resident A operand / CTA pairs
+del os.environ["GLL_B200_KNN_ARES"], os.environ["GLL_B200_KNN_PAIR"]
+for path in ("tc",):
+    pass
 os.environ["GLL_B200_KNN_PATH"] = "tc"
 os.environ["GLL_B200_CG_PATH"] = "streaming"
 run(pkg.LaplaceLearningSparseHard.apply, 2, 100, 900, 33, 5, "auto", 0.0)          # streaming CG, d % 4 != 0
