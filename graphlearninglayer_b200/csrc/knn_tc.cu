@@ -56,7 +56,7 @@ constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_MAX_STAGES = 9;
 constexpr size_t TC_STAGE_REGION = 152 * 1024;
 // CTA pairs (cta_group::2, M = 256).  Measured (profiles/r02q_knn_experiments.txt): 4-7 % faster on the 1M-node graph (whole
 // row tiles per CTA, drain-bound epilogue: fewer operand bytes and TMA issues per SM), no difference at 10-16 k nodes (bound
-// by the candidate insertions).  Default: on in the large-graph mode only; GLL_B200_KNN_PAIR=0/1 forces it.
+// by the candidate insertions).  Default: on from 8192 rows; GLL_B200_KNN_PAIR=0/1 forces it.
 constexpr int TC_EPI_WARPS = 8;                        // two per TMEM lane quarter: each takes one half of the 256 columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS + 32;  // + the second TMA producer warp
 constexpr int TC_WARP_PRODUCER_B = 2 + TC_EPI_WARPS;
@@ -935,7 +935,9 @@ TcPlan knn_tc_plan(int n, int d, int row_begin, int row_end, int col_begin) {
   p.aligned = (row_tiles >= 4 * sms) ? 1 : 0;  // big graphs: whole row tiles per CTA, one candidate set per row
   // GLL_B200_KNN_PAIR: CTA pairs (clusters of 2, tcgen05.mma.cta_group::2 with M = 256): a third fewer operand bytes per CTA.
   const char* pr = getenv("GLL_B200_KNN_PAIR");
-  const bool pair = pr ? (pr[0] == '1') : (p.aligned != 0);
+  // Default: from 64 row tiles (8192 rows) up -- measured -1 % at 10512 x 512, -6 % at 16384 x 512, -4 % at 32768 x 256, -10 % on
+  // the 1M-node graph, no difference at 4608 x 512 (profiles/r02zm_knn_pair.txt)
+  const bool pair = pr ? (pr[0] == '1') : (p.aligned != 0 || row_tiles >= 64);
   p.rstep = (pair && row_tiles >= 2 && sms >= 2) ? 2 : 1;
   p.row_tiles = ceil_div(row_tiles, p.rstep);  // row groups: the unit of work is (row group, column tile)
   p.units = (long long)p.row_tiles * p.col_tiles;
