@@ -175,7 +175,8 @@ def _forward_impl(X: torch.Tensor, label_matrix: torch.Tensor, tau, epsilon, k: 
     return pred, st, Xc
 
 
-def _backward_impl(st: _State, Xc: torch.Tensor, grad_output: torch.Tensor) -> torch.Tensor:
+def _backward_impl(st: _State, Xc: torch.Tensor, grad_output: torch.Tensor, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dX for d loss / d Pred = grad_output (times the 0-dim device tensor `scale`, if given: read by the kernel, no host sync)."""
     dev = Xc.device
     g = grad_output.detach().to(device=dev)
     if g.dtype not in (torch.float32, torch.float64):
@@ -189,9 +190,16 @@ def _backward_impl(st: _State, Xc: torch.Tensor, grad_output: torch.Tensor) -> t
         ws_bytes = lib.gll_workspace_bytes(st.n, st.d, st.k, st.l, st.k_lab)
         ws = _bytes(ws_bytes, dev)
         # negative tolerance = relative to the largest column norm of the right-hand side (see gll_cg_solve)
-        rc = lib.gll_backward(Xc.data_ptr(), g.data_ptr(), int(g.dtype == torch.float64), st.n, st.d, st.k, st.l, st.k_lab,
-                              st.eps_auto, -_cg_tol(), _cg_maxit(), st.buf.data_ptr(), dX.data_ptr(), ws.data_ptr(),
-                              ws_bytes, _stream_ptr(dev))
+        sc = None
+        if scale is not None:
+            sc = scale.detach().to(device=dev)
+            if sc.dtype not in (torch.float32, torch.float64):
+                sc = sc.float()
+            sc = sc.reshape(1).contiguous()
+        rc = lib.gll_backward_scaled(Xc.data_ptr(), g.data_ptr(), int(g.dtype == torch.float64),
+                                     sc.data_ptr() if sc is not None else None, int(sc is not None and sc.dtype == torch.float64),
+                                     st.n, st.d, st.k, st.l, st.k_lab, st.eps_auto, -_cg_tol(), _cg_maxit(), st.buf.data_ptr(),
+                                     dX.data_ptr(), ws.data_ptr(), ws_bytes, _stream_ptr(dev))
     _lib.check(rc, "gll_backward")
     _check_status(st.view("info", torch.int32, _lib.INFO_WORDS), "adjoint")
     return dX

@@ -98,13 +98,14 @@ namespace {
 // rhs = grad_output padded to lp class columns (fp32); optionally also wt[0 : zero_count] = 0 (the labeled rows of the
 // padded adjoint solution, GLL.py:104) so that the backward needs no separate memset
 __global__ void pack_grad_kernel(const void* __restrict__ g, int is_f64, int m, int l, int lp, float* __restrict__ rhs,
-                                 float* __restrict__ zero_ptr, long long zero_count) {
+                                 float* __restrict__ zero_ptr, long long zero_count, const void* __restrict__ scale, int scale_f64) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   for (long long z = t; z < zero_count; z += (long long)gridDim.x * blockDim.x) zero_ptr[z] = 0.f;
   if (t >= (long long)m * lp) return;
   int r = (int)(t / lp), c = (int)(t % lp);
+  const double sc = (scale == nullptr) ? 1.0 : (scale_f64 ? *(const double*)scale : (double)*(const float*)scale);
   float v = 0.f;
-  if (c < l) v = is_f64 ? (float)((const double*)g)[(size_t)r * l + c] : ((const float*)g)[(size_t)r * l + c];
+  if (c < l) v = is_f64 ? (float)(sc * ((const double*)g)[(size_t)r * l + c]) : (float)(sc * (double)((const float*)g)[(size_t)r * l + c]);
   rhs[t] = v;
 }
 
@@ -246,9 +247,10 @@ int unpack_columns(const float* src, int rows, int lp_src, int c0, int cnt, floa
   return GLL_OK;
 }
 
-int pack_grad(const void* g, int is_f64, int m, int l, int lp, float* rhs, cudaStream_t st, float* zero_ptr, long long zero_count) {
+int pack_grad(const void* g, int is_f64, int m, int l, int lp, float* rhs, cudaStream_t st, float* zero_ptr, long long zero_count,
+              const void* scale, int scale_f64) {
   GLL_PROF(KID_PACK, st);
-  pack_grad_kernel<<<ceil_div((long long)m * lp, 256), 256, 0, st>>>(g, is_f64, m, l, lp, rhs, zero_ptr, zero_count);
+  pack_grad_kernel<<<ceil_div((long long)m * lp, 256), 256, 0, st>>>(g, is_f64, m, l, lp, rhs, zero_ptr, zero_count, scale, scale_f64);
   GLL_LAUNCH_CHECK();
   return GLL_OK;
 }
@@ -574,7 +576,7 @@ int gll_forward(const float* X, const float* Y, int n, int d, int k, int l, int 
                          (float*)(S + L.diag), (float*)(S + L.rhs), (float*)(S + L.ut), info, workspace, workspace_bytes, st);
   if (rc) return rc;
   float* u_out = (float*)(S + L.ut) + (size_t)k_lab * lp;
-  const CgIo io = {nullptr, 0, pred_out, pred_is_f64};  // Pred (GLL.py:66) is written by the solver itself
+  const CgIo io = {nullptr, 0, pred_out, pred_is_f64, nullptr, 0};  // Pred (GLL.py:66) is written by the solver itself
   return cg_run((int*)(S + L.uu_ptr), (int*)(S + L.uu_col), (float*)(S + L.uu_val), (float*)(S + L.diag),
                 (float*)(S + L.rhs), m, l, cg_tol, cg_max_iter, u_out, info + GLL_INFO_CG_ITERS_FWD,
                 (float*)(info + GLL_INFO_CG_RESID_FWD), info + GLL_INFO_STATUS, workspace, workspace_bytes, st,
@@ -584,6 +586,13 @@ int gll_forward(const float* X, const float* Y, int n, int d, int k, int l, int 
 int gll_backward(const float* X, const void* grad_out, int grad_is_f64, int n, int d, int k, int l, int k_lab, int eps_auto,
                  float cg_tol, int cg_max_iter, void* state, float* dX, void* workspace, size_t workspace_bytes,
                  void* stream) {
+  return gll_backward_scaled(X, grad_out, grad_is_f64, nullptr, 0, n, d, k, l, k_lab, eps_auto, cg_tol, cg_max_iter, state, dX, workspace,
+                             workspace_bytes, stream);
+}
+
+int gll_backward_scaled(const float* X, const void* grad_out, int grad_is_f64, const void* scale, int scale_is_f64, int n, int d, int k,
+                        int l, int k_lab, int eps_auto, float cg_tol, int cg_max_iter, void* state, float* dX, void* workspace,
+                        size_t workspace_bytes, void* stream) {
   GLL_REQUIRE(X && grad_out && state && dX && workspace, "null pointer");
   gll_layout L;
   if (gll_state_layout(n, k, l, k_lab, &L)) return GLL_ERR_ARG;
@@ -598,7 +607,7 @@ int gll_backward(const float* X, const void* grad_out, int grad_is_f64, int n, i
   float* wt = (float*)(S + L.wt);
   // GLL.py:104: the solver reads the incoming gradient itself; the labeled rows of the padded adjoint solution (zeros) are
   // never read -- edge_grad substitutes them
-  const CgIo io = {grad_out, grad_is_f64 ? 2 : 1, nullptr, 0};
+  const CgIo io = {grad_out, grad_is_f64 ? 2 : 1, nullptr, 0, scale, scale_is_f64};
   int rc = cg_run((int*)(S + L.uu_ptr), (int*)(S + L.uu_col), (float*)(S + L.uu_val), (float*)(S + L.diag),
                   (float*)(S + L.rhs), m, l, cg_tol, cg_max_iter, wt + (size_t)k_lab * lp, info + GLL_INFO_CG_ITERS_BWD,
                   (float*)(info + GLL_INFO_CG_RESID_BWD), info + GLL_INFO_STATUS, workspace, workspace_bytes, st,

@@ -328,7 +328,7 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
   const bool has_src = io != nullptr && io->rhs_src != nullptr, has_copy = io != nullptr && io->x_copy != nullptr;
   if (lp > CG_MAX_LP) {
     if (has_src) {
-      const int rc = pack_grad(io->rhs_src, io->rhs_kind == 2, m, l, lp, const_cast<float*>(rhs), st);
+      const int rc = pack_grad(io->rhs_src, io->rhs_kind == 2, m, l, lp, const_cast<float*>(rhs), st, nullptr, 0, io->rhs_scale, io->rhs_scale_f64);
       if (rc) return rc;
     }
     const int chunks = ceil_div(l, CG_MAX_LP);
@@ -379,6 +379,8 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
   P.rhs_kind = io ? io->rhs_kind : 0;
   P.x_copy = io ? io->x_copy : nullptr;
   P.x_copy_f64 = io ? io->x_copy_f64 : 0;
+  P.rhs_scale = io ? io->rhs_scale : nullptr;
+  P.rhs_scale_f64 = io ? io->rhs_scale_f64 : 0;
   {  // systems that fit on chip (every config except the sharded 1M-node graph) take the shared-memory-resident kernel
     const char* force = getenv("GLL_B200_CG_PATH");  // "streaming" / "resident" / "small": testing knobs
     const bool only_small = force != nullptr && strcmp(force, "small") == 0;
@@ -398,7 +400,7 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
     }
   }
   if (has_src) {  // streaming kernel: conversions as separate kernels
-    const int rc = pack_grad(io->rhs_src, io->rhs_kind == 2, m, l, lp, const_cast<float*>(rhs), st);
+    const int rc = pack_grad(io->rhs_src, io->rhs_kind == 2, m, l, lp, const_cast<float*>(rhs), st, nullptr, 0, io->rhs_scale, io->rhs_scale_f64);
     if (rc) return rc;
     P.rhs_src = nullptr;
   }

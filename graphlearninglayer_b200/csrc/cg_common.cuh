@@ -33,19 +33,24 @@ struct CgParams {
   int rhs_kind;
   void* x_copy;         // if set: the solution is also written as an [m][l] array (fp64 if x_copy_f64, else fp32)
   int x_copy_f64;
+  const void* rhs_scale;  // optional device scalar (fp64 if rhs_scale_f64, else fp32) multiplied into rhs_src: the upstream gradient
+  int rhs_scale_f64;      // of a loss head whose d loss / d pred is rhs_src (losses.py: LaplaceLearningCELoss)
 };
 
 // right-hand side of class quad q of a row, from the padded fp32 array or straight from the caller's [m][l] array
 __device__ __forceinline__ float4 cg_load_rhs4(const CgParams& P, int row, int q) {
   if (P.rhs_src == nullptr) return __ldg(reinterpret_cast<const float4*>(P.rhs + (size_t)row * P.lp + 4 * q));
+  double sc = 1.0;
+  if (P.rhs_scale != nullptr)
+    sc = P.rhs_scale_f64 ? __ldg(reinterpret_cast<const double*>(P.rhs_scale)) : (double)__ldg(reinterpret_cast<const float*>(P.rhs_scale));
   float v[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int col = 4 * q + c;
     v[c] = 0.f;
     if (col < P.l)
-      v[c] = (P.rhs_kind == 2) ? (float)__ldg(reinterpret_cast<const double*>(P.rhs_src) + (size_t)row * P.l + col)
-                               : __ldg(reinterpret_cast<const float*>(P.rhs_src) + (size_t)row * P.l + col);
+      v[c] = (P.rhs_kind == 2) ? (float)(sc * __ldg(reinterpret_cast<const double*>(P.rhs_src) + (size_t)row * P.l + col))
+                               : (float)(sc * (double)__ldg(reinterpret_cast<const float*>(P.rhs_src) + (size_t)row * P.l + col));
   }
   return make_float4(v[0], v[1], v[2], v[3]);
 }

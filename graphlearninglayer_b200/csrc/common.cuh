@@ -143,6 +143,8 @@ struct CgIo {
   int rhs_kind;
   void* x_copy;
   int x_copy_f64;
+  const void* rhs_scale;  // optional device scalar multiplied into rhs_src (fp64 if rhs_scale_f64)
+  int rhs_scale_f64;
 };
 int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, const float* rhs, int m,
            int l, float tol, int max_iter, float* x, int* iters_out, float* resid_out, int* status_out, void* ws,
@@ -175,7 +177,7 @@ int unpack_columns(const float* src, int rows, int lp_src, int c0, int cnt, floa
 
 // small utility kernels (api.cu)
 int pack_grad(const void* g, int is_f64, int m, int l, int lp, float* rhs, cudaStream_t st, float* zero_ptr = nullptr,
-              long long zero_count = 0);
+              long long zero_count = 0, const void* scale = nullptr, int scale_f64 = 0);
 int unpack_pred(const float* ut_u, int m, int l, int lp, void* pred, int is_f64, cudaStream_t st);
 
 inline int padded_classes(int l) { return (l + 3) / 4 * 4; }

@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from ._lib import lib
 
-__all__ = ["custom_ce_loss"]
+__all__ = ["custom_ce_loss", "LaplaceLearningCELoss", "laplace_ce_loss"]
 
 
 class _CELoss(torch.autograd.Function):
@@ -48,3 +48,55 @@ class _CELoss(torch.autograd.Function):
 def custom_ce_loss(softmax_logits: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
     """-sum(one_hot(targets) * log(softmax_logits + 1e-8)) / batch_size  (losses.py:128-136)."""
     return _CELoss.apply(softmax_logits, targets)
+
+
+class LaplaceLearningCELoss(torch.autograd.Function):
+    """The layer with the loss behind it in ONE autograd node:
+
+        pred = LaplaceLearningSparseHard.apply(features, label_matrix, tau, epsilon)      # FullySup.py:156
+        loss = custom_ce_loss(pred, targets)                                               # FullySup.py:158, losses.py:128-136
+
+    becomes ``loss, pred = LaplaceLearningCELoss.apply(features, label_matrix, targets, tau, epsilon)``.  The loss kernel leaves
+    d loss / d pred on the device; backward hands it to the adjoint solve as its right-hand side together with the incoming
+    (scalar) gradient, which the solver kernel multiplies in itself -- no elementwise kernels between the loss and the solve, no
+    host read.  Same numbers as the two calls.  ``pred`` is returned for accuracy bookkeeping and carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, X, label_matrix, targets, tau=0, epsilon="auto"):
+        from .GLL import _forward_impl, _stream_ptr
+
+        pred, st, Xc = _forward_impl(X, label_matrix, tau, epsilon)
+        m, l = pred.shape
+        t = targets.detach().to(device=pred.device, dtype=torch.int64).contiguous()
+        if t.numel() != m:
+            raise ValueError("targets must hold one class index per unlabeled row")
+        loss = torch.empty((), dtype=pred.dtype, device=pred.device)
+        grad = torch.empty_like(pred)
+        wsb = lib.gll_ce_loss_workspace_bytes(m)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=pred.device) if wsb else None
+        with torch.cuda.device(pred.device):
+            _lib.check(lib.gll_ce_loss(pred.data_ptr(), int(pred.dtype == torch.float64), t.data_ptr(), m, l, loss.data_ptr(),
+                                       grad.data_ptr(), None, ws.data_ptr() if wsb else None, wsb, _stream_ptr(pred.device)),
+                       "gll_ce_loss")
+        ctx.gll_state = st
+        ctx.x_dtype = X.dtype
+        ctx.save_for_backward(Xc, grad)
+        ctx.mark_non_differentiable(pred)
+        ctx.set_materialize_grads(True)
+        return loss, pred
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_loss, _grad_pred):
+        from .GLL import _backward_impl
+
+        Xc, grad = ctx.saved_tensors
+        dX = _backward_impl(ctx.gll_state, Xc, grad, scale=grad_loss)
+        if dX.dtype != ctx.x_dtype:
+            dX = dX.to(ctx.x_dtype)
+        return dX, None, None, None, None
+
+
+def laplace_ce_loss(features, label_matrix, targets, tau=0, epsilon="auto"):
+    """``custom_ce_loss(LaplaceLearningSparseHard.apply(features, label_matrix, tau, epsilon), targets)`` as one node: (loss, pred)."""
+    return LaplaceLearningCELoss.apply(features, label_matrix, targets, tau, epsilon)

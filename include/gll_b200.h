@@ -273,6 +273,11 @@ int gll_forward(const float* X, const float* Y, int n, int d, int k, int l, int 
 int gll_backward(const float* X, const void* grad_out, int grad_is_f64, int n, int d, int k, int l, int k_lab,
                  int eps_auto, float cg_tol, int cg_max_iter, void* state, float* dX, void* workspace,
                  size_t workspace_bytes, void* stream);
+/* The same with a device scalar multiplied into grad_out (scale == NULL: 1): the upstream gradient of a loss head whose
+ * d loss / d Pred is grad_out (custom_ce_loss fused behind the layer, losses.py:128-136 after FullySup.py:156-158); no host read. */
+int gll_backward_scaled(const float* X, const void* grad_out, int grad_is_f64, const void* scale, int scale_is_f64, int n, int d,
+                        int k, int l, int k_lab, int eps_auto, float cg_tol, int cg_max_iter, void* state, float* dX,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

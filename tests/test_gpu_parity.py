@@ -1024,6 +1024,27 @@ def test_fused_ce_loss_matches_reference_formula(gll, dtype):
     assert torch.allclose(b.grad, a.grad, rtol=tol, atol=0.0)
 
 
+@pytest.mark.parametrize("upstream", [1.0, 0.37])
+def test_layer_with_loss_head_equals_two_calls(gll, upstream):
+    """LaplaceLearningCELoss (layer + custom_ce_loss in one autograd node; the adjoint solve reads d loss / d pred and the upstream
+    scalar itself) against the two separate calls: the same loss bits, the same prediction bits, dX within fp32 rounding of the
+    one extra multiplication."""
+    pkg, _ = gll
+    from graphlearninglayer_b200.losses import custom_ce_loss, laplace_ce_loss
+    X, Y, _, yq = O.synth_inputs(21, 600, 300, 48, 7, 3.0)
+    Yt, tq = torch.as_tensor(Y).cuda(), torch.as_tensor(yq).cuda()
+    Xa = torch.as_tensor(X).cuda().requires_grad_(True)
+    pred_a = pkg.LaplaceLearningSparseHard.apply(Xa, Yt, 0.01, "auto")
+    loss_a = custom_ce_loss(pred_a, tq)
+    (loss_a * upstream).backward()
+    Xb = torch.as_tensor(X).cuda().requires_grad_(True)
+    loss_b, pred_b = laplace_ce_loss(Xb, Yt, tq, 0.01, "auto")
+    (loss_b * upstream).backward()
+    assert torch.equal(pred_a.detach(), pred_b) and torch.equal(loss_a.detach(), loss_b.detach())
+    assert not pred_b.requires_grad
+    assert O.max_rel(Xb.grad.cpu().numpy(), Xa.grad.cpu().numpy()) < 2e-6
+
+
 def test_fused_ce_loss_many_rows(gll):
     """More than 4096 rows: several CTAs, partial sums added by a second tiny launch (sharded 1M-node graph path)."""
     from graphlearninglayer_b200.losses import custom_ce_loss
