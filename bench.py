@@ -181,7 +181,7 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-CONFIG_KEYS = ("workload", "l2", "parallelism", "cg_tol", "loss", "what", "execution", "eager_calls_per_sec", "c4_calls_per_sec", "c4_ms_per_call",
+CONFIG_KEYS = ("workload", "l2", "parallelism", "cg_tol", "loss", "what", "execution", "eager_calls_per_sec", "loss_head_calls_per_sec", "c4_calls_per_sec", "c4_ms_per_call",
                "c5_ms_per_call", "c5_nodes", "c5_cg_partition", "c5_knn_ms", "c5_cg_solve_ms_fwd", "c5_cg_solve_ms_bwd",
                "c5s_ms_per_call_columns", "c5s_ms_per_call_rows_p2p", "c5s_parity_pred_vs_unsharded",
                "c5s_parity_dx_vs_unsharded", "c5s_parity_rows_p2p_pred", "c5s_parity_rows_p2p_dx")
@@ -401,6 +401,7 @@ def run_b200(args, rank, world, local_rank):
     # the same step replayed from CUDA graphs (graphlearninglayer_b200.graphed: forward + loss and backward captured once,
     # two graph launches per step, the same kernels): this is `value`; the eager figure is kept beside it
     tot_ms, execution = eager_ms, "eager launches through LaplaceLearningSparseHard.apply"
+    extra_cfg = {}
     if not sharded and not args.no_cuda_graph and args.loss == "fused":
         try:
             from graphlearninglayer_b200.graphed import GraphedStep
@@ -412,6 +413,13 @@ def run_b200(args, rank, world, local_rank):
             execution = "CUDA graph replay (GraphedStep: 2 graph launches per step, same kernels)"
         except Exception as e:  # capture not available: say so, keep the eager number
             execution += f" (graph capture failed: {type(e).__name__}: {e})"[:300]
+        try:  # extra, NOT the headline: the same step with the loss fused behind the layer in one autograd node (8f-3)
+            gh = GraphedStep(shp["n"], shp["d"], shp["k_lab"], shp["l"], dev, tau=tn["tau"], epsilon=tn["eps"],
+                             warmup_inputs=(tn["Xd"].detach(), tn["Yd"], tn["yq"]), loss_head=True)
+            head_ms = timed(lambda: gh(tn["Xd"], tn["Yd"], tn["yq"]), args.steps, args.warmup)
+            extra_cfg["loss_head_calls_per_sec"] = jobs * 1e3 / (head_ms / args.steps)
+        except Exception as e:
+            print(f"bench.py: loss-head variant not measured: {type(e).__name__}: {e}", file=sys.stderr)
     clocks = sampler.stop() if sampler else None
     e2e_ms = timed(e2e, args.steps, args.warmup)
     pipe_ms = None
@@ -536,7 +544,7 @@ def run_b200(args, rank, world, local_rank):
                   if args.loss == "fused" else "custom_ce_loss with the reference's PyTorch ops (losses.py:128-136)"),
             what="libgll_b200.so (sm_100a kernels) through LaplaceLearningSparseHard.apply",
             execution=execution, eager_calls_per_sec=jobs * 1e3 / (eager_ms / args.steps),
-            **shard_cfg)
+            **shard_cfg, **extra_cfg)
         if c4 is not None:
             cfg.update(c4_calls_per_sec=c4["calls_per_sec"], c4_ms_per_call=c4["ms_per_call"])
         line = {

@@ -3,6 +3,7 @@
     step = GraphedStep(n, d, k_lab, l, device, tau=0.0, epsilon="auto", loss="ce")
     loss = step(X, Y, y_query)        # forward + loss + backward as TWO graph launches; step.dX holds dL/dX afterwards
     pred = step.pred                  # (m, l) float64, the layer's output of the last call
+    step = GraphedStep(..., loss_head=True)   # the same with layer + custom_ce_loss fused into one node (losses.laplace_ce_loss)
 
 Every kernel of ``gll_forward`` / ``gll_backward`` is enqueued on the caller's stream with host-known launch
 configurations, worst-case allocations and no host synchronisation (include/gll_b200.h), so the whole call can be
@@ -26,7 +27,7 @@ from .losses import custom_ce_loss
 class GraphedStep:
     def __init__(self, n: int, d: int, k_lab: int, l: int, device, tau: float = 0.0, epsilon="auto",
                  loss: Optional[Callable] = None, label_dtype: torch.dtype = torch.float32, layer: Optional[Callable] = None,
-                 warmup_inputs=None):
+                 warmup_inputs=None, loss_head: bool = False):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("GraphedStep needs a CUDA device (graphlearninglayer_b200 has no CPU path)")
@@ -35,6 +36,10 @@ class GraphedStep:
         loss_fn = loss or custom_ce_loss  # custom_ce_loss(pred, target), losses.py:128-136
 
         def step(X, Y, yq):
+            if loss_head:  # layer + custom_ce_loss as ONE autograd node (losses.LaplaceLearningCELoss)
+                from .losses import laplace_ce_loss
+
+                return laplace_ce_loss(X, Y, yq, tau, epsilon)
             pred = layer(X, Y, tau, epsilon)
             return loss_fn(pred, yq), pred
 

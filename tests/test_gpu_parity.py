@@ -505,6 +505,7 @@ def test_graphed_step_replays_the_layer(gll):
 
     k_lab, m, d, l = 700, 500, 64, 10
     step = GraphedStep(k_lab + m, d, k_lab, l, "cuda", tau=0.0, epsilon="auto")
+    head = GraphedStep(k_lab + m, d, k_lab, l, "cuda", tau=0.0, epsilon="auto", loss_head=True)  # layer + loss in one node
     for seed in (3, 4):
         X, Y, _, yq = O.synth_inputs(seed, k_lab, m, d, l, 2.0)
         Xt = torch.as_tensor(X).cuda().requires_grad_(True)
@@ -517,6 +518,8 @@ def test_graphed_step_replays_the_layer(gll):
         assert _lib.launch_count() == before          # nothing was launched through the API: the graphs replayed
         assert torch.equal(step.pred, pred.detach()) and torch.equal(step.dX, Xt.grad)
         assert loss_g.item() == loss.item()
+        loss_h = head(torch.as_tensor(X).cuda(), Yt, yt)
+        assert loss_h.item() == loss.item() and torch.equal(head.pred, pred.detach()) and torch.equal(head.dX, Xt.grad)
     f, loss_ref, gout, bw = O.fwd_bwd(X, Y, yq, 0.0, "auto", solver="lu")
     assert O.max_rel(step.pred.cpu().numpy(), f.pred) < TOL and O.max_rel(step.dX.cpu().numpy(), bw.dX) < TOL
 
