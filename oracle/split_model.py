@@ -76,6 +76,28 @@ def approx_d2_f16(hi, lo, E, sq, passes: int = 1, fp32_accumulate: bool = False,
     return (key + sq[:, None]).astype(np.float32)
 
 
+def epilogue_values_packed(hi, lo, E, sq, passes: int = 1, fp32_accumulate: bool = True):
+    """What the tensor-core epilogue STORES and FLUSHES since round 2 (knn_tc.cu, packed keys): the column value is shifted by
+    Cs = 2 max|x|^2 (so that it is positive and its bits order like unsigned integers), v' = fl(t cj + fl(|x_j|^2 + Cs)) with
+    t = acc 2^E_i (exact), five mantissa bits are cleared, and a flushed candidate carries fl(fl(v'_cleared - Cs) + |x_i|^2).
+    Returns (flushed (n, n) float32, cleared v' (n, n) float32): selection inside a row happens on the cleared values."""
+    if passes == 1:
+        lo = np.zeros_like(lo)
+    if fp32_accumulate:
+        acc = (hi.astype(np.float32) @ hi.astype(np.float32).T + lo.astype(np.float32) @ hi.astype(np.float32).T).astype(np.float32)
+    else:
+        acc = ((hi.astype(np.float64) + lo.astype(np.float64)) @ hi.astype(np.float64).T).astype(np.float32)
+    ri = np.ldexp(np.float32(1.0), E).astype(np.float32)
+    cj = (np.float32(-2.0) * ri).astype(np.float32)
+    cs = np.float32(2.0) * np.float32(sq.max())
+    sj = (sq + cs).astype(np.float32)                                            # staged column value, one rounding
+    t = (acc * ri[:, None]).astype(np.float32)                                   # exact: power of two
+    v = (t.astype(np.float64) * cj[None, :].astype(np.float64) + sj[None, :].astype(np.float64)).astype(np.float32)  # one FMA
+    cleared = (v.view(np.uint32) & np.uint32(0xFFFFFFE0)).view(np.float32)
+    flushed = ((cleared - cs).astype(np.float32) + sq[:, None]).astype(np.float32)
+    return flushed, cleared
+
+
 def err_coef(d: int, passes: int = 1) -> float:
     """knn_tc_err_coef (knn_tc.cu)."""
     steps = passes * math.ceil(d / 16) + 8.0

@@ -101,3 +101,44 @@ def test_proven_rows_equal_exact_knn(name, X, passes):
         assert proven.mean() > 0.98
     if name == "tight_blob":
         assert proven.mean() < 0.5   # gaps of ~1e-6 against a bound of ~1e-4: the proof has to give up, and does
+
+
+@pytest.mark.parametrize("name,X", list(_datasets()), ids=[n for n, _ in _datasets()])
+@pytest.mark.parametrize("passes", [1, 2])
+def test_packed_key_epilogue_values_within_bound(name, X, passes):
+    """The epilogue's packed keys (knn_tc.cu): shifting the column value by 2 max|x|^2 and un-shifting it when a set is flushed
+    adds a few roundings at the magnitude of max|x|^2 -- budgeted in err_coef (12 ulps x 4) -- and the shifted value must be
+    positive for its bits to order like integers.  Clearing five mantissa bits only LOWERS a stored value (by < 2^-18 of it): the
+    proof needs every non-candidate's true approximate distance to be >= the 32nd candidate's stored one, which clearing keeps;
+    what a flushed candidate carries must still be a lower bound of its own uncleared value and within bound + 2^-18 of exact."""
+    hi, lo, E, sq, rho = S.split_f16(X)
+    d = X.shape[1]
+    flushed, cleared = S.epilogue_values_packed(hi, lo, E, sq, passes=passes)
+    assert (cleared.view(np.uint32) >> 31 == 0).all() and (cleared >= 0).all()       # positive: unsigned order == value order
+    exact = S.exact_d2(X)
+    bound = S.err_bound(d, sq, rho, passes)[:, None]
+    slack = 2.0 ** -18 * 5.0 * float(sq.max())                                        # what clearing five bits can take away
+    assert ((flushed.astype(np.float64) - exact) <= bound).all(), name              # never above exact + bound
+    assert ((exact - flushed.astype(np.float64)) <= bound + slack).all(), name      # below by at most bound + the cleared bits
+    # un-cleared, the shifted arithmetic alone stays inside the bound on both sides
+    cs = np.float32(2.0) * np.float32(sq.max())
+    ri = np.ldexp(np.float32(1.0), E).astype(np.float32)
+    acc = (hi.astype(np.float32) @ hi.astype(np.float32).T + (lo.astype(np.float32) @ hi.astype(np.float32).T if passes == 2 else 0)).astype(np.float32)
+    v = ((acc * ri[:, None]).astype(np.float64) * (-2.0 * ri[None, :].astype(np.float64)) + (sq + cs).astype(np.float32)[None, :].astype(np.float64)).astype(np.float32)
+    plain = ((v - cs).astype(np.float32) + sq[:, None]).astype(np.float32).astype(np.float64)
+    assert (np.abs(plain - exact) <= bound).all(), name
+
+
+@pytest.mark.parametrize("name,X", list(_hard_datasets()), ids=[n for n, _ in _hard_datasets()])
+def test_proven_rows_equal_exact_knn_with_packed_keys(name, X):
+    """The same pipeline test as above on what the packed-key epilogue flushes: selection on cleared values (ties by index),
+    exact re-rank, proof -- proven rows carry the oracle's lists, on lattice ties and duplicates too."""
+    hi, lo, E, sq, rho = S.split_f16(X)
+    flushed, _ = S.epilogue_values_packed(hi, lo, E, sq, passes=1)
+    bound = S.err_bound(X.shape[1], sq, rho, 1)
+    ind, proven = S.select_rerank_prove(X, flushed, bound)
+    ref_ind, ref_dist = O.exact_knn(X, 25)
+    exact, tie, bad = O.knn_sets_match(ind[proven], ref_ind[proven], ref_dist[proven])
+    assert bad == 0, (name, exact, tie, bad)
+    if name == "clusters_d128":
+        assert proven.mean() > 0.98
