@@ -806,9 +806,19 @@ knn_rerank64_kernel(const float* __restrict__ X, const float* __restrict__ sq, c
   float* xi = xs + (size_t)warp * d;
   for (int t = lane; t < d; t += 32) xi[t] = X[(size_t)i * d + t];
   __syncwarp();
-  const u64 ca = m1[(size_t)(i - row_begin) * KC + lane], cb = m2[(size_t)(i - row_begin) * KC + lane];
+  const u64 ca = m1[(size_t)(i - row_begin) * KC + lane];
+  u64 cb = m2[(size_t)(i - row_begin) * KC + lane];
   const u64 last = __shfl_sync(FULL, cb, KC - 1);
   const float lower = (last == KEY_INF) ? INFINITY : key_dist(last);  // every non-candidate has d~^2 >= lower
+  // the second round re-admits first-round members whose stored value ties with the first round's 32nd (knn_tc.cu): drop them
+  {
+    bool dup = false;
+    for (int c = 0; c < KC; ++c) {
+      const u64 oa = __shfl_sync(FULL, ca, c);
+      dup |= (oa != KEY_INF && cb != KEY_INF && key_idx(oa) == key_idx(cb));
+    }
+    if (dup) cb = KEY_INF;
+  }
   double da = INFINITY, db = INFINITY;
   int ja = -1, jb = -1;
   for (int c = 0; c < 2 * KC; ++c) {

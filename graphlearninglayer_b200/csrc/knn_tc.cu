@@ -712,9 +712,16 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
             const float s2a = (c & 8) ? s4[1] : s4[0], s2b = (c & 8) ? s4[3] : s4[2];
             const float dsel = (c & 16) ? s2b : s2a;
             const uint32_t kbits = __float_as_uint(dsel) & ~31u;
-            // second round: the key is rebuilt exactly as the first round flushed it, so the lexicographic test excludes
-            // precisely the first round's set
-            const bool fresh = (P.excl == nullptr) || (make_key(unshift(__uint_as_float(kbits), sqi_row), j0 + c) > excl_row);
+            // second round (k > 33): the key is rebuilt exactly as the first round flushed it.  Admitted: every column whose
+            // stored value is >= the first round's 32nd value, except that 32nd entry itself.  (Not "key > 32nd key": a column
+            // that TIES with the 32nd value and has a smaller index may have been evicted from its set in the first round --
+            // the entry a set drops among tied maxima is picked by slot, not by index -- and would be lost to both rounds.
+            // First-round members that tie come back as duplicates; knn_rerank64 drops them by index.)
+            bool fresh = true;
+            if (P.excl != nullptr) {
+              const u64 key = make_key(unshift(__uint_as_float(kbits), sqi_row), j0 + c);
+              fresh = (key != excl_row) && ((uint32_t)(key >> 32) >= (uint32_t)(excl_row >> 32));
+            }
             if (dsel < thr && fresh) {  // thr may have tightened since the scan
               // replace the set's largest entry (one integer max over the four cached group maxima names it), reload its
               // group of eight and take the group's new maximum
