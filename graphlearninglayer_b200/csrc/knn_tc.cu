@@ -766,8 +766,10 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
         process(rawA, 0);
         if (tg != 0xffffffffu) {
           // another set's bound, shifted (rounded up) and moved to the START OF THE NEXT five-bit bucket: a column whose
-          // stored value would tie with that set's largest entry stays admissible (it may have the smaller index: the
-          // merged lists and the second round of a k > 33 search order candidates by (value, index))
+          // stored value would tie with that set's largest entry stays admissible.  (The completeness proof only needs the
+          // statement on values -- every rejected column has a stored value >= the 32nd candidate's, tests/
+          // test_candidate_sets_model.py -- which the plain bound gives as well; this keeps the merged list's tie order by
+          // index intact wherever it can.)
           const float t_sh = __fadd_ru(ordered_to_float(tg + 1u), Cs);
           if (t_sh < INFINITY) {  // nothing published yet: +inf (or the NaN one past it)
             tlim = fminf(tlim, __uint_as_float((__float_as_uint(t_sh) | 31u) + 1u));
