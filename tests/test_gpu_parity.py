@@ -397,6 +397,30 @@ def test_cg_vs_direct_solve(gll, monkeypatch, l, path):
     assert true_res < 5e-5  # fp32 storage of A and x bounds the true residual
 
 
+@pytest.mark.parametrize("m,l", [(64, 1), (65, 13), (511, 10), (2048, 3), (2048, 16), (700, 40)])
+def test_cg_cluster_kernel_edge_sizes(gll, m, l):
+    """The eight-CTA cluster kernel at the edges of its range (64 and 2048 rows, a last CTA with one row or none, one class, up to
+    four items per thread; 40 classes at 700 rows exceed its item budget and must fall through to another kernel)."""
+    _, _lib = gll
+    X, Y, *_ = O.synth_inputs(31 + m + l, 120, m, 20, l, 1.5)
+    f = O.forward(X, Y, 0.03, 1.0, solver="lu")
+    x, iters, resid, status = run_cg(_lib, f.Luu, f.B, tol=1e-7)
+    assert status == 0 and 0 < iters < 500 and resid <= 1e-7
+    assert O.max_rel(x, f.pred) < TOL
+
+
+def test_knn_cta_pairs_by_default_with_an_odd_number_of_row_tiles(gll):
+    """From 8192 rows the search runs on CTA pairs by default; 8300 rows = 65 row tiles: the last pair has one real row tile."""
+    _, _lib = gll
+    X, *_ = O.synth_inputs(41, 4000, 4300, 32, 10, 3.0)
+    idx, dist, info = run_knn(_lib, X)
+    rows = np.arange(0, X.shape[0], 37)
+    rows = np.concatenate([rows, np.arange(X.shape[0] - 140, X.shape[0])])   # all of the last (ragged) row tiles
+    ref_idx, ref_dist = O.exact_knn_rows(X, rows, 25)
+    assert np.array_equal(idx.cpu().numpy()[rows], ref_idx)
+    assert np.array_equal(dist.cpu().numpy()[rows], ref_dist.astype(np.float32))
+
+
 @pytest.mark.parametrize("path", ["", "streaming", "small"])
 def test_cg_zero_rhs_column_and_maxiter(gll, monkeypatch, path):
     _, _lib = gll
