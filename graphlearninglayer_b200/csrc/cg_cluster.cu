@@ -362,8 +362,9 @@ int cc_launch(const CgParams& P, cudaStream_t st) {
 // 1: the solve was taken; 0: the system is not of this kind (caller falls through to the other kernels); < 0: error
 int cg_cluster_try(const CgParams& P, cudaStream_t st) {
   if (P.m < 64 || P.m > 2048) return 0;  // below 64 rows there is nothing to share
-  // (256 / 320 / 384 threads per CTA measured the same at C2, 2.95-3.2 us per iteration; ONE CTA of 1024 threads: 5.0 us --
-  //  32 warps in lockstep on one SM, with spills at 64 registers)
+  // (256 / 320 / 384 threads per CTA measured the same at C2, 2.95-3.2 us per iteration; the same item layout on ONE CTA: 3.8 us
+  //  with 512 threads, 5.0 us with 1024 (spills at 64 registers) -- an iteration is ~450 mostly dependent instructions per warp,
+  //  and what the cluster buys is a shorter chain per warp, not bandwidth)
   return cc_launch<8, 320>(P, st);
 }
 
