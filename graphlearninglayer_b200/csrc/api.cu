@@ -413,6 +413,14 @@ int gll_cg_solve(const int* uu_ptr, const int* uu_col, const float* uu_val, cons
                 workspace_bytes, (cudaStream_t)stream);
 }
 
+int gll_cg_solve_hint(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, const float* rhs, int m, int l,
+                      float tol, int max_iter, float* x, int* iters_out, float* resid_out, int* status_out, void* workspace,
+                      size_t workspace_bytes, void* stream, float uu_degree_hint) {
+  const CgIo io = {nullptr, 0, nullptr, 0, nullptr, 0, uu_degree_hint};
+  return cg_run(uu_ptr, uu_col, uu_val, diag, rhs, m, l, tol, max_iter, x, iters_out, resid_out, status_out, workspace,
+                workspace_bytes, (cudaStream_t)stream, nullptr, &io);
+}
+
 int gll_backward_edges(const float* X, int n, int d, int l, int k_lab, int eps_auto, const int* row_ptr, const int* col,
                        const float* dist, const float* w, const float* eps, const int* kappa, const float* ut,
                        const float* wt, float* gv, float* bvec, float* dX, void* stream) {
@@ -576,7 +584,8 @@ int gll_forward(const float* X, const float* Y, int n, int d, int k, int l, int 
                          (float*)(S + L.diag), (float*)(S + L.rhs), (float*)(S + L.ut), info, workspace, workspace_bytes, st);
   if (rc) return rc;
   float* u_out = (float*)(S + L.ut) + (size_t)k_lab * lp;
-  const CgIo io = {nullptr, 0, pred_out, pred_is_f64, nullptr, 0};  // Pred (GLL.py:66) is written by the solver itself
+  const float uu_hint = 1.2f * (float)(k - 1) * (float)m / (float)n;  // expected off-diagonal entries per row of L_uu
+  const CgIo io = {nullptr, 0, pred_out, pred_is_f64, nullptr, 0, uu_hint};  // Pred (GLL.py:66) is written by the solver itself
   return cg_run((int*)(S + L.uu_ptr), (int*)(S + L.uu_col), (float*)(S + L.uu_val), (float*)(S + L.diag),
                 (float*)(S + L.rhs), m, l, cg_tol, cg_max_iter, u_out, info + GLL_INFO_CG_ITERS_FWD,
                 (float*)(info + GLL_INFO_CG_RESID_FWD), info + GLL_INFO_STATUS, workspace, workspace_bytes, st,
@@ -607,7 +616,7 @@ int gll_backward_scaled(const float* X, const void* grad_out, int grad_is_f64, c
   float* wt = (float*)(S + L.wt);
   // GLL.py:104: the solver reads the incoming gradient itself; the labeled rows of the padded adjoint solution (zeros) are
   // never read -- edge_grad substitutes them
-  const CgIo io = {grad_out, grad_is_f64 ? 2 : 1, nullptr, 0, scale, scale_is_f64};
+  const CgIo io = {grad_out, grad_is_f64 ? 2 : 1, nullptr, 0, scale, scale_is_f64, 1.2f * (float)(k - 1) * (float)m / (float)n};
   int rc = cg_run((int*)(S + L.uu_ptr), (int*)(S + L.uu_col), (float*)(S + L.uu_val), (float*)(S + L.diag),
                   (float*)(S + L.rhs), m, l, cg_tol, cg_max_iter, wt + (size_t)k_lab * lp, info + GLL_INFO_CG_ITERS_BWD,
                   (float*)(info + GLL_INFO_CG_RESID_BWD), info + GLL_INFO_STATUS, workspace, workspace_bytes, st,

@@ -382,10 +382,16 @@ int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const floa
   P.rhs_scale = io ? io->rhs_scale : nullptr;
   P.rhs_scale_f64 = io ? io->rhs_scale_f64 : 0;
   {  // systems that fit on chip (every config except the sharded 1M-node graph) take the shared-memory-resident kernel
-    const char* force = getenv("GLL_B200_CG_PATH");  // "streaming" / "resident" / "small": testing knobs
+    const char* force = getenv("GLL_B200_CG_PATH");  // "streaming" / "resident" / "small" / "cluster": testing knobs
     const bool only_small = force != nullptr && strcmp(force, "small") == 0;
-    if (force == nullptr || force[0] == 0 || only_small) {  // minibatch-sized systems: the latency-organised kernels
-      int rc = only_small ? 0 : cg_cluster_try(P, st);  // one cluster of eight CTAs (64 <= m <= 2048, a few items per thread)
+    const bool force_cluster = force != nullptr && strcmp(force, "cluster") == 0;
+    // The cluster kernel gathers neighbour rows through distributed shared memory, which moves few transactions per clock: it
+    // wins on SPARSE systems (C2: 1.4 off-diagonal entries per row, C3: 3.2 -- 35 us per solve against 41 for the one-CTA kernel)
+    // and loses on dense ones (C1: 14.5 per row -- 154 us against 94 for the multi-CTA kernel).  The host cannot see nnz; the
+    // layer passes what it expects, (k - 1) m / n, and callers that pass nothing get the other kernels.
+    const bool sparse = io != nullptr && io->uu_degree_hint > 0.f && io->uu_degree_hint <= 5.f;
+    if (force == nullptr || force[0] == 0 || only_small || force_cluster) {  // minibatch-sized systems: the latency-organised kernels
+      int rc = (force_cluster || (sparse && !only_small)) ? cg_cluster_try(P, st) : 0;  // one cluster of eight CTAs (64 <= m <= 2048)
       if (rc < 0) return rc;
       if (rc == 1) return GLL_OK;
       rc = cg_small_try(P, st);  // one CTA, a thread per row (m <= 512)

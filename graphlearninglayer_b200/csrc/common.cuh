@@ -145,6 +145,7 @@ struct CgIo {
   int x_copy_f64;
   const void* rhs_scale;  // optional device scalar multiplied into rhs_src (fp64 if rhs_scale_f64)
   int rhs_scale_f64;
+  float uu_degree_hint;   // expected off-diagonal entries per row of the system (0: unknown) -- picks the minibatch kernel
 };
 int cg_run(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag, const float* rhs, int m,
            int l, float tol, int max_iter, float* x, int* iters_out, float* resid_out, int* status_out, void* ws,

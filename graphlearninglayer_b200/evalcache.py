@@ -26,6 +26,13 @@ from ._lib import lib
 from .GLL import K_NEIGHBOURS, _bytes, _cg_maxit, _cg_tol, _require_cuda, _stream_ptr
 
 
+def _uu_hint(k: int, m: int, n: int) -> float:
+    """gll_forward's own number, in its own float32 arithmetic (api.cu): 1.2f * (k - 1) * m / n."""
+    import numpy as np
+
+    return float(np.float32(1.2) * np.float32(k - 1) * np.float32(m) / np.float32(n))
+
+
 class BaseSetEvaluator:
     def __init__(self, base_features: torch.Tensor, label_matrix: torch.Tensor, tau: float = 0.0, epsilon="auto",
                  k: int = K_NEIGHBOURS):
@@ -101,10 +108,11 @@ class BaseSetEvaluator:
                                             diag.data_ptr(), rhs.data_ptr(), ut.data_ptr(), info.data_ptr(), ws.data_ptr(), wsb, s),
                        "gll_edge_weights")
             u = ut[k_lab:]
-            _lib.check(lib.gll_cg_solve(uu_ptr.data_ptr(), uu_col.data_ptr(), uu_val.data_ptr(), diag.data_ptr(), rhs.data_ptr(), m, l,
-                                        _cg_tol(), _cg_maxit(), u.data_ptr(), info[_lib.INFO_CG_ITERS_FWD:].data_ptr(),
-                                        info[_lib.INFO_CG_RESID_FWD:].data_ptr(), info[_lib.INFO_STATUS:].data_ptr(), ws.data_ptr(),
-                                        wsb, s), "gll_cg_solve")
+            # the same sparsity hint as gll_forward passes, so that the same solver kernel runs: bit-identical predictions
+            _lib.check(lib.gll_cg_solve_hint(uu_ptr.data_ptr(), uu_col.data_ptr(), uu_val.data_ptr(), diag.data_ptr(), rhs.data_ptr(), m,
+                                             l, _cg_tol(), _cg_maxit(), u.data_ptr(), info[_lib.INFO_CG_ITERS_FWD:].data_ptr(),
+                                             info[_lib.INFO_CG_RESID_FWD:].data_ptr(), info[_lib.INFO_STATUS:].data_ptr(),
+                                             ws.data_ptr(), wsb, s, _uu_hint(k, m, n)), "gll_cg_solve")
             pred64 = os.environ.get("GLL_B200_PRED_DTYPE", "float64") != "float32"
             pred = torch.empty((m, l), dtype=torch.float64 if pred64 else f32, device=dev)
             _lib.check(lib.gll_unpack_pred(u.data_ptr(), m, l, pred.data_ptr(), int(pred64), s), "gll_unpack_pred")

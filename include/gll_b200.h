@@ -142,6 +142,13 @@ size_t gll_cg_workspace_bytes(int m, int l);
 int gll_cg_solve(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag,
                  const float* rhs, int m, int l, float tol, int max_iter, float* x, int* iters_out,
                  float* resid_out, int* status_out, void* workspace, size_t workspace_bytes, void* stream);
+/* The same with the caller's expectation of off-diagonal entries per row (0: unknown).  The solver cannot see nnz from the host;
+ * sparse minibatch systems (up to 5 entries per row, 64..2048 rows) take the thread-block-cluster kernel.  gll_forward /
+ * gll_backward pass 1.2 (k - 1) m / n; a caller that wants bit-identical results to the layer passes the same number. */
+int gll_cg_solve_hint(const int* uu_ptr, const int* uu_col, const float* uu_val, const float* diag,
+                      const float* rhs, int m, int l, float tol, int max_iter, float* x, int* iters_out,
+                      float* resid_out, int* status_out, void* workspace, size_t workspace_bytes, void* stream,
+                      float uu_degree_hint);
 
 /* K5+K6. Backward edge pass (GLL.py:104-159): G_ij = -<wt_i-wt_j, ut_i-ut_j>, gv = G*V, b_i = sum_j G_ij modV_ij
  * (auto only), dX_i = sum_j t_ij (x_i - x_j) with t_ij = gv_ij - [j==kappa(i)] b_i - [kappa(j)==i] b_j. */

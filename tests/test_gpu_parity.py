@@ -379,10 +379,11 @@ def test_graph_drops_zero_distance_edges(gll):
 # ----------------------------------------------------------------------------------------------------------------
 # K4: CG
 # ----------------------------------------------------------------------------------------------------------------
-# "": the dispatch by size (here: the eight-CTA cluster kernel up to 12 class columns, the multi-CTA on-chip kernel beyond);
+# "": the dispatch by size (here the multi-CTA on-chip kernel: the stage entry point passes no sparsity hint); "cluster": the
+# eight-CTA cluster kernel where its item budget allows (up to 12 class columns here), the multi-CTA kernel beyond;
 # "resident": the multi-CTA on-chip kernel for every l; "streaming": the global-memory kernel that only ~1M-row systems reach on
 # their own, forced so that it is covered at a size the CPU checker can solve
-@pytest.mark.parametrize("path", ["", "streaming", "resident"])
+@pytest.mark.parametrize("path", ["", "streaming", "resident", "cluster"])
 @pytest.mark.parametrize("l", [1, 3, 10, 37, 100, 150])  # 150 > 128 class columns: solved in column chunks
 def test_cg_vs_direct_solve(gll, monkeypatch, l, path):
     _, _lib = gll
@@ -398,10 +399,12 @@ def test_cg_vs_direct_solve(gll, monkeypatch, l, path):
 
 
 @pytest.mark.parametrize("m,l", [(64, 1), (65, 13), (511, 10), (2048, 3), (2048, 16), (700, 40)])
-def test_cg_cluster_kernel_edge_sizes(gll, m, l):
+def test_cg_cluster_kernel_edge_sizes(gll, monkeypatch, m, l):
     """The eight-CTA cluster kernel at the edges of its range (64 and 2048 rows, a last CTA with one row or none, one class, up to
-    four items per thread; 40 classes at 700 rows exceed its item budget and must fall through to another kernel)."""
+    four items per thread; 40 classes at 700 rows exceed its item budget and must fall through to another kernel).  Forced: the
+    stage entry point passes no sparsity hint and would pick the other kernels."""
     _, _lib = gll
+    monkeypatch.setenv("GLL_B200_CG_PATH", "cluster")
     X, Y, *_ = O.synth_inputs(31 + m + l, 120, m, 20, l, 1.5)
     f = O.forward(X, Y, 0.03, 1.0, solver="lu")
     x, iters, resid, status = run_cg(_lib, f.Luu, f.B, tol=1e-7)
@@ -421,11 +424,11 @@ def test_knn_cta_pairs_by_default_with_an_odd_number_of_row_tiles(gll):
     assert np.array_equal(dist.cpu().numpy()[rows], ref_dist.astype(np.float32))
 
 
-@pytest.mark.parametrize("path", ["", "streaming", "small"])
+@pytest.mark.parametrize("path", ["", "streaming", "small", "cluster"])
 def test_cg_zero_rhs_column_and_maxiter(gll, monkeypatch, path):
     _, _lib = gll
     if path:
-        monkeypatch.setenv("GLL_B200_CG_PATH", path)  # "": the cluster kernel; "small": the one-CTA kernel (<= 512 rows)
+        monkeypatch.setenv("GLL_B200_CG_PATH", path)  # "small": the one-CTA kernel (<= 512 rows)
     X, Y, *_ = O.synth_inputs(5, 100, 400 if path == "small" else 900, 16, 4, 1.5)
     f = O.forward(X, Y, 0.05, 1.0, solver="lu")
     B = f.B.copy()
