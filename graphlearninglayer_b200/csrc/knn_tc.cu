@@ -218,7 +218,6 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[TC_CHUNK]) {
 #undef TC_R8
 #undef TC_OUT
 #undef TC_INOUT
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory"); }  // the epilogue warps
 
 struct TcParams {
   int n, kblocks, col_tiles, max_splits;
@@ -238,7 +237,7 @@ struct TcParams {
   const unsigned* small;  // small[3], small[4]: range of E_i over the rows (written by sqnorm_split_f16_kernel)
   unsigned long long* trace;  // debug timeline of CTA 0 (gll_debug_knn_trace, tools/knn_trace.py), or NULL
 };
-constexpr int TC_TRACE_UNITS = 1024, TC_TRACE_PHASES = 8, TC_TRACE_WARPS = 4;  // MMA warp, epilogue warps 2 and 6, producer A
+constexpr int TC_TRACE_UNITS = 1024, TC_TRACE_PHASES = 8;  // four traced warps: MMA warp, epilogue warps 2 and 6, producer A
 
 __host__ __device__ inline uint32_t a_bytes_of(int passes) { return passes == 2 ? 2u * TC_A_BYTES : (uint32_t)TC_A_BYTES; }  // A_hi (+ A_lo)
 
@@ -289,7 +288,6 @@ knn_gram_topk_tc_kernel(const __grid_constant__ CUtensorMap mapAH, const __grid_
   const uint32_t ring_base = base + (ares ? (uint32_t)KB * a_bytes : 0u);
   const uint32_t stage_stride = ares ? b_bytes : a_bytes + b_bytes;  // = bytes this CTA loads per stage
   const int nstages = min(TC_MAX_STAGES, (int)(((uint32_t)TC_STAGE_REGION - (ring_base - base)) / stage_stride));
-  const uint32_t stage_bytes = stage_stride;
   const uint32_t bar_full = base + (uint32_t)TC_OFF_BAR;        // [TC_MAX_STAGES]
   const uint32_t bar_empty = bar_full + 8 * TC_MAX_STAGES;      // [TC_MAX_STAGES]
   const uint32_t bar_tfull = bar_empty + 8 * TC_MAX_STAGES;     // [2]
